@@ -1,0 +1,667 @@
+// C ABI + host orchestration of the CPT cross-modal BERT path on one B200 (see include/cpt_b200.h).
+// Kernel sequence of one encoder forward (K-numbers: SURVEY.md 2.4b):
+//   ext_mask (K4) | embed_text_ln (K1) | cast_pad + GEMM(bias) + LN -> region rows (K2,K3)
+//   per layer: GEMM QKV(bias) (K5) | attention (K6-K9) | GEMM out(bias+resid) + LN (K10)
+//              | GEMM up(bias+GELU) (K11) | GEMM down(bias+resid) + LN (K12)
+//   heads: pooler/NSP mat-vec (K13,K17) | MLM transform + decoder at the [MASK] rows (K14,K15)
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cpt_b200.h"
+#include "attention_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+using namespace cptk;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKL(what)                                                                                      \
+  do {                                                                                                 \
+    cudaError_t e_ = cudaGetLastError();                                                               \
+    if (e_ != cudaSuccess) return fail("launch of %s failed: %s (%s:%d)", what, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)              \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+static int get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode ? 0 : fail("cuTensorMapEncodeTiled is not available from this driver");
+}
+// 2-D row-major 16-bit tensor [rows, cols] with pitch ld (elements); box = 64 cols x box_rows, 128B swizzle,
+// out-of-bounds elements read as zero.
+static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long long rows, unsigned long long cols,
+                     unsigned long long ld, unsigned box_rows) {
+  TRY(get_encode());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+    return fail("TMA operand must be 16-byte aligned with a 16-byte-multiple pitch (ptr=%p ld=%llu)", ptr, ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct LayerDev {
+  void *w_qkv, *w_ao, *w_i, *w_o;  // 16-bit [3H,H] [H,H] [I,H] [H,I]
+  float *b_qkv, *b_ao, *ao_g, *ao_b, *b_i, *b_o, *o_g, *o_b;
+};
+struct cpt_handle {
+  cpt_config cfg;
+  int device = 0, num_sms = 148;
+  int Fp = 0;  // padded region-feature pitch
+  bool has_weights = false, has_mlm = false, has_nsp = false, has_pooler = false;
+  std::vector<void*> owned;
+  const float *word = nullptr, *pos = nullptr, *type = nullptr;
+  float *emb_g = nullptr, *emb_b = nullptr;
+  void* w_img = nullptr;
+  float *b_img = nullptr, *img_g = nullptr, *img_b = nullptr;
+  float *pool_w = nullptr, *pool_b = nullptr;
+  float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
+  void *mlm_w16 = nullptr, *word16 = nullptr;
+  float *nsp_w = nullptr, *nsp_b = nullptr;
+  std::vector<LayerDev> layers;
+  int* err_flag = nullptr;
+  int attn_impl = 0, block_n = 0;
+};
+
+static int dev_alloc(cpt_handle* h, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  h->owned.push_back(*p);
+  return 0;
+}
+static void free_owned(cpt_handle* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int d) {
+    cudaGetDevice(&prev);
+    if (prev != d) cudaSetDevice(d);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <typename F>
+static int set_smem_attr(F* fn, size_t bytes) {
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int BN, int EPI, typename OutT, typename T16>
+static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
+                         const GemmParams& p) {
+  auto* fn = gemm_kernel<BN, EPI, OutT, T16>;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    TRY(set_smem_attr(fn, GemmCfg<BN>::kSmemBytes));
+    attr_set[h->device & 63] = true;
+  }
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  fn<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  CKL("gemm_kernel");
+  return 0;
+}
+
+template <int EPI, typename OutT, typename T16>
+static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, int bn, const CUtensorMap& ta, const CUtensorMap& tb,
+                          const GemmParams& p) {
+  switch (bn) {
+    case 64: return launch_gemm_t<64, EPI, OutT, T16>(h, st, ta, tb, p);
+    case 128: return launch_gemm_t<128, EPI, OutT, T16>(h, st, ta, tb, p);
+    case 256: return launch_gemm_t<256, EPI, OutT, T16>(h, st, ta, tb, p);
+  }
+  return fail("unsupported GEMM block_n %d", bn);
+}
+
+static int pick_bn(const cpt_handle* h, int M, int N, int block_n) {
+  if (block_n) return block_n;
+  if (h->block_n) return h->block_n;
+  (void)M;
+  return N >= 2048 ? 256 : 128;
+}
+
+// A [M,K] lda, W [N,K] ldw (16-bit) -> out.  p.M/N/K and epilogue fields must be filled in.
+template <typename T16>
+static int gemm(cpt_handle* h, cudaStream_t st, const void* A, long long lda, const void* W, long long ldw,
+                GemmParams p, int epi, bool out_fp32, int block_n = 0) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+  const int bn = pick_bn(h, p.M, p.N, block_n);
+  const int dt = Cvt<T16>::kFmt;
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
+  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, bn));
+  if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, bn, ta, tb, p);
+  if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, bn, ta, tb, p);
+  if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, bn, ta, tb, p);
+  if (epi == EPI_BIAS_GELU && out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, float, T16>(h, st, bn, ta, tb, p);
+  if (epi == EPI_BIAS_RESID && out_fp32) return launch_gemm_bn<EPI_BIAS_RESID, float, T16>(h, st, bn, ta, tb, p);
+  return fail("unsupported GEMM epilogue/output combination (epi=%d out_fp32=%d)", epi, (int)out_fp32);
+}
+
+template <typename T16>
+static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const float* ext_mask, int B, int S, void* ctx,
+                     int impl) {
+  const int H = h->cfg.hidden_size, nH = h->cfg.num_attention_heads;
+  if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
+  if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
+  AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f};
+  if (impl == 1) {
+    auto* fn = attn_simt_kernel<T16>;
+    const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
+    TRY(set_smem_attr(fn, smem));
+    fn<<<dim3(nH, B), 128, smem, st>>>(reinterpret_cast<const T16*>(qkv), p);
+    CKL("attn_simt_kernel");
+    return 0;
+  }
+  CUtensorMap tq;
+  TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
+  auto* fn = attn_tc_kernel<T16>;
+  const size_t smem = attn_smem_bytes(S);
+  TRY(set_smem_attr(fn, smem));
+  fn<<<dim3(nH, (S + 127) / 128, B), kAttnThreads, smem, st>>>(tq, p);
+  CKL("attn_tc_kernel");
+  return 0;
+}
+
+template <typename T16>
+static int layernorm(cudaStream_t st, const float* x, long long ldx, int M, int H, const float* g, const float* b,
+                     float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0) {
+  if (M <= 0) return 0;
+  ln_rows_kernel<T16><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, M, H, g, b, eps, do_ln ? 1 : 0, o32,
+                                                   reinterpret_cast<T16*>(o16), rin, rout, roff);
+  CKL("ln_rows_kernel");
+  return 0;
+}
+
+static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long ldx, int x_rows_per_b,
+                       const long long* x_pos, const float* ln_g, const float* ln_b, float eps, const float* W,
+                       long long ldw, const float* bias, const long long* w_ids, int w_rows, int B, int H, int O,
+                       int act, float* Y, long long ldy) {
+  if (B <= 0 || O <= 0) return 0;
+  const size_t smem = (size_t)kHeadRows * H * sizeof(float);
+  dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + 63) / 64);
+  head_matvec_kernel<<<grid, 256, smem, st>>>(X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw, bias, w_ids,
+                                              w_rows, B, H, O, act, Y, ldy, h->err_flag);
+  CKL("head_matvec_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+struct Workspace {
+  float *ext_mask, *h32, *a32, *pre32, *head_t;
+  char *h16, *a16, *ctx16, *qkv16, *inter16, *img16;
+  size_t total;
+};
+static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
+  const cpt_config& c = h->cfg;
+  const size_t M = (size_t)B * (T + R), H = c.hidden_size, I = c.intermediate_size;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += al(bytes);
+    return p;
+  };
+  Workspace w;
+  w.ext_mask = (float*)take(M * 4);
+  w.h32 = (float*)take(M * H * 4);
+  w.a32 = (float*)take(M * H * 4);
+  w.pre32 = (float*)take(M * H * 4);
+  w.head_t = (float*)take((size_t)B * H * 4);
+  w.h16 = take(M * H * 2);
+  w.a16 = take(M * H * 2);
+  w.ctx16 = take(M * H * 2);
+  w.qkv16 = take(M * 3 * H * 2);
+  w.inter16 = take(M * I * 2);
+  w.img16 = take((size_t)B * R * h->Fp * 2);
+  w.total = off + 256;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+template <typename T16>
+static int cast_w(cudaStream_t st, const float* src, long long rows, int cols, int ldo, void* dst) {
+  const long long total = rows * ldo;
+  const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  cast_weight_kernel<T16><<<grid, 256, 0, st>>>(src, rows, cols, ldo, reinterpret_cast<T16*>(dst));
+  CKL("cast_weight_kernel");
+  return 0;
+}
+static int copy_vec(cpt_handle* h, cudaStream_t st, const float* src, size_t n, float** dst) {
+  if (!src) {
+    *dst = nullptr;
+    return 0;
+  }
+  TRY(dev_alloc(h, (void**)dst, n * 4));
+  CK(cudaMemcpyAsync(*dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+template <typename T16>
+static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, F = c.img_feature_dim;
+  int* flag = h->err_flag;
+  h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)flag), h->owned.end());
+  free_owned(h);
+  h->owned.push_back(flag);
+  h->has_weights = false;
+  if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b || !w->layers)
+    return fail("cpt_set_weights: embedding tables / LayerNorm / layers must be non-NULL");
+  h->word = w->word_emb;
+  h->pos = w->pos_emb;
+  h->type = w->type_emb;
+  TRY(copy_vec(h, st, w->emb_ln_g, H, &h->emb_g));
+  TRY(copy_vec(h, st, w->emb_ln_b, H, &h->emb_b));
+  h->w_img = nullptr;
+  if (w->img_w) {
+    if (!w->img_b) return fail("cpt_set_weights: img_w without img_b");
+    if (c.use_img_layernorm && (!w->img_ln_g || !w->img_ln_b))
+      return fail("cpt_set_weights: use_img_layernorm=1 needs bert.LayerNorm weights");
+    TRY(dev_alloc(h, &h->w_img, (size_t)H * h->Fp * 2));
+    TRY(cast_w<T16>(st, w->img_w, H, F, h->Fp, h->w_img));
+    TRY(copy_vec(h, st, w->img_b, H, &h->b_img));
+    TRY(copy_vec(h, st, w->img_ln_g, H, &h->img_g));
+    TRY(copy_vec(h, st, w->img_ln_b, H, &h->img_b));
+  }
+  h->layers.assign(L, LayerDev{});
+  for (int l = 0; l < L; ++l) {
+    const cpt_layer_weights& s = w->layers[l];
+    LayerDev& d = h->layers[l];
+    const float* need[] = {s.q_w, s.q_b, s.k_w, s.k_b, s.v_w, s.v_b, s.ao_w, s.ao_b, s.ao_ln_g, s.ao_ln_b,
+                           s.i_w, s.i_b, s.o_w, s.o_b, s.o_ln_g, s.o_ln_b};
+    for (const float* q : need)
+      if (!q) return fail("cpt_set_weights: layer %d has a NULL tensor", l);
+    TRY(dev_alloc(h, &d.w_qkv, (size_t)3 * H * H * 2));
+    TRY(cast_w<T16>(st, s.q_w, H, H, H, d.w_qkv));
+    TRY(cast_w<T16>(st, s.k_w, H, H, H, (char*)d.w_qkv + (size_t)H * H * 2));
+    TRY(cast_w<T16>(st, s.v_w, H, H, H, (char*)d.w_qkv + (size_t)2 * H * H * 2));
+    TRY(dev_alloc(h, (void**)&d.b_qkv, (size_t)3 * H * 4));
+    CK(cudaMemcpyAsync(d.b_qkv, s.q_b, H * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d.b_qkv + H, s.k_b, H * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d.b_qkv + 2 * H, s.v_b, H * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(dev_alloc(h, &d.w_ao, (size_t)H * H * 2));
+    TRY(cast_w<T16>(st, s.ao_w, H, H, H, d.w_ao));
+    TRY(copy_vec(h, st, s.ao_b, H, &d.b_ao));
+    TRY(copy_vec(h, st, s.ao_ln_g, H, &d.ao_g));
+    TRY(copy_vec(h, st, s.ao_ln_b, H, &d.ao_b));
+    TRY(dev_alloc(h, &d.w_i, (size_t)I * H * 2));
+    TRY(cast_w<T16>(st, s.i_w, I, H, H, d.w_i));
+    TRY(copy_vec(h, st, s.i_b, I, &d.b_i));
+    TRY(dev_alloc(h, &d.w_o, (size_t)H * I * 2));
+    TRY(cast_w<T16>(st, s.o_w, H, I, I, d.w_o));
+    TRY(copy_vec(h, st, s.o_b, H, &d.b_o));
+    TRY(copy_vec(h, st, s.o_ln_g, H, &d.o_g));
+    TRY(copy_vec(h, st, s.o_ln_b, H, &d.o_b));
+  }
+  h->has_pooler = w->pooler_w && w->pooler_b;
+  if (h->has_pooler) {
+    TRY(copy_vec(h, st, w->pooler_w, (size_t)H * H, &h->pool_w));
+    TRY(copy_vec(h, st, w->pooler_b, H, &h->pool_b));
+  }
+  h->has_mlm = w->mlm_dense_w && w->mlm_dense_b && w->mlm_ln_g && w->mlm_ln_b && w->mlm_bias;
+  if (h->has_mlm) {
+    TRY(copy_vec(h, st, w->mlm_dense_w, (size_t)H * H, &h->mlm_w));
+    TRY(copy_vec(h, st, w->mlm_dense_b, H, &h->mlm_b));
+    TRY(copy_vec(h, st, w->mlm_ln_g, H, &h->mlm_g));
+    TRY(copy_vec(h, st, w->mlm_ln_b, H, &h->mlm_beta));
+    TRY(copy_vec(h, st, w->mlm_bias, c.vocab_size, &h->mlm_bias));
+    // 16-bit copies for the full-vocabulary scores path (tensor-core GEMM over all rows)
+    TRY(dev_alloc(h, &h->mlm_w16, (size_t)H * H * 2));
+    TRY(cast_w<T16>(st, w->mlm_dense_w, H, H, H, h->mlm_w16));
+    TRY(dev_alloc(h, &h->word16, (size_t)c.vocab_size * H * 2));
+    TRY(cast_w<T16>(st, w->word_emb, c.vocab_size, H, H, h->word16));
+  }
+  h->has_nsp = w->nsp_w && w->nsp_b;
+  if (h->has_nsp) {
+    TRY(copy_vec(h, st, w->nsp_w, (size_t)c.num_contrast_classes * H, &h->nsp_w));
+    TRY(copy_vec(h, st, w->nsp_b, c.num_contrast_classes, &h->nsp_b));
+  }
+  h->has_weights = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <typename T16>
+static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids, const int64_t* seg,
+                                const int64_t* mask, const int64_t* pos_ids, const float* img, int B, int T, int R,
+                                void* ws_ptr, size_t ws_bytes, float* seq_out, float* pooled, float* hidden_states) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S;
+  if (!h->has_weights) return fail("cpt_encoder_forward called before cpt_set_weights");
+  if (B <= 0 || T <= 0 || R < 0) return fail("bad shape B=%d T=%d R=%d", B, T, R);
+  if (T > c.max_position_embeddings) return fail("T=%d exceeds max_position_embeddings=%d", T, c.max_position_embeddings);
+  if (R > 0 && (!img || !h->w_img)) return fail("img_feats given but no img_embedding weights (or NULL img_feats)");
+  if (S > 256) return fail("sequence length T+R=%d exceeds the 256 this build's attention kernel supports", S);
+  Workspace w = carve(h, B, T, R, (char*)(((uintptr_t)ws_ptr + 255) & ~uintptr_t(255)));
+  if (!ws_ptr || ws_bytes < w.total) return fail("workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
+  if (!ids || !seq_out) return fail("input_ids and seq_out must be non-NULL");
+
+  // K4: additive mask
+  if (mask) {
+    ext_mask_kernel<<<(M + 255) / 256, 256, 0, st>>>((const long long*)mask, M, w.ext_mask);
+    CKL("ext_mask_kernel");
+  } else {
+    CK(cudaMemsetAsync(w.ext_mask, 0, (size_t)M * 4, st));
+  }
+  // K1: text rows
+  embed_text_ln_kernel<T16><<<(B * T + 7) / 8, 256, 0, st>>>(
+      (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g,
+      h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, w.h32,
+      reinterpret_cast<T16*>(w.h16), h->err_flag);
+  CKL("embed_text_ln_kernel");
+  // K2+K3: region rows
+  if (R > 0) {
+    const int F = c.img_feature_dim, Mi = B * R;
+    const long long pairs = (long long)Mi * (h->Fp / 2);
+    const int grid = (int)((pairs + 255) / 256 < 8192 ? (pairs + 255) / 256 : 8192);
+    cast_pad_kernel<T16><<<grid, 256, 0, st>>>(img, Mi, F, h->Fp, reinterpret_cast<T16*>(w.img16));
+    CKL("cast_pad_kernel");
+    GemmParams p{};
+    p.M = Mi; p.N = H; p.K = F; p.out = w.pre32; p.ldo = H; p.bias = h->b_img;
+    TRY(gemm<T16>(h, st, w.img16, h->Fp, h->w_img, h->Fp, p, EPI_BIAS, true));
+    TRY(layernorm<T16>(st, w.pre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps, c.use_img_layernorm != 0,
+                       w.h32, w.h16, R, S, T));
+  }
+  if (hidden_states) CK(cudaMemcpyAsync(hidden_states, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
+
+  for (int l = 0; l < L; ++l) {
+    const LayerDev& d = h->layers[l];
+    {  // K5
+      GemmParams p{};
+      p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
+      TRY(gemm<T16>(h, st, w.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
+    }
+    TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));  // K6-K9
+    {  // K10
+      GemmParams p{};
+      p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao; p.resid = w.h32; p.ldr = H;
+      TRY(gemm<T16>(h, st, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
+      TRY(layernorm<T16>(st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
+    }
+    {  // K11
+      GemmParams p{};
+      p.M = M; p.N = I; p.K = H; p.out = w.inter16; p.ldo = I; p.bias = d.b_i;
+      TRY(gemm<T16>(h, st, w.a16, H, d.w_i, H, p, EPI_BIAS_GELU, false));
+    }
+    {  // K12
+      GemmParams p{};
+      p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o; p.resid = w.a32; p.ldr = H;
+      TRY(gemm<T16>(h, st, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
+      float* o32 = (l == L - 1) ? seq_out : w.h32;
+      TRY(layernorm<T16>(st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+                         (l == L - 1) ? nullptr : w.h16));
+      if (hidden_states)
+        CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4,
+                           cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (L == 0) CK(cudaMemcpyAsync(seq_out, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
+  if (pooled) {  // K13
+    if (!h->has_pooler) return fail("pooled output requested but bert.pooler weights were not provided");
+    TRY(head_matvec(h, st, seq_out, H, S, nullptr, nullptr, nullptr, 0.f, h->pool_w, H, h->pool_b, nullptr, H, B, H,
+                    H, ACT_TANH, pooled, H));
+  }
+  return 0;
+}
+
+template <typename T16>
+static int mlm_scores_impl(cpt_handle* h, cudaStream_t st, const float* seq_out, long long rows, void* ws_ptr,
+                           size_t ws_bytes, float* scores) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, V = c.vocab_size;
+  const size_t need = cpt_mlm_scores_workspace_bytes(h, rows);
+  if (!ws_ptr || ws_bytes < need) return fail("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  char* base = (char*)(((uintptr_t)ws_ptr + 255) & ~uintptr_t(255));
+  char* x16 = base;
+  float* t32 = (float*)(base + al((size_t)rows * H * 2));
+  char* t16 = (char*)t32 + al((size_t)rows * H * 4);
+  TRY(layernorm<T16>(st, seq_out, H, (int)rows, H, nullptr, nullptr, 0.f, false, nullptr, x16));  // fp32 -> 16-bit
+  GemmParams p{};
+  p.M = (int)rows; p.N = H; p.K = H; p.out = t32; p.ldo = H; p.bias = h->mlm_b;
+  TRY(gemm<T16>(h, st, x16, H, h->mlm_w16, H, p, EPI_BIAS_GELU, true));
+  TRY(layernorm<T16>(st, t32, H, (int)rows, H, h->mlm_g, h->mlm_beta, c.layer_norm_eps, true, nullptr, t16));
+  GemmParams q{};
+  q.M = (int)rows; q.N = V; q.K = H; q.out = scores; q.ldo = V; q.bias = h->mlm_bias;
+  TRY(gemm<T16>(h, st, t16, H, h->word16, H, q, EPI_BIAS, true));
+  return 0;
+}
+
+#define DISPATCH_DTYPE(h, CALL)                                  \
+  ((h)->cfg.dtype == 0 ? CALL(__half) : CALL(__nv_bfloat16))
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* cpt_last_error(void) { return g_err.c_str(); }
+int cpt_abi_version(void) { return CPT_B200_ABI_VERSION; }
+
+int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
+  if (!cfg || !out) return fail("cpt_create: NULL argument");
+  *out = nullptr;
+  const cpt_config& c = *cfg;
+  if (c.hidden_size <= 0 || c.hidden_size % 128 || c.hidden_size > 1024)
+    return fail("hidden_size must be a multiple of 128 and <= 1024 (got %d)", c.hidden_size);
+  if (c.num_attention_heads <= 0 || c.hidden_size != c.num_attention_heads * 64)
+    return fail("head size must be 64 (hidden %d / heads %d)", c.hidden_size, c.num_attention_heads);
+  if (c.intermediate_size <= 0 || c.intermediate_size % 8) return fail("intermediate_size must be a multiple of 8");
+  if (c.dtype != 0 && c.dtype != 1) return fail("dtype must be 0 (fp16) or 1 (bf16)");
+  if (c.num_hidden_layers < 0 || c.vocab_size <= 0 || c.max_position_embeddings <= 0 || c.type_vocab_size <= 0)
+    return fail("bad config");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d CUDA devices visible)", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("cpt_b200 is built for sm_100a (B200) only; device %d is sm_%d%d — there is no fallback path", device,
+                prop.major, prop.minor);
+  DeviceGuard g(device);
+  cpt_handle* h = new cpt_handle();
+  h->cfg = c;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->Fp = (c.img_feature_dim + 7) & ~7;
+  if (cudaMalloc((void**)&h->err_flag, 16) != cudaSuccess) {
+    delete h;
+    return fail("cudaMalloc failed");
+  }
+  cudaMemset(h->err_flag, 0, 16);
+  h->owned.push_back(h->err_flag);
+  if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
+  if (const char* e = getenv("CPT_B200_BN")) h->block_n = atoi(e);
+  *out = h;
+  return 0;
+}
+
+int cpt_destroy(cpt_handle* h) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  free_owned(h);
+  delete h;
+  return 0;
+}
+
+int cpt_set_weights(cpt_handle* h, const cpt_weights* w, void* stream) {
+  if (!h || !w) return fail("cpt_set_weights: NULL argument");
+  DeviceGuard g(h->device);
+  CK(cudaDeviceSynchronize());  // no kernel may still be reading the buffers we are about to free
+#define CALL(T) set_weights_impl<T>(h, w, (cudaStream_t)stream)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+size_t cpt_workspace_bytes(const cpt_handle* h, int B, int T, int R) {
+  if (!h || B <= 0 || T <= 0 || R < 0) return 0;
+  return carve(h, B, T, R, nullptr).total;
+}
+
+int cpt_encoder_forward(cpt_handle* h, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                        const int64_t* attention_mask, const int64_t* position_ids, const float* img_feats, int B,
+                        int T, int R, void* workspace, size_t workspace_bytes, float* seq_out, float* pooled,
+                        float* hidden_states) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+#define CALL(T16)                                                                                             \
+  encoder_forward_impl<T16>(h, (cudaStream_t)stream, input_ids, token_type_ids, attention_mask, position_ids, \
+                            img_feats, B, T, R, workspace, workspace_bytes, seq_out, pooled, hidden_states)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_mlm_gather_forward(cpt_handle* h, void* stream, const float* seq_out, int B, int S, const int64_t* mask_pos,
+                           const int64_t* vocab_ids, int K, void* workspace, size_t workspace_bytes, float* logits) {
+  if (!h) return fail("NULL handle");
+  if (!h->has_mlm) return fail("MLM head weights (cls.predictions.*) were not provided");
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size;
+  if (!seq_out || !mask_pos || !logits) return fail("NULL argument");
+  if (!vocab_ids && K != c.vocab_size) return fail("vocab_ids NULL requires K == vocab_size");
+  if ((size_t)B * H * 4 + 256 > workspace_bytes || !workspace) return fail("workspace too small for the MLM head");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* t = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  // transform: gelu(dense(x[mask_pos]))            (BertPredictionHeadTransform, LN folded into the next kernel)
+  TRY(head_matvec(h, st, seq_out, H, S, (const long long*)mask_pos, nullptr, nullptr, 0.f, h->mlm_w, H, h->mlm_b,
+                  nullptr, H, B, H, H, ACT_GELU, t, H));
+  // decoder over the gathered vocabulary rows (tied to word embeddings) + bias
+  TRY(head_matvec(h, st, t, H, 1, nullptr, h->mlm_g, h->mlm_beta, c.layer_norm_eps, h->word, H, h->mlm_bias,
+                  (const long long*)vocab_ids, c.vocab_size, B, H, K, ACT_NONE, logits, K));
+  return 0;
+}
+
+size_t cpt_mlm_scores_workspace_bytes(const cpt_handle* h, long long rows) {
+  if (!h || rows <= 0) return 0;
+  const size_t H = h->cfg.hidden_size;
+  return al(rows * H * 2) * 2 + al(rows * H * 4) + 512;
+}
+
+int cpt_mlm_scores_forward(cpt_handle* h, void* stream, const float* seq_out, long long rows, void* workspace,
+                           size_t workspace_bytes, float* scores) {
+  if (!h) return fail("NULL handle");
+  if (!h->has_mlm) return fail("MLM head weights (cls.predictions.*) were not provided");
+  if (!seq_out || !scores || rows <= 0 || rows > 0x7fffffff) return fail("bad argument");
+  DeviceGuard g(h->device);
+#define CALL(T16) mlm_scores_impl<T16>(h, (cudaStream_t)stream, seq_out, rows, workspace, workspace_bytes, scores)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_nsp_forward(cpt_handle* h, void* stream, const float* pooled, int B, float* out) {
+  if (!h) return fail("NULL handle");
+  if (!h->has_nsp) return fail("NSP head weights (cls.seq_relationship.*) were not provided");
+  if (!pooled || !out) return fail("NULL argument");
+  DeviceGuard g(h->device);
+  const int H = h->cfg.hidden_size, C = h->cfg.num_contrast_classes;
+  return head_matvec(h, (cudaStream_t)stream, pooled, H, 1, nullptr, nullptr, nullptr, 0.f, h->nsp_w, H, h->nsp_b,
+                     nullptr, C, B, H, C, ACT_NONE, out, C);
+}
+
+int cpt_check_async_error(cpt_handle* h, void* stream) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  int flag = 0;
+  CK(cudaMemcpy(&flag, h->err_flag, 4, cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(h->err_flag, 0, 4);
+    static const char* what[] = {"", "token / segment / position id out of range", "mask position out of range",
+                                 "vocabulary id out of range"};
+    return fail("device-side input check failed: %s", what[flag < 4 ? flag : 0]);
+  }
+  return 0;
+}
+
+int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const void* W, long long ldw, int M, int N,
+             int K, const float* bias, const float* resid, long long ldr, int epi, int out_fp32, void* out,
+             long long ldo, int block_n) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
+#define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, A, lda, W, ldw, p, epi, out_fp32 != 0, block_n)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_attention(cpt_handle* h, void* stream, const void* qkv, const float* ext_mask, int B, int S, void* ctx,
+                  int impl) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+#define CALL(T16) attention<T16>(h, (cudaStream_t)stream, qkv, ext_mask, B, S, ctx, impl)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_layernorm(cpt_handle* h, void* stream, const float* x, int M, const float* gamma, const float* beta,
+                  float eps, float* out32, void* out16) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+  const int H = h->cfg.hidden_size;
+#define CALL(T16) layernorm<T16>((cudaStream_t)stream, x, H, M, H, gamma, beta, eps, gamma != nullptr, out32, out16)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_cast16(cpt_handle* h, void* stream, const float* x, long long rows, int cols, int ld_out, void* out16) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+#define CALL(T16) cast_w<T16>((cudaStream_t)stream, x, rows, cols, ld_out, out16)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+}  // extern "C"

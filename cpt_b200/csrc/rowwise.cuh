@@ -1,0 +1,238 @@
+// HBM/L2-bound row kernels of the CPT path: text-embedding gather + LayerNorm, (residual-)LayerNorm with a
+// 16-bit shadow copy for the next GEMM, region-feature cast/pad, and the small fp32 head mat-vecs
+// (MLM transform/decoder at the [MASK] rows only, pooler, NSP).  One warp owns one row of H floats
+// (H % 128 == 0, H <= 1024), read and written as float4 / 8-byte packed 16-bit.
+#pragma once
+#include "ptx.cuh"
+
+namespace cptk {
+
+constexpr int kMaxVec = 8;  // H <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// BertLayerNorm on a row held as nv float4 per lane: biased variance, eps inside the sqrt, two-pass.
+template <typename T16>
+__device__ __forceinline__ void ln_store_row(float4* x, int nv, int H, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float eps, float* __restrict__ out32,
+                                             T16* __restrict__ out16, int lane, bool do_ln) {
+  float mean = 0.f, rstd = 1.f;
+  if (do_ln) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 4;
+      float4 y = x[i];
+      if (do_ln) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+        y.x = (y.x - mean) * rstd * g.x + b.x;
+        y.y = (y.y - mean) * rstd * g.y + b.y;
+        y.z = (y.z - mean) * rstd * g.z + b.z;
+        y.w = (y.w - mean) * rstd * g.w + b.w;
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + col) = y;
+      if (out16) {
+        uint2 u;
+        u.x = Cvt<T16>::pack2(y.x, y.y);
+        u.y = Cvt<T16>::pack2(y.z, y.w);
+        *reinterpret_cast<uint2*>(out16 + col) = u;
+      }
+    }
+}
+
+// K1: LN(word[ids] + pos[t or position_ids] + type[seg]) -> rows [b*S + t] of the [B,S,H] stream.
+template <typename T16>
+__global__ void __launch_bounds__(256) embed_text_ln_kernel(
+    const long long* __restrict__ ids, const long long* __restrict__ seg, const long long* __restrict__ pos_ids,
+    const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int B, int T, int S, int H,
+    int vocab, int max_pos, int n_type, float* __restrict__ out32, T16* __restrict__ out16, int* __restrict__ err) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const int b = row / T, t = row % T;
+  long long id = ids[row];
+  long long sg = seg ? seg[row] : 0;
+  long long ps = pos_ids ? pos_ids[row] : t;
+  if (id < 0 || id >= vocab || sg < 0 || sg >= n_type || ps < 0 || ps >= max_pos) {
+    if (lane == 0) atomicExch(err, 1);  // surfaced as an error by the host; clamp so we do not fault
+    id = min(max(id, 0ll), (long long)vocab - 1);
+    sg = min(max(sg, 0ll), (long long)n_type - 1);
+    ps = min(max(ps, 0ll), (long long)max_pos - 1);
+  }
+  const int nv = H >> 7;
+  float4 x[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
+      x[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
+    }
+  const long long orow = (long long)b * S + t;
+  ln_store_row<T16>(x, nv, H, gamma, beta, eps, out32 + orow * H, out16 + orow * H, lane, true);
+}
+
+// LayerNorm of fp32 rows (already bias+residual-added by the GEMM epilogue) -> fp32 stream + 16-bit shadow.
+// Row remap as in GemmParams (used to drop the region embeddings behind the text rows: the `cat` of
+// modeling_bert.py:269 is never materialised).
+template <typename T16>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, long long ld_in, int M, int H,
+                                                      const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, int do_ln,
+                                                      float* __restrict__ out32, T16* __restrict__ out16, int rin,
+                                                      int rout, int roff) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nv = H >> 7;
+  float4 x[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + (i * 32 + lane) * 4);
+  long long orow = row;
+  if (rin > 0) orow = (long long)(row / rin) * rout + roff + (row % rin);
+  ln_store_row<T16>(x, nv, H, gamma, beta, eps, out32 ? out32 + orow * H : nullptr,
+                    out16 ? out16 + orow * H : nullptr, lane, do_ln != 0);
+}
+
+// fp32 [rows, F] -> 16-bit [rows, Fp] (Fp = F rounded up to 8, zero padded) so the row pitch is a legal TMA stride.
+template <typename T16>
+__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ in, int rows, int F, int Fp,
+                                                       T16* __restrict__ out) {
+  const long long pairs_per_row = Fp >> 1;
+  const long long total = (long long)rows * pairs_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / pairs_per_row;
+    const int c = int(i % pairs_per_row) * 2;
+    float a = 0.f, b = 0.f;
+    const float* src = in + r * F + c;
+    if (c + 1 < F) {
+      if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+        a = v.x; b = v.y;
+      } else {
+        a = __ldg(src); b = __ldg(src + 1);
+      }
+    } else if (c < F) {
+      a = __ldg(src);
+    }
+    *reinterpret_cast<uint32_t*>(out + r * Fp + c) = Cvt<T16>::pack2(a, b);
+  }
+}
+
+// fp32 weight [rows, cols] -> 16-bit [rows, ldo] (zero padded); used once per weight (re)load.
+template <typename T16>
+__global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restrict__ in, long long rows, int cols,
+                                                          int ldo, T16* __restrict__ out) {
+  const long long total = rows * ldo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ldo;
+    const int c = int(i % ldo);
+    out[i] = Cvt<T16>::from(c < cols ? in[r * cols + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Small fp32 head mat-vec:  Y[b, o] = act( W[wrow(o), :] . LN?(X[xrow(b), :]) + bias[wrow(o)] )
+//   xrow(b) = b * x_rows_per_b + (x_pos ? x_pos[b] : 0)        (gather the [MASK] / [CLS] row of sample b)
+//   wrow(o) = w_ids ? w_ids[o] : o                              (gather the colour / answer vocabulary rows)
+// One CTA handles kHeadRows samples x 64 outputs; the weight row is read once for all kHeadRows samples.
+// All fp32: the heads add no rounding beyond the encoder's (BertLMPredictionHead / BertPooler / seq_relationship).
+constexpr int kHeadRows = 8;
+enum HeadAct { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
+
+__global__ void __launch_bounds__(256) head_matvec_kernel(
+    const float* __restrict__ X, long long ldx, int x_rows_per_b, const long long* __restrict__ x_pos,
+    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, const float* __restrict__ W,
+    long long ldw, const float* __restrict__ bias, const long long* __restrict__ w_ids, int w_rows, int B, int H,
+    int O, int act, float* __restrict__ Y, long long ldy, int* __restrict__ err) {
+  extern __shared__ float xs[];  // [kHeadRows][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * kHeadRows;
+  const int nb = min(kHeadRows, B - b0);
+  // stage (and optionally normalise) the input rows: warp w owns row w
+  if (warp < nb) {
+    const int b = b0 + warp;
+    long long pos = x_pos ? x_pos[b] : 0;
+    if (pos < 0 || pos >= x_rows_per_b) {
+      if (lane == 0) atomicExch(err, 2);
+      pos = 0;
+    }
+    const float* xr = X + ((long long)b * x_rows_per_b + pos) * ldx;
+    float s = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const float v = xr[c];
+      xs[warp * H + c] = v;
+      s += v;
+    }
+    if (ln_g != nullptr) {
+      const float mean = warp_sum(s) / (float)H;
+      float q = 0.f;
+      for (int c = lane; c < H; c += 32) {
+        const float d = xs[warp * H + c] - mean;
+        q += d * d;
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + ln_eps);
+      for (int c = lane; c < H; c += 32) xs[warp * H + c] = (xs[warp * H + c] - mean) * rstd * ln_g[c] + ln_b[c];
+    }
+  } else if (warp < kHeadRows) {
+    for (int c = lane; c < H; c += 32) xs[warp * H + c] = 0.f;
+  }
+  __syncthreads();
+  for (int oo = warp; oo < 64; oo += 8) {
+    const int o = blockIdx.y * 64 + oo;
+    if (o >= O) break;
+    long long wr = w_ids ? w_ids[o] : o;
+    if (wr < 0 || wr >= w_rows) {
+      if (lane == 0) atomicExch(err, 3);
+      wr = 0;
+    }
+    const float* w = W + wr * ldw;
+    float acc[kHeadRows];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const float wv = __ldg(w + c);
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(wv, xs[r * H + c], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane < nb) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r)
+        if (lane == r) v = acc[r];
+      if (bias) v += bias[wr];
+      if (act == ACT_GELU) v = v * 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+      else if (act == ACT_TANH) v = tanhf(v);
+      Y[(long long)(b0 + lane) * ldy + o] = v;
+    }
+  }
+}
+
+}  // namespace cptk

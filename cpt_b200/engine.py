@@ -1,0 +1,244 @@
+"""Host-side engine: owns one C-ABI handle per (model, device), feeds it torch tensors' device pointers and the
+current CUDA stream.  PyTorch is plumbing here (device memory, streams); all arithmetic happens in
+cpt_b200/csrc.  No CPU path exists: tensors must live on a CUDA device of compute capability 10.x.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CptError  # noqa: F401  (re-exported)
+
+DTYPES = {"fp16": 0, "float16": 0, "half": 0, "bf16": 1, "bfloat16": 1}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_tensor(name, t, dtype, device, shape=None):
+    if t.device != device:
+        raise CptError("cpt_b200: %s is on %s but the model is on %s" % (name, t.device, device))
+    if t.dtype != dtype:
+        raise CptError("cpt_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise CptError("cpt_b200: %s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t.contiguous()
+
+
+def layer_keys(i):
+    p = "bert.encoder.layer.%d." % i
+    return {"q_w": p + "attention.self.query.weight", "q_b": p + "attention.self.query.bias",
+            "k_w": p + "attention.self.key.weight", "k_b": p + "attention.self.key.bias",
+            "v_w": p + "attention.self.value.weight", "v_b": p + "attention.self.value.bias",
+            "ao_w": p + "attention.output.dense.weight", "ao_b": p + "attention.output.dense.bias",
+            "ao_ln_g": p + "attention.output.LayerNorm.weight", "ao_ln_b": p + "attention.output.LayerNorm.bias",
+            "i_w": p + "intermediate.dense.weight", "i_b": p + "intermediate.dense.bias",
+            "o_w": p + "output.dense.weight", "o_b": p + "output.dense.bias",
+            "o_ln_g": p + "output.LayerNorm.weight", "o_ln_b": p + "output.LayerNorm.bias"}
+
+
+GLOBAL_KEYS = {"word_emb": "bert.embeddings.word_embeddings.weight",
+               "pos_emb": "bert.embeddings.position_embeddings.weight",
+               "type_emb": "bert.embeddings.token_type_embeddings.weight",
+               "emb_ln_g": "bert.embeddings.LayerNorm.weight", "emb_ln_b": "bert.embeddings.LayerNorm.bias",
+               "img_w": "bert.img_embedding.weight", "img_b": "bert.img_embedding.bias",
+               "img_ln_g": "bert.LayerNorm.weight", "img_ln_b": "bert.LayerNorm.bias",
+               "pooler_w": "bert.pooler.dense.weight", "pooler_b": "bert.pooler.dense.bias",
+               "mlm_dense_w": "cls.predictions.transform.dense.weight",
+               "mlm_dense_b": "cls.predictions.transform.dense.bias",
+               "mlm_ln_g": "cls.predictions.transform.LayerNorm.weight",
+               "mlm_ln_b": "cls.predictions.transform.LayerNorm.bias",
+               "mlm_bias": "cls.predictions.bias",
+               "nsp_w": "cls.seq_relationship.weight", "nsp_b": "cls.seq_relationship.bias"}
+OPTIONAL = {"img_w", "img_b", "img_ln_g", "img_ln_b", "pooler_w", "pooler_b", "mlm_dense_w", "mlm_dense_b",
+            "mlm_ln_g", "mlm_ln_b", "mlm_bias", "nsp_w", "nsp_b"}
+
+
+class Engine(object):
+    """One handle on one device.  `load_state_dict` takes tensors keyed like BertImgForPreTraining's
+    state_dict; fp32, on `device`."""
+
+    def __init__(self, cfg, device, dtype="fp16"):
+        self.lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise CptError("cpt_b200 runs on a CUDA device (sm_100a) only; got device '%s' — no CPU path exists"
+                           % device)
+        if not torch.cuda.is_available():
+            raise CptError("cpt_b200: no CUDA device is available")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self.cfg = cfg
+        self.dtype = dtype
+        c = _lib.Config(cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size,
+                        cfg.vocab_size, cfg.max_position_embeddings, cfg.type_vocab_size,
+                        getattr(cfg, "img_feature_dim", 2054), int(getattr(cfg, "use_img_layernorm", 0) or 0),
+                        int(getattr(cfg, "num_contrast_classes", 2)), float(cfg.layer_norm_eps),
+                        float(getattr(cfg, "img_layer_norm_eps", cfg.layer_norm_eps)), DTYPES[dtype])
+        h = C.c_void_p()
+        _lib.check(self.lib.cpt_create(C.byref(c), device.index, C.byref(h)))
+        self._h = h
+        self._ws = None
+        self._keep = None  # tensors the handle references in place (embedding tables)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cpt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd):
+        dev = self.device
+        keep = []
+
+        def get(key, optional):
+            t = sd.get(key)
+            if t is None:
+                if optional:
+                    return None
+                raise CptError("cpt_b200: state_dict is missing '%s'" % key)
+            t = t.detach()
+            if t.device != dev or t.dtype != torch.float32:
+                raise CptError("cpt_b200: '%s' must be a float32 tensor on %s (got %s on %s)"
+                               % (key, dev, t.dtype, t.device))
+            t = t.contiguous()
+            keep.append(t)
+            return t
+
+        w = _lib.Weights()
+        for f, key in GLOBAL_KEYS.items():
+            setattr(w, f, _ptr(get(key, f in OPTIONAL)))
+        L = self.cfg.num_hidden_layers
+        layers = (_lib.LayerWeights * max(L, 1))()
+        for i in range(L):
+            for f, key in layer_keys(i).items():
+                setattr(layers[i], f, _ptr(get(key, False)))
+        w.layers = C.cast(layers, C.POINTER(_lib.LayerWeights))
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.cpt_set_weights(self._h, C.byref(w), _stream()))
+        # only the embedding tables are referenced in place by the handle; keep them alive
+        self._keep = [sd[GLOBAL_KEYS[k]] for k in ("word_emb", "pos_emb", "type_emb")]
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def encoder_forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None,
+                        img_feats=None, want_pooled=True, want_hidden=False):
+        dev = self.device
+        if input_ids.dim() != 2:
+            raise CptError("cpt_b200: input_ids must be [B,T]")
+        B, T = input_ids.shape
+        R = 0 if img_feats is None else img_feats.shape[1]
+        S = T + R
+        H = self.cfg.hidden_size
+        i64 = torch.int64
+        ids = _chk_tensor("input_ids", input_ids, i64, dev)
+        seg = None if token_type_ids is None else _chk_tensor("token_type_ids", token_type_ids, i64, dev, (B, T))
+        msk = None if attention_mask is None else _chk_tensor("attention_mask", attention_mask, i64, dev, (B, S))
+        pos = None
+        if position_ids is not None:
+            pos = _chk_tensor("position_ids", position_ids.expand(B, T) if position_ids.dim() == 2 else position_ids,
+                              i64, dev, (B, T))
+        img = None
+        if img_feats is not None:
+            img = _chk_tensor("img_feats", img_feats, torch.float32, dev, (B, R, self.cfg.img_feature_dim))
+        with torch.cuda.device(dev):
+            seq = torch.empty(B, S, H, dtype=torch.float32, device=dev)
+            pooled = torch.empty(B, H, dtype=torch.float32, device=dev) if want_pooled else None
+            hidden = (torch.empty(self.cfg.num_hidden_layers + 1, B, S, H, dtype=torch.float32, device=dev)
+                      if want_hidden else None)
+            nbytes = self.lib.cpt_workspace_bytes(self._h, B, T, R)
+            ws = self._workspace(nbytes)
+            _lib.check(self.lib.cpt_encoder_forward(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos),
+                                                    _ptr(img), B, T, R, _ptr(ws), ws.numel(), _ptr(seq),
+                                                    _ptr(pooled), _ptr(hidden)))
+        return seq, pooled, hidden
+
+    def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
+        dev = self.device
+        B, S, H = seq_out.shape
+        seq = _chk_tensor("sequence_output", seq_out, torch.float32, dev)
+        mp = _chk_tensor("mask_pos", mask_pos, torch.int64, dev, (B,))
+        if vocab_ids is None:
+            K, vid = self.cfg.vocab_size, None
+        else:
+            vid = _chk_tensor("vocab_ids", vocab_ids, torch.int64, dev)
+            K = vid.numel()
+        with torch.cuda.device(dev):
+            out = torch.empty(B, K, dtype=torch.float32, device=dev)
+            ws = self._workspace(B * H * 4 + 512)
+            _lib.check(self.lib.cpt_mlm_gather_forward(self._h, _stream(), _ptr(seq), B, S, _ptr(mp), _ptr(vid), K,
+                                                       _ptr(ws), ws.numel(), _ptr(out)))
+        return out
+
+    def mlm_scores(self, seq_out):
+        dev = self.device
+        seq = _chk_tensor("sequence_output", seq_out, torch.float32, dev)
+        rows = seq.numel() // seq.shape[-1]
+        with torch.cuda.device(dev):
+            out = torch.empty(tuple(seq.shape[:-1]) + (self.cfg.vocab_size,), dtype=torch.float32, device=dev)
+            # the encoder workspace may still be in flight on this stream: that is fine, same-stream order
+            nbytes = self.lib.cpt_mlm_scores_workspace_bytes(self._h, rows)
+            ws = self._workspace(nbytes)
+            _lib.check(self.lib.cpt_mlm_scores_forward(self._h, _stream(), _ptr(seq), rows, _ptr(ws), ws.numel(),
+                                                       _ptr(out)))
+        return out
+
+    def nsp(self, pooled):
+        dev = self.device
+        p = _chk_tensor("pooled_output", pooled, torch.float32, dev)
+        B = p.shape[0]
+        with torch.cuda.device(dev):
+            out = torch.empty(B, int(getattr(self.cfg, "num_contrast_classes", 2)), dtype=torch.float32, device=dev)
+            _lib.check(self.lib.cpt_nsp_forward(self._h, _stream(), _ptr(p), B, _ptr(out)))
+        return out
+
+    def check(self):
+        """Synchronise and surface device-side input errors (out-of-range ids, the reference's IndexError)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_check_async_error(self._h, _stream()))
+
+    # ------------------------------------------------------------------ kernel-level hooks (tests / bench)
+    def _t16(self):
+        return torch.float16 if DTYPES[self.dtype] == 0 else torch.bfloat16
+
+    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, block_n=0):
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else self._t16(), device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_gemm(self._h, _stream(), _ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K,
+                                         _ptr(bias), _ptr(resid), 0 if resid is None else resid.stride(0), epi,
+                                         1 if out_fp32 else 0, _ptr(out), out.stride(0), block_n))
+        return out
+
+    def attention(self, qkv, ext_mask, B, S, impl=0):
+        H = self.cfg.hidden_size
+        ctx = torch.empty(B * S, H, dtype=self._t16(), device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_attention(self._h, _stream(), _ptr(qkv), _ptr(ext_mask), B, S, _ptr(ctx), impl))
+        return ctx
+
+    def layernorm(self, x, gamma, beta, eps):
+        M, H = x.shape
+        o32 = torch.empty_like(x)
+        o16 = torch.empty(M, H, dtype=self._t16(), device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_layernorm(self._h, _stream(), _ptr(x), M, _ptr(gamma), _ptr(beta), eps,
+                                              _ptr(o32), _ptr(o16)))
+        return o32, o16

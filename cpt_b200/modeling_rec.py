@@ -1,0 +1,54 @@
+"""REC_MLM_CPT — the CPT masked-colour-token model for RefCOCO / GQA / VG, backed by the sm_100a engine.
+
+Reference: /root/reference/Oscar/oscar/modeling/modeling_rec.py:100-152.  Same constructor,
+`copy_from_pretraining_model`, `tie_weights` and forward signature / return tuple.  Two extra keyword-only
+arguments expose what every CPT caller does right after the call
+(zeroshot/refcoco_cpt.py:219,234-235, fewshot/gqa_cpt.py:597-600):
+
+    scores = model(ids, seg, mask, img_feats=f)[0][arange(B), mask_pos][:, vocab_ids]     # reference
+    logits = model(ids, seg, mask, img_feats=f, mask_pos=mask_pos, vocab_ids=vocab_ids)[0]  # same values
+
+so the [B,S,V] score tensor (937 MB at B=64) is never formed.  Without them the full tensor is returned.
+"""
+from torch import nn
+
+from .modeling_bert import BertImgModel, BertLMPredictionHead, BertPreTrainedModel
+
+
+class REC_MLM_CPT(BertPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.bert = BertImgModel(config)
+        self.cls = BertLMPredictionHead(config)
+        self.num_seq_relations = getattr(config, "num_contrast_classes", 2)
+        self.apply(self.init_weights)
+        self.tie_weights()
+
+    def copy_from_pretraining_model(self, model, possible_colors=[]):
+        self.bert = model.bert
+        self.cls = model.cls.predictions
+        self.tie_weights()
+
+    def tie_weights(self):
+        self._tie_or_clone_weights(self.cls.decoder, self.bert.embeddings.word_embeddings)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None,
+                position_ids=None, head_mask=None, img_feats=None, *, mask_pos=None, vocab_ids=None):
+        if self.cls.decoder.weight is not self.bert.embeddings.word_embeddings.weight:
+            raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
+                               "(modeling_rec.py:130-135); call tie_weights()")
+        self.bert.register_head_tensors(self.cls.head_tensors())
+        outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
+                            attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
+        eng = self.bert.engine()
+        if mask_pos is not None:
+            if masked_lm_labels is not None:
+                raise ValueError("mask_pos/vocab_ids (gathered logits) and masked_lm_labels are exclusive")
+            return (eng.mlm_gather(outputs[0], mask_pos, vocab_ids),) + outputs[2:]
+        scores = eng.mlm_scores(outputs[0])
+        out = (scores,) + outputs[2:]
+        if masked_lm_labels is not None:
+            loss = nn.functional.cross_entropy(scores.view(-1, self.config.vocab_size), masked_lm_labels.view(-1),
+                                               ignore_index=-1)
+            out = (loss,) + out
+        return out

@@ -1,0 +1,43 @@
+"""NSPCPT — the CPT next-sentence-style scorer for VCR, backed by the sm_100a engine.
+
+Reference: /root/reference/Oscar/oscar/modeling/modeling_vcr.py:79-129: the pooled [CLS] vector goes through the
+pre-training `seq_relationship` Linear(H, num_contrast_classes); the caller scores a choice as
+1 - softmax(out)[:, 1] (fewshot/vcr_nsp_cpt.py:600).
+"""
+from torch import nn
+
+from .modeling_bert import BertImgModel, BertLMPredictionHead, BertPreTrainedModel, nsp_head_tensors
+
+
+class NSPCPT(BertPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.bert = BertImgModel(config)
+        self.cls = BertLMPredictionHead(config)  # replaced by seq_relationship in copy_from_pretraining_model
+        self.num_seq_relations = getattr(config, "num_contrast_classes", 2)
+        self.apply(self.init_weights)
+        self.tie_weights()
+
+    def copy_from_pretraining_model(self, model, possible_colors=[]):
+        self.bert = model.bert
+        self.cls = model.cls.seq_relationship
+
+    def tie_weights(self):
+        if isinstance(self.cls, BertLMPredictionHead):
+            self._tie_or_clone_weights(self.cls.decoder, self.bert.embeddings.word_embeddings)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, next_sentence_label=None,
+                position_ids=None, head_mask=None, img_feats=None):
+        if not isinstance(self.cls, nn.Linear):
+            raise RuntimeError("cpt_b200: NSPCPT scores with the pre-training seq_relationship head; call "
+                               "copy_from_pretraining_model(BertImgForPreTraining) first (modeling_vcr.py:90-92)")
+        self.bert.register_head_tensors(nsp_head_tensors(self.cls))
+        outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
+                            attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
+        score = self.bert.engine().nsp(outputs[1])
+        out = (score,) + outputs[2:]
+        if next_sentence_label is not None:
+            loss = nn.functional.cross_entropy(score.view(-1, self.num_seq_relations), next_sentence_label.view(-1),
+                                               ignore_index=-1)
+            out = (loss,) + out
+        return out

@@ -1,0 +1,123 @@
+/* cpt_b200 C ABI — the B200-native implementation of CPT's cross-modal BERT hot path.
+ *
+ * The reference (thunlp/CPT) has NO FFI for this path: it is a stack of Python nn.Modules
+ * (SURVEY.md 8b).  Each entry point below therefore cites the reference *Python* interface it replaces;
+ * cpt_b200/modeling_*.py binds them with ctypes behind drop-in modules of the same names
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.  All data pointers are DEVICE pointers on the
+ *     handle's device unless noted "host".  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - every function returns 0 on success; on failure a non-zero code, and cpt_last_error() (thread-local)
+ *     describes it.  The Python binding raises RuntimeError (the reference's per-step
+ *     `except RuntimeError: continue`, Oscar/oscar/fewshot/refcoco_cpt.py:244-253, keeps working).
+ *   - nothing is allocated per call: scratch is a caller-provided workspace of cpt_workspace_bytes().
+ *   - all launches are asynchronous on `stream`; no entry point synchronises except cpt_check_async_error.
+ */
+#ifndef CPT_B200_H
+#define CPT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPT_B200_ABI_VERSION 1
+
+typedef struct cpt_handle cpt_handle;
+
+/* Mirrors the BertConfig fields the path reads: Oscar/oscar/modeling/modeling_bert.py:96-97,159-181. */
+typedef struct {
+  int32_t hidden_size, num_hidden_layers, num_attention_heads, intermediate_size;
+  int32_t vocab_size, max_position_embeddings, type_vocab_size, img_feature_dim;
+  int32_t use_img_layernorm, num_contrast_classes;
+  float layer_norm_eps, img_layer_norm_eps;
+  int32_t dtype; /* arithmetic type of the tensor-core GEMM operands: 0 = fp16 (default), 1 = bf16 */
+} cpt_config;
+
+/* One CaptionBertLayer (modeling_bert.py:129-147); fp32, row-major [out, in] like nn.Linear.weight. */
+typedef struct {
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b; /* attention.self.{query,key,value}            */
+  const float *ao_w, *ao_b, *ao_ln_g, *ao_ln_b;   /* attention.output.{dense,LayerNorm}          */
+  const float *i_w, *i_b;                         /* intermediate.dense                          */
+  const float *o_w, *o_b, *o_ln_g, *o_ln_b;       /* output.{dense,LayerNorm}                    */
+} cpt_layer_weights;
+
+/* The state_dict of BertImgForPreTraining (modeling_bert.py:927-1021); head pointers may be NULL when the
+ * caller only runs the encoder.  Embedding tables are used IN PLACE (caller keeps them alive until the next
+ * cpt_set_weights / cpt_destroy); every other tensor is copied (and the GEMM weights converted to 16-bit). */
+typedef struct {
+  const float *word_emb, *pos_emb, *type_emb, *emb_ln_g, *emb_ln_b; /* bert.embeddings.*                  */
+  const float *img_w, *img_b, *img_ln_g, *img_ln_b;                 /* bert.img_embedding, bert.LayerNorm */
+  const float *pooler_w, *pooler_b;                                 /* bert.pooler.dense                  */
+  const float *mlm_dense_w, *mlm_dense_b, *mlm_ln_g, *mlm_ln_b;     /* cls.predictions.transform.*        */
+  const float *mlm_bias;      /* cls.predictions.bias; decoder.weight IS word_emb (modeling_rec.py:130-135) */
+  const float *nsp_w, *nsp_b; /* cls.seq_relationship                                                     */
+  const cpt_layer_weights *layers; /* host array [num_hidden_layers]                                      */
+} cpt_weights;
+
+const char *cpt_last_error(void);
+int cpt_abi_version(void);
+
+/* Model(config) + .to(device)  — BertImgModel.__init__, modeling_bert.py:153-197 */
+int cpt_create(const cpt_config *cfg, int device, cpt_handle **out);
+int cpt_destroy(cpt_handle *h);
+/* from_pretrained / load_state_dict — Oscar/oscar/modeling/modeling_utils.py:803-851 */
+int cpt_set_weights(cpt_handle *h, const cpt_weights *w, void *stream);
+
+size_t cpt_workspace_bytes(const cpt_handle *h, int B, int T, int R);
+
+/* BertImgModel.forward — modeling_bert.py:199-279 (2-D attention_mask, head_mask=None,
+ * encoder_history_states=None: everything the CPT callers use).
+ *   input_ids, token_type_ids (nullable -> 0), position_ids (nullable -> arange(T)) : int64 [B,T]
+ *   attention_mask : int64 [B,T+R] (nullable -> all ones)
+ *   img_feats      : fp32 [B,R,img_feature_dim] (R may be 0)
+ *   seq_out        : fp32 [B,T+R,H]  ("sequence_output")
+ *   pooled         : fp32 [B,H], nullable (BertPooler, only the NSP path needs it)
+ *   hidden_states  : fp32 [L+1,B,T+R,H], nullable (config.output_hidden_states) */
+int cpt_encoder_forward(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
+                        const int64_t *attention_mask, const int64_t *position_ids, const float *img_feats,
+                        int B, int T, int R, void *workspace, size_t workspace_bytes, float *seq_out,
+                        float *pooled, float *hidden_states);
+
+/* BertLMPredictionHead at the [MASK] rows and the caller's vocabulary gather, fused:
+ *   logits[b,k] = scores[b, mask_pos[b], vocab_ids[k]]
+ * — modeling_rec.py:143 + Oscar/oscar/zeroshot/refcoco_cpt.py:219,234-235, fewshot/gqa_cpt.py:597-600.
+ * vocab_ids NULL => all V columns (K must be vocab_size).  mask_pos int64 [B], vocab_ids int64 [K]. */
+int cpt_mlm_gather_forward(cpt_handle *h, void *stream, const float *seq_out, int B, int S,
+                           const int64_t *mask_pos, const int64_t *vocab_ids, int K, void *workspace,
+                           size_t workspace_bytes, float *logits);
+
+/* The reference's full output: scores[rows, V] = cls(sequence_output) over ALL rows — modeling_rec.py:143. */
+int cpt_mlm_scores_forward(cpt_handle *h, void *stream, const float *seq_out, long long rows, void *workspace,
+                           size_t workspace_bytes, float *scores);
+size_t cpt_mlm_scores_workspace_bytes(const cpt_handle *h, long long rows);
+
+/* NSPCPT head: cls.seq_relationship(pooled) — Oscar/oscar/modeling/modeling_vcr.py:120-121.  out fp32 [B,C]. */
+int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, float *out);
+
+/* Blocks until `stream` drains; reports device-side input errors (token id / position out of range, the
+ * IndexError the reference's nn.Embedding would raise) and launch failures. */
+int cpt_check_async_error(cpt_handle *h, void *stream);
+
+/* ---- kernel-level entry points (unit tests, bench roofline leg) ----------------------------------------- */
+/* out[M,N] = epi(A[M,K] . W[N,K]^T): A, W 16-bit (dtype as in cfg) with leading dims lda/ldw (elements, multiples
+ * of 8); epi: 0 bias, 1 bias+erf-GELU, 2 bias+fp32 residual; out_fp32: 0 -> 16-bit out, 1 -> fp32 out.
+ * block_n: 0 = library default, else 64/128/256. */
+int cpt_gemm(cpt_handle *h, void *stream, const void *A, long long lda, const void *W, long long ldw, int M, int N,
+             int K, const float *bias, const float *resid, long long ldr, int epi, int out_fp32, void *out,
+             long long ldo, int block_n);
+/* ctx[B*S,H] = softmax(QK^T/sqrt(dH) + (1-mask)*-1e4) V from packed qkv[B*S,3H] (16-bit); ext_mask fp32 [B,S].
+ * impl: 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel. */
+int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,
+                  int impl);
+/* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
+int cpt_layernorm(cpt_handle *h, void *stream, const float *x, int M, const float *gamma, const float *beta,
+                  float eps, float *out32, void *out16);
+int cpt_cast16(cpt_handle *h, void *stream, const float *x, long long rows, int cols, int ld_out, void *out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPT_B200_H */

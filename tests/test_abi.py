@@ -1,0 +1,95 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/cpt_b200.h declares;
+the host layer refuses to run without a CUDA device (no CPU fallback exists)."""
+import os
+import re
+
+import pytest
+import torch
+
+from cpt_b200 import _lib
+from cpt_b200 import config as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    hdr = open(os.path.join(ROOT, "include", "cpt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cpt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cpt_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    hdr = open(os.path.join(ROOT, "include", "cpt_b200.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} cpt_layer_weights;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\*(\w+)", body)
+    assert tuple(names) == _lib.LAYER_FIELDS
+    body = re.search(r"typedef struct \{([^}]*)\} cpt_weights;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\*(\w+)", body)
+    assert tuple(names) == _lib.GLOBAL_FIELDS + ("layers",)
+    body = re.search(r"typedef struct \{([^}]*)\} cpt_config;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body) for n in re.findall(r"\w+", decl)]
+    assert names == [f[0] for f in _lib.Config._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(lib):
+    from cpt_b200.engine import CptError, Engine
+    from cpt_b200.modeling_rec import REC_MLM_CPT
+    with pytest.raises(CptError):
+        Engine(C.oscar_tiny(), "cpu")
+    with pytest.raises(CptError):
+        Engine(C.oscar_tiny(), "cuda:0")
+    m = REC_MLM_CPT(C.oscar_tiny()).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_module_state_dict_keys_match_reference(golden_dir):
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    g = torch.load(os.path.join(golden_dir, "tiny_s120.pt"))
+    d = dict(g["cfg"])
+    v = d.pop("vocab_size")
+    m = BertImgForPreTraining(C.BertConfig(v, **d))
+    assert sorted(m.state_dict().keys()) == g["state_dict_keys"]
+    assert m.cls.predictions.decoder.weight is m.bert.embeddings.word_embeddings.weight
+
+
+def test_from_pretrained_roundtrip(tmp_path):
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    from cpt_b200.modeling_rec import REC_MLM_CPT
+    import copy
+    cfg = C.oscar_tiny()
+    m = BertImgForPreTraining(cfg)
+    m.save_pretrained(str(tmp_path))
+    sd = torch.load(os.path.join(str(tmp_path), "pytorch_model.bin"))
+    legacy = {k.replace("LayerNorm.weight", "LayerNorm.gamma").replace("LayerNorm.bias", "LayerNorm.beta"): v
+              for k, v in sd.items()}
+    torch.save(legacy, os.path.join(str(tmp_path), "pytorch_model.bin"))
+    m2 = BertImgForPreTraining.from_pretrained(str(tmp_path), config=cfg)
+    assert not m2.training
+    for (k1, v1), (k2, v2) in zip(sorted(m.state_dict().items()), sorted(m2.state_dict().items())):
+        assert k1 == k2 and torch.equal(v1, v2)
+    assert m2.cls.predictions.decoder.weight is m2.bert.embeddings.word_embeddings.weight
+    rec = REC_MLM_CPT(cfg)
+    rec.copy_from_pretraining_model(m2)
+    assert rec.bert is m2.bert and rec.cls is m2.cls.predictions
+    rec2 = copy.deepcopy(rec)   # fewshot/gqa_cpt.py:384 deep-copies the model
+    assert rec2.cls.decoder.weight is rec2.bert.embeddings.word_embeddings.weight
+    names = [n for n, _ in rec.named_parameters()]
+    assert any("LayerNorm.weight" in n for n in names) and any(n.endswith("bias") for n in names)

@@ -1,0 +1,108 @@
+"""GPU: each hand-written sm_100a kernel against a plain PyTorch fp32 statement of the same op, called through
+the C ABI (cpt_b200.engine.Engine -> libcpt_b200.so)."""
+import math
+
+import pytest
+import torch
+
+from cpt_b200 import config as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cpt_b200.engine import Engine
+    e = Engine(C.oscar_base(), "cuda:0")
+    yield e
+    e.close()
+
+
+def _gelu(x):
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+GEMM_CASES = [
+    # M, N, K, epi, out_fp32, block_n
+    (128, 128, 64, 0, True, 128),
+    (128, 128, 256, 0, True, 128),
+    (256, 256, 128, 0, True, 256),
+    (256, 64, 128, 0, True, 64),
+    (300, 200, 136, 0, True, 128),       # ragged M, N, K (TMA zero-fill + masked epilogue)
+    (1000, 2304, 768, 0, False, 0),      # QKV projection shape, 16-bit out, default tile
+    (1000, 2304, 768, 0, False, 128),
+    (777, 3072, 768, 1, False, 0),       # FFN up: bias + erf-GELU
+    (777, 768, 3072, 2, True, 0),        # FFN down: bias + fp32 residual
+    (777, 768, 3072, 2, True, 64),
+    (450, 768, 2054, 0, True, 0),        # region embedding: K = 2054 (tail of 6 in the last 64-wide k-block)
+    (130, 1001, 768, 0, True, 0),        # vocabulary-decoder-like: N not a multiple of anything, unaligned rows
+    (7680, 768, 768, 2, True, 0),        # many tiles per CTA: exercises the TMEM double buffer + ring wrap
+]
+
+
+@pytest.mark.parametrize("M,N,K,epi,out_fp32,bn", GEMM_CASES)
+def test_gemm_against_torch(eng, M, N, K, epi, out_fp32, bn):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device="cuda", dtype=torch.float16)
+    W = torch.zeros(N, Kp, device="cuda", dtype=torch.float16)
+    A[:, :K] = torch.randn(M, K, device="cuda", generator=g).half()
+    W[:, :K] = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if epi == 2 else None
+    out = eng.gemm(A[:, :K], W[:, :K], bias=bias, resid=resid, epi=epi, out_fp32=out_fp32, block_n=bn)
+    torch.cuda.synchronize()
+    ref = A[:, :K].double() @ W[:, :K].double().t() + bias.double()
+    if epi == 1:
+        ref = _gelu(ref)
+    if epi == 2:
+        ref = ref + resid.double()
+    scale = ref.abs().max().item()
+    err = (out.double() - ref).abs().max().item()
+    tol = (2e-5 if out_fp32 else 1.2e-3) * scale   # fp32 accumulate / one 16-bit rounding of the output
+    assert err <= tol, "max err %.3e (scale %.3e)" % (err, scale)
+
+
+@pytest.mark.parametrize("B,S", [(2, 120), (3, 210), (1, 40), (2, 128), (2, 129), (1, 256), (2, 1), (5, 17)])
+def test_attention_against_torch_and_simt(eng, B, S):
+    H, nH, dH = 768, 12, 64
+    g = torch.Generator(device="cuda").manual_seed(S * 31 + B)
+    qkv = (torch.randn(B * S, 3 * H, device="cuda", generator=g) * 1.5).half()
+    mask = (torch.rand(B, S, device="cuda", generator=g) > 0.3).long()
+    mask[:, 0] = 1
+    ext = (1.0 - mask.float()) * -10000.0
+    ctx_tc = eng.attention(qkv, ext, B, S, impl=0)
+    ctx_simt = eng.attention(qkv, ext, B, S, impl=1)
+    torch.cuda.synchronize()
+    q, k, v = (t.float().view(B, S, nH, dH).permute(0, 2, 1, 3) for t in qkv.split(H, dim=1))
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext[:, None, None, :], -1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    scale = ref.abs().max().item()
+    assert (ctx_simt.float() - ref).abs().max().item() <= 1.5e-3 * scale
+    assert (ctx_tc.float() - ref).abs().max().item() <= 3e-3 * scale   # P is rounded to 16 bits before P.V
+    assert (ctx_tc.float() - ctx_simt.float()).abs().max().item() <= 3e-3 * scale
+
+
+def test_attention_fully_masked_row_matches_additive_mask_semantics(eng):
+    # (1 - mask) * -10000 is ADDITIVE: an all-zero mask row yields softmax over the raw scores, not NaN
+    B, S, H = 1, 24, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(B * S, 3 * H, device="cuda", generator=g).half()
+    ext = torch.full((B, S), -10000.0, device="cuda")
+    ctx = eng.attention(qkv, ext, B, S, impl=0).float()
+    q, k, v = (t.float().view(B, S, 12, 64).permute(0, 2, 1, 3) for t in qkv.split(H, dim=1))
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext[:, None, None, :], -1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    assert torch.isfinite(ctx).all()
+    assert (ctx - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
+
+
+def test_layernorm_against_torch(eng):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(1001, 768, device="cuda", generator=g) * 3 + 0.5
+    gamma = torch.rand(768, device="cuda", generator=g) + 0.5
+    beta = torch.randn(768, device="cuda", generator=g)
+    o32, o16 = eng.layernorm(x, gamma, beta, 1e-12)
+    ref = torch.nn.functional.layer_norm(x, (768,), gamma, beta, 1e-12)
+    assert (o32 - ref).abs().max().item() < 2e-5
+    assert (o16.float() - ref).abs().max().item() < 4e-3
