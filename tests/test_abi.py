@@ -33,17 +33,15 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 def test_struct_layouts_match_header():
     hdr = open(os.path.join(ROOT, "include", "cpt_b200.h")).read()
-    body = re.search(r"typedef struct \{([^}]*)\} cpt_layer_weights;", hdr, re.S).group(1)
-    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = re.findall(r"\*(\w+)", body)
-    assert tuple(names) == _lib.LAYER_FIELDS
-    body = re.search(r"typedef struct \{([^}]*)\} cpt_weights;", hdr, re.S).group(1)
-    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = re.findall(r"\*(\w+)", body)
-    assert tuple(names) == _lib.GLOBAL_FIELDS + ("layers",)
-    body = re.search(r"typedef struct \{([^}]*)\} cpt_config;", hdr, re.S).group(1)
-    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = [n for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body) for n in re.findall(r"\w+", decl)]
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    def body(name):
+        return re.search(r"typedef struct \{([^}]*)\} %s;" % name, hdr, re.S).group(1)
+
+    assert tuple(re.findall(r"\*(\w+)", body("cpt_layer_weights"))) == _lib.LAYER_FIELDS
+    assert tuple(re.findall(r"\*(\w+)", body("cpt_weights"))) == _lib.GLOBAL_FIELDS + ("layers",)
+    names = [n for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body("cpt_config"))
+             for n in re.findall(r"\w+", decl)]
     assert names == [f[0] for f in _lib.Config._fields_]
 
 
