@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcpt_b200.so")
 ABI_VERSION = 1
+K_COUNT = 13  # CPT_K_COUNT
 
 
 class CptError(RuntimeError):
@@ -55,6 +56,10 @@ SYMBOLS = {
     "cpt_mlm_scores_workspace_bytes": (_sz, [_p, _ll]),
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
     "cpt_check_async_error": (_i, [_p, _p]),
+    "cpt_kernel_name": (C.c_char_p, [_i]),
+    "cpt_launch_count": (_ll, [_p]),
+    "cpt_profile_enable": (_i, [_p, _i]),
+    "cpt_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "cpt_gemm": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _i, _p, _ll, _i]),
     "cpt_attention": (_i, [_p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),

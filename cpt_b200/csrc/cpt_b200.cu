@@ -107,6 +107,29 @@ struct cpt_handle {
   std::vector<LayerDev> layers;
   int* err_flag = nullptr;
   int attn_impl = 0, block_n = 0;
+  // launch accounting / optional per-kernel-class CUDA-event timing (cpt_profile_*)
+  long long launches = 0;
+  bool profiling = false;
+  struct ProfRec { int tag; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[CPT_K_COUNT] = {};
+  long long prof_n[CPT_K_COUNT] = {};
+};
+
+// Brackets one kernel launch: counts it, and when profiling is on records CUDA events on the launch stream.
+struct ProfScope {
+  cpt_handle* h; cudaStream_t st; cudaEvent_t b = nullptr;
+  ProfScope(cpt_handle* h_, cudaStream_t st_, int tag) : h(h_), st(st_) {
+    h->launches++;
+    h->prof_n[tag]++;
+    if (!h->profiling) return;
+    auto get = [&]() { cudaEvent_t e; if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    cudaEvent_t a = get(); b = get();
+    cudaEventRecord(a, st);
+    h->prof.push_back({tag, a, b});
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
 static int dev_alloc(cpt_handle* h, void** p, size_t bytes) {
@@ -174,9 +197,10 @@ static int pick_bn(const cpt_handle* h, int M, int N, int block_n) {
 
 // A [M,K] lda, W [N,K] ldw (16-bit) -> out.  p.M/N/K and epilogue fields must be filled in.
 template <typename T16>
-static int gemm(cpt_handle* h, cudaStream_t st, const void* A, long long lda, const void* W, long long ldw,
+static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W, long long ldw,
                 GemmParams p, int epi, bool out_fp32, int block_n = 0) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+  ProfScope ps(h, st, tag);
   const int bn = pick_bn(h, p.M, p.N, block_n);
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
@@ -197,6 +221,7 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
   if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
   AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f};
+  ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {
     auto* fn = attn_simt_kernel<T16>;
     const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
@@ -216,9 +241,10 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
 }
 
 template <typename T16>
-static int layernorm(cudaStream_t st, const float* x, long long ldx, int M, int H, const float* g, const float* b,
+static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long ldx, int M, int H, const float* g, const float* b,
                      float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0) {
   if (M <= 0) return 0;
+  ProfScope ps(h, st, CPT_K_LN);
   ln_rows_kernel<T16><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, M, H, g, b, eps, do_ln ? 1 : 0, o32,
                                                    reinterpret_cast<T16*>(o16), rin, rout, roff);
   CKL("ln_rows_kernel");
@@ -232,6 +258,7 @@ static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long
   if (B <= 0 || O <= 0) return 0;
   const size_t smem = (size_t)kHeadRows * H * sizeof(float);
   dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + 63) / 64);
+  ProfScope ps(h, st, CPT_K_HEAD);
   head_matvec_kernel<<<grid, 256, smem, st>>>(X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw, bias, w_ids,
                                               w_rows, B, H, O, act, Y, ldy, h->err_flag);
   CKL("head_matvec_kernel");
@@ -391,28 +418,34 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
 
   // K4: additive mask
   if (mask) {
+    ProfScope ps(h, st, CPT_K_EXTMASK);
     ext_mask_kernel<<<(M + 255) / 256, 256, 0, st>>>((const long long*)mask, M, w.ext_mask);
     CKL("ext_mask_kernel");
   } else {
     CK(cudaMemsetAsync(w.ext_mask, 0, (size_t)M * 4, st));
   }
-  // K1: text rows
-  embed_text_ln_kernel<T16><<<(B * T + 7) / 8, 256, 0, st>>>(
-      (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g,
-      h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, w.h32,
-      reinterpret_cast<T16*>(w.h16), h->err_flag);
-  CKL("embed_text_ln_kernel");
+  {  // K1: text rows
+    ProfScope ps(h, st, CPT_K_EMBED);
+    embed_text_ln_kernel<T16><<<(B * T + 7) / 8, 256, 0, st>>>(
+        (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g,
+        h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, w.h32,
+        reinterpret_cast<T16*>(w.h16), h->err_flag);
+    CKL("embed_text_ln_kernel");
+  }
   // K2+K3: region rows
   if (R > 0) {
     const int F = c.img_feature_dim, Mi = B * R;
     const long long pairs = (long long)Mi * (h->Fp / 2);
     const int grid = (int)((pairs + 255) / 256 < 8192 ? (pairs + 255) / 256 : 8192);
-    cast_pad_kernel<T16><<<grid, 256, 0, st>>>(img, Mi, F, h->Fp, reinterpret_cast<T16*>(w.img16));
-    CKL("cast_pad_kernel");
+    {
+      ProfScope ps(h, st, CPT_K_CAST);
+      cast_pad_kernel<T16><<<grid, 256, 0, st>>>(img, Mi, F, h->Fp, reinterpret_cast<T16*>(w.img16));
+      CKL("cast_pad_kernel");
+    }
     GemmParams p{};
     p.M = Mi; p.N = H; p.K = F; p.out = w.pre32; p.ldo = H; p.bias = h->b_img;
-    TRY(gemm<T16>(h, st, w.img16, h->Fp, h->w_img, h->Fp, p, EPI_BIAS, true));
-    TRY(layernorm<T16>(st, w.pre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps, c.use_img_layernorm != 0,
+    TRY(gemm<T16>(h, st, CPT_K_GEMM_IMG, w.img16, h->Fp, h->w_img, h->Fp, p, EPI_BIAS, true));
+    TRY(layernorm<T16>(h, st, w.pre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps, c.use_img_layernorm != 0,
                        w.h32, w.h16, R, S, T));
   }
   if (hidden_states) CK(cudaMemcpyAsync(hidden_states, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
@@ -422,26 +455,26 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
     {  // K5
       GemmParams p{};
       p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
-      TRY(gemm<T16>(h, st, w.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
     }
     TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));  // K6-K9
     {  // K10
       GemmParams p{};
       p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao; p.resid = w.h32; p.ldr = H;
-      TRY(gemm<T16>(h, st, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
-      TRY(layernorm<T16>(st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
+      TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
     }
     {  // K11
       GemmParams p{};
       p.M = M; p.N = I; p.K = H; p.out = w.inter16; p.ldo = I; p.bias = d.b_i;
-      TRY(gemm<T16>(h, st, w.a16, H, d.w_i, H, p, EPI_BIAS_GELU, false));
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, w.a16, H, d.w_i, H, p, EPI_BIAS_GELU, false));
     }
     {  // K12
       GemmParams p{};
       p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o; p.resid = w.a32; p.ldr = H;
-      TRY(gemm<T16>(h, st, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
       float* o32 = (l == L - 1) ? seq_out : w.h32;
-      TRY(layernorm<T16>(st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+      TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
                          (l == L - 1) ? nullptr : w.h16));
       if (hidden_states)
         CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4,
@@ -468,14 +501,14 @@ static int mlm_scores_impl(cpt_handle* h, cudaStream_t st, const float* seq_out,
   char* x16 = base;
   float* t32 = (float*)(base + al((size_t)rows * H * 2));
   char* t16 = (char*)t32 + al((size_t)rows * H * 4);
-  TRY(layernorm<T16>(st, seq_out, H, (int)rows, H, nullptr, nullptr, 0.f, false, nullptr, x16));  // fp32 -> 16-bit
+  TRY(layernorm<T16>(h, st, seq_out, H, (int)rows, H, nullptr, nullptr, 0.f, false, nullptr, x16));  // fp32 -> 16-bit
   GemmParams p{};
   p.M = (int)rows; p.N = H; p.K = H; p.out = t32; p.ldo = H; p.bias = h->mlm_b;
-  TRY(gemm<T16>(h, st, x16, H, h->mlm_w16, H, p, EPI_BIAS_GELU, true));
-  TRY(layernorm<T16>(st, t32, H, (int)rows, H, h->mlm_g, h->mlm_beta, c.layer_norm_eps, true, nullptr, t16));
+  TRY(gemm<T16>(h, st, CPT_K_GEMM_HEAD, x16, H, h->mlm_w16, H, p, EPI_BIAS_GELU, true));
+  TRY(layernorm<T16>(h, st, t32, H, (int)rows, H, h->mlm_g, h->mlm_beta, c.layer_norm_eps, true, nullptr, t16));
   GemmParams q{};
   q.M = (int)rows; q.N = V; q.K = H; q.out = scores; q.ldo = V; q.bias = h->mlm_bias;
-  TRY(gemm<T16>(h, st, t16, H, h->word16, H, q, EPI_BIAS, true));
+  TRY(gemm<T16>(h, st, CPT_K_GEMM_HEAD, t16, H, h->word16, H, q, EPI_BIAS, true));
   return 0;
 }
 
@@ -531,6 +564,8 @@ int cpt_destroy(cpt_handle* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   free_owned(h);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -625,6 +660,39 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
   return 0;
 }
 
+static const char* kKernelNames[CPT_K_COUNT] = {"ext_mask", "embed_text_ln", "cast_pad", "gemm_img", "layernorm",
+                                                 "gemm_qkv", "attention", "gemm_attn_out", "gemm_ffn_up",
+                                                 "gemm_ffn_down", "head_matvec", "gemm_head", "gemm_other"};
+const char* cpt_kernel_name(int tag) { return (tag >= 0 && tag < CPT_K_COUNT) ? kKernelNames[tag] : ""; }
+long long cpt_launch_count(const cpt_handle* h) { return h ? h->launches : 0; }
+
+int cpt_profile_enable(cpt_handle* h, int on) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+  CK(cudaDeviceSynchronize());
+  for (auto& r : h->prof) { h->ev_pool.push_back(r.a); h->ev_pool.push_back(r.b); }
+  h->prof.clear();
+  for (int i = 0; i < CPT_K_COUNT; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  h->profiling = on != 0;
+  return 0;
+}
+
+int cpt_profile_read(cpt_handle* h, double* ms, long long* launches) {
+  if (!h || !ms || !launches) return fail("NULL argument");
+  DeviceGuard g(h->device);
+  CK(cudaDeviceSynchronize());
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    h->prof_ms[r.tag] += t;
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  for (int i = 0; i < CPT_K_COUNT; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  return 0;
+}
+
 int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const void* W, long long ldw, int M, int N,
              int K, const float* bias, const float* resid, long long ldr, int epi, int out_fp32, void* out,
              long long ldo, int block_n) {
@@ -632,7 +700,7 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
   DeviceGuard g(h->device);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
-#define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, A, lda, W, ldw, p, epi, out_fp32 != 0, block_n)
+#define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, block_n)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }
@@ -651,7 +719,7 @@ int cpt_layernorm(cpt_handle* h, void* stream, const float* x, int M, const floa
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
   const int H = h->cfg.hidden_size;
-#define CALL(T16) layernorm<T16>((cudaStream_t)stream, x, H, M, H, gamma, beta, eps, gamma != nullptr, out32, out16)
+#define CALL(T16) layernorm<T16>(h, (cudaStream_t)stream, x, H, M, H, gamma, beta, eps, gamma != nullptr, out32, out16)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

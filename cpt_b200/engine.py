@@ -213,6 +213,20 @@ class Engine(object):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cpt_check_async_error(self._h, _stream()))
 
+    # ------------------------------------------------------------------ launch accounting / profiling
+    def launch_count(self):
+        return int(self.lib.cpt_launch_count(self._h))
+
+    def profile(self, on=True):
+        _lib.check(self.lib.cpt_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel class: (device ms, launches)} accumulated since profile(True) / the previous read."""
+        ms = (C.c_double * _lib.K_COUNT)()
+        n = (C.c_longlong * _lib.K_COUNT)()
+        _lib.check(self.lib.cpt_profile_read(self._h, ms, n))
+        return {self.lib.cpt_kernel_name(i).decode(): (ms[i], int(n[i])) for i in range(_lib.K_COUNT) if n[i]}
+
     # ------------------------------------------------------------------ kernel-level hooks (tests / bench)
     def _t16(self):
         return torch.float16 if DTYPES[self.dtype] == 0 else torch.bfloat16

@@ -101,6 +101,21 @@ int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, flo
  * IndexError the reference's nn.Embedding would raise) and launch failures. */
 int cpt_check_async_error(cpt_handle *h, void *stream);
 
+/* ---- launch accounting and per-kernel-class timing (bench.py roofline leg) ------------------------------- */
+enum {
+  CPT_K_EXTMASK = 0, CPT_K_EMBED, CPT_K_CAST, CPT_K_GEMM_IMG, CPT_K_LN, CPT_K_GEMM_QKV, CPT_K_ATTN,
+  CPT_K_GEMM_AO, CPT_K_GEMM_UP, CPT_K_GEMM_DOWN, CPT_K_HEAD, CPT_K_GEMM_HEAD, CPT_K_GEMM_OTHER, CPT_K_COUNT
+};
+const char *cpt_kernel_name(int tag);
+/* kernels launched by this handle since cpt_create */
+long long cpt_launch_count(const cpt_handle *h);
+/* on != 0: bracket every subsequent launch with CUDA events on its stream (a few us of host time per launch;
+ * leave off in timed runs).  Resets the accumulators.  Synchronises the device. */
+int cpt_profile_enable(cpt_handle *h, int on);
+/* Synchronises, then returns per-class device milliseconds and launch counts accumulated since the last
+ * enable/read (arrays of CPT_K_COUNT), and resets them. */
+int cpt_profile_read(cpt_handle *h, double *ms, long long *launches);
+
 /* ---- kernel-level entry points (unit tests, bench roofline leg) ----------------------------------------- */
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): A, W 16-bit (dtype as in cfg) with leading dims lda/ldw (elements, multiples
  * of 8); epi: 0 bias, 1 bias+erf-GELU, 2 bias+fp32 residual; out_fp32: 0 -> 16-bit out, 1 -> fp32 out.
