@@ -106,7 +106,8 @@ struct cpt_handle {
   float *nsp_w = nullptr, *nsp_b = nullptr;
   std::vector<LayerDev> layers;
   int* err_flag = nullptr;
-  int attn_impl = 0, block_n = 0;
+  int attn_impl = 0;
+  struct { int bn, cm, cn; } gemm_choice[16] = {};  // per kernel class, 0 = default (CPT_B200_GEMM overrides)
   // launch accounting / optional per-kernel-class CUDA-event timing (cpt_profile_*)
   long long launches = 0;
   bool profiling = false;
@@ -161,56 +162,90 @@ static int set_smem_attr(F* fn, size_t bytes) {
   return 0;
 }
 
-template <int BN, int EPI, typename OutT, typename T16>
+struct GemmChoice { int bn, cm, cn; };
+
+template <int BN, int CM, int CN, int EPI, typename OutT, typename T16>
 static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
                          const GemmParams& p) {
-  auto* fn = gemm_kernel<BN, EPI, OutT, T16>;
+  using Cfg = GemmCfg<BN, (int)sizeof(OutT)>;
+  auto* fn = gemm_kernel<BN, CM, CN, EPI, OutT, T16>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
-    TRY(set_smem_attr(fn, GemmCfg<BN>::kSmemBytes));
+    TRY(set_smem_attr(fn, Cfg::kSmemBytes));
     attr_set[h->device & 63] = true;
   }
-  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  fn<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
-  CKL("gemm_kernel");
+  constexpr int kCluster = CM * CN;
+  const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM, n_tiles = (p.N + BN - 1) / BN;
+  const int ctiles = ((m_tiles + CM - 1) / CM) * ((n_tiles + CN - 1) / CN);
+  int clusters = h->num_sms / kCluster;
+  if (ctiles < clusters) clusters = ctiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * kCluster);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, fn, ta, tb, p));
   return 0;
 }
 
-template <int EPI, typename OutT, typename T16>
-static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, int bn, const CUtensorMap& ta, const CUtensorMap& tb,
+template <int BN, int EPI, typename OutT, typename T16>
+static int launch_gemm_cl(cpt_handle* h, cudaStream_t st, GemmChoice c, const CUtensorMap& ta, const CUtensorMap& tb,
                           const GemmParams& p) {
-  switch (bn) {
-    case 64: return launch_gemm_t<64, EPI, OutT, T16>(h, st, ta, tb, p);
-    case 128: return launch_gemm_t<128, EPI, OutT, T16>(h, st, ta, tb, p);
-    case 256: return launch_gemm_t<256, EPI, OutT, T16>(h, st, ta, tb, p);
-  }
-  return fail("unsupported GEMM block_n %d", bn);
+  if (c.cm == 1 && c.cn == 1) return launch_gemm_t<BN, 1, 1, EPI, OutT, T16>(h, st, ta, tb, p);
+  if (c.cm == 2 && c.cn == 1) return launch_gemm_t<BN, 2, 1, EPI, OutT, T16>(h, st, ta, tb, p);
+  if (c.cm == 1 && c.cn == 2) return launch_gemm_t<BN, 1, 2, EPI, OutT, T16>(h, st, ta, tb, p);
+  if (c.cm == 2 && c.cn == 2) return launch_gemm_t<BN, 2, 2, EPI, OutT, T16>(h, st, ta, tb, p);
+  if (c.cm == 4 && c.cn == 1) return launch_gemm_t<BN, 4, 1, EPI, OutT, T16>(h, st, ta, tb, p);
+  return fail("unsupported GEMM cluster %dx%d", c.cm, c.cn);
 }
 
-static int pick_bn(const cpt_handle* h, int M, int N, int block_n) {
-  if (block_n) return block_n;
-  if (h->block_n) return h->block_n;
-  (void)M;
-  return N >= 2048 ? 256 : 128;
+template <int EPI, typename OutT, typename T16>
+static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, GemmChoice c, const CUtensorMap& ta, const CUtensorMap& tb,
+                          const GemmParams& p) {
+  switch (c.bn) {
+    case 64: return launch_gemm_cl<64, EPI, OutT, T16>(h, st, c, ta, tb, p);
+    case 128: return launch_gemm_cl<128, EPI, OutT, T16>(h, st, c, ta, tb, p);
+    case 192: return launch_gemm_cl<192, EPI, OutT, T16>(h, st, c, ta, tb, p);
+    case 256: return launch_gemm_cl<256, EPI, OutT, T16>(h, st, c, ta, tb, p);
+  }
+  return fail("unsupported GEMM block_n %d", c.bn);
+}
+
+// tile / cluster choice per GEMM class; cfg = block_n + 1000 * (10 * CM + CN), 0 = default for the class
+static GemmChoice pick_gemm(const cpt_handle* h, int tag, int N, int cfg) {
+  GemmChoice c{h->gemm_choice[tag].bn, h->gemm_choice[tag].cm, h->gemm_choice[tag].cn};
+  if (c.bn == 0) c = GemmChoice{N >= 2048 ? 256 : 128, 2, 1};
+  if (cfg > 0) {
+    if (cfg % 1000) c.bn = cfg % 1000;
+    if (cfg / 1000) { c.cm = (cfg / 1000) / 10; c.cn = (cfg / 1000) % 10; }
+  }
+  return c;
 }
 
 // A [M,K] lda, W [N,K] ldw (16-bit) -> out.  p.M/N/K and epilogue fields must be filled in.
 template <typename T16>
 static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W, long long ldw,
-                GemmParams p, int epi, bool out_fp32, int block_n = 0) {
+                GemmParams p, int epi, bool out_fp32, int cfg = 0) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   ProfScope ps(h, st, tag);
-  const int bn = pick_bn(h, p.M, p.N, block_n);
+  const GemmChoice c = pick_gemm(h, tag, p.N, cfg);
+  if (c.cm < 1 || c.cn < 1 || (kGemmBM / c.cn) % 8 || (c.bn / c.cm) % 8) return fail("bad GEMM cluster choice");
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
-  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
-  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, bn));
-  if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, bn, ta, tb, p);
-  if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, bn, ta, tb, p);
-  if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, bn, ta, tb, p);
-  if (epi == EPI_BIAS_GELU && out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, float, T16>(h, st, bn, ta, tb, p);
-  if (epi == EPI_BIAS_RESID && out_fp32) return launch_gemm_bn<EPI_BIAS_RESID, float, T16>(h, st, bn, ta, tb, p);
+  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM / c.cn));
+  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.bn / c.cm));
+  if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, p);
+  if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, p);
+  if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, p);
+  if (epi == EPI_BIAS_GELU && out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, float, T16>(h, st, c, ta, tb, p);
+  if (epi == EPI_BIAS_RESID && out_fp32) return launch_gemm_bn<EPI_BIAS_RESID, float, T16>(h, st, c, ta, tb, p);
   return fail("unsupported GEMM epilogue/output combination (epi=%d out_fp32=%d)", epi, (int)out_fp32);
 }
 
@@ -518,6 +553,7 @@ static int mlm_scores_impl(cpt_handle* h, cudaStream_t st, const float* seq_out,
 // ================================================================================================ C ABI
 extern "C" {
 
+const char* cpt_kernel_name(int tag);
 const char* cpt_last_error(void) { return g_err.c_str(); }
 int cpt_abi_version(void) { return CPT_B200_ABI_VERSION; }
 
@@ -554,7 +590,21 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   cudaMemset(h->err_flag, 0, 16);
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
-  if (const char* e = getenv("CPT_B200_BN")) h->block_n = atoi(e);
+  // CPT_B200_GEMM="gemm_qkv:256:2x1,gemm_ffn_down:128:2x2"  (tuning / A-B experiments)
+  if (const char* e = getenv("CPT_B200_GEMM")) {
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size()) {
+      size_t end = s.find(',', pos);
+      if (end == std::string::npos) end = s.size();
+      char name[64];
+      int bn = 0, cm = 0, cn = 0;
+      if (sscanf(s.substr(pos, end - pos).c_str(), "%63[^:]:%d:%dx%d", name, &bn, &cm, &cn) == 4)
+        for (int t = 0; t < CPT_K_COUNT; ++t)
+          if (strcmp(name, cpt_kernel_name(t)) == 0) { h->gemm_choice[t].bn = bn; h->gemm_choice[t].cm = cm; h->gemm_choice[t].cn = cn; }
+      pos = end + 1;
+    }
+  }
   *out = h;
   return 0;
 }
@@ -695,12 +745,12 @@ int cpt_profile_read(cpt_handle* h, double* ms, long long* launches) {
 
 int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const void* W, long long ldw, int M, int N,
              int K, const float* bias, const float* resid, long long ldr, int epi, int out_fp32, void* out,
-             long long ldo, int block_n) {
+             long long ldo, int tile_cfg) {
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
-#define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, block_n)
+#define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, tile_cfg)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

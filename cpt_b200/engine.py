@@ -231,14 +231,14 @@ class Engine(object):
     def _t16(self):
         return torch.float16 if DTYPES[self.dtype] == 0 else torch.bfloat16
 
-    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, block_n=0):
+    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, tile_cfg=0):
         M, K = A.shape
         N = W.shape[0]
         out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else self._t16(), device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cpt_gemm(self._h, _stream(), _ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K,
                                          _ptr(bias), _ptr(resid), 0 if resid is None else resid.stride(0), epi,
-                                         1 if out_fp32 else 0, _ptr(out), out.stride(0), block_n))
+                                         1 if out_fp32 else 0, _ptr(out), out.stride(0), tile_cfg))
         return out
 
     def attention(self, qkv, ext_mask, B, S, impl=0):

@@ -119,10 +119,11 @@ int cpt_profile_read(cpt_handle *h, double *ms, long long *launches);
 /* ---- kernel-level entry points (unit tests, bench roofline leg) ----------------------------------------- */
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): A, W 16-bit (dtype as in cfg) with leading dims lda/ldw (elements, multiples
  * of 8); epi: 0 bias, 1 bias+erf-GELU, 2 bias+fp32 residual; out_fp32: 0 -> 16-bit out, 1 -> fp32 out.
- * block_n: 0 = library default, else 64/128/256. */
+ * tile_cfg: 0 = library default, else block_n (64/128/192/256) + 1000 * (10*CM + CN) for a CM x CN multicast
+ * cluster (e.g. 21256 = 256-wide tiles, 2 CTAs sharing each weight tile). */
 int cpt_gemm(cpt_handle *h, void *stream, const void *A, long long lda, const void *W, long long ldw, int M, int N,
              int K, const float *bias, const float *resid, long long ldr, int epi, int out_fp32, void *out,
-             long long ldo, int block_n);
+             long long ldo, int tile_cfg);
 /* ctx[B*S,H] = softmax(QK^T/sqrt(dH) + (1-mask)*-1e4) V from packed qkv[B*S,3H] (16-bit); ext_mask fp32 [B,S].
  * impl: 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel. */
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,

@@ -23,25 +23,35 @@ def _gelu(x):
 
 
 GEMM_CASES = [
-    # M, N, K, epi, out_fp32, block_n
-    (128, 128, 64, 0, True, 128),
-    (128, 128, 256, 0, True, 128),
-    (256, 256, 128, 0, True, 256),
-    (256, 64, 128, 0, True, 64),
-    (300, 200, 136, 0, True, 128),       # ragged M, N, K (TMA zero-fill + masked epilogue)
+    # M, N, K, epi, out_fp32, tile_cfg  (block_n + 1000 * (10*CM + CN); 0 = library default)
+    (128, 128, 64, 0, True, 11128),
+    (128, 128, 256, 0, True, 11128),
+    (256, 256, 128, 0, True, 11256),
+    (256, 64, 128, 0, True, 11064),
+    (300, 200, 136, 0, True, 11128),     # ragged M, N, K (TMA zero-fill + masked epilogue)
+    (300, 200, 136, 0, False, 11192),
     (1000, 2304, 768, 0, False, 0),      # QKV projection shape, 16-bit out, default tile
-    (1000, 2304, 768, 0, False, 128),
+    (1000, 2304, 768, 0, False, 11128),
+    (1000, 2304, 768, 0, False, 21256),  # 2 CTAs share each weight tile (TMA multicast)
+    (1000, 2304, 768, 0, False, 12256),  # 2 CTAs share each activation tile
+    (1000, 2304, 768, 0, False, 22192),  # 2x2 cluster
     (777, 3072, 768, 1, False, 0),       # FFN up: bias + erf-GELU
+    (777, 3072, 768, 1, False, 22256),
     (777, 768, 3072, 2, True, 0),        # FFN down: bias + fp32 residual
-    (777, 768, 3072, 2, True, 64),
+    (777, 768, 3072, 2, True, 11064),
+    (777, 768, 3072, 2, True, 41128),
+    (777, 768, 3072, 2, True, 22128),
     (450, 768, 2054, 0, True, 0),        # region embedding: K = 2054 (tail of 6 in the last 64-wide k-block)
     (130, 1001, 768, 0, True, 0),        # vocabulary-decoder-like: N not a multiple of anything, unaligned rows
+    (130, 1001, 768, 0, True, 21256),
     (7680, 768, 768, 2, True, 0),        # many tiles per CTA: exercises the TMEM double buffer + ring wrap
+    (7680, 768, 768, 2, True, 22128),
+    (7680, 2304, 768, 0, False, 21256),
 ]
 
 
-@pytest.mark.parametrize("M,N,K,epi,out_fp32,bn", GEMM_CASES)
-def test_gemm_against_torch(eng, M, N, K, epi, out_fp32, bn):
+@pytest.mark.parametrize("M,N,K,epi,out_fp32,cfg", GEMM_CASES)
+def test_gemm_against_torch(eng, M, N, K, epi, out_fp32, cfg):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     Kp = (K + 7) // 8 * 8
     A = torch.zeros(M, Kp, device="cuda", dtype=torch.float16)
@@ -50,7 +60,7 @@ def test_gemm_against_torch(eng, M, N, K, epi, out_fp32, bn):
     W[:, :K] = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
     bias = torch.randn(N, device="cuda", generator=g)
     resid = torch.randn(M, N, device="cuda", generator=g) if epi == 2 else None
-    out = eng.gemm(A[:, :K], W[:, :K], bias=bias, resid=resid, epi=epi, out_fp32=out_fp32, block_n=bn)
+    out = eng.gemm(A[:, :K], W[:, :K], bias=bias, resid=resid, epi=epi, out_fp32=out_fp32, tile_cfg=cfg)
     torch.cuda.synchronize()
     ref = A[:, :K].double() @ W[:, :K].double().t() + bias.double()
     if epi == 1:
