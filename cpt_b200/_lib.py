@@ -60,6 +60,7 @@ SYMBOLS = {
     "cpt_launch_count": (_ll, [_p]),
     "cpt_profile_enable": (_i, [_p, _i]),
     "cpt_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "cpt_gemm_trace": (_i, [_p, C.POINTER(_ll), _i]),
     "cpt_gemm": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _i, _p, _ll, _i]),
     "cpt_attention": (_i, [_p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),

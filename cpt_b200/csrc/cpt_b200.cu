@@ -107,9 +107,10 @@ struct cpt_handle {
   std::vector<LayerDev> layers;
   int* err_flag = nullptr;
   int attn_impl = 0;
-  struct { int bn, cm, cn; } gemm_choice[16] = {};  // per kernel class, 0 = default (CPT_B200_GEMM overrides)
+  struct { int bn, pair; } gemm_choice[16] = {};  // per kernel class, bn 0 = default (CPT_B200_GEMM overrides)
   // launch accounting / optional per-kernel-class CUDA-event timing (cpt_profile_*)
   long long launches = 0;
+  long long* trace = nullptr;  // [num_sms][8] GEMM cycle counters when CPT_B200_TRACE=1
   bool profiling = false;
   struct ProfRec { int tag; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -162,21 +163,21 @@ static int set_smem_attr(F* fn, size_t bytes) {
   return 0;
 }
 
-struct GemmChoice { int bn, cm, cn; };
+struct GemmChoice { int bn, pair; };
 
-template <int BN, int CM, int CN, int EPI, typename OutT, typename T16>
+template <int BN, bool PAIR, int EPI, typename OutT, typename T16>
 static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
                          const GemmParams& p) {
-  using Cfg = GemmCfg<BN, (int)sizeof(OutT)>;
-  auto* fn = gemm_kernel<BN, CM, CN, EPI, OutT, T16>;
+  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR>;
+  auto* fn = gemm_kernel<BN, PAIR, EPI, OutT, T16>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
     TRY(set_smem_attr(fn, Cfg::kSmemBytes));
     attr_set[h->device & 63] = true;
   }
-  constexpr int kCluster = CM * CN;
+  constexpr int kCluster = PAIR ? 2 : 1;
   const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM, n_tiles = (p.N + BN - 1) / BN;
-  const int ctiles = ((m_tiles + CM - 1) / CM) * ((n_tiles + CN - 1) / CN);
+  const int ctiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
   int clusters = h->num_sms / kCluster;
   if (ctiles < clusters) clusters = ctiles;
   cudaLaunchConfig_t cfg{};
@@ -195,36 +196,30 @@ static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, 
   return 0;
 }
 
-template <int BN, int EPI, typename OutT, typename T16>
-static int launch_gemm_cl(cpt_handle* h, cudaStream_t st, GemmChoice c, const CUtensorMap& ta, const CUtensorMap& tb,
-                          const GemmParams& p) {
-  if (c.cm == 1 && c.cn == 1) return launch_gemm_t<BN, 1, 1, EPI, OutT, T16>(h, st, ta, tb, p);
-  if (c.cm == 2 && c.cn == 1) return launch_gemm_t<BN, 2, 1, EPI, OutT, T16>(h, st, ta, tb, p);
-  if (c.cm == 1 && c.cn == 2) return launch_gemm_t<BN, 1, 2, EPI, OutT, T16>(h, st, ta, tb, p);
-  if (c.cm == 2 && c.cn == 2) return launch_gemm_t<BN, 2, 2, EPI, OutT, T16>(h, st, ta, tb, p);
-  if (c.cm == 4 && c.cn == 1) return launch_gemm_t<BN, 4, 1, EPI, OutT, T16>(h, st, ta, tb, p);
-  return fail("unsupported GEMM cluster %dx%d", c.cm, c.cn);
-}
-
 template <int EPI, typename OutT, typename T16>
 static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, GemmChoice c, const CUtensorMap& ta, const CUtensorMap& tb,
                           const GemmParams& p) {
+#define CPT_BN_CASE(BN_)                                                                \
+  case BN_:                                                                             \
+    return c.pair ? launch_gemm_t<BN_, true, EPI, OutT, T16>(h, st, ta, tb, p)         \
+                  : launch_gemm_t<BN_, false, EPI, OutT, T16>(h, st, ta, tb, p);
   switch (c.bn) {
-    case 64: return launch_gemm_cl<64, EPI, OutT, T16>(h, st, c, ta, tb, p);
-    case 128: return launch_gemm_cl<128, EPI, OutT, T16>(h, st, c, ta, tb, p);
-    case 192: return launch_gemm_cl<192, EPI, OutT, T16>(h, st, c, ta, tb, p);
-    case 256: return launch_gemm_cl<256, EPI, OutT, T16>(h, st, c, ta, tb, p);
+    CPT_BN_CASE(64)
+    CPT_BN_CASE(128)
+    CPT_BN_CASE(192)
+    CPT_BN_CASE(256)
   }
+#undef CPT_BN_CASE
   return fail("unsupported GEMM block_n %d", c.bn);
 }
 
-// tile / cluster choice per GEMM class; cfg = block_n + 1000 * (10 * CM + CN), 0 = default for the class
+// tile choice per GEMM class; cfg = block_n + 1000 * (1 + pair), 0 = default for the class
 static GemmChoice pick_gemm(const cpt_handle* h, int tag, int N, int cfg) {
-  GemmChoice c{h->gemm_choice[tag].bn, h->gemm_choice[tag].cm, h->gemm_choice[tag].cn};
-  if (c.bn == 0) c = GemmChoice{N >= 2048 ? 256 : 128, 2, 1};
+  GemmChoice c{h->gemm_choice[tag].bn, h->gemm_choice[tag].pair};
+  if (c.bn == 0) c = GemmChoice{N >= 2048 ? 256 : 192, 0};  // tools/tune_gemm.py on B200, M = 7680
   if (cfg > 0) {
     if (cfg % 1000) c.bn = cfg % 1000;
-    if (cfg / 1000) { c.cm = (cfg / 1000) / 10; c.cn = (cfg / 1000) % 10; }
+    if (cfg / 1000) c.pair = (cfg / 1000) - 1;
   }
   return c;
 }
@@ -236,11 +231,11 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   ProfScope ps(h, st, tag);
   const GemmChoice c = pick_gemm(h, tag, p.N, cfg);
-  if (c.cm < 1 || c.cn < 1 || (kGemmBM / c.cn) % 8 || (c.bn / c.cm) % 8) return fail("bad GEMM cluster choice");
+  p.trace = h->trace;
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
-  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM / c.cn));
-  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.bn / c.cm));
+  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
+  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
   if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, p);
   if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, p);
   if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, p);
@@ -292,7 +287,7 @@ static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long
                        int act, float* Y, long long ldy) {
   if (B <= 0 || O <= 0) return 0;
   const size_t smem = (size_t)kHeadRows * H * sizeof(float);
-  dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + 63) / 64);
+  dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + kHeadOuts - 1) / kHeadOuts);
   ProfScope ps(h, st, CPT_K_HEAD);
   head_matvec_kernel<<<grid, 256, smem, st>>>(X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw, bias, w_ids,
                                               w_rows, B, H, O, act, Y, ldy, h->err_flag);
@@ -357,8 +352,10 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, F = c.img_feature_dim;
   int* flag = h->err_flag;
   h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)flag), h->owned.end());
+  h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)h->trace), h->owned.end());
   free_owned(h);
   h->owned.push_back(flag);
+  if (h->trace) h->owned.push_back(h->trace);
   h->has_weights = false;
   if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b || !w->layers)
     return fail("cpt_set_weights: embedding tables / LayerNorm / layers must be non-NULL");
@@ -590,18 +587,27 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   cudaMemset(h->err_flag, 0, 16);
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
-  // CPT_B200_GEMM="gemm_qkv:256:2x1,gemm_ffn_down:128:2x2"  (tuning / A-B experiments)
+  if (getenv("CPT_B200_TRACE")) {
+    if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 64) == cudaSuccess) {
+      cudaMemset(h->trace, 0, (size_t)h->num_sms * 64);
+      h->owned.push_back(h->trace);
+    }
+  }
+  // CPT_B200_GEMM="gemm_qkv:256:2,gemm_ffn_down:128:1"  (class:block_n:CTAs per MMA; tuning / A-B experiments)
   if (const char* e = getenv("CPT_B200_GEMM")) {
-    std::string s(e);
+    std::string str(e);
     size_t pos = 0;
-    while (pos < s.size()) {
-      size_t end = s.find(',', pos);
-      if (end == std::string::npos) end = s.size();
+    while (pos < str.size()) {
+      size_t end = str.find(',', pos);
+      if (end == std::string::npos) end = str.size();
       char name[64];
-      int bn = 0, cm = 0, cn = 0;
-      if (sscanf(s.substr(pos, end - pos).c_str(), "%63[^:]:%d:%dx%d", name, &bn, &cm, &cn) == 4)
+      int bn = 0, ncta = 0;
+      if (sscanf(str.substr(pos, end - pos).c_str(), "%63[^:]:%d:%d", name, &bn, &ncta) == 3)
         for (int t = 0; t < CPT_K_COUNT; ++t)
-          if (strcmp(name, cpt_kernel_name(t)) == 0) { h->gemm_choice[t].bn = bn; h->gemm_choice[t].cm = cm; h->gemm_choice[t].cn = cn; }
+          if (strcmp(name, cpt_kernel_name(t)) == 0) {
+            h->gemm_choice[t].bn = bn;
+            h->gemm_choice[t].pair = ncta == 2;
+          }
       pos = end + 1;
     }
   }
@@ -740,6 +746,16 @@ int cpt_profile_read(cpt_handle* h, double* ms, long long* launches) {
   }
   h->prof.clear();
   for (int i = 0; i < CPT_K_COUNT; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  return 0;
+}
+
+int cpt_gemm_trace(cpt_handle* h, long long* out, int max_ctas) {
+  if (!h || !out) return fail("NULL argument");
+  if (!h->trace) return fail("tracing is off (set CPT_B200_TRACE=1 before cpt_create)");
+  DeviceGuard g(h->device);
+  CK(cudaDeviceSynchronize());
+  const int n = max_ctas < h->num_sms ? max_ctas : h->num_sms;
+  CK(cudaMemcpy(out, h->trace, (size_t)n * 64, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -4,11 +4,13 @@
 //          main loop of tile i+1
 //   roles: warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane), warps 2..9 = epilogue
 //          (TMEM lane quadrant = warp_idx % 4, two warps per quadrant splitting the BN columns)
-//   cluster CM x CN (thread-block cluster of CM*CN CTAs): the CM CTAs that share an N tile each fetch 1/CM of the B
-//          tile and TMA-multicast it to the others; the CN CTAs that share an M tile do the same with A.  The
-//          kernel is bound by L2->SM operand bandwidth at these shapes (K = 768), so every multicast halves the
-//          bytes one operand costs.  Stage release is a multicast tcgen05.commit to every CTA that writes into
-//          this CTA's ring.
+//   PAIR : thread-block cluster of 2 CTAs issuing tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its
+//          own 128 A rows but only HALF of the B tile, so a CTA ingests (128 + BN/2) x 64 operands per k-block
+//          instead of (128 + BN) x 64.  Measured on B200 this kernel is bound by per-SM operand ingest
+//          (~41.5 B/clk/SM on every shape tried; TMA multicast inside a 2/4-CTA cluster did not move it), so the
+//          pair raises the ceiling by the same factor.  The leader CTA (cluster rank 0) issues all MMAs; both
+//          CTAs' TMA loads signal the leader's full barrier; stage release / accumulator-ready are multicast
+//          tcgen05.commit; both CTAs' epilogues release the accumulator on the leader's barrier.
 // Epilogues (fused; the reference runs them as separate ATen ops):
 //   EPI_BIAS       : + bias                      (QKV projection, region embedding, vocabulary decoder)
 //   EPI_BIAS_GELU  : erf-GELU(+ bias)            (BertIntermediate)
@@ -29,7 +31,7 @@ struct GemmParams {
   const float* bias;  // [N] or nullptr
   const float* resid; // fp32 [M, ldr] (EPI_BIAS_RESID)
   long long ldr;
-  int rin, rout, roff;  // output row remap: (m / rin) * rout + roff + m % rin   (identity when rin == 0)
+  long long* trace;     // optional [gridDim.x][8] cycle counters (debug): see cpt_gemm_trace
 };
 
 constexpr int kGemmBM = 128;
@@ -38,11 +40,11 @@ constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
-template <int BN, int OutBytes>
+template <int BN, int OutBytes, bool PAIR>
 struct GemmCfg {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64, 128, 192 or 256");
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kGemmBK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kPadPitch = (OutBytes == 4) ? 144 : 80;        // bytes per staged row (32 outputs + 16 B)
   static constexpr int kPadBytes = 32 * kPadPitch;                    // per epilogue warp
@@ -55,28 +57,29 @@ struct GemmCfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-// erf-form GELU, x * 0.5 * (1 + erf(x / sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), which is
-// two orders below the 16-bit rounding of the value it feeds and ~2x cheaper than erff() in the epilogue.
+// erf-form GELU, x * Phi(x) = x * 0.5 * (1 + erf(x / sqrt 2)) (hidden_act == "gelu"), evaluated as
+//     x * sigmoid(p(x)),  p(x) = x (c0 + c1 x^2 + c2 x^4)  = a minimax fit of logit(Phi(x)) on |x| <= 6
+// (argument clamped to +-6, where Phi is 0 / 1 to 1e-9).  Max abs error vs the exact erf form 2.6e-5 in fp32
+// (tools/fit_gelu.py), i.e. ~5x below the 16-bit rounding of the value it produces; 10 instructions and two
+// MUFU ops per element instead of ~20 for erff(): the FFN-up epilogue must retire 128 x 256 activations per
+// 6144 tensor-core cycles.  The coefficients below are c_i * -log2(e) so the exponential is a bare ex2.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t;
-  const float e = fmaf(-p, __expf(-z * z), 1.0f);  // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float u = xc * xc;
+  float q = fmaf(u, 0.0010142651153728366f, -0.10677573829889297f);
+  q = fmaf(u, q, -2.301121234893799f);
+  q *= xc;
+  return __fdividef(x, 1.0f + exp2f(q));
 }
 
-template <int BN, int CM, int CN, int EPI, typename OutT, typename T16>
+template <int BN, bool PAIR, int EPI, typename OutT, typename T16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN, (int)sizeof(OutT)>;
+  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kCluster = CM * CN;
-  static_assert((kGemmBM / CN) % 8 == 0 && (BN / CM) % 8 == 0, "multicast slices must be whole swizzle atoms");
+  constexpr int kCluster = PAIR ? 2 : 1;
+  static_assert(!PAIR || BN % 32 == 0, "cta_group::2 needs N % 16 == 0 and whole swizzle atoms per half");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -93,17 +96,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int ct_m = (m_tiles + CM - 1) / CM, ct_n = (n_tiles + CN - 1) / CN;
-  const int num_ctiles = ct_m * ct_n;  // cluster tiles: (CM*128) x (CN*BN)
+  const int ct_m = (m_tiles + kCluster - 1) / kCluster;
+  const int num_ctiles = ct_m * n_tiles;  // cluster tiles: (kCluster*128) x BN
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
-  const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
-  const int rm = crank % CM, rn = crank / CM;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
   const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
-  uint16_t mask_a = 0, mask_b = 0;  // CTAs sharing my A tile (same rm) / my B tile (same rn)
-#pragma unroll
-  for (int j = 0; j < CN; ++j) mask_a |= uint16_t(1u << (rm + j * CM));
-#pragma unroll
-  for (int i = 0; i < CM; ++i) mask_b |= uint16_t(1u << (i + rn * CM));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -113,21 +111,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), CM + CN - 1);  // every CTA whose ring my multicasts land in releases the stage
+        mbar_init(empty_bar(s), 1);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), kGemmEpiWarps);
+        mbar_init(tempty_bar(a), kCluster * kGemmEpiWarps);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -137,25 +140,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0, t_start = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        const int m0 = ((ct / ct_n) * CM + rm) * kGemmBM;
-        const int n0 = ((ct % ct_n) * CN + rn) * BN;
+        const int m0 = ((ct / n_tiles) * kCluster + (int)crank) * kGemmBM;
+        const int n0 = (ct % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const long long t0 = clock64();
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          t_wait += clock64() - t0;
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if (CN == 1) {
+          if (!PAIR) {
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kGemmBK, m0);
-          } else {
-            constexpr int rows = kGemmBM / CN;
-            tma_load_2d_mc(sa + rn * rows * 128, &tmap_a, full_bar(stage), kb * kGemmBK, m0 + rn * rows, mask_a);
-          }
-          if (CM == 1) {
             tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kGemmBK, n0);
           } else {
-            constexpr int rows = BN / CM;
-            tma_load_2d_mc(sb + rm * rows * 128, &tmap_b, full_bar(stage), kb * kGemmBK, n0 + rm * rows, mask_b);
+            // both CTAs' bytes are counted on the leader's barrier (the leader alone issues the MMAs)
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+            tma_load_2d_2cta(sa, &tmap_a, lbar, kb * kGemmBK, m0);
+            tma_load_2d_2cta(sb, &tmap_b, lbar, kb * kGemmBK, n0 + (int)crank * (BN / 2));
           }
           if (++stage == kStages) {
             stage = 0;
@@ -163,22 +167,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       }
+      if (p.trace) {
+        p.trace[blockIdx.x * 8 + 0] = clock64() - t_start;  // producer: total
+        p.trace[blockIdx.x * 8 + 1] = t_wait;               // producer: waiting for a free stage
+      }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kGemmBM, BN, Cvt<T16>::kFmt, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long t_full = 0, t_tmem = 0, t_start = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        long long t0 = clock64();
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        t_tmem += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          t0 = clock64();
           mbar_wait(full_bar(stage), phase);
+          t_full += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
@@ -186,16 +199,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // +32 B per UMMA_K=16 step inside the 128-byte swizzle row (descriptor address is in 16-B units)
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (PAIR) umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          if (kCluster == 1) umma_commit(empty_bar(stage));
-          else umma_commit_mc(empty_bar(stage), uint16_t(mask_a | mask_b));
+          if (PAIR) umma_commit_2cta_mc(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
+        if (PAIR) umma_commit_2cta_mc(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
+      }
+      if (p.trace) {
+        p.trace[blockIdx.x * 8 + 2] = clock64() - t_start;  // MMA issuer: total
+        p.trace[blockIdx.x * 8 + 3] = t_full;               // ... waiting for operands (TMA)
+        p.trace[blockIdx.x * 8 + 4] = t_tmem;               // ... waiting for a drained accumulator (epilogue)
       }
     }
   } else {
@@ -208,28 +228,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const bool vec_ok = ((p.ldo * (long long)sizeof(OutT)) % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int it = 0;
+    long long t_acc = 0, t_start = clock64();
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = ((ct / ct_n) * CM + rm) * kGemmBM;
-      const int n0 = ((ct % ct_n) * CN + rn) * BN;
+      const int m0 = ((ct / n_tiles) * kCluster + (int)crank) * kGemmBM;
+      const int n0 = (ct % n_tiles) * BN;
       const int mrow0 = m0 + q * 32;  // first row of this warp's 32-row band
 
+      const long long t0 = clock64();
       mbar_wait(tfull_bar(acc), acc_phase);
+      t_acc += clock64() - t0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
       if (mrow0 < p.M) {
-#pragma unroll 1
-        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        constexpr int NC = kColsPerWarp / 32;
+        constexpr bool kResid = (EPI == EPI_BIAS_RESID);
+        // chunk c+1's TMEM load and residual rows are in flight while chunk c is processed
+        uint32_t rbuf[2][32];
+        float4 res[2][kResid ? 8 : 1];
+        const bool res_vec = kResid && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
+        auto prefetch_resid = [&](int c, float4* dst) {
           const int nc = n0 + half * kColsPerWarp + c * 32;
-          if (nc >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          if (kResid && res_vec && nc + 32 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + i * 4 + (lane >> 3), n = nc + (lane & 7) * 4;
+              dst[i] = (m < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)m * p.ldr + n)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        };
+        tmem_ld_32x32b_x32(t_row, rbuf[0]);
+        prefetch_resid(0, res[0]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int nc = n0 + half * kColsPerWarp + c * 32;
+          const bool live = nc < p.N;           // warp-uniform
+          const bool full = (nc + 32 <= p.N);
           tmem_ld_wait();
+          if (c + 1 < NC) {
+            tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
+            prefetch_resid(c + 1, res[(c + 1) & 1]);
+          }
+          if (!live) continue;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = (nc + 32 <= p.N);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]);
           if (p.bias != nullptr) {
             if (full) {
 #pragma unroll
@@ -260,12 +305,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const int m = mrow0 + rr, n = nc + cc;
               float4 x = *reinterpret_cast<const float4*>(pad + rr * Cfg::kPadPitch + cc * 4);
               if (m < p.M && n < p.N) {
-                long long orow = m;
-                if (p.rin > 0) orow = (long long)(m / p.rin) * p.rout + p.roff + (m % p.rin);
-                float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
-                if (full && vec_ok) {
-                  if (EPI == EPI_BIAS_RESID) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(p.resid + (long long)m * p.ldr + n);
+                float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+                if (full && vec_ok && (!kResid || res_vec)) {
+                  if (kResid) {
+                    const float4 r4 = res[c & 1][i];
                     x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
                   }
                   *reinterpret_cast<float4*>(o) = x;
@@ -275,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   for (int e = 0; e < 4; ++e)
                     if (n + e < p.N) {
                       float y = xs[e];
-                      if (EPI == EPI_BIAS_RESID) y += p.resid[(long long)m * p.ldr + n + e];
+                      if (kResid) y += p.resid[(long long)m * p.ldr + n + e];
                       o[e] = y;
                     }
                 }
@@ -299,9 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const int m = mrow0 + rr, n = nc + cc;
               const uint4 u = *reinterpret_cast<const uint4*>(pad + rr * Cfg::kPadPitch + cc * 2);
               if (m < p.M && n < p.N) {
-                long long orow = m;
-                if (p.rin > 0) orow = (long long)(m / p.rin) * p.rout + p.roff + (m % p.rin);
-                T16* o = reinterpret_cast<T16*>(p.out) + orow * p.ldo + n;
+                T16* o = reinterpret_cast<T16*>(p.out) + (long long)m * p.ldo + n;
                 if (full && vec_ok) {
                   *reinterpret_cast<uint4*>(o) = u;
                 } else {
@@ -318,16 +359,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (!PAIR || leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+      }
+    }
+    if (p.trace && ew == 0 && lane == 0) {
+      p.trace[blockIdx.x * 8 + 5] = clock64() - t_start;  // epilogue warp 0: total
+      p.trace[blockIdx.x * 8 + 6] = t_acc;                // ... waiting for a finished accumulator (MMA)
+      p.trace[blockIdx.x * 8 + 7] = it;                   // tiles processed by this CTA
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into / signal it
+  if (PAIR) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer may still signal it / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

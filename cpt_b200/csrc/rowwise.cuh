@@ -160,9 +160,11 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
 // Small fp32 head mat-vec:  Y[b, o] = act( W[wrow(o), :] . LN?(X[xrow(b), :]) + bias[wrow(o)] )
 //   xrow(b) = b * x_rows_per_b + (x_pos ? x_pos[b] : 0)        (gather the [MASK] / [CLS] row of sample b)
 //   wrow(o) = w_ids ? w_ids[o] : o                              (gather the colour / answer vocabulary rows)
-// One CTA handles kHeadRows samples x 64 outputs; the weight row is read once for all kHeadRows samples.
+// One CTA handles kHeadRows samples x kHeadOuts outputs (2 per warp); the weight row is read once for all
+// kHeadRows samples.
 // All fp32: the heads add no rounding beyond the encoder's (BertLMPredictionHead / BertPooler / seq_relationship).
 constexpr int kHeadRows = 8;
+constexpr int kHeadOuts = 16;
 enum HeadAct { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
 
 __global__ void __launch_bounds__(256) head_matvec_kernel(
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(256) head_matvec_kernel(
     for (int c = lane; c < H; c += 32) xs[warp * H + c] = 0.f;
   }
   __syncthreads();
-  for (int oo = warp; oo < 64; oo += 8) {
-    const int o = blockIdx.y * 64 + oo;
+  for (int oo = warp; oo < kHeadOuts; oo += 8) {
+    const int o = blockIdx.y * kHeadOuts + oo;
     if (o >= O) break;
     long long wr = w_ids ? w_ids[o] : o;
     if (wr < 0 || wr >= w_rows) {
@@ -215,10 +217,13 @@ __global__ void __launch_bounds__(256) head_matvec_kernel(
     float acc[kHeadRows];
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
-    for (int c = lane; c < H; c += 32) {
-      const float wv = __ldg(w + c);
+    for (int c = lane * 4; c < H; c += 128) {  // H % 128 == 0
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(wv, xs[r * H + c], acc[r]);
+      for (int r = 0; r < kHeadRows; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + r * H + c);
+        acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[r]))));
+      }
     }
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) acc[r] = warp_sum(acc[r]);

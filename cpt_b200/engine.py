@@ -241,6 +241,11 @@ class Engine(object):
                                          1 if out_fp32 else 0, _ptr(out), out.stride(0), tile_cfg))
         return out
 
+    def gemm_trace(self, n=148):
+        buf = (C.c_longlong * (8 * n))()
+        _lib.check(self.lib.cpt_gemm_trace(self._h, buf, n))
+        return [list(buf[8 * i:8 * i + 8]) for i in range(n)]
+
     def attention(self, qkv, ext_mask, B, S, impl=0):
         H = self.cfg.hidden_size
         ctx = torch.empty(B * S, H, dtype=self._t16(), device=self.device)

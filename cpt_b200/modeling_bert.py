@@ -285,6 +285,13 @@ class BertImgModel(BertPreTrainedModel):
     # -- forward ------------------------------------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,
                 img_feats=None, encoder_history_states=None):
+        return self._encode(input_ids, token_type_ids, attention_mask, position_ids, head_mask, img_feats,
+                            encoder_history_states, want_pooled=True)
+
+    def _encode(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,
+                img_feats=None, encoder_history_states=None, want_pooled=True):
+        """forward() with the BertPooler made optional: the MLM wrappers never read pooled_output (the reference
+        computes it anyway, modeling_bert.py:275), so they pass want_pooled=False and get None in its place."""
         if head_mask is not None:
             raise NotImplementedError("cpt_b200: head_mask is never used on the CPT path (modeling_bert.py:60-61)")
         if encoder_history_states is not None:
@@ -302,7 +309,7 @@ class BertImgModel(BertPreTrainedModel):
             attention_mask = attention_mask.to(torch.int64)
         want_hidden = bool(getattr(self.config, "output_hidden_states", False))
         seq, pooled, hidden = eng.encoder_forward(input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                                                  want_pooled=True, want_hidden=want_hidden)
+                                                  want_pooled=want_pooled, want_hidden=want_hidden)
         out = (seq, pooled)
         if want_hidden:
             out = out + (tuple(hidden.unbind(0)),)

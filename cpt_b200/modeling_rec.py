@@ -38,8 +38,9 @@ class REC_MLM_CPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
         self.bert.register_head_tensors(self.cls.head_tensors())
-        outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
-                            attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
+        outputs = self.bert._encode(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
+                                    attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats,
+                                    want_pooled=False)
         eng = self.bert.engine()
         if mask_pos is not None:
             if masked_lm_labels is not None:

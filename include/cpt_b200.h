@@ -119,11 +119,15 @@ int cpt_profile_read(cpt_handle *h, double *ms, long long *launches);
 /* ---- kernel-level entry points (unit tests, bench roofline leg) ----------------------------------------- */
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): A, W 16-bit (dtype as in cfg) with leading dims lda/ldw (elements, multiples
  * of 8); epi: 0 bias, 1 bias+erf-GELU, 2 bias+fp32 residual; out_fp32: 0 -> 16-bit out, 1 -> fp32 out.
- * tile_cfg: 0 = library default, else block_n (64/128/192/256) + 1000 * (10*CM + CN) for a CM x CN multicast
- * cluster (e.g. 21256 = 256-wide tiles, 2 CTAs sharing each weight tile). */
+ * tile_cfg: 0 = library default, else block_n (64/128/192/256) + 1000 * (CTAs per MMA: 1 or 2), e.g. 2256 =
+ * 256-wide tiles computed by CTA pairs (tcgen05 cta_group::2). */
 int cpt_gemm(cpt_handle *h, void *stream, const void *A, long long lda, const void *W, long long ldw, int M, int N,
              int K, const float *bias, const float *resid, long long ldr, int epi, int out_fp32, void *out,
              long long ldo, int tile_cfg);
+/* Debug: per-CTA cycle counters of the LAST GEMM launch (needs CPT_B200_TRACE=1 in the environment at cpt_create):
+ * out[cta][8] = {producer total, producer waiting for a free stage, MMA total, MMA waiting for operands,
+ * MMA waiting for a drained accumulator, epilogue total, epilogue waiting for MMA, tiles}. */
+int cpt_gemm_trace(cpt_handle *h, long long *out, int max_ctas);
 /* ctx[B*S,H] = softmax(QK^T/sqrt(dH) + (1-mask)*-1e4) V from packed qkv[B*S,3H] (16-bit); ext_mask fp32 [B,S].
  * impl: 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel. */
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,

@@ -23,30 +23,30 @@ def _gelu(x):
 
 
 GEMM_CASES = [
-    # M, N, K, epi, out_fp32, tile_cfg  (block_n + 1000 * (10*CM + CN); 0 = library default)
-    (128, 128, 64, 0, True, 11128),
-    (128, 128, 256, 0, True, 11128),
-    (256, 256, 128, 0, True, 11256),
-    (256, 64, 128, 0, True, 11064),
-    (300, 200, 136, 0, True, 11128),     # ragged M, N, K (TMA zero-fill + masked epilogue)
-    (300, 200, 136, 0, False, 11192),
+    # M, N, K, epi, out_fp32, tile_cfg  (block_n + 1000 * CTAs-per-MMA; 0 = library default)
+    (128, 128, 64, 0, True, 1128),
+    (128, 128, 256, 0, True, 1128),
+    (256, 256, 128, 0, True, 1256),
+    (256, 64, 128, 0, True, 1064),
+    (300, 200, 136, 0, True, 1128),     # ragged M, N, K (TMA zero-fill + masked epilogue)
+    (300, 200, 136, 0, False, 1192),
     (1000, 2304, 768, 0, False, 0),      # QKV projection shape, 16-bit out, default tile
-    (1000, 2304, 768, 0, False, 11128),
-    (1000, 2304, 768, 0, False, 21256),  # 2 CTAs share each weight tile (TMA multicast)
-    (1000, 2304, 768, 0, False, 12256),  # 2 CTAs share each activation tile
-    (1000, 2304, 768, 0, False, 22192),  # 2x2 cluster
+    (1000, 2304, 768, 0, False, 1128),
+    (1000, 2304, 768, 0, False, 2256),  # CTA pair, tcgen05 cta_group::2
+    (1000, 2304, 768, 0, False, 2128),  
+    (1000, 2304, 768, 0, False, 2192),  
     (777, 3072, 768, 1, False, 0),       # FFN up: bias + erf-GELU
-    (777, 3072, 768, 1, False, 22256),
+    (777, 3072, 768, 1, False, 2256),
     (777, 768, 3072, 2, True, 0),        # FFN down: bias + fp32 residual
-    (777, 768, 3072, 2, True, 11064),
-    (777, 768, 3072, 2, True, 41128),
-    (777, 768, 3072, 2, True, 22128),
+    (777, 768, 3072, 2, True, 1064),
+    (777, 768, 3072, 2, True, 2064),
+    (777, 768, 3072, 2, True, 2128),
     (450, 768, 2054, 0, True, 0),        # region embedding: K = 2054 (tail of 6 in the last 64-wide k-block)
     (130, 1001, 768, 0, True, 0),        # vocabulary-decoder-like: N not a multiple of anything, unaligned rows
-    (130, 1001, 768, 0, True, 21256),
+    (130, 1001, 768, 0, True, 2256),
     (7680, 768, 768, 2, True, 0),        # many tiles per CTA: exercises the TMEM double buffer + ring wrap
-    (7680, 768, 768, 2, True, 22128),
-    (7680, 2304, 768, 0, False, 21256),
+    (7680, 768, 768, 2, True, 2128),
+    (7680, 2304, 768, 0, False, 2256),
 ]
 
 
