@@ -22,6 +22,7 @@ struct AttnParams {
   const float* ext_mask;  // [B, S] additive fp32
   void* ctx;              // T16 [B*S, H]
   float scale;            // 1/sqrt(dH)
+  long long* trace;       // optional [gridDim.x][8] cycle counters (debug)
 };
 
 __host__ __device__ inline int attn_nkb(int S) { return (S + 63) / 64; }
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_tc_kernel(const __grid_cons
   const uint32_t tmem_cols = (NK <= 128) ? 256u : 512u;
   const uint32_t o_col = (NK <= 128) ? 128u : 256u;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(bar_qk, 1);
@@ -62,13 +64,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_tc_kernel(const __grid_cons
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  for (int j = threadIdx.x; j < nkb * 64; j += kAttnThreads)
-    maskp[j] = (j < S) ? p.ext_mask[(long long)b * S + j] : 0.f;
   if (warp == 0) {
     __syncwarp();
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();
+  for (int j = threadIdx.x; j < nkb * 64; j += kAttnThreads)
+    maskp[j] = (j < S) ? p.ext_mask[(long long)b * S + j] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,6 +191,284 @@ __global__ void __launch_bounds__(kAttnThreads) attn_tc_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Production kernel: the same math as attn_tc_kernel, restructured as a persistent, warp-specialised pipeline
+// (one CTA per SM, work item = (sample, head, 128-query tile)) so that TMA, the two tensor-core GEMMs and the
+// softmax of consecutive items overlap:
+//   warp 0      : TMA producer            (Q, K, V tiles up to NSLOT-1 items ahead)
+//   warp 1      : tcgen05.mma issuer      (S(i+1) = Q K^T is issued before waiting for P(i); O(i) = P V)
+//   warps 2..9  : softmax + output        (2 threads per query row, each owning half of the keys / of dH; the
+//                                          half-row of scores is read from TMEM ONCE and stays in registers for
+//                                          max, exp and sum; with >= 3 slots the O(i) read-out is deferred until
+//                                          after the softmax of item i+1 so it never waits for the P V MMA)
+// Per slot the probability tile P aliases the Q/K tiles (dead once S is in TMEM) and the output accumulator O
+// aliases the first 64 TMEM columns of S (dead once P is in smem).  NCH = 64-key blocks (= 32-column score chunks
+// per thread): S <= 128 -> NCH 2, 4 slots (192 KB smem, 512 TMEM columns); S <= 256 -> NCH 4, 2 slots.
+constexpr int kAttn2Threads = 64 + 256;
+
+template <int NCH>
+struct Attn2Cfg {
+  static constexpr int kQK = 16384 + NCH * 8192, kP = NCH * 16384;
+  static constexpr int kSlotBytes = (kQK > kP ? kQK : kP) + NCH * 8192;
+  static constexpr int kVOff = kSlotBytes - NCH * 8192;
+  static constexpr int kTmemStride = NCH * 64;                 // score columns per slot (O aliases the first 64)
+  static constexpr int kSlots = (NCH <= 2) ? 4 : 2;
+  static constexpr int kSmemBytes = 1024 + kSlots * kSlotBytes + 1024 /*mask*/ + 2048 /*row stats*/ + 256;
+  static_assert(kSlots * kTmemStride <= 512, "TMEM");
+};
+
+template <typename T16, int NCH>
+__global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                     const AttnParams p) {
+  using Cfg = Attn2Cfg<NCH>;
+  constexpr int NSLOT = Cfg::kSlots;
+  constexpr bool kDefer = NSLOT >= 3;
+  extern __shared__ uint8_t smem_raw[];
+  const int S = p.S;
+  const int NK = (S + 15) & ~15;          // UMMA N of S = Q K^T and K extent of O = P V
+  const int nchunk = (NK + 31) / 32;      // live 32-column score chunks (<= 2 * NCH)
+  const int n_mt = (S + 127) / 128;
+  const int n_items = p.B * p.nH * n_mt;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);
+  float* hmax = mask_s + 256;   // [2][128]
+  float* hsum = hmax + 256;     // [2][128]
+  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + 1024 + 2048;
+  enum { QK_FULL = 0, V_FULL, S_FULL, P_READY, O_FULL, SLOT_FREE };
+  auto bar = [&](int which, int s) { return bars + 8u * (which * NSLOT + s); };
+  const uint32_t tmem_slot = bars + 8u * 6 * NSLOT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(bar(QK_FULL, s), 1);
+      mbar_init(bar(V_FULL, s), 1);
+      mbar_init(bar(S_FULL, s), 1);
+      mbar_init(bar(P_READY, s), 1);
+      mbar_init(bar(O_FULL, s), 1);
+      mbar_init(bar(SLOT_FREE, s), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int item, int& b, int& h, int& mt) {
+    mt = item % n_mt;
+    h = (item / n_mt) % p.nH;
+    b = item / (n_mt * p.nH);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % NSLOT;
+        const uint32_t par = (i / NSLOT) & 1u;
+        int b, h, mt;
+        decode(item, b, h, mt);
+        const int row0 = b * S;
+        const uint32_t sQ = base + s * Cfg::kSlotBytes, sK = sQ + 16384, sV = sQ + Cfg::kVOff;
+        const long long t0 = clock64();
+        mbar_wait(bar(SLOT_FREE, s), par ^ 1u);
+        if (p.trace) p.trace[blockIdx.x * 8 + 0] += clock64() - t0;  // producer: waiting for a free slot
+        mbar_expect_tx(bar(QK_FULL, s), 16384 + NCH * 8192);
+        tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128);
+        tma_load_2d(sQ + 8192, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128 + 64);
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+          tma_load_2d(sK + kb * 8192, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0 + kb * 64);
+        mbar_expect_tx(bar(V_FULL, s), NCH * 8192);
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+          tma_load_2d(sV + kb * 8192, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0 + kb * 64);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, NK, Cvt<T16>::kFmt, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(128, kAttnDH, Cvt<T16>::kFmt, 0, 1);
+      const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      auto issue_qk = [&](int i) {
+        const int s = i % NSLOT;
+        const uint32_t par = (i / NSLOT) & 1u;
+        const long long t0 = clock64();
+        mbar_wait(bar(QK_FULL, s), par);
+        if (p.trace) p.trace[blockIdx.x * 8 + 1] += clock64() - t0;  // MMA: waiting for Q/K tiles (TMA)
+        tc_fence_after();
+        const uint32_t sQ = base + s * Cfg::kSlotBytes;
+        const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sQ + 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + s * Cfg::kTmemStride, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        umma_commit(bar(S_FULL, s));
+      };
+      if (n_mine > 0) issue_qk(0);
+      for (int i = 0; i < n_mine; ++i) {
+        const int s = i % NSLOT;
+        const uint32_t par = (i / NSLOT) & 1u;
+        if (i + 1 < n_mine) issue_qk(i + 1);
+        const long long t0 = clock64();
+        mbar_wait(bar(P_READY, s), par);
+        if (p.trace) p.trace[blockIdx.x * 8 + 2] += clock64() - t0;  // MMA: waiting for the softmax
+        mbar_wait(bar(V_FULL, s), par);
+        tc_fence_after();
+        const uint32_t sP = base + s * Cfg::kSlotBytes, sV = sP + Cfg::kVOff;
+        for (int k = 0; k < NK / 16; ++k) {
+          const uint64_t pd = make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t vd = make_smem_desc(sV + k * 2048, 1024, 1024);
+          umma_f16(tmem_base + s * Cfg::kTmemStride, pd, vd, idesc_o, k != 0);
+        }
+        umma_commit(bar(O_FULL, s));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (256 threads)
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int tid = threadIdx.x - 64;
+    const int r = q * 32 + lane;        // query row within the tile == TMEM lane
+    const int c0 = half * NCH;          // my chunks: [c0, c0 + NCH), live while < nchunk
+    // read-out of one finished item: O / rowsum -> 16-bit ctx
+    auto read_out = [&](int i, int item, float inv) {
+      const int s = i % NSLOT;
+      const uint32_t par = (i / NSLOT) & 1u;
+      int b, h, mt;
+      decode(item, b, h, mt);
+      const long long t0 = clock64();
+      mbar_wait(bar(O_FULL, s), par);
+      if (p.trace && tid == 0) p.trace[blockIdx.x * 8 + 4] += clock64() - t0;  // softmax warps: waiting for O
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + s * Cfg::kTmemStride + half * 32, v);
+      tmem_ld_wait();
+      const int qi = mt * 128 + r;
+      if (qi < S) {
+        T16* dst = reinterpret_cast<T16*>(p.ctx) + ((long long)b * S + qi) * p.H + h * kAttnDH + half * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = Cvt<T16>::pack2(__uint_as_float(v[8 * k + 0]) * inv, __uint_as_float(v[8 * k + 1]) * inv);
+          u.y = Cvt<T16>::pack2(__uint_as_float(v[8 * k + 2]) * inv, __uint_as_float(v[8 * k + 3]) * inv);
+          u.z = Cvt<T16>::pack2(__uint_as_float(v[8 * k + 4]) * inv, __uint_as_float(v[8 * k + 5]) * inv);
+          u.w = Cvt<T16>::pack2(__uint_as_float(v[8 * k + 6]) * inv, __uint_as_float(v[8 * k + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + k * 8) = u;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(SLOT_FREE, s));
+    };
+
+    int i = 0, prev_item = -1;
+    float prev_inv = 0.f;
+    const long long t_begin = clock64();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+      const int s = i % NSLOT;
+      const uint32_t par = (i / NSLOT) & 1u;
+      const int b = item / (n_mt * p.nH);
+      if (tid < NCH * 64) mask_s[tid] = (tid < S) ? p.ext_mask[(long long)b * S + tid] : 0.f;
+      named_bar_sync(1, 256);
+      const long long t0 = clock64();
+      mbar_wait(bar(S_FULL, s), par);
+      if (p.trace && tid == 0) p.trace[blockIdx.x * 8 + 3] += clock64() - t0;  // softmax warps: waiting for S
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * Cfg::kTmemStride;
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c0 + c < nchunk) tmem_ld_32x32b_x32(t_row + (c0 + c) * 32, v[c]);
+      tmem_ld_wait();
+      // t = s / sqrt(dH) + ext_mask (modeling_bert.py:47-50), kept in place; columns >= S are excluded outright
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c0 + c < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = (c0 + c) * 32 + j;
+            const float4 m4 = *reinterpret_cast<const float4*>(mask_s + col);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float t = (col + e < S) ? fmaf(__uint_as_float(v[c][j + e]), p.scale, mm[e]) : -INFINITY;
+              v[c][j + e] = __float_as_uint(t);
+              mx = fmaxf(mx, t);
+            }
+          }
+        }
+      }
+      hmax[half * 128 + r] = mx;
+      named_bar_sync(1, 256);
+      mx = fmaxf(hmax[r], hmax[128 + r]);
+      float sum = 0.f;
+      uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c0 + c < nchunk) {
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            e[j] = __expf(__uint_as_float(v[c][j]) - mx);
+            sum += e[j];
+          }
+          // P[r, chunk] -> K-major 128B-swizzled A-operand tile (64-key block, 16-byte piece ^ (row & 7))
+          const int cc = c0 + c;
+          uint8_t* prow = p_gen + (cc >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = Cvt<T16>::pack2(e[8 * k + 0], e[8 * k + 1]);
+            u.y = Cvt<T16>::pack2(e[8 * k + 2], e[8 * k + 3]);
+            u.z = Cvt<T16>::pack2(e[8 * k + 4], e[8 * k + 5]);
+            u.w = Cvt<T16>::pack2(e[8 * k + 6], e[8 * k + 7]);
+            const int piece = ((cc & 1) * 4 + k) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + piece * 16) = u;
+          }
+        }
+      }
+      hsum[half * 128 + r] = sum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, 256);
+      if (tid == 0) mbar_arrive(bar(P_READY, s));
+      const float inv = 1.0f / (hsum[r] + hsum[128 + r]);
+      if (kDefer) {
+        if (prev_item >= 0) read_out(i - 1, prev_item, prev_inv);
+        prev_item = item;
+        prev_inv = inv;
+      } else {
+        read_out(i, item, inv);
+      }
+    }
+    if (kDefer && prev_item >= 0) read_out(i - 1, prev_item, prev_inv);
+    if (p.trace && tid == 0) {
+      p.trace[blockIdx.x * 8 + 5] = clock64() - t_begin;  // softmax warps: total
+      p.trace[blockIdx.x * 8 + 7] = i;                    // items
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Plain CUDA-core restatement of the same op (fp32 math on the same 16-bit Q/K/V): used by the GPU tests as an
 // on-device cross-check of the tensor-core kernel, and selectable with CPT_B200_ATTN=simt for debugging.  It is
 // a CUDA kernel, not a CPU fallback.
@@ -199,6 +480,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T16* __restrict__ 
   T16* sV = sK + (size_t)S * kAttnDH;
   float* sM = reinterpret_cast<float*>(sV + (size_t)S * kAttnDH);
   const int h = blockIdx.x, b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   const T16* base = qkv + (long long)b * S * 3 * H;
   for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
     const int j = i >> 3, c = (i & 7) * 8;
@@ -244,6 +527,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T16* __restrict__ 
 // K4: ext_mask = (1 - mask) * -10000 in fp32, exactly as modeling_bert.py:213-226 for a 2-D mask.
 __global__ void ext_mask_kernel(const long long* __restrict__ mask, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i < n) out[i] = (1.0f - (float)mask[i]) * -10000.0f;
 }
 

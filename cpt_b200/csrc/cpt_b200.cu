@@ -157,6 +157,32 @@ struct DeviceGuard {
 };
 
 // ------------------------------------------------------------------------------------------------ launchers
+// Launch on `st` with programmatic stream serialization (PDL) and, optionally, a thread-block cluster.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+}
+
 template <typename F>
 static int set_smem_attr(F* fn, size_t bytes) {
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -180,19 +206,7 @@ static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, 
   const int ctiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
   int clusters = h->num_sms / kCluster;
   if (ctiles < clusters) clusters = ctiles;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(clusters * kCluster);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, fn, ta, tb, p));
+  CK(launch_k(fn, dim3(clusters * kCluster), dim3(kGemmThreads), Cfg::kSmemBytes, st, kCluster, ta, tb, p));
   return 0;
 }
 
@@ -250,23 +264,48 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   const int H = h->cfg.hidden_size, nH = h->cfg.num_attention_heads;
   if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
   if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
-  AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f};
+  AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f, h->trace};
+  if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 64, st));
   ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {
     auto* fn = attn_simt_kernel<T16>;
     const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
     TRY(set_smem_attr(fn, smem));
-    fn<<<dim3(nH, B), 128, smem, st>>>(reinterpret_cast<const T16*>(qkv), p);
-    CKL("attn_simt_kernel");
+    CK(launch_k(fn, dim3(nH, B), dim3(128), smem, st, 1, reinterpret_cast<const T16*>(qkv), p));
     return 0;
   }
   CUtensorMap tq;
   TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
+  if (impl == 0) {  // production: persistent pipelined kernel, one CTA per SM
+    const int items = B * nH * ((S + 127) / 128);
+    const int grid = items < h->num_sms ? items : h->num_sms;
+    const int nch = (S + 63) / 64;
+#define CPT_ATTN_CASE(N_)                                                              \
+  case N_: {                                                                           \
+    auto* fn = attn_pipe_kernel<T16, N_>;                                              \
+    static bool attr_set[64] = {};                                                     \
+    if (!attr_set[h->device & 63]) {                                                   \
+      TRY(set_smem_attr(fn, Attn2Cfg<N_>::kSmemBytes));                                \
+      attr_set[h->device & 63] = true;                                                 \
+    }                                                                                  \
+    CK(launch_k(fn, dim3(grid), dim3(kAttn2Threads), Attn2Cfg<N_>::kSmemBytes, st, 1, tq, p)); \
+    break;                                                                             \
+  }
+    switch (nch) {
+      CPT_ATTN_CASE(1)
+      CPT_ATTN_CASE(2)
+      CPT_ATTN_CASE(3)
+      CPT_ATTN_CASE(4)
+      default: return fail("attention: unsupported S=%d", S);
+    }
+#undef CPT_ATTN_CASE
+    CKL("attn_pipe_kernel");
+    return 0;
+  }
   auto* fn = attn_tc_kernel<T16>;
   const size_t smem = attn_smem_bytes(S);
   TRY(set_smem_attr(fn, smem));
-  fn<<<dim3(nH, (S + 127) / 128, B), kAttnThreads, smem, st>>>(tq, p);
-  CKL("attn_tc_kernel");
+  CK(launch_k(fn, dim3(nH, (S + 127) / 128, B), dim3(kAttnThreads), smem, st, 1, tq, p));
   return 0;
 }
 
@@ -275,9 +314,8 @@ static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long l
                      float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN);
-  ln_rows_kernel<T16><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, M, H, g, b, eps, do_ln ? 1 : 0, o32,
-                                                   reinterpret_cast<T16*>(o16), rin, rout, roff);
-  CKL("ln_rows_kernel");
+  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, ldx, M, H, g, b, eps, do_ln ? 1 : 0, o32,
+              reinterpret_cast<T16*>(o16), rin, rout, roff));
   return 0;
 }
 
@@ -289,9 +327,8 @@ static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long
   const size_t smem = (size_t)kHeadRows * H * sizeof(float);
   dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + kHeadOuts - 1) / kHeadOuts);
   ProfScope ps(h, st, CPT_K_HEAD);
-  head_matvec_kernel<<<grid, 256, smem, st>>>(X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw, bias, w_ids,
-                                              w_rows, B, H, O, act, Y, ldy, h->err_flag);
-  CKL("head_matvec_kernel");
+  CK(launch_k(head_matvec_kernel, grid, dim3(256), smem, st, 1, X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw,
+              bias, w_ids, w_rows, B, H, O, act, Y, ldy, h->err_flag));
   return 0;
 }
 
@@ -451,18 +488,16 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   // K4: additive mask
   if (mask) {
     ProfScope ps(h, st, CPT_K_EXTMASK);
-    ext_mask_kernel<<<(M + 255) / 256, 256, 0, st>>>((const long long*)mask, M, w.ext_mask);
-    CKL("ext_mask_kernel");
+    CK(launch_k(ext_mask_kernel, dim3((M + 255) / 256), dim3(256), 0, st, 1, (const long long*)mask, M, w.ext_mask));
   } else {
     CK(cudaMemsetAsync(w.ext_mask, 0, (size_t)M * 4, st));
   }
   {  // K1: text rows
     ProfScope ps(h, st, CPT_K_EMBED);
-    embed_text_ln_kernel<T16><<<(B * T + 7) / 8, 256, 0, st>>>(
-        (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g,
-        h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, w.h32,
-        reinterpret_cast<T16*>(w.h16), h->err_flag);
-    CKL("embed_text_ln_kernel");
+    CK(launch_k(embed_text_ln_kernel<T16>, dim3((B * T + 7) / 8), dim3(256), 0, st, 1, (const long long*)ids,
+                (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, (const float*)h->emb_g,
+                (const float*)h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings,
+                c.type_vocab_size, w.h32, reinterpret_cast<T16*>(w.h16), h->err_flag));
   }
   // K2+K3: region rows
   if (R > 0) {
@@ -471,8 +506,8 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
     const int grid = (int)((pairs + 255) / 256 < 8192 ? (pairs + 255) / 256 : 8192);
     {
       ProfScope ps(h, st, CPT_K_CAST);
-      cast_pad_kernel<T16><<<grid, 256, 0, st>>>(img, Mi, F, h->Fp, reinterpret_cast<T16*>(w.img16));
-      CKL("cast_pad_kernel");
+      CK(launch_k(cast_pad_kernel<T16>, dim3(grid), dim3(256), 0, st, 1, img, Mi, F, h->Fp,
+                  reinterpret_cast<T16*>(w.img16)));
     }
     GemmParams p{};
     p.M = Mi; p.N = H; p.K = F; p.out = w.pre32; p.ldo = H; p.bias = h->b_img;

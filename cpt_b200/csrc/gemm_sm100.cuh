@@ -103,6 +103,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -132,6 +133,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 

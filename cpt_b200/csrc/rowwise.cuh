@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(
     int vocab, int max_pos, int n_type, float* __restrict__ out32, T16* __restrict__ out16, int* __restrict__ err) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= B * T) return;
   const int b = row / T, t = row % T;
   long long id = ids[row];
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
                                                       int rout, int roff) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= M) return;
   const int nv = H >> 7;
   float4 x[kMaxVec];
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
                                                        T16* __restrict__ out) {
   const long long pairs_per_row = Fp >> 1;
   const long long total = (long long)rows * pairs_per_row;
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / pairs_per_row;
@@ -174,6 +180,8 @@ __global__ void __launch_bounds__(256) head_matvec_kernel(
     int O, int act, float* __restrict__ Y, long long ldy, int* __restrict__ err) {
   extern __shared__ float xs[];  // [kHeadRows][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b0 = blockIdx.x * kHeadRows;
   const int nb = min(kHeadRows, B - b0);
   // stage (and optionally normalise) the input rows: warp w owns row w

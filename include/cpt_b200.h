@@ -129,7 +129,8 @@ int cpt_gemm(cpt_handle *h, void *stream, const void *A, long long lda, const vo
  * MMA waiting for a drained accumulator, epilogue total, epilogue waiting for MMA, tiles}. */
 int cpt_gemm_trace(cpt_handle *h, long long *out, int max_ctas);
 /* ctx[B*S,H] = softmax(QK^T/sqrt(dH) + (1-mask)*-1e4) V from packed qkv[B*S,3H] (16-bit); ext_mask fp32 [B,S].
- * impl: 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel. */
+ * impl: 0 = persistent pipelined tcgen05 kernel (production), 1 = CUDA-core cross-check kernel,
+ * 2 = single-tile tcgen05 kernel (one CTA per (head, query tile, sample); kept as a second cross-check). */
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,
                   int impl);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */

@@ -73,7 +73,8 @@ def test_gemm_against_torch(eng, M, N, K, epi, out_fp32, cfg):
     assert err <= tol, "max err %.3e (scale %.3e)" % (err, scale)
 
 
-@pytest.mark.parametrize("B,S", [(2, 120), (3, 210), (1, 40), (2, 128), (2, 129), (1, 256), (2, 1), (5, 17)])
+@pytest.mark.parametrize("B,S", [(2, 120), (3, 210), (1, 40), (2, 128), (2, 129), (1, 256), (2, 1), (5, 17), (64, 120),
+                                 (16, 210), (3, 64), (2, 65), (2, 192)])
 def test_attention_against_torch_and_simt(eng, B, S):
     H, nH, dH = 768, 12, 64
     g = torch.Generator(device="cuda").manual_seed(S * 31 + B)
@@ -83,6 +84,7 @@ def test_attention_against_torch_and_simt(eng, B, S):
     ext = (1.0 - mask.float()) * -10000.0
     ctx_tc = eng.attention(qkv, ext, B, S, impl=0)
     ctx_simt = eng.attention(qkv, ext, B, S, impl=1)
+    ctx_tile = eng.attention(qkv, ext, B, S, impl=2)
     torch.cuda.synchronize()
     q, k, v = (t.float().view(B, S, nH, dH).permute(0, 2, 1, 3) for t in qkv.split(H, dim=1))
     p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext[:, None, None, :], -1)
@@ -91,6 +93,7 @@ def test_attention_against_torch_and_simt(eng, B, S):
     assert (ctx_simt.float() - ref).abs().max().item() <= 1.5e-3 * scale
     assert (ctx_tc.float() - ref).abs().max().item() <= 3e-3 * scale   # P is rounded to 16 bits before P.V
     assert (ctx_tc.float() - ctx_simt.float()).abs().max().item() <= 3e-3 * scale
+    assert (ctx_tile.float() - ref).abs().max().item() <= 3e-3 * scale
 
 
 def test_attention_fully_masked_row_matches_additive_mask_semantics(eng):
