@@ -38,6 +38,11 @@ class REC_MLM_CPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
         self.bert.register_head_tensors(self.cls.head_tensors())
+        if (mask_pos is not None and masked_lm_labels is None and head_mask is None
+                and not getattr(self.config, "output_hidden_states", False)):
+            # the CPT inference call: one fused (and CUDA-graph-cached) encoder + gathered-head launch sequence
+            return (self.bert._cpt_logits(input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
+                                          vocab_ids),)
         outputs = self.bert._encode(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
                                     attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats,
                                     want_pooled=False)

@@ -160,3 +160,36 @@ def test_weight_update_is_picked_up():
         rec.bert.encoder.layer[0].intermediate.dense.weight.mul_(1.5)
         c = rec.bert(b["input_ids"], img_feats=b["img_feats"])[0]
     assert (a - c).abs().max().item() > 1e-3
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_buffer_contents():
+    cfg = C.oscar_tiny()
+    pre, rec, nsp = build(cfg, synth_state_dict(cfg, seed=5))
+    vids = synth_vocab_ids(cfg, 4, seed=1).cuda()
+    b = cuda(synth_batch(cfg, 3, 30, 10, seed=2))
+    other = cuda(synth_batch(cfg, 3, 30, 10, seed=9))
+
+    def call():
+        return rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
+                   mask_pos=b["mask_pos"], vocab_ids=vids)[0]
+
+    eng = rec.bert.engine()
+    with torch.no_grad():
+        eng.use_graphs = False
+        ref_a = call().clone()
+        eng.use_graphs = True
+        outs = [call().clone() for _ in range(4)]          # 1st eager, 2nd captures, 3rd/4th replay
+        assert len(eng._graphs) == 1
+        for o in outs:
+            assert torch.equal(o, ref_a)
+        for k in b:                                         # same buffers, new contents
+            b[k].copy_(other[k])
+        got = call().clone()
+        eng.use_graphs = False
+        ref_b = call().clone()
+    assert torch.equal(got, ref_b) and not torch.equal(got, ref_a)
+    n0 = eng.launch_count()
+    eng.use_graphs = True
+    with torch.no_grad():
+        call()
+    assert eng.launch_count() - n0 > 10                     # replays are counted as launches
