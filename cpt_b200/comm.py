@@ -1,0 +1,103 @@
+"""Multi-GPU plumbing of the CPT path: one process per GPU over torch.distributed (NCCL on the GPUs; gloo in the CPU
+tests).  The path shards by ROWS — samples are independent — so there is no collective inside the
+encoder; the only exchange is the final [B_local, K] logits, gathered with ONE collective instead of the
+reference's two pickle-over-NCCL all_gathers of Python dicts (/root/reference/Oscar/oscar/utils/comm.py:102-142,
+called from oscar/zeroshot/refcoco_cpt.py:256,262).
+
+The small helpers keep the reference's names and meaning (comm.py:14-46) so its callers read the same.
+"""
+import torch
+import torch.distributed as dist
+
+
+def get_world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def get_rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def is_main_process():
+    return get_rank() == 0
+
+
+def synchronize():
+    if get_world_size() > 1:
+        dist.barrier()
+
+
+def shard_queries(fanouts, rank=None, world=None):
+    """Partition queries over ranks, contiguously and balanced by ROW count, never splitting a query's fan-out rows
+    (RefCOCO: one row per proposal set, zeroshot/refcoco_cpt.py:224-246; VCR: 4 answer rows, vcr_nsp_cpt.py:602-604)
+    so the per-query argmax stays local.  Returns (first_query, end_query, first_row, end_row) for `rank`."""
+    rank = get_rank() if rank is None else rank
+    world = get_world_size() if world is None else world
+    total = sum(fanouts)
+    bounds, acc, q = [0], 0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while q < len(fanouts) and acc + fanouts[q] / 2.0 <= target:
+            acc += fanouts[q]
+            q += 1
+        bounds.append(q)
+    bounds.append(len(fanouts))
+    q0, q1 = bounds[rank], bounds[rank + 1]
+    r0 = sum(fanouts[:q0])
+    return q0, q1, r0, r0 + sum(fanouts[q0:q1])
+
+
+def all_gather_logits(local):
+    """[B_local, K] -> [sum_r B_r, K] on every rank, rank order preserved.  Ranks may hold different B_r (the last
+    shard of a split is ragged): sizes are exchanged first, then one padded all_gather."""
+    world = get_world_size()
+    if world == 1:
+        return local
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    if local.shape[0] != mx:
+        pad = torch.zeros((mx - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        local = torch.cat((local, pad), 0)
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    if all(s == mx for s in sizes):
+        return out
+    return torch.cat([out[r * mx:r * mx + s] for r, s in enumerate(sizes)], 0)
+
+
+def merge_by_key(dicts):
+    """De-duplicate per-rank result dicts the way the reference does after its gather (DistributedSampler pads by
+    repeating samples): the same key must carry the same value on every rank (zeroshot/refcoco_cpt.py:256-260)."""
+    merged = {}
+    for d in dicts:
+        for k, v in d.items():
+            assert (k not in merged) or (merged[k] == v), "rank results disagree for key %r" % (k,)
+            merged[k] = v
+    return merged
+
+
+def pick_per_query(logits, fanouts, mode="zsl"):
+    """CPT decision per query from the gathered colour logits [rows, K] (last column = the "none" token):
+      zsl: argmax over all rows' colour columns                       (zeroshot/refcoco_cpt.py:242-246)
+      fsl: argmax of colour / none                                     (fewshot/refcoco_cpt.py:291-294)
+      vcr: logits are NSP scores [rows, C]; score = 1 - softmax[:, 1]  (fewshot/vcr_nsp_cpt.py:600-604)
+    Returns a LongTensor [n_queries] of flat indices into each query's (rows x columns) block; one device->host
+    sync for the whole batch instead of one per image."""
+    if mode == "vcr":
+        score = (1.0 - torch.softmax(logits, -1)[:, 1]).unsqueeze(1)
+    elif mode == "fsl":
+        score = logits[:, :-1] / logits[:, -1:]
+    else:
+        score = logits[:, :-1]
+    n_q, width = len(fanouts), score.shape[1]
+    fan = torch.as_tensor(fanouts, device=score.device)
+    mx = int(fan.max()) if n_q else 0
+    starts = torch.cumsum(fan, 0) - fan
+    idx = starts[:, None] + torch.arange(mx, device=score.device)[None, :]
+    valid = torch.arange(mx, device=score.device)[None, :] < fan[:, None]
+    block = score[idx.clamp(max=score.shape[0] - 1)]                       # [n_q, mx, width]
+    block = torch.where(valid[:, :, None], block, torch.full_like(block, float("-inf")))
+    return block.reshape(n_q, mx * width).argmax(1)
