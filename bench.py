@@ -100,17 +100,55 @@ def oracle_step(sd, cfg, b, vids):
         return scores[torch.arange(scores.size(0)), b["mask_pos"]][:, vids]
 
 
+def make_cpu_reference(cfg, sd, vids):
+    """Returns (step_fn(batch) -> [B,K] logits, kind, description).  Preferred: the reference's OWN modules
+    (oscar.modeling.modeling_rec.REC_MLM_CPT from the offline install in baseline/_ref, its un-vendored
+    pytorch-transformers dependency supplied by oracle/ref_shim.py) called exactly as
+    oscar/zeroshot/refcoco_cpt.py:217-219 does; otherwise the oracle port."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        if not os.path.isfile(os.path.join(ref_root, "oscar", "modeling", "modeling_rec.py")):
+            raise ImportError("baseline/_ref/oscar is not installed")
+        from oracle import ref_shim
+        ref_shim.install(ref_root)
+        from oscar.modeling.modeling_bert import BertImgForPreTraining as RefPre
+        from oscar.modeling.modeling_rec import REC_MLM_CPT as RefRec
+        d = cfg.to_dict()
+        v = d.pop("vocab_size")
+        rcfg = ref_shim.BertConfig(v, **d)
+        pre = RefPre(rcfg)
+        missing, unexpected = pre.load_state_dict(sd, strict=False)
+        assert not missing and not unexpected
+        pre.tie_weights()
+        rec = RefRec(rcfg)
+        rec.copy_from_pretraining_model(pre)
+        rec.eval()
+
+        def step(b):
+            with torch.no_grad():
+                out = rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"])[0]
+                return out[torch.arange(out.size(0)), b["mask_pos"]][:, vids]
+        return step, "reference", ("the reference's own oscar.modeling.modeling_rec.REC_MLM_CPT (unmodified, installed "
+                                   "offline into baseline/_ref; pytorch-transformers 1.x blocks from oracle/ref_shim.py), "
+                                   "fp32 CPU, called as zeroshot/refcoco_cpt.py:217-219")
+    except Exception as ex:  # noqa: BLE001
+        why = "%s: %s" % (type(ex).__name__, str(ex)[:80])
+        return (lambda b: oracle_step(sd, cfg, b, vids)), "port", \
+            "oracle/cpt_oracle.py (torch fp32 CPU restatement; reference modules unavailable: %s)" % why
+
+
 def cpu_leg(cfg, sd, vids, batch, iters, warmup=1):
     torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, what = make_cpu_reference(cfg, sd, vids)
     b = synth_batch(cfg, batch, T_TEXT, R_REG, seed=88)
     for _ in range(warmup):
-        oracle_step(sd, cfg, b, vids)
+        step(b)
     ts = []
     for _ in range(iters):
         t0 = time.perf_counter()
-        oracle_step(sd, cfg, b, vids)
+        step(b)
         ts.append(time.perf_counter() - t0)
-    return batch * len(ts) / sum(ts), sum(ts) / len(ts)
+    return batch * len(ts) / sum(ts), sum(ts) / len(ts), kind, what
 
 
 def run_reference(args):
@@ -122,25 +160,24 @@ def run_reference(args):
     vids = synth_vocab_ids(cfg, K_IDS, seed=88)
     bs = args.ref_batch
     torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, what = make_cpu_reference(cfg, sd, vids)
     b = synth_batch(cfg, bs, T_TEXT, R_REG, seed=88)
     for _ in range(args.warmup):
-        oracle_step(sd, cfg, b, vids)
+        step(b)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(sd, cfg, b, vids)
+        step(b)
     dt = time.perf_counter() - t0
     val = bs * args.steps / dt
     cores = torch.get_num_threads()
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "RefCOCO CPT inference, Oscar-base, T=70 R=50 F=2054, K=2 colour ids; each step = "
-                                  "a bounded sample of %d rows (full-vocab head over all S, then gather, as the "
-                                  "reference runs it)" % bs, "batch_per_step": bs},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "%d steps x %d rows, oracle/cpt_oracle.py (torch fp32 CPU restatement of the "
-                                      "reference modules; the reference's pinned transformers dependency is absent "
-                                      "so its own files cannot run on this box)" % (args.steps, bs)},
+           "config": {"workload": "RefCOCO CPT inference (BASELINE.json configs[1] shape): Oscar-base, T=70 R=50 F=2054, "
+                                  "K=2 colour ids; each step = a bounded sample of %d rows (full-vocab head over all S, "
+                                  "then gather, as the reference runs it)" % bs, "batch_per_step": bs},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": "%d steps x %d rows; %s" % (args.steps, bs, what)},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -322,11 +359,10 @@ def main():
 
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            v, per = cpu_leg(cfg, sd, vids_cpu, 32, 4)
-            cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "4 timed passes (1 warm-up) of a 32-row batch of the same workload through "
-                             "oracle/cpt_oracle.py exactly as the reference runs it (full [B,S,V] head then gather), "
-                             "fp32, %.2f s per pass" % per}
+            v, per, kind, what = cpu_leg(cfg, sd, vids_cpu, 32, 4)
+            cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": "4 timed passes (1 warm-up) of a 32-row batch of the same workload (full [B,S,V] head "
+                             "then gather), %.2f s per pass; %s" % (per, what)}
 
     if rank == 0:
         total = B * world * args.steps

@@ -26,7 +26,7 @@ It is a functional, state-dict-driven restatement (plain torch fp32 ops, no nn.M
 Pinning: the reference ships no tests or golden vectors for this path, so
 the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF RUN IN THE BUILD CONTAINER:
 tests/golden/make_golden.py imports the reference's unmodified oscar/modeling files
-(via tests/golden/ref_shim.py) and stores their outputs under tests/golden/*.pt;
+(via oracle/ref_shim.py) and stores their outputs under tests/golden/*.pt;
 tests/test_oracle_golden.py checks this file against them (and, where transformers 5.x is
 importable, against HF's eager BERT blocks as an independent second opinion).
 """

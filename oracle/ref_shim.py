@@ -1,7 +1,8 @@
 """Shim that lets the reference's OWN, unmodified Oscar files run in this container.
 
-Test infrastructure only (used by tests/golden/make_golden.py and by the
-"reference present" tests).  Nothing in the product imports this.
+Test infrastructure only (used by tests/golden/make_golden.py and by bench.py's CPU reference legs, which run the
+reference's own modules from baseline/_ref when that offline install is present).  Nothing in the product
+imports this.
 
 The reference imports its BERT building blocks from an un-vendored git clone
 (`transformers.pytorch_transformers`, pinned at huggingface/transformers commit

@@ -1,5 +1,5 @@
 """Generate golden vectors by running the REFERENCE'S OWN files (unmodified, from
-/root/reference/Oscar) on CPU fp32, through tests/golden/ref_shim.py.
+/root/reference/Oscar) on CPU fp32, through oracle/ref_shim.py.
 
 Run in the build container only (the reference does not travel to the GPU box):
     python tests/golden/make_golden.py
@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
-import ref_shim  # noqa: E402
+from oracle import ref_shim  # noqa: E402
 from cpt_b200 import config as C  # noqa: E402
 from cpt_b200.synthetic import synth_state_dict, synth_batch, synth_vocab_ids  # noqa: E402
 
