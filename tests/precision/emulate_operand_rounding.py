@@ -1,4 +1,5 @@
-"""Analysis script (test infrastructure, CPU): emulates 16-bit GEMM-operand rounding on the fp32 oracle to size the\nparity budget quoted in DESIGN.md "Precision".  python tests/precision/<this file>"""
+"""Analysis script (test infrastructure, CPU): emulates 16-bit GEMM-operand rounding on the fp32 oracle to size the
+parity budget quoted in DESIGN.md "Precision".  python tests/precision/<this file>"""
 import sys, math, torch, torch.nn.functional as F
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from cpt_b200 import config as C
