@@ -89,6 +89,9 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long l
 struct LayerDev {
   void *w_qkv, *w_ao, *w_i, *w_o;  // 16-bit [3H,H] [H,H] [I,H] [H,I]
   float *b_qkv, *b_ao, *ao_g, *ao_b, *b_i, *b_o, *o_g, *o_b;
+  // LayerNorm-folded copies (DESIGN.md "LayerNorm folding"): W .* gamma of the LayerNorm that feeds the GEMM
+  void *w_qkv_f = nullptr, *w_i_f = nullptr;
+  float *g_qkv = nullptr, *c_qkv = nullptr, *g_i = nullptr, *c_i = nullptr;
 };
 struct cpt_handle {
   cpt_config cfg;
@@ -107,6 +110,8 @@ struct cpt_handle {
   std::vector<LayerDev> layers;
   int* err_flag = nullptr;
   int attn_impl = 0;
+  int fold_ln = 0;       // CPT_B200_FOLD_LN=1: LayerNorm folded into the neighbouring GEMM epilogues (slower, kept for study)
+  int resid_in_ln = 1;   // residual added by the (streaming) LayerNorm kernel instead of the GEMM epilogue
   struct { int bn, pair; } gemm_choice[16] = {};  // per kernel class, bn 0 = default (CPT_B200_GEMM overrides)
   // launch accounting / optional per-kernel-class CUDA-event timing (cpt_profile_*)
   long long launches = 0;
@@ -228,9 +233,11 @@ static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, GemmChoice c, const CU
 }
 
 // tile choice per GEMM class; cfg = block_n + 1000 * (1 + pair), 0 = default for the class
-static GemmChoice pick_gemm(const cpt_handle* h, int tag, int N, int cfg) {
+static GemmChoice pick_gemm(const cpt_handle* h, int tag, int N, int K, int cfg) {
   GemmChoice c{h->gemm_choice[tag].bn, h->gemm_choice[tag].pair};
-  if (c.bn == 0) c = GemmChoice{N >= 2048 ? 256 : 192, 0};  // tools/tune_gemm.py on B200, M = 7680
+  // A/B-measured in situ on B200 at M = 7680 (scripts in tools/, results in profiles/): wide N -> 256-wide CTA-pair
+  // tiles; N = 768 -> 192-wide tiles (4 per row, better wave balance), paired only when K is long
+  if (c.bn == 0) c = N >= 2048 ? GemmChoice{256, 1} : GemmChoice{192, K >= 2048 ? 1 : 0};
   if (cfg > 0) {
     if (cfg % 1000) c.bn = cfg % 1000;
     if (cfg / 1000) c.pair = (cfg / 1000) - 1;
@@ -244,7 +251,7 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
                 GemmParams p, int epi, bool out_fp32, int cfg = 0) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   ProfScope ps(h, st, tag);
-  const GemmChoice c = pick_gemm(h, tag, p.N, cfg);
+  const GemmChoice c = pick_gemm(h, tag, p.N, p.K, cfg);
   p.trace = h->trace;
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
@@ -311,10 +318,11 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
 
 template <typename T16>
 static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long ldx, int M, int H, const float* g, const float* b,
-                     float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0) {
+                     float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0,
+                     const float* resid = nullptr) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN);
-  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, ldx, M, H, g, b, eps, do_ln ? 1 : 0, o32,
+  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, ldx, resid, M, H, g, b, eps, do_ln ? 1 : 0, o32,
               reinterpret_cast<T16*>(o16), rin, rout, roff));
   return 0;
 }
@@ -335,7 +343,8 @@ static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long
 // ------------------------------------------------------------------------------------------------ workspace
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 struct Workspace {
-  float *ext_mask, *h32, *a32, *pre32, *head_t;
+  float *ext_mask, *h32, *a32, *pre32, *head_t, *stats;
+  size_t stats_bytes;
   char *h16, *a16, *ctx16, *qkv16, *inter16, *img16;
   size_t total;
 };
@@ -360,6 +369,8 @@ static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
   w.qkv16 = take(M * 3 * H * 2);
   w.inter16 = take(M * I * 2);
   w.img16 = take((size_t)B * R * h->Fp * 2);
+  w.stats_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * 2 * M * 2 * 4;  // [L][2][M](sum, sumsq)
+  w.stats = (float*)take(w.stats_bytes);
   w.total = off + 256;
   return w;
 }
@@ -441,6 +452,28 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     TRY(copy_vec(h, st, s.o_b, H, &d.b_o));
     TRY(copy_vec(h, st, s.o_ln_g, H, &d.o_g));
     TRY(copy_vec(h, st, s.o_ln_b, H, &d.o_b));
+    // folded copies: FFN-up reads pre-LN1 rows (gamma/beta of this layer's attention.output.LayerNorm); the QKV
+    // projection of layer l >= 1 reads pre-LN2 rows of layer l-1 (gamma/beta of its output.LayerNorm)
+    TRY(dev_alloc(h, &d.w_i_f, (size_t)I * H * 2));
+    TRY(dev_alloc(h, (void**)&d.g_i, (size_t)I * 4));
+    TRY(dev_alloc(h, (void**)&d.c_i, (size_t)I * 4));
+    fold_weight_kernel<T16><<<(I + 7) / 8, 256, 0, st>>>(s.i_w, s.ao_ln_g, s.ao_ln_b, s.i_b, I, H,
+                                                         reinterpret_cast<T16*>(d.w_i_f), d.g_i, d.c_i);
+    CKL("fold_weight_kernel");
+    if (l > 0) {
+      const cpt_layer_weights& pv = w->layers[l - 1];
+      TRY(dev_alloc(h, &d.w_qkv_f, (size_t)3 * H * H * 2));
+      TRY(dev_alloc(h, (void**)&d.g_qkv, (size_t)3 * H * 4));
+      TRY(dev_alloc(h, (void**)&d.c_qkv, (size_t)3 * H * 4));
+      const float* ws[3] = {s.q_w, s.k_w, s.v_w};
+      const float* bs[3] = {s.q_b, s.k_b, s.v_b};
+      for (int j = 0; j < 3; ++j) {
+        fold_weight_kernel<T16><<<(H + 7) / 8, 256, 0, st>>>(
+            ws[j], pv.o_ln_g, pv.o_ln_b, bs[j], H, H, reinterpret_cast<T16*>(d.w_qkv_f) + (size_t)j * H * H,
+            d.g_qkv + j * H, d.c_qkv + j * H);
+        CKL("fold_weight_kernel");
+      }
+    }
   }
   h->has_pooler = w->pooler_w && w->pooler_b;
   if (h->has_pooler) {
@@ -517,35 +550,98 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   }
   if (hidden_states) CK(cudaMemcpyAsync(hidden_states, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
 
+  const bool fold = h->fold_ln && !hidden_states && L > 0;
+  if (fold) {
+    // LayerNorm folded into the GEMMs on either side of it (DESIGN.md "LayerNorm folding"): the stream buffers hold
+    // PRE-LayerNorm rows (fp32 + 16-bit) plus per-row (sum, sum of squares); no LayerNorm kernel runs between GEMMs.
+    CK(cudaMemsetAsync(w.stats, 0, w.stats_bytes, st));
+    auto stats = [&](int l, int which) { return w.stats + ((size_t)l * 2 + which) * (size_t)M * 2; };
+    for (int l = 0; l < L; ++l) {
+      const LayerDev& d = h->layers[l];
+      {  // K5: QKV projection; for l >= 1 its A operand is the pre-LN2 stream of layer l-1
+        GemmParams p{};
+        p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H;
+        const void* W = d.w_qkv;
+        p.bias = d.b_qkv;
+        if (l > 0) {
+          W = d.w_qkv_f; p.bias = d.c_qkv; p.gvec = d.g_qkv; p.nstats = stats(l - 1, 1);
+          p.neps = c.layer_norm_eps; p.nH = H;
+        }
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, W, H, p, EPI_BIAS, false));
+      }
+      TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));  // K6-K9
+      {  // K10: x1 = ctx Wo^T + b + LN2_{l-1}(x2) -> fp32 + 16-bit + row statistics
+        GemmParams p{};
+        p.M = M; p.N = H; p.K = H; p.out = w.a32; p.ldo = H; p.bias = d.b_ao; p.resid = w.h32; p.ldr = H;
+        if (l > 0) {
+          p.rstats = stats(l - 1, 1); p.rgamma = h->layers[l - 1].o_g; p.rbeta = h->layers[l - 1].o_b;
+          p.reps = c.layer_norm_eps;
+        }
+        p.nH = H; p.out16 = w.a16; p.ldo16 = H; p.stats_out = stats(l, 0);
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
+      }
+      {  // K11: gelu(LN1(x1) W1^T + b1) with LN1 folded
+        GemmParams p{};
+        p.M = M; p.N = I; p.K = H; p.out = w.inter16; p.ldo = I; p.bias = d.c_i; p.gvec = d.g_i;
+        p.nstats = stats(l, 0); p.neps = c.layer_norm_eps; p.nH = H;
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, w.a16, H, d.w_i_f, H, p, EPI_BIAS_GELU, false));
+      }
+      {  // K12: x2 = inter W2^T + b2 + LN1(x1) -> fp32 + 16-bit + row statistics
+        GemmParams p{};
+        p.M = M; p.N = H; p.K = I; p.out = w.h32; p.ldo = H; p.bias = d.b_o; p.resid = w.a32; p.ldr = H;
+        p.rstats = stats(l, 0); p.rgamma = d.ao_g; p.rbeta = d.ao_b; p.reps = c.layer_norm_eps; p.nH = H;
+        p.out16 = (l == L - 1) ? nullptr : w.h16; p.ldo16 = H;
+        p.stats_out = (l == L - 1) ? nullptr : stats(l, 1);
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
+      }
+    }
+    const LayerDev& last = h->layers[L - 1];
+    TRY(layernorm<T16>(h, st, w.h32, H, M, H, last.o_g, last.o_b, c.layer_norm_eps, true, seq_out, nullptr));
+  } else {
   for (int l = 0; l < L; ++l) {
-    const LayerDev& d = h->layers[l];
-    {  // K5
-      GemmParams p{};
-      p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
-    }
-    TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));  // K6-K9
-    {  // K10
-      GemmParams p{};
-      p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao; p.resid = w.h32; p.ldr = H;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
-      TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
-    }
-    {  // K11
-      GemmParams p{};
-      p.M = M; p.N = I; p.K = H; p.out = w.inter16; p.ldo = I; p.bias = d.b_i;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, w.a16, H, d.w_i, H, p, EPI_BIAS_GELU, false));
-    }
-    {  // K12
-      GemmParams p{};
-      p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o; p.resid = w.a32; p.ldr = H;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
-      float* o32 = (l == L - 1) ? seq_out : w.h32;
-      TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
-                         (l == L - 1) ? nullptr : w.h16));
-      if (hidden_states)
-        CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4,
-                           cudaMemcpyDeviceToDevice, st));
+      const LayerDev& d = h->layers[l];
+      {  // K5
+        GemmParams p{};
+        p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
+      }
+      TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));  // K6-K9
+      {  // K10
+        GemmParams p{};
+        p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao;
+        if (h->resid_in_ln) {
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS, true));
+          TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16, 0, 0, 0,
+                             w.h32));
+        } else {
+          p.resid = w.h32; p.ldr = H;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS_RESID, true));
+          TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
+        }
+      }
+      {  // K11
+        GemmParams p{};
+        p.M = M; p.N = I; p.K = H; p.out = w.inter16; p.ldo = I; p.bias = d.b_i;
+        TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, w.a16, H, d.w_i, H, p, EPI_BIAS_GELU, false));
+      }
+      {  // K12
+        GemmParams p{};
+        p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o;
+        float* o32 = (l == L - 1) ? seq_out : w.h32;
+        if (h->resid_in_ln) {
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, true));
+          TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+                             (l == L - 1) ? nullptr : w.h16, 0, 0, 0, w.a32));
+        } else {
+          p.resid = w.a32; p.ldr = H;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS_RESID, true));
+          TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+                             (l == L - 1) ? nullptr : w.h16));
+        }
+        if (hidden_states)
+          CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4,
+                             cudaMemcpyDeviceToDevice, st));
+      }
     }
   }
   if (L == 0) CK(cudaMemcpyAsync(seq_out, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
@@ -622,6 +718,8 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   cudaMemset(h->err_flag, 0, 16);
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
+  if (const char* e = getenv("CPT_B200_FOLD_LN")) h->fold_ln = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 64) == cudaSuccess) {
       cudaMemset(h->trace, 0, (size_t)h->num_sms * 64);

@@ -32,6 +32,22 @@ struct GemmParams {
   const float* resid; // fp32 [M, ldr] (EPI_BIAS_RESID)
   long long ldr;
   long long* trace;     // optional [gridDim.x][8] cycle counters (debug): see cpt_gemm_trace
+  // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
+  // EPI_BIAS / EPI_BIAS_GELU: the A operand is a PRE-LayerNorm tensor x (16-bit) and W already carries gamma;
+  //   out = rstd_m * (acc - mu_m * gvec_n) + bias_n, with (mu, rstd) from nstats[m] = (sum x, sum x^2) over nH
+  const float* nstats;
+  const float* gvec;
+  float neps;
+  int nH;
+  // EPI_BIAS_RESID: the residual is LN(resid_raw) applied on the fly from rstats/rgamma/rbeta; the sum x is also
+  //   written as 16 bits (next GEMM's A operand) and its row statistics accumulated into stats_out (atomicAdd)
+  const float* rstats;
+  const float* rgamma;
+  const float* rbeta;
+  float reps;
+  void* out16;
+  long long ldo16;
+  float* stats_out;
 };
 
 constexpr int kGemmBM = 128;
@@ -48,7 +64,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kPadPitch = (OutBytes == 4) ? 144 : 80;        // bytes per staged row (32 outputs + 16 B)
   static constexpr int kPadBytes = 32 * kPadPitch;                    // per epilogue warp
-  static constexpr int kBiasBytes = (BN / 2) * 4;                       // per epilogue warp: its columns' bias
+  static constexpr int kBiasBytes = 3 * (BN / 2) * 4;                   // per epilogue warp: 3 column vectors
   static constexpr int kEpiBytes = kGemmEpiWarps * (kPadBytes + kBiasBytes);
   static constexpr int kFixed = 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
   static constexpr int kStagesFit = (kSmemLimit - kFixed) / kStageBytes;
@@ -228,9 +244,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int half = ew >> 2;      // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
     uint8_t* pad = epi_gen + ew * (Cfg::kPadBytes + Cfg::kBiasBytes);
-    float* sbias = reinterpret_cast<float*>(pad + Cfg::kPadBytes);
+    float* sv0 = reinterpret_cast<float*>(pad + Cfg::kPadBytes);  // bias (or folded-LN constant c_n)
+    float* sv1 = sv0 + kColsPerWarp;                              // gvec  | residual-LN gamma
+    float* sv2 = sv1 + kColsPerWarp;                              //       | residual-LN beta
+    constexpr bool kResid = (EPI == EPI_BIAS_RESID);
     const bool vec_ok = ((p.ldo * (long long)sizeof(OutT)) % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool norm = !kResid && p.nstats != nullptr;
+    const bool rnorm = kResid && p.rstats != nullptr;
+    // this warp's slice of a per-column vector -> smem (zero beyond N)
+    auto stage_vec = [&](float* dst, const float* src, int n_first) {
+      const int nb = n_first + lane * 4;
+      if (lane * 4 < kColsPerWarp) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr) {
+          if (nb + 3 < p.N) {
+            b4 = __ldg(reinterpret_cast<const float4*>(src + nb));
+          } else {
+            if (nb < p.N) b4.x = __ldg(src + nb);
+            if (nb + 1 < p.N) b4.y = __ldg(src + nb + 1);
+            if (nb + 2 < p.N) b4.z = __ldg(src + nb + 2);
+          }
+        }
+        *reinterpret_cast<float4*>(dst + lane * 4) = b4;
+      }
+    };
     int it = 0;
     long long t_acc = 0, t_start = clock64();
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
@@ -239,25 +277,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m0 = ((ct / n_tiles) * kCluster + (int)crank) * kGemmBM;
       const int n0 = (ct % n_tiles) * BN;
       const int mrow0 = m0 + q * 32;  // first row of this warp's 32-row band
+      const int ncol0 = n0 + half * kColsPerWarp;
 
-      // this warp's bias slice -> smem while the tile's MMAs are still running (a global load per chunk sat on the
+      // per-column vectors -> smem while the tile's MMAs are still running (a global load per chunk sat on the
       // critical path of every chunk: ncu long_scoreboard on the bias FADDs)
-      {
-        const int nb = n0 + half * kColsPerWarp + lane * 4;
-        if (lane * 4 < kColsPerWarp) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) {
-            if (nb + 3 < p.N) {
-              b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
-            } else {
-              if (nb < p.N) b4.x = __ldg(p.bias + nb);
-              if (nb + 1 < p.N) b4.y = __ldg(p.bias + nb + 1);
-              if (nb + 2 < p.N) b4.z = __ldg(p.bias + nb + 2);
-            }
+      stage_vec(sv0, p.bias, ncol0);
+      if (norm) stage_vec(sv1, p.gvec, ncol0);
+      if (rnorm) {
+        stage_vec(sv1, p.rgamma, ncol0);
+        stage_vec(sv2, p.rbeta, ncol0);
+      }
+      __syncwarp();
+      // folded LayerNorm of the A operand: this thread's row (TMEM lane) statistics
+      float mu = 0.f, rstd = 1.f;
+      if (norm) {
+        const int m = min(mrow0 + lane, p.M - 1);
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.nstats) + m);
+        mu = st.x / (float)p.nH;
+        rstd = rsqrtf(fmaxf(st.y / (float)p.nH - mu * mu, 0.f) + p.neps);
+      }
+      // on-the-fly LayerNorm of the residual: statistics of the 8 rows this thread touches after the transpose
+      float rmu[kResid ? 8 : 1], rrs[kResid ? 8 : 1], acc_s[kResid ? 8 : 1], acc_q[kResid ? 8 : 1];
+      if (kResid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rmu[i] = 0.f; rrs[i] = 1.f; acc_s[i] = 0.f; acc_q[i] = 0.f;
+          if (rnorm) {
+            const int m = min(mrow0 + i * 4 + (lane >> 3), p.M - 1);
+            const float2 st = __ldg(reinterpret_cast<const float2*>(p.rstats) + m);
+            rmu[i] = st.x / (float)p.nH;
+            rrs[i] = rsqrtf(fmaxf(st.y / (float)p.nH - rmu[i] * rmu[i], 0.f) + p.reps);
           }
-          *reinterpret_cast<float4*>(sbias + lane * 4) = b4;
         }
-        __syncwarp();
       }
       const long long t0 = clock64();
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -266,13 +317,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
       if (mrow0 < p.M) {
         constexpr int NC = kColsPerWarp / 32;
-        constexpr bool kResid = (EPI == EPI_BIAS_RESID);
-        // chunk c+1's TMEM load and residual rows are in flight while chunk c is processed
-        uint32_t rbuf[2][32];
+        // chunk c+1's TMEM load and residual rows are issued as soon as chunk c sits in the transpose pad
+        uint32_t rbuf[32];
         float4 res[2][kResid ? 8 : 1];
         const bool res_vec = kResid && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
         auto prefetch_resid = [&](int c, float4* dst) {
-          const int nc = n0 + half * kColsPerWarp + c * 32;
+          const int nc = ncol0 + c * 32;
           if (kResid && res_vec && nc + 32 <= p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -282,26 +332,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
         };
-        tmem_ld_32x32b_x32(t_row, rbuf[0]);
+        tmem_ld_32x32b_x32(t_row, rbuf);
         prefetch_resid(0, res[0]);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const int nc = n0 + half * kColsPerWarp + c * 32;
+          const int nc = ncol0 + c * 32;
           const bool live = nc < p.N;           // warp-uniform
           const bool full = (nc + 32 <= p.N);
           tmem_ld_wait();
-          if (c + 1 < NC) {
-            tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
-            prefetch_resid(c + 1, res[(c + 1) & 1]);
-          }
-          if (!live) continue;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]);
-#pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            const float4 b4 = *reinterpret_cast<const float4*>(sv0 + c * 32 + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            if (norm) {
+              const float4 g4 = *reinterpret_cast<const float4*>(sv1 + c * 32 + j);
+              const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                v[j + e] = fmaf(rstd, fmaf(-mu, gg[e], __uint_as_float(rbuf[j + e])), bb[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[j + e] = __uint_as_float(rbuf[j + e]) + bb[e];
+            }
           }
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
@@ -309,67 +362,118 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           // ---- transpose through the per-warp pad: thread = row  ->  thread = (row group, 16-byte column chunk)
           if (sizeof(OutT) == 4) {
-            float* prow = reinterpret_cast<float*>(pad + lane * Cfg::kPadPitch);
+            if (live) {
+              float* prow = reinterpret_cast<float*>(pad + lane * Cfg::kPadPitch);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(prow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(prow + 4 * j) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
             __syncwarp();
+            if (c + 1 < NC) {
+              tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+              prefetch_resid(c + 1, res[(c + 1) & 1]);
+            }
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {  // 4 rows x 128 B per warp instruction
-              const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
-              const int m = mrow0 + rr, n = nc + cc;
-              float4 x = *reinterpret_cast<const float4*>(pad + rr * Cfg::kPadPitch + cc * 4);
-              if (m < p.M && n < p.N) {
-                float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-                if (full && vec_ok && (!kResid || res_vec)) {
-                  if (kResid) {
-                    const float4 r4 = res[c & 1][i];
-                    x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-                  }
-                  *reinterpret_cast<float4*>(o) = x;
-                } else {
-                  const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (n + e < p.N) {
-                      float y = xs[e];
-                      if (kResid) y += p.resid[(long long)m * p.ldr + n + e];
-                      o[e] = y;
+              for (int i = 0; i < 8; ++i) {  // 4 rows x 128 B per warp instruction
+                const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
+                const int m = mrow0 + rr, n = nc + cc;
+                float4 x = *reinterpret_cast<const float4*>(pad + rr * Cfg::kPadPitch + cc * 4);
+                if (m < p.M && n < p.N) {
+                  float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+                  if (full && vec_ok && (!kResid || res_vec)) {
+                    if (kResid) {
+                      float4 r4 = res[c & 1][i];
+                      if (rnorm) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(sv1 + c * 32 + cc);
+                        const float4 e4 = *reinterpret_cast<const float4*>(sv2 + c * 32 + cc);
+                        const float a = rrs[i], b = -rmu[i] * rrs[i];
+                        r4.x = fmaf(fmaf(r4.x, a, b), g4.x, e4.x);
+                        r4.y = fmaf(fmaf(r4.y, a, b), g4.y, e4.y);
+                        r4.z = fmaf(fmaf(r4.z, a, b), g4.z, e4.z);
+                        r4.w = fmaf(fmaf(r4.w, a, b), g4.w, e4.w);
+                      }
+                      x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                      if (p.stats_out != nullptr) {
+                        acc_s[i] += (x.x + x.y) + (x.z + x.w);
+                        acc_q[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+                      }
+                      if (p.out16 != nullptr) {
+                        uint2 u;
+                        u.x = Cvt<T16>::pack2(x.x, x.y);
+                        u.y = Cvt<T16>::pack2(x.z, x.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out16) + (long long)m * p.ldo16 + n) = u;
+                      }
                     }
+                    *reinterpret_cast<float4*>(o) = x;
+                  } else {
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                      if (n + e < p.N) {
+                        float y = xs[e];
+                        if (kResid) y += p.resid[(long long)m * p.ldr + n + e];
+                        o[e] = y;
+                      }
+                  }
                 }
               }
             }
           } else {
-            uint32_t* prow = reinterpret_cast<uint32_t*>(pad + lane * Cfg::kPadPitch);
+            if (live) {
+              uint32_t* prow = reinterpret_cast<uint32_t*>(pad + lane * Cfg::kPadPitch);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = Cvt<T16>::pack2(v[8 * j + 0], v[8 * j + 1]);
-              u.y = Cvt<T16>::pack2(v[8 * j + 2], v[8 * j + 3]);
-              u.z = Cvt<T16>::pack2(v[8 * j + 4], v[8 * j + 5]);
-              u.w = Cvt<T16>::pack2(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(prow + 4 * j) = u;
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = Cvt<T16>::pack2(v[8 * j + 0], v[8 * j + 1]);
+                u.y = Cvt<T16>::pack2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = Cvt<T16>::pack2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = Cvt<T16>::pack2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(prow + 4 * j) = u;
+              }
             }
             __syncwarp();
+            if (c + 1 < NC) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // 8 rows x 64 B per warp instruction
-              const int rr = i * 8 + (lane >> 2), cc = (lane & 3) * 8;
-              const int m = mrow0 + rr, n = nc + cc;
-              const uint4 u = *reinterpret_cast<const uint4*>(pad + rr * Cfg::kPadPitch + cc * 2);
-              if (m < p.M && n < p.N) {
-                T16* o = reinterpret_cast<T16*>(p.out) + (long long)m * p.ldo + n;
-                if (full && vec_ok) {
-                  *reinterpret_cast<uint4*>(o) = u;
-                } else {
-                  const T16* us = reinterpret_cast<const T16*>(&u);
+              for (int i = 0; i < 4; ++i) {  // 8 rows x 64 B per warp instruction
+                const int rr = i * 8 + (lane >> 2), cc = (lane & 3) * 8;
+                const int m = mrow0 + rr, n = nc + cc;
+                const uint4 u = *reinterpret_cast<const uint4*>(pad + rr * Cfg::kPadPitch + cc * 2);
+                if (m < p.M && n < p.N) {
+                  T16* o = reinterpret_cast<T16*>(p.out) + (long long)m * p.ldo + n;
+                  if (full && vec_ok) {
+                    *reinterpret_cast<uint4*>(o) = u;
+                  } else {
+                    const T16* us = reinterpret_cast<const T16*>(&u);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (n + e < p.N) o[e] = us[e];
+                    for (int e = 0; e < 8; ++e)
+                      if (n + e < p.N) o[e] = us[e];
+                  }
                 }
               }
             }
           }
           __syncwarp();
+        }
+        tmem_ld_wait();
+        if (kResid && p.stats_out != nullptr) {
+          // row statistics of x over this warp's columns: 8 lanes share a row -> shuffle-reduce, one atomic pair
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float s = acc_s[i], qq = acc_q[i];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, o);
+              qq += __shfl_xor_sync(0xffffffffu, qq, o);
+            }
+            const int m = mrow0 + i * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && m < p.M) {
+              atomicAdd(p.stats_out + 2 * (long long)m, s);
+              atomicAdd(p.stats_out + 2 * (long long)m + 1, qq);
+            }
+          }
         }
       }
       tc_fence_before();

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(
 // Row remap as in GemmParams (used to drop the region embeddings behind the text rows: the `cat` of
 // modeling_bert.py:269 is never materialised).
 template <typename T16>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, long long ld_in, int M, int H,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, long long ld_in,
+                                                      const float* __restrict__ resid, int M, int H,
                                                       const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, int do_ln,
                                                       float* __restrict__ out32, T16* __restrict__ out16, int rin,
@@ -115,6 +116,14 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i)
     if (i < nv) x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + (i * 32 + lane) * 4);
+  if (resid != nullptr) {  // residual added here (a streaming kernel) rather than in the GEMM epilogue
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * H + (i * 32 + lane) * 4);
+        x[i].x += r.x; x[i].y += r.y; x[i].z += r.z; x[i].w += r.w;
+      }
+  }
   long long orow = row;
   if (rin > 0) orow = (long long)(row / rin) * rout + roff + (row % rin);
   ln_store_row<T16>(x, nv, H, gamma, beta, eps, out32 ? out32 + orow * H : nullptr,
@@ -159,6 +168,35 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
     const long long r = i / ldo;
     const int c = int(i % ldo);
     out[i] = Cvt<T16>::from(c < cols ? in[r * cols + c] : 0.f);
+  }
+}
+
+// LayerNorm folding, weight side (once per weight load): the consumer GEMM of a LayerNorm output
+//   LN(x) W^T + b = rstd * (x (gamma .* W)^T - mu * g) + c,   g_n = sum_k fp16(gamma_k W_nk),  c_n = sum_k beta_k W_nk + b_n
+// so the GEMM can read the PRE-LayerNorm rows x and finish the normalisation in its epilogue.  g is summed from the
+// ROUNDED weights so that the mean term cancels exactly against what the tensor cores accumulated.
+template <typename T16>
+__global__ void __launch_bounds__(256) fold_weight_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ bias, int N, int K,
+                                                          T16* __restrict__ W16, float* __restrict__ g,
+                                                          float* __restrict__ c) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float gs = 0.f, cs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(long long)n * K + k];
+    const T16 h = Cvt<T16>::from(gamma ? w * gamma[k] : w);
+    W16[(long long)n * K + k] = h;
+    gs += Cvt<T16>::to(h);
+    if (beta) cs = fmaf(beta[k], w, cs);
+  }
+  gs = warp_sum(gs);
+  cs = warp_sum(cs);
+  if (lane == 0) {
+    g[n] = gs;
+    c[n] = cs + (bias ? bias[n] : 0.f);
   }
 }
 

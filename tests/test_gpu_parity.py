@@ -193,3 +193,28 @@ def test_cuda_graph_replay_matches_eager_and_tracks_buffer_contents():
     with torch.no_grad():
         call()
     assert eng.launch_count() - n0 > 10                     # replays are counted as launches
+
+
+def test_layernorm_folding_agrees_with_separate_layernorm_kernels(monkeypatch):
+    """CPT_B200_FOLD_LN=1: LayerNorm is applied inside the neighbouring GEMM epilogues from row statistics;
+    =0 (default): separate LayerNorm kernels.  Same math, different rounding points: both must sit within the parity budget of
+    the oracle and close to each other."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=4)
+    sd = synth_state_dict(cfg, seed=21)
+    b = synth_batch(cfg, 6, 70, 50, seed=4)
+    d = cuda(b)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("CPT_B200_FOLD_LN", flag)
+        pre, rec, nsp = build(cfg, sd)
+        with torch.no_grad():
+            outs.append(rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0].cpu())
+    with torch.no_grad():
+        ref = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                               img_feats=b["img_feats"])[0]
+    scale = ref.abs().max().item()
+    assert (outs[0] - ref).abs().max().item() <= RTOL * scale
+    assert (outs[1] - ref).abs().max().item() <= RTOL * scale
+    assert (outs[0] - outs[1]).abs().max().item() <= RTOL * scale
+    assert not torch.equal(outs[0], outs[1])   # the flag really switched the path
