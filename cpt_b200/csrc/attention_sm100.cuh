@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
         const uint32_t sQ = base + s * Cfg::kSlotBytes, sK = sQ + 16384, sV = sQ + Cfg::kVOff;
         const long long t0 = clock64();
         mbar_wait(bar(SLOT_FREE, s), par ^ 1u);
-        if (p.trace) p.trace[blockIdx.x * 8 + 0] += clock64() - t0;  // producer: waiting for a free slot
+        if (p.trace) p.trace[blockIdx.x * 16 + 0] += clock64() - t0;  // producer: waiting for a free slot
         mbar_expect_tx(bar(QK_FULL, s), 16384 + NCH * 8192);
         tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128);
         tma_load_2d(sQ + 8192, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128 + 64);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
         const uint32_t par = (i / NSLOT) & 1u;
         const long long t0 = clock64();
         mbar_wait(bar(QK_FULL, s), par);
-        if (p.trace) p.trace[blockIdx.x * 8 + 1] += clock64() - t0;  // MMA: waiting for Q/K tiles (TMA)
+        if (p.trace) p.trace[blockIdx.x * 16 + 1] += clock64() - t0;  // MMA: waiting for Q/K tiles (TMA)
         tc_fence_after();
         const uint32_t sQ = base + s * Cfg::kSlotBytes;
         const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sQ + 16384, 16, 1024);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
         if (i + 1 < n_mine) issue_qk(i + 1);
         const long long t0 = clock64();
         mbar_wait(bar(P_READY, s), par);
-        if (p.trace) p.trace[blockIdx.x * 8 + 2] += clock64() - t0;  // MMA: waiting for the softmax
+        if (p.trace) p.trace[blockIdx.x * 16 + 2] += clock64() - t0;  // MMA: waiting for the softmax
         mbar_wait(bar(V_FULL, s), par);
         tc_fence_after();
         const uint32_t sP = base + s * Cfg::kSlotBytes, sV = sP + Cfg::kVOff;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
       decode(item, b, h, mt);
       const long long t0 = clock64();
       mbar_wait(bar(O_FULL, s), par);
-      if (p.trace && tid == 0) p.trace[blockIdx.x * 8 + 4] += clock64() - t0;  // softmax warps: waiting for O
+      if (p.trace && tid == 0) p.trace[blockIdx.x * 16 + 4] += clock64() - t0;  // softmax warps: waiting for O
       tc_fence_after();
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + s * Cfg::kTmemStride + half * 32, v);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
       named_bar_sync(1, 256);
       const long long t0 = clock64();
       mbar_wait(bar(S_FULL, s), par);
-      if (p.trace && tid == 0) p.trace[blockIdx.x * 8 + 3] += clock64() - t0;  // softmax warps: waiting for S
+      if (p.trace && tid == 0) p.trace[blockIdx.x * 16 + 3] += clock64() - t0;  // softmax warps: waiting for S
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * Cfg::kTmemStride;
       uint32_t v[NCH][32];
@@ -455,8 +455,219 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
     }
     if (kDefer && prev_item >= 0) read_out(i - 1, prev_item, prev_inv);
     if (p.trace && tid == 0) {
-      p.trace[blockIdx.x * 8 + 5] = clock64() - t_begin;  // softmax warps: total
-      p.trace[blockIdx.x * 8 + 7] = i;                    // items
+      p.trace[blockIdx.x * 16 + 5] = clock64() - t_begin;  // softmax warps: total
+      p.trace[blockIdx.x * 16 + 7] = i;                    // items
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// S <= 128 (RefCOCO: S = 120): ping-pong variant of the pipelined kernel.  Two softmax groups of 4 warps each take
+// alternate work items; a thread owns a WHOLE query row (128 score columns read from TMEM once into registers), so
+// there is no cross-thread max/sum exchange and no CTA-wide barrier in the loop, and while one group is in its
+// MUFU-bound exp phase the other is in its TMEM-bound load / read-out phase.  4 slots; P aliases Q/K, O aliases S.
+template <typename T16>
+__global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                   const AttnParams p) {
+  using Cfg = Attn2Cfg<2>;
+  constexpr int NSLOT = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const int S = p.S;                      // <= 128, one query tile per (sample, head)
+  const int NK = (S + 15) & ~15;
+  const int nchunk = (NK + 31) / 32;      // <= 4
+  const int n_items = p.B * p.nH;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);   // [2 groups][128]
+  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + 1024 + 2048;
+  enum { QK_FULL = 0, V_FULL, S_FULL, P_READY, O_FULL, SLOT_FREE };
+  auto bar = [&](int which, int s) { return bars + 8u * (which * NSLOT + s); };
+  const uint32_t tmem_slot = bars + 8u * 6 * NSLOT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(bar(QK_FULL, s), 1);
+      mbar_init(bar(V_FULL, s), 1);
+      mbar_init(bar(S_FULL, s), 1);
+      mbar_init(bar(P_READY, s), 4);
+      mbar_init(bar(O_FULL, s), 1);
+      mbar_init(bar(SLOT_FREE, s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % NSLOT;
+        const uint32_t par = (i / NSLOT) & 1u;
+        const int h = item % p.nH, b = item / p.nH;
+        const int row0 = b * S;
+        const uint32_t sQ = base + s * Cfg::kSlotBytes, sK = sQ + 16384, sV = sQ + Cfg::kVOff;
+        mbar_wait(bar(SLOT_FREE, s), par ^ 1u);
+        mbar_expect_tx(bar(QK_FULL, s), 16384 + 2 * 8192);
+        tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0);
+        tma_load_2d(sQ + 8192, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + 64);
+        tma_load_2d(sK, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0);
+        tma_load_2d(sK + 8192, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0 + 64);
+        mbar_expect_tx(bar(V_FULL, s), 2 * 8192);
+        tma_load_2d(sV, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0);
+        tma_load_2d(sV + 8192, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0 + 64);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, NK, Cvt<T16>::kFmt, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(128, kAttnDH, Cvt<T16>::kFmt, 0, 1);
+      const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      auto issue_qk = [&](int i) {
+        const int s = i % NSLOT;
+        mbar_wait(bar(QK_FULL, s), (i / NSLOT) & 1u);
+        tc_fence_after();
+        const uint32_t sQ = base + s * Cfg::kSlotBytes;
+        const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sQ + 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + s * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        umma_commit(bar(S_FULL, s));
+      };
+      // both softmax groups always have a score tile waiting: S is issued two items ahead of P V
+      if (n_mine > 0) issue_qk(0);
+      if (n_mine > 1) issue_qk(1);
+      for (int i = 0; i < n_mine; ++i) {
+        const int s = i % NSLOT;
+        const uint32_t par = (i / NSLOT) & 1u;
+        mbar_wait(bar(P_READY, s), par);
+        mbar_wait(bar(V_FULL, s), par);
+        tc_fence_after();
+        const uint32_t sP = base + s * Cfg::kSlotBytes, sV = sP + Cfg::kVOff;
+        for (int k = 0; k < NK / 16; ++k) {
+          const uint64_t pd = make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t vd = make_smem_desc(sV + k * 2048, 1024, 1024);
+          umma_f16(tmem_base + s * 128, pd, vd, idesc_o, k != 0);
+        }
+        umma_commit(bar(O_FULL, s));
+        if (i + 2 < n_mine) issue_qk(i + 2);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ two softmax groups (4 warps each)
+    const int grp = (warp - 2) >> 2, q = warp & 3;
+    const int r = q * 32 + lane;             // query row == TMEM lane
+    const int gt = (warp - 2 - grp * 4) * 32 + lane;  // thread index within the group
+    float* gmask = mask_s + grp * 128;
+    const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int i = grp; i < n_mine; i += 2) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const int s = i % NSLOT;
+      const uint32_t par = (i / NSLOT) & 1u;
+      const int h = item % p.nH, b = item / p.nH;
+      gmask[gt] = (gt < S) ? p.ext_mask[(long long)b * S + gt] : 0.f;
+      named_bar_sync(1 + grp, 128);
+      mbar_wait(bar(S_FULL, s), par);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * 128;
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nchunk) tmem_ld_32x32b_x32(t_row + c * 32, v[c]);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = c * 32 + j;
+            const float4 m4 = *reinterpret_cast<const float4*>(gmask + col);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float t = (col + e < S) ? fmaf(__uint_as_float(v[c][j + e]), p.scale, mm[e]) : -INFINITY;
+              v[c][j + e] = __float_as_uint(t);
+              mx = fmaxf(mx, t);
+            }
+          }
+        }
+      }
+      float sum = 0.f;
+      uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = __expf(__uint_as_float(v[c][j]) - mx);
+            sum += e;
+            v[c][j] = __float_as_uint(e);
+          }
+          uint8_t* prow = p_gen + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 0]), __uint_as_float(v[c][8 * k + 1]));
+            u.y = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 2]), __uint_as_float(v[c][8 * k + 3]));
+            u.z = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 4]), __uint_as_float(v[c][8 * k + 5]));
+            u.w = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 6]), __uint_as_float(v[c][8 * k + 7]));
+            const int piece = ((c & 1) * 4 + k) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + piece * 16) = u;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(P_READY, s));
+      const float inv = 1.0f / sum;
+      mbar_wait(bar(O_FULL, s), par);
+      tc_fence_after();
+      {
+        uint32_t o[2][32];
+        tmem_ld_32x32b_x32(t_row, o[0]);
+        tmem_ld_32x32b_x32(t_row + 32, o[1]);
+        tmem_ld_wait();
+        if (r < S) {
+          T16* dst = reinterpret_cast<T16*>(p.ctx) + ((long long)b * S + r) * p.H + h * kAttnDH;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 u;
+              u.x = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 0]) * inv, __uint_as_float(o[c][8 * k + 1]) * inv);
+              u.y = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 2]) * inv, __uint_as_float(o[c][8 * k + 3]) * inv);
+              u.z = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 4]) * inv, __uint_as_float(o[c][8 * k + 5]) * inv);
+              u.w = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 6]) * inv, __uint_as_float(o[c][8 * k + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c * 32 + k * 8) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(SLOT_FREE, s));
     }
   }
 

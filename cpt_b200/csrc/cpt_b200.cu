@@ -68,21 +68,27 @@ static int get_encode() {
 }
 // 2-D row-major 16-bit tensor [rows, cols] with pitch ld (elements); box = 64 cols x box_rows, 128B swizzle,
 // out-of-bounds elements read as zero.
-static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long long rows, unsigned long long cols,
-                     unsigned long long ld, unsigned box_rows) {
+// dtype: 0 = fp16, 1 = bf16, 2 = fp32
+static int make_tmap_ex(CUtensorMap* m, const void* ptr, int dtype, unsigned long long rows, unsigned long long cols,
+                        unsigned long long ld, unsigned box_cols, unsigned box_rows, CUtensorMapSwizzle swz) {
   TRY(get_encode());
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
-    return fail("TMA operand must be 16-byte aligned with a 16-byte-multiple pitch (ptr=%p ld=%llu)", ptr, ld);
+  const unsigned esz = dtype == 2 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esz) & 15))
+    return fail("TMA tensor must be 16-byte aligned with a 16-byte-multiple pitch (ptr=%p ld=%llu)", ptr, ld);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                            : (dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = g_encode(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long long rows, unsigned long long cols,
+                     unsigned long long ld, unsigned box_rows) {
+  return make_tmap_ex(m, ptr, dtype, rows, cols, ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -112,6 +118,8 @@ struct cpt_handle {
   int attn_impl = 0;
   int fold_ln = 0;       // CPT_B200_FOLD_LN=1: LayerNorm folded into the neighbouring GEMM epilogues (slower, kept for study)
   int resid_in_ln = 1;   // residual added by the (streaming) LayerNorm kernel instead of the GEMM epilogue
+  int tma_store = 1;     // CPT_B200_TMA_STORE=0: LSU stores in the GEMM epilogue (A/B experiments)
+  int delta16 = 0;       // CPT_B200_DELTA16=1: hand the dense+bias delta to it as 16 bits (2% faster, ~1.8x the logit error)
   struct { int bn, pair; } gemm_choice[16] = {};  // per kernel class, bn 0 = default (CPT_B200_GEMM overrides)
   // launch accounting / optional per-kernel-class CUDA-event timing (cpt_profile_*)
   long long launches = 0;
@@ -198,8 +206,8 @@ struct GemmChoice { int bn, pair; };
 
 template <int BN, bool PAIR, int EPI, typename OutT, typename T16>
 static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
-                         const GemmParams& p) {
-  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR>;
+                         const CUtensorMap& to, const GemmParams& p) {
+  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR, (EPI == EPI_BIAS_RESID) ? 3 : 2>;
   auto* fn = gemm_kernel<BN, PAIR, EPI, OutT, T16>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
@@ -211,17 +219,17 @@ static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, 
   const int ctiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
   int clusters = h->num_sms / kCluster;
   if (ctiles < clusters) clusters = ctiles;
-  CK(launch_k(fn, dim3(clusters * kCluster), dim3(kGemmThreads), Cfg::kSmemBytes, st, kCluster, ta, tb, p));
+  CK(launch_k(fn, dim3(clusters * kCluster), dim3(kGemmThreads), Cfg::kSmemBytes, st, kCluster, ta, tb, to, p));
   return 0;
 }
 
 template <int EPI, typename OutT, typename T16>
 static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, GemmChoice c, const CUtensorMap& ta, const CUtensorMap& tb,
-                          const GemmParams& p) {
+                          const CUtensorMap& to, const GemmParams& p) {
 #define CPT_BN_CASE(BN_)                                                                \
   case BN_:                                                                             \
-    return c.pair ? launch_gemm_t<BN_, true, EPI, OutT, T16>(h, st, ta, tb, p)         \
-                  : launch_gemm_t<BN_, false, EPI, OutT, T16>(h, st, ta, tb, p);
+    return c.pair ? launch_gemm_t<BN_, true, EPI, OutT, T16>(h, st, ta, tb, to, p)     \
+                  : launch_gemm_t<BN_, false, EPI, OutT, T16>(h, st, ta, tb, to, p);
   switch (c.bn) {
     CPT_BN_CASE(64)
     CPT_BN_CASE(128)
@@ -253,15 +261,26 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
   ProfScope ps(h, st, tag);
   const GemmChoice c = pick_gemm(h, tag, p.N, p.K, cfg);
   p.trace = h->trace;
+  if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
   TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
   TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
-  if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, p);
-  if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, p);
-  if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, p);
-  if (epi == EPI_BIAS_GELU && out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, float, T16>(h, st, c, ta, tb, p);
-  if (epi == EPI_BIAS_RESID && out_fp32) return launch_gemm_bn<EPI_BIAS_RESID, float, T16>(h, st, c, ta, tb, p);
+  // outputs leave through TMA bulk stores (32x32 blocks) whenever the destination is 16-byte aligned and pitched;
+  // otherwise (e.g. the [rows, 30522] fp32 score matrix) through the LSU path
+  const unsigned osz = out_fp32 ? 4 : 2;
+  CUtensorMap to = ta;
+  p.tma_store = 0;
+  if (epi != EPI_BIAS_RESID && h->tma_store && !(reinterpret_cast<uintptr_t>(p.out) & 15) && !((p.ldo * osz) & 15)) {
+    TRY(make_tmap_ex(&to, p.out, out_fp32 ? 2 : dt, p.M, p.N, p.ldo, 32, 32,
+                     out_fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
+    p.tma_store = 1;
+  }
+  if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, to, p);
+  if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, to, p);
+  if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, to, p);
+  if (epi == EPI_BIAS_GELU && out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, float, T16>(h, st, c, ta, tb, to, p);
+  if (epi == EPI_BIAS_RESID && out_fp32) return launch_gemm_bn<EPI_BIAS_RESID, float, T16>(h, st, c, ta, tb, to, p);
   return fail("unsupported GEMM epilogue/output combination (epi=%d out_fp32=%d)", epi, (int)out_fp32);
 }
 
@@ -272,7 +291,7 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
   if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
   AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f, h->trace};
-  if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 64, st));
+  if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {
     auto* fn = attn_simt_kernel<T16>;
@@ -283,7 +302,19 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   }
   CUtensorMap tq;
   TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
-  if (impl == 0) {  // production: persistent pipelined kernel, one CTA per SM
+  if (impl == 0 && S <= 128) {  // production, S <= 128: ping-pong softmax groups, one thread per query row
+    auto* fn = attn_pp_kernel<T16>;
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      TRY(set_smem_attr(fn, Attn2Cfg<2>::kSmemBytes));
+      attr_set[h->device & 63] = true;
+    }
+    const int items = B * nH;
+    CK(launch_k(fn, dim3(items < h->num_sms ? items : h->num_sms), dim3(kAttn2Threads), Attn2Cfg<2>::kSmemBytes, st, 1,
+                tq, p));
+    return 0;
+  }
+  if (impl == 0 || impl == 3) {  // S > 128 (or impl 3): persistent pipelined kernel, two threads per query row
     const int items = B * nH * ((S + 127) / 128);
     const int grid = items < h->num_sms ? items : h->num_sms;
     const int nch = (S + 63) / 64;
@@ -319,10 +350,11 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
 template <typename T16>
 static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long ldx, int M, int H, const float* g, const float* b,
                      float eps, bool do_ln, float* o32, void* o16, int rin = 0, int rout = 0, int roff = 0,
-                     const float* resid = nullptr) {
+                     const float* resid = nullptr, const void* x16 = nullptr) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN);
-  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, ldx, resid, M, H, g, b, eps, do_ln ? 1 : 0, o32,
+  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, reinterpret_cast<const T16*>(x16), ldx,
+              resid, M, H, g, b, eps, do_ln ? 1 : 0, o32,
               reinterpret_cast<T16*>(o16), rin, rout, roff));
   return 0;
 }
@@ -344,6 +376,7 @@ static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 struct Workspace {
   float *ext_mask, *h32, *a32, *pre32, *head_t, *stats;
+  char* pre16;
   size_t stats_bytes;
   char *h16, *a16, *ctx16, *qkv16, *inter16, *img16;
   size_t total;
@@ -366,6 +399,7 @@ static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
   w.h16 = take(M * H * 2);
   w.a16 = take(M * H * 2);
   w.ctx16 = take(M * H * 2);
+  w.pre16 = take(M * H * 2);
   w.qkv16 = take(M * 3 * H * 2);
   w.inter16 = take(M * I * 2);
   w.img16 = take((size_t)B * R * h->Fp * 2);
@@ -609,7 +643,12 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
       {  // K10
         GemmParams p{};
         p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao;
-        if (h->resid_in_ln) {
+        if (h->resid_in_ln && h->delta16) {
+          p.out = w.pre16;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS, false));
+          TRY(layernorm<T16>(h, st, nullptr, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16, 0, 0, 0,
+                             w.h32, w.pre16));
+        } else if (h->resid_in_ln) {
           TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS, true));
           TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16, 0, 0, 0,
                              w.h32));
@@ -628,7 +667,12 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
         GemmParams p{};
         p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o;
         float* o32 = (l == L - 1) ? seq_out : w.h32;
-        if (h->resid_in_ln) {
+        if (h->resid_in_ln && h->delta16) {
+          p.out = w.pre16;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, false));
+          TRY(layernorm<T16>(h, st, nullptr, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+                             (l == L - 1) ? nullptr : w.h16, 0, 0, 0, w.a32, w.pre16));
+        } else if (h->resid_in_ln) {
           TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, true));
           TRY(layernorm<T16>(h, st, w.pre32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
                              (l == L - 1) ? nullptr : w.h16, 0, 0, 0, w.a32));
@@ -720,9 +764,11 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
   if (const char* e = getenv("CPT_B200_FOLD_LN")) h->fold_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_DELTA16")) h->delta16 = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_TMA_STORE")) h->tma_store = atoi(e) != 0;
   if (getenv("CPT_B200_TRACE")) {
-    if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 64) == cudaSuccess) {
-      cudaMemset(h->trace, 0, (size_t)h->num_sms * 64);
+    if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
+      cudaMemset(h->trace, 0, (size_t)h->num_sms * 128);
       h->owned.push_back(h->trace);
     }
   }
@@ -888,7 +934,7 @@ int cpt_gemm_trace(cpt_handle* h, long long* out, int max_ctas) {
   DeviceGuard g(h->device);
   CK(cudaDeviceSynchronize());
   const int n = max_ctas < h->num_sms ? max_ctas : h->num_sms;
-  CK(cudaMemcpy(out, h->trace, (size_t)n * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, h->trace, (size_t)n * 128, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -31,7 +31,8 @@ struct GemmParams {
   const float* bias;  // [N] or nullptr
   const float* resid; // fp32 [M, ldr] (EPI_BIAS_RESID)
   long long ldr;
-  long long* trace;     // optional [gridDim.x][8] cycle counters (debug): see cpt_gemm_trace
+  int tma_store;        // outputs leave through tmap_out (set by the host when `out` is 16-byte aligned and pitched)
+  long long* trace;     // optional [gridDim.x][16] cycle counters (debug): see cpt_gemm_trace
   // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
   // EPI_BIAS / EPI_BIAS_GELU: the A operand is a PRE-LayerNorm tensor x (16-bit) and W already carries gamma;
   //   out = rstd_m * (acc - mu_m * gvec_n) + bias_n, with (mu, rstd) from nstats[m] = (sum x, sum x^2) over nH
@@ -56,16 +57,19 @@ constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
-template <int BN, int OutBytes, bool PAIR>
+template <int BN, int OutBytes, bool PAIR, int NVEC = 3>
 struct GemmCfg {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64, 128, 192 or 256");
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kGemmBK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kPadPitch = (OutBytes == 4) ? 144 : 80;        // bytes per staged row (32 outputs + 16 B)
-  static constexpr int kPadBytes = 32 * kPadPitch;                    // per epilogue warp
-  static constexpr int kBiasBytes = 3 * (BN / 2) * 4;                   // per epilogue warp: 3 column vectors
-  static constexpr int kEpiBytes = kGemmEpiWarps * (kPadBytes + kBiasBytes);
+  // per epilogue warp: a staging area for one 32x32 output block.  TMA-store path: the block in the TMA box layout
+  // (fp32: one 4 KB buffer, 128B swizzle; 16-bit: one 2 KB buffer, 64B swizzle).  LSU path (unaligned outputs,
+  // residual epilogue): a padded transpose area (pitch 144 B / 80 B).
+  static constexpr int kPadPitch = (OutBytes == 4) ? 144 : 80;
+  static constexpr int kStageEpi = (OutBytes == 4) ? 5120 : 3072;     // multiple of 1024, >= 32 * kPadPitch
+  static constexpr int kBiasBytes = NVEC * (BN / 2) * 4;              // per epilogue warp: NVEC column vectors
+  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kBiasBytes);
   static constexpr int kFixed = 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
   static constexpr int kStagesFit = (kSmemLimit - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -92,22 +96,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, bool PAIR, int EPI, typename OutT, typename T16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const GemmParams p) {
-  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR>;
+            const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using Cfg = GemmCfg<BN, (int)sizeof(OutT), PAIR, (EPI == EPI_BIAS_RESID) ? 3 : 2>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kCluster = PAIR ? 2 : 1;
   static_assert(!PAIR || BN % 32 == 0, "cta_group::2 needs N % 16 == 0 and whole swizzle atoms per half");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t bars = smem_base + kStages * Cfg::kStageBytes + Cfg::kEpiBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
-  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes + 256;
+  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;  // 1024-aligned: the TMA-store staging needs it
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +124,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
 
+  long long t_entry = 0, g_entry = 0;
+  if (p.trace && threadIdx.x == 0) {
+    t_entry = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+  }
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -150,7 +159,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 8] = clock64() - t_entry;   // prologue (before PDL wait)
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 9] = clock64() - t_entry;   // ... incl. the PDL wait
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -187,8 +198,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       if (p.trace) {
-        p.trace[blockIdx.x * 8 + 0] = clock64() - t_start;  // producer: total
-        p.trace[blockIdx.x * 8 + 1] = t_wait;               // producer: waiting for a free stage
+        p.trace[blockIdx.x * 16 + 0] = clock64() - t_start;  // producer: total
+        p.trace[blockIdx.x * 16 + 1] = t_wait;               // producer: waiting for a free stage
       }
     }
   } else if (warp == 1) {
@@ -232,9 +243,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else umma_commit(tfull_bar(acc));
       }
       if (p.trace) {
-        p.trace[blockIdx.x * 8 + 2] = clock64() - t_start;  // MMA issuer: total
-        p.trace[blockIdx.x * 8 + 3] = t_full;               // ... waiting for operands (TMA)
-        p.trace[blockIdx.x * 8 + 4] = t_tmem;               // ... waiting for a drained accumulator (epilogue)
+        p.trace[blockIdx.x * 16 + 2] = clock64() - t_start;  // MMA issuer: total
+        p.trace[blockIdx.x * 16 + 3] = t_full;               // ... waiting for operands (TMA)
+        p.trace[blockIdx.x * 16 + 4] = t_tmem;               // ... waiting for a drained accumulator (epilogue)
       }
     }
   } else {
@@ -243,14 +254,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int q = warp & 3;        // TMEM lane quadrant this warp may read
     const int half = ew >> 2;      // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
-    uint8_t* pad = epi_gen + ew * (Cfg::kPadBytes + Cfg::kBiasBytes);
-    float* sv0 = reinterpret_cast<float*>(pad + Cfg::kPadBytes);  // bias (or folded-LN constant c_n)
+    uint8_t* pad = epi_gen + ew * Cfg::kStageEpi;
+    const uint32_t pad_u32 = smem_base + kStages * Cfg::kStageBytes + ew * Cfg::kStageEpi;
+    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * Cfg::kStageEpi + ew * Cfg::kBiasBytes);  // bias / c_n
     float* sv1 = sv0 + kColsPerWarp;                              // gvec  | residual-LN gamma
-    float* sv2 = sv1 + kColsPerWarp;                              //       | residual-LN beta
+    float* sv2 = sv1 + kColsPerWarp;                              //       | residual-LN beta (EPI_BIAS_RESID only)
     constexpr bool kResid = (EPI == EPI_BIAS_RESID);
     const bool vec_ok = ((p.ldo * (long long)sizeof(OutT)) % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const bool norm = !kResid && p.nstats != nullptr;
+    const bool tma_out = !kResid && p.tma_store != 0;  // aligned output: async TMA stores instead of LSU stores
+    int n_stores = 0;                                  // TMA stores issued by this warp (16-bit: 2 buffers)
     const bool rnorm = kResid && p.rstats != nullptr;
     // this warp's slice of a per-column vector -> smem (zero beyond N)
     auto stage_vec = [&](float* dst, const float* src, int n_first) {
@@ -283,7 +297,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // critical path of every chunk: ncu long_scoreboard on the bias FADDs)
       stage_vec(sv0, p.bias, ncol0);
       if (norm) stage_vec(sv1, p.gvec, ncol0);
-      if (rnorm) {
+      if (kResid && rnorm) {
         stage_vec(sv1, p.rgamma, ncol0);
         stage_vec(sv2, p.rbeta, ncol0);
       }
@@ -339,7 +353,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int nc = ncol0 + c * 32;
           const bool live = nc < p.N;           // warp-uniform
           const bool full = (nc + 32 <= p.N);
+          const long long tp0 = p.trace ? clock64() : 0;
           tmem_ld_wait();
+          const long long tp1 = p.trace ? clock64() : 0;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -360,8 +376,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
-          // ---- transpose through the per-warp pad: thread = row  ->  thread = (row group, 16-byte column chunk)
-          if (sizeof(OutT) == 4) {
+          if (tma_out) {
+            // ---- async path: the 32x32 block goes to smem in the TMA box layout (row = this thread; 16-byte pieces
+            // XOR-swizzled so the quarter-warp stores are bank-conflict free) and one lane issues a bulk tensor
+            // store.  The LSU store loop this replaces was the epilogue's critical path (cpt_gemm_trace: ~1100
+            // cycles per block waiting on global stores while TMA loads saturate the memory system).
+            constexpr int kBufBytes = 32 * 32 * (int)sizeof(OutT);
+            constexpr int kNBuf = 1;  // one staging buffer: a second one costs a pipeline stage and buys nothing
+            const int buf = n_stores % kNBuf;
+            if (n_stores >= kNBuf) {  // the store that last read this buffer must have drained its smem reads
+              if (lane == 0) {
+                if (kNBuf == 1) tma_store_wait_read<0>();
+                else tma_store_wait_read<1>();
+              }
+              __syncwarp();
+            }
+            if (c + 1 < NC) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+            if (live) {
+              uint8_t* brow = pad + buf * kBufBytes + lane * (32 * (int)sizeof(OutT));
+              if (sizeof(OutT) == 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(brow + ((j ^ (lane & 7)) * 16)) =
+                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 u;
+                  u.x = Cvt<T16>::pack2(v[8 * j + 0], v[8 * j + 1]);
+                  u.y = Cvt<T16>::pack2(v[8 * j + 2], v[8 * j + 3]);
+                  u.z = Cvt<T16>::pack2(v[8 * j + 4], v[8 * j + 5]);
+                  u.w = Cvt<T16>::pack2(v[8 * j + 6], v[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(brow + ((j ^ ((lane >> 1) & 3)) * 16)) = u;
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_out, pad_u32 + buf * kBufBytes, nc, mrow0);
+                tma_store_commit();
+              }
+              ++n_stores;
+            }
+          } else if (sizeof(OutT) == 4) {
+            // ---- LSU path: transpose through the per-warp pad: thread = row -> thread = (row group, 16-byte piece)
             if (live) {
               float* prow = reinterpret_cast<float*>(pad + lane * Cfg::kPadPitch);
 #pragma unroll
@@ -434,7 +492,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             __syncwarp();
+            const long long tp2 = p.trace ? clock64() : 0;
             if (c + 1 < NC) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+            if (p.trace && ew == 0 && lane == 0) {
+              p.trace[blockIdx.x * 16 + 13] += tp1 - tp0;
+              p.trace[blockIdx.x * 16 + 14] += tp2 - tp1;
+            }
             if (live) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {  // 8 rows x 64 B per warp instruction
@@ -454,6 +517,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
               }
             }
+            if (p.trace && ew == 0 && lane == 0) p.trace[blockIdx.x * 16 + 15] += clock64() - tp2;
           }
           __syncwarp();
         }
@@ -483,10 +547,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
       }
     }
+    if (tma_out && lane == 0) tma_store_wait<0>();  // all bulk stores of this warp have completed
     if (p.trace && ew == 0 && lane == 0) {
-      p.trace[blockIdx.x * 8 + 5] = clock64() - t_start;  // epilogue warp 0: total
-      p.trace[blockIdx.x * 8 + 6] = t_acc;                // ... waiting for a finished accumulator (MMA)
-      p.trace[blockIdx.x * 8 + 7] = it;                   // tiles processed by this CTA
+      p.trace[blockIdx.x * 16 + 5] = clock64() - t_start;  // epilogue warp 0: total
+      p.trace[blockIdx.x * 16 + 6] = t_acc;                // ... waiting for a finished accumulator (MMA)
+      p.trace[blockIdx.x * 16 + 7] = it;                   // tiles processed by this CTA
     }
   }
 
@@ -497,6 +562,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc_fence_after();
     if (PAIR) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+  if (p.trace && threadIdx.x == 0) {
+    long long g_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+    p.trace[blockIdx.x * 16 + 10] = clock64() - t_entry;  // CTA lifetime (cycles)
+    p.trace[blockIdx.x * 16 + 11] = g_entry;              // globaltimer at entry / exit (ns)
+    p.trace[blockIdx.x * 16 + 12] = g_exit;
   }
 }
 

@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(
 // Row remap as in GemmParams (used to drop the region embeddings behind the text rows: the `cat` of
 // modeling_bert.py:269 is never materialised).
 template <typename T16>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, long long ld_in,
-                                                      const float* __restrict__ resid, int M, int H,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, const T16* __restrict__ in16,
+                                                      long long ld_in, const float* __restrict__ resid, int M, int H,
                                                       const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, int do_ln,
                                                       float* __restrict__ out32, T16* __restrict__ out16, int rin,
@@ -115,7 +115,15 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   float4 x[kMaxVec];
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + (i * 32 + lane) * 4);
+    if (i < nv) {
+      if (in16 != nullptr) {  // 16-bit GEMM output (the dense+bias delta); the fp32 residual is added below
+        const uint2 u = *reinterpret_cast<const uint2*>(in16 + (long long)row * ld_in + (i * 32 + lane) * 4);
+        const T16* e = reinterpret_cast<const T16*>(&u);
+        x[i] = make_float4(Cvt<T16>::to(e[0]), Cvt<T16>::to(e[1]), Cvt<T16>::to(e[2]), Cvt<T16>::to(e[3]));
+      } else {
+        x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + (i * 32 + lane) * 4);
+      }
+    }
   if (resid != nullptr) {  // residual added here (a streaming kernel) rather than in the GEMM epilogue
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i)

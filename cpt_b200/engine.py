@@ -293,9 +293,9 @@ class Engine(object):
         return out
 
     def gemm_trace(self, n=148):
-        buf = (C.c_longlong * (8 * n))()
+        buf = (C.c_longlong * (16 * n))()
         _lib.check(self.lib.cpt_gemm_trace(self._h, buf, n))
-        return [list(buf[8 * i:8 * i + 8]) for i in range(n)]
+        return [list(buf[16 * i:16 * i + 16]) for i in range(n)]
 
     def attention(self, qkv, ext_mask, B, S, impl=0):
         H = self.cfg.hidden_size

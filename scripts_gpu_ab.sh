@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k gemm -x --tb=short 2>&1 | tail -15 > gpurun_out/t_gemm.log
+echo "== gemm: $(tail -1 gpurun_out/t_gemm.log)"
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu --tb=short 2>&1 | tail -15 > gpurun_out/t_parity.log
+echo "== parity: $(tail -1 gpurun_out/t_parity.log)"
 run() { # name, env...
   name=$1; shift
   env "$@" timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
@@ -10,9 +14,6 @@ k=d['kernels']
 print('%-22s %.3f ms/step %6.0f samples/s e2e %6.0f | '%(sys.argv[1],d['ms_per_step'],d['value'],d['e2e']['value'])+' '.join('%s %.1f'%(n.replace('gemm_',''),k[n]['us_per_launch']) for n in ('gemm_qkv','attention','gemm_attn_out','gemm_ffn_up','gemm_ffn_down','layernorm')))
 PY
 }
-run default X=1
-run down192p CPT_B200_GEMM=gemm_ffn_down:192:2
-run ao192p CPT_B200_GEMM=gemm_attn_out:192:2
-run down128p_ao128p CPT_B200_GEMM=gemm_ffn_down:128:2,gemm_attn_out:128:2
-run ao64 CPT_B200_GEMM=gemm_attn_out:64:1
-run qkv192p_up192p CPT_B200_GEMM=gemm_qkv:192:2,gemm_ffn_up:192:2
+run tma_store X=1
+run lsu_store CPT_B200_TMA_STORE=0
+timeout 300 python tools/trace_gemm.py 2>&1 | tee gpurun_out/trace4.log

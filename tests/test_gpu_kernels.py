@@ -85,6 +85,7 @@ def test_attention_against_torch_and_simt(eng, B, S):
     ctx_tc = eng.attention(qkv, ext, B, S, impl=0)
     ctx_simt = eng.attention(qkv, ext, B, S, impl=1)
     ctx_tile = eng.attention(qkv, ext, B, S, impl=2)
+    ctx_pipe = eng.attention(qkv, ext, B, S, impl=3)
     torch.cuda.synchronize()
     q, k, v = (t.float().view(B, S, nH, dH).permute(0, 2, 1, 3) for t in qkv.split(H, dim=1))
     p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext[:, None, None, :], -1)
@@ -94,6 +95,7 @@ def test_attention_against_torch_and_simt(eng, B, S):
     assert (ctx_tc.float() - ref).abs().max().item() <= 3e-3 * scale   # P is rounded to 16 bits before P.V
     assert (ctx_tc.float() - ctx_simt.float()).abs().max().item() <= 3e-3 * scale
     assert (ctx_tile.float() - ref).abs().max().item() <= 3e-3 * scale
+    assert (ctx_pipe.float() - ref).abs().max().item() <= 3e-3 * scale
 
 
 def test_attention_fully_masked_row_matches_additive_mask_semantics(eng):
