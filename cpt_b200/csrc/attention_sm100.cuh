@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
   constexpr bool kDefer = NSLOT >= 3;
   extern __shared__ uint8_t smem_raw[];
   const int S = p.S;
-  const int NK = (S + 15) & ~15;          // UMMA N of S = Q K^T and K extent of O = P V
+  // UMMA N of S = Q K^T and K extent of O = P V: whole 32-column softmax chunks, so every score column the softmax
+  // reads was written by the MMA (extra key rows are other samples' rows or TMA zero fill; their mask is -inf)
+  const int NK = (S + 31) & ~31;
   const int nchunk = (NK + 31) / 32;      // live 32-column score chunks (<= 2 * NCH)
   const int n_mt = (S + 127) / 128;
   const int n_items = p.B * p.nH * n_mt;
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
       const int s = i % NSLOT;
       const uint32_t par = (i / NSLOT) & 1u;
       const int b = item / (n_mt * p.nH);
-      if (tid < NCH * 64) mask_s[tid] = (tid < S) ? p.ext_mask[(long long)b * S + tid] : 0.f;
+      if (tid < NCH * 64)
+        mask_s[tid] = (tid < S) ? p.ext_mask[(long long)b * S + tid] * 1.4426950408889634f : -INFINITY;
       named_bar_sync(1, 256);
       const long long t0 = clock64();
       mbar_wait(bar(S_FULL, s), par);
@@ -391,29 +394,31 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
       for (int c = 0; c < NCH; ++c)
         if (c0 + c < nchunk) tmem_ld_32x32b_x32(t_row + (c0 + c) * 32, v[c]);
       tmem_ld_wait();
-      // t = s / sqrt(dH) + ext_mask (modeling_bert.py:47-50), kept in place; columns >= S are excluded outright
-      float mx = -INFINITY;
+      // t = (s / sqrt(dH) + ext_mask) * log2 e (modeling_bert.py:47-50), kept in place; the mask of padded key
+      // columns is -inf so they are excluded outright
+      const float sc2 = p.scale * 1.4426950408889634f;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (c0 + c < nchunk) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int col = (c0 + c) * 32 + j;
-            const float4 m4 = *reinterpret_cast<const float4*>(mask_s + col);
+            const float4 m4 = *reinterpret_cast<const float4*>(mask_s + (c0 + c) * 32 + j);
             const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float t = (col + e < S) ? fmaf(__uint_as_float(v[c][j + e]), p.scale, mm[e]) : -INFINITY;
+              const float t = fmaf(__uint_as_float(v[c][j + e]), sc2, mm[e]);
               v[c][j + e] = __float_as_uint(t);
-              mx = fmaxf(mx, t);
+              mx4[e] = fmaxf(mx4[e], t);
             }
           }
         }
       }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       hmax[half * 128 + r] = mx;
       named_bar_sync(1, 256);
       mx = fmaxf(hmax[r], hmax[128 + r]);
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -421,8 +426,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
           float e[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            e[j] = __expf(__uint_as_float(v[c][j]) - mx);
-            sum += e[j];
+            e[j] = ex2_approx(__uint_as_float(v[c][j]) - mx);
+            sum4[j & 3] += e[j];
           }
           // P[r, chunk] -> K-major 128B-swizzled A-operand tile (64-key block, 16-byte piece ^ (row & 7))
           const int cc = c0 + c;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
           }
         }
       }
-      hsum[half * 128 + r] = sum;
+      hsum[half * 128 + r] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(1, 256);
@@ -475,13 +480,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
 // MUFU-bound exp phase the other is in its TMEM-bound load / read-out phase.  4 slots; P aliases Q/K, O aliases S.
 template <typename T16>
 __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                   const __grid_constant__ CUtensorMap tmap_ctx,
                                                                    const AttnParams p) {
   using Cfg = Attn2Cfg<2>;
   constexpr int NSLOT = 4;
   extern __shared__ uint8_t smem_raw[];
   const int S = p.S;                      // <= 128, one query tile per (sample, head)
-  const int NK = (S + 15) & ~15;
-  const int nchunk = (NK + 31) / 32;      // <= 4
+  const int NK = (S + 31) & ~31;          // whole 32-column chunks (see attn_pipe_kernel)
+  const int nchunk = NK / 32;             // <= 4
   const int n_items = p.B * p.nH;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -580,95 +586,133 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     const int gt = (warp - 2 - grp * 4) * 32 + lane;  // thread index within the group
     float* gmask = mask_s + grp * 128;
     const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool tr = p.trace != nullptr && warp == 2 && lane == 0;
+    long long tq = tr ? clock64() : 0;
+    auto lap = [&](int slot) {
+      if (tr) {
+        const long long now = clock64();
+        p.trace[blockIdx.x * 16 + slot] += now - tq;
+        tq = now;
+      }
+    };
+    // this thread's mask element of the group's NEXT item is fetched one item ahead (a global load at item start sat
+    // on the critical path); pre-multiplied by log2(e): softmax(t) = 2^((t - max) log2 e), exp is a bare ex2.approx
+    auto fetch_mask = [&](int i) -> float {
+      if (i >= n_mine) return 0.f;
+      const int b = (blockIdx.x + i * gridDim.x) / p.nH;
+      return (gt < S) ? p.ext_mask[(long long)b * S + gt] * 1.4426950408889634f : -INFINITY;
+    };
+    float next_mask = fetch_mask(grp);
+    const float sc2 = p.scale * 1.4426950408889634f;
     for (int i = grp; i < n_mine; i += 2) {
       const int item = blockIdx.x + i * gridDim.x;
       const int s = i % NSLOT;
       const uint32_t par = (i / NSLOT) & 1u;
       const int h = item % p.nH, b = item / p.nH;
-      gmask[gt] = (gt < S) ? p.ext_mask[(long long)b * S + gt] : 0.f;
+      gmask[gt] = next_mask;
+      next_mask = fetch_mask(i + 2);
       named_bar_sync(1 + grp, 128);
+      lap(0);  // mask + group barrier
       mbar_wait(bar(S_FULL, s), par);
       tc_fence_after();
+      lap(1);  // wait S
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * 128;
       uint32_t v[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < nchunk) tmem_ld_32x32b_x32(t_row + c * 32, v[c]);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      lap(2);  // TMEM -> registers
+      // t = (s / sqrt(dH) + ext_mask) * log2(e), in place; padded key columns carry mask = -inf (excluded outright).
+      // 4 independent max / sum chains keep the FP pipes busy with only two warps per scheduler.
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nchunk) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int col = c * 32 + j;
-            const float4 m4 = *reinterpret_cast<const float4*>(gmask + col);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float t = (col + e < S) ? fmaf(__uint_as_float(v[c][j + e]), p.scale, mm[e]) : -INFINITY;
-              v[c][j + e] = __float_as_uint(t);
-              mx = fmaxf(mx, t);
-            }
+            const float4 m4 = *reinterpret_cast<const float4*>(gmask + c * 32 + j);
+            v[c][j + 0] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 0]), sc2, m4.x));
+            v[c][j + 1] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 1]), sc2, m4.y));
+            v[c][j + 2] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 2]), sc2, m4.z));
+            v[c][j + 3] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 3]), sc2, m4.w));
+            mx4[0] = fmaxf(mx4[0], __uint_as_float(v[c][j + 0]));
+            mx4[1] = fmaxf(mx4[1], __uint_as_float(v[c][j + 1]));
+            mx4[2] = fmaxf(mx4[2], __uint_as_float(v[c][j + 2]));
+            mx4[3] = fmaxf(mx4[3], __uint_as_float(v[c][j + 3]));
           }
         }
       }
-      float sum = 0.f;
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      lap(3);  // scale + mask + max
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nchunk) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = __expf(__uint_as_float(v[c][j]) - mx);
-            sum += e;
-            v[c][j] = __float_as_uint(e);
-          }
           uint8_t* prow = p_gen + (c >> 1) * 16384 + r * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              e[j] = ex2_approx(__uint_as_float(v[c][8 * k + j]) - mx);
+              sum4[j & 3] += e[j];
+            }
             uint4 u;
-            u.x = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 0]), __uint_as_float(v[c][8 * k + 1]));
-            u.y = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 2]), __uint_as_float(v[c][8 * k + 3]));
-            u.z = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 4]), __uint_as_float(v[c][8 * k + 5]));
-            u.w = Cvt<T16>::pack2(__uint_as_float(v[c][8 * k + 6]), __uint_as_float(v[c][8 * k + 7]));
+            u.x = Cvt<T16>::pack2(e[0], e[1]);
+            u.y = Cvt<T16>::pack2(e[2], e[3]);
+            u.z = Cvt<T16>::pack2(e[4], e[5]);
+            u.w = Cvt<T16>::pack2(e[6], e[7]);
             const int piece = ((c & 1) * 4 + k) ^ (r & 7);
             *reinterpret_cast<uint4*>(prow + piece * 16) = u;
           }
         }
       }
+      lap(4);  // exp + P -> smem
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_READY, s));
-      const float inv = 1.0f / sum;
+      lap(5);  // fences + arrive
+      const float inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       mbar_wait(bar(O_FULL, s), par);
       tc_fence_after();
+      lap(6);  // wait O
       {
-        uint32_t o[2][32];
-        tmem_ld_32x32b_x32(t_row, o[0]);
-        tmem_ld_32x32b_x32(t_row + 32, o[1]);
-        tmem_ld_wait();
-        if (r < S) {
-          T16* dst = reinterpret_cast<T16*>(p.ctx) + ((long long)b * S + r) * p.H + h * kAttnDH;
+        // O / rowsum -> 16-bit, staged in the slot's dead P tile (this warp's 32 rows x 128 B, 128B-swizzled) and
+        // written out by ONE bulk tensor store per warp; the [B][S][H] map clips the tile's rows >= S.
+        const uint32_t stage_u32 = base + s * Cfg::kSlotBytes + q * 4096;
+        uint8_t* srow = gen + s * Cfg::kSlotBytes + q * 4096 + lane * 128;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint4 u;
-              u.x = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 0]) * inv, __uint_as_float(o[c][8 * k + 1]) * inv);
-              u.y = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 2]) * inv, __uint_as_float(o[c][8 * k + 3]) * inv);
-              u.z = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 4]) * inv, __uint_as_float(o[c][8 * k + 5]) * inv);
-              u.w = Cvt<T16>::pack2(__uint_as_float(o[c][8 * k + 6]) * inv, __uint_as_float(o[c][8 * k + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + c * 32 + k * 8) = u;
-            }
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = Cvt<T16>::pack2(__uint_as_float(o[8 * k + 0]) * inv, __uint_as_float(o[8 * k + 1]) * inv);
+            u.y = Cvt<T16>::pack2(__uint_as_float(o[8 * k + 2]) * inv, __uint_as_float(o[8 * k + 3]) * inv);
+            u.z = Cvt<T16>::pack2(__uint_as_float(o[8 * k + 4]) * inv, __uint_as_float(o[8 * k + 5]) * inv);
+            u.w = Cvt<T16>::pack2(__uint_as_float(o[8 * k + 6]) * inv, __uint_as_float(o[8 * k + 7]) * inv);
+            *reinterpret_cast<uint4*>(srow + (((c * 4 + k) ^ (lane & 7)) * 16)) = u;
           }
         }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_ctx, stage_u32, h * kAttnDH, q * 32, b);
+          tma_store_commit();
+          tma_store_wait_read<0>();  // the slot may be refilled once the store has read its smem
+          mbar_arrive(bar(SLOT_FREE, s));
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(SLOT_FREE, s));
+      lap(7);  // read-out + store
+      if (tr) p.trace[blockIdx.x * 16 + 8] += 1;
     }
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();

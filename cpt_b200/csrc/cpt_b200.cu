@@ -86,6 +86,23 @@ static int make_tmap_ex(CUtensorMap* m, const void* ptr, int dtype, unsigned lon
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
+// 16-bit [B][S][H] view of a [B*S, H] matrix, box = 64 cols x box_rows x 1, 128B swizzle: a store whose rows run past
+// S is clipped at the sample boundary
+static int make_tmap_bsh(CUtensorMap* m, const void* ptr, int dtype, unsigned long long B, unsigned long long S,
+                         unsigned long long H, unsigned box_rows) {
+  TRY(get_encode());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((H * 2) & 15)) return fail("TMA tensor must be 16-byte aligned");
+  cuuint64_t dims[3] = {H, S, B};
+  cuuint64_t strides[2] = {H * 2, S * H * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
 static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long long rows, unsigned long long cols,
                      unsigned long long ld, unsigned box_rows) {
   return make_tmap_ex(m, ptr, dtype, rows, cols, ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -310,8 +327,10 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
       attr_set[h->device & 63] = true;
     }
     const int items = B * nH;
+    CUtensorMap tc;
+    TRY(make_tmap_bsh(&tc, ctx, Cvt<T16>::kFmt, B, S, H, 32));
     CK(launch_k(fn, dim3(items < h->num_sms ? items : h->num_sms), dim3(kAttn2Threads), Attn2Cfg<2>::kSmemBytes, st, 1,
-                tq, p));
+                tq, tc, p));
     return 0;
   }
   if (impl == 0 || impl == 3) {  // S > 128 (or impl 3): persistent pipelined kernel, two threads per query row

@@ -4,6 +4,7 @@ timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k attention -x
 echo "== attention: $(tail -1 gpurun_out/t_attention.log)"
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu --tb=short 2>&1 | tail -15 > gpurun_out/t_parity.log
 echo "== parity: $(tail -1 gpurun_out/t_parity.log)"
+timeout 300 python tools/trace_attn.py 2>&1 | tail -11
 timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
 python - <<'PY'
 import json

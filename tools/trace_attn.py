@@ -1,4 +1,4 @@
-"""Per-role wait breakdown of the pipelined attention kernel (CPT_B200_TRACE=1)."""
+"""Per-phase cycle breakdown of the ping-pong attention kernel's softmax group 0 (CPT_B200_TRACE=1)."""
 import os
 import sys
 
@@ -10,20 +10,18 @@ from cpt_b200 import config as C  # noqa: E402
 from cpt_b200.engine import Engine  # noqa: E402
 
 eng = Engine(C.oscar_base(), "cuda:0")
-for B, S in ((64, 120), (32, 210)):
+names = ["mask+bar", "wait S", "tmem ld", "scale+max", "exp+P->smem", "fence+arrive", "wait O", "readout+store"]
+for B, S in ((64, 120),):
     qkv = (torch.randn(B * S, 2304, device="cuda") * 1.5).half()
     ext = torch.zeros(B, S, device="cuda")
     for _ in range(3):
         eng.attention(qkv, ext, B, S, 0)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        eng.attention(qkv, ext, B, S, 0)
-    e1.record()
+    eng.attention(qkv, ext, B, S, 0)
     torch.cuda.synchronize()
-    tr = [t for t in eng.gemm_trace() if t[7] > 0]
-    av = lambda i: sum(t[i] for t in tr) / len(tr)  # noqa: E731
-    print("B=%d S=%d: %.1f us/launch | items/cta %.1f | producer wait_slot %.0f | mma wait_qk %.0f wait_softmax %.0f | "
-          "softmax wait_S %.0f wait_O %.0f total %.0f (avg cycles per CTA)"
-          % (B, S, e0.elapsed_time(e1) * 100, av(7), av(0), av(1), av(2), av(3), av(4), av(5)), flush=True)
+    tr = [t for t in eng.gemm_trace() if t[8] > 0]
+    items = sum(t[8] for t in tr) / len(tr)
+    print("B=%d S=%d: group-0 items per CTA %.1f; cycles per item:" % (B, S, items))
+    for i, n in enumerate(names):
+        print("   %-14s %7.0f" % (n, sum(t[i] for t in tr) / len(tr) / items))
+    print("   total          %7.0f" % (sum(sum(t[:8]) for t in tr) / len(tr) / items))
