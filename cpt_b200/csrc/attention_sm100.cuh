@@ -473,6 +473,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
   }
 }
 
+constexpr int kAttnPPSmemBytes = 1024 + 4 * Attn2Cfg<2>::kSlotBytes + 4096 /*per-warp masks*/ + 256;
+
 // ------------------------------------------------------------------------------------------------------------
 // S <= 128 (RefCOCO: S = 120): ping-pong variant of the pipelined kernel.  Two softmax groups of 4 warps each take
 // alternate work items; a thread owns a WHOLE query row (128 score columns read from TMEM once into registers), so
@@ -491,8 +493,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
   const int n_items = p.B * p.nH;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);   // [2 groups][128]
-  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + 1024 + 2048;
+  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);   // [8 softmax warps][128] (3 KB region)
+  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + 4096;  // after the 8 per-warp mask copies
   enum { QK_FULL = 0, V_FULL, S_FULL, P_READY, O_FULL, SLOT_FREE };
   auto bar = [&](int which, int s) { return bars + 8u * (which * NSLOT + s); };
   const uint32_t tmem_slot = bars + 8u * 6 * NSLOT;
@@ -583,8 +585,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     // ------------------------------------------------------------------ two softmax groups (4 warps each)
     const int grp = (warp - 2) >> 2, q = warp & 3;
     const int r = q * 32 + lane;             // query row == TMEM lane
-    const int gt = (warp - 2 - grp * 4) * 32 + lane;  // thread index within the group
-    float* gmask = mask_s + grp * 128;
+    float* gmask = mask_s + (warp - 2) * 128;  // this warp's private copy of the item's key mask (no group barrier)
     const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool tr = p.trace != nullptr && warp == 2 && lane == 0;
     long long tq = tr ? clock64() : 0;
@@ -597,22 +598,32 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     };
     // this thread's mask element of the group's NEXT item is fetched one item ahead (a global load at item start sat
     // on the critical path); pre-multiplied by log2(e): softmax(t) = 2^((t - max) log2 e), exp is a bare ex2.approx
-    auto fetch_mask = [&](int i) -> float {
-      if (i >= n_mine) return 0.f;
-      const int b = (blockIdx.x + i * gridDim.x) / p.nH;
-      return (gt < S) ? p.ext_mask[(long long)b * S + gt] * 1.4426950408889634f : -INFINITY;
+    auto fetch_mask = [&](int i) -> float4 {
+      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (i < n_mine) {
+        const float* src = p.ext_mask + (long long)((blockIdx.x + i * gridDim.x) / p.nH) * S;
+        const int c = lane * 4;
+        if (c + 0 < S) m.x = src[c + 0];  // raw values: the scaling happens when they are consumed, one item later,
+        if (c + 1 < S) m.y = src[c + 1];  // so nothing waits on these loads
+        if (c + 2 < S) m.z = src[c + 2];
+        if (c + 3 < S) m.w = src[c + 3];
+      }
+      return m;
     };
-    float next_mask = fetch_mask(grp);
+    float4 next_mask = fetch_mask(grp);
+    int pending_free = -1;  // slot whose read-out store is still draining its smem reads
     const float sc2 = p.scale * 1.4426950408889634f;
     for (int i = grp; i < n_mine; i += 2) {
       const int item = blockIdx.x + i * gridDim.x;
       const int s = i % NSLOT;
       const uint32_t par = (i / NSLOT) & 1u;
       const int h = item % p.nH, b = item / p.nH;
-      gmask[gt] = next_mask;
+      *reinterpret_cast<float4*>(gmask + lane * 4) =
+          make_float4(next_mask.x * 1.4426950408889634f, next_mask.y * 1.4426950408889634f,
+                      next_mask.z * 1.4426950408889634f, next_mask.w * 1.4426950408889634f);
       next_mask = fetch_mask(i + 2);
-      named_bar_sync(1 + grp, 128);
-      lap(0);  // mask + group barrier
+      __syncwarp();
+      lap(0);  // mask
       mbar_wait(bar(S_FULL, s), par);
       tc_fence_after();
       lap(1);  // wait S
@@ -674,6 +685,13 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_READY, s));
+      if (pending_free >= 0) {  // the previous item's bulk store has long read its staging tile: release that slot
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive(bar(SLOT_FREE, pending_free));
+        }
+        pending_free = -1;
+      }
       lap(5);  // fences + arrive
       const float inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       mbar_wait(bar(O_FULL, s), par);
@@ -705,14 +723,16 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
         if (lane == 0) {
           tma_store_3d(&tmap_ctx, stage_u32, h * kAttnDH, q * 32, b);
           tma_store_commit();
-          tma_store_wait_read<0>();  // the slot may be refilled once the store has read its smem
-          mbar_arrive(bar(SLOT_FREE, s));
         }
+        pending_free = s;  // released at the top of this group's next item (or after the loop)
       }
       lap(7);  // read-out + store
       if (tr) p.trace[blockIdx.x * 16 + 8] += 1;
     }
-    if (lane == 0) tma_store_wait<0>();
+    if (lane == 0) {
+      tma_store_wait<0>();
+      if (pending_free >= 0) mbar_arrive(bar(SLOT_FREE, pending_free));
+    }
   }
 
   tc_fence_before();

@@ -323,14 +323,14 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
     auto* fn = attn_pp_kernel<T16>;
     static bool attr_set[64] = {};
     if (!attr_set[h->device & 63]) {
-      TRY(set_smem_attr(fn, Attn2Cfg<2>::kSmemBytes));
+      TRY(set_smem_attr(fn, kAttnPPSmemBytes));
       attr_set[h->device & 63] = true;
     }
     const int items = B * nH;
     CUtensorMap tc;
     TRY(make_tmap_bsh(&tc, ctx, Cvt<T16>::kFmt, B, S, H, 32));
-    CK(launch_k(fn, dim3(items < h->num_sms ? items : h->num_sms), dim3(kAttn2Threads), Attn2Cfg<2>::kSmemBytes, st, 1,
-                tq, tc, p));
+    CK(launch_k(fn, dim3(items < h->num_sms ? items : h->num_sms), dim3(kAttn2Threads), kAttnPPSmemBytes, st, 1, tq, tc,
+                p));
     return 0;
   }
   if (impl == 0 || impl == 3) {  // S > 128 (or impl 3): persistent pipelined kernel, two threads per query row
