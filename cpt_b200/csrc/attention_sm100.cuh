@@ -628,47 +628,61 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       tc_fence_after();
       lap(1);  // wait S
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * 128;
-      uint32_t v[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < nchunk) tmem_ld_32x32b_x32(t_row + c * 32, v[c]);
-      tmem_ld_wait();
-      lap(2);  // TMEM -> registers
-      // t = (s / sqrt(dH) + ext_mask) * log2(e), in place; padded key columns carry mask = -inf (excluded outright).
-      // 4 independent max / sum chains keep the FP pipes busy with only two warps per scheduler.
+      // Two passes over the score row, 32 columns at a time, re-reading TMEM (a 32-column read costs ~30 cycles;
+      // holding all 128 scores in registers spilled).  t = (s / sqrt(dH) + ext_mask) * log2(e); padded key columns
+      // carry mask = -inf and are excluded outright.  Packed fp32x2 FMAs, 4 independent max / sum chains.
+      const f32x2 sc22 = pack_f2(sc2, sc2);
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nchunk) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(gmask + c * 32 + j);
-            v[c][j + 0] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 0]), sc2, m4.x));
-            v[c][j + 1] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 1]), sc2, m4.y));
-            v[c][j + 2] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 2]), sc2, m4.z));
-            v[c][j + 3] = __float_as_uint(fmaf(__uint_as_float(v[c][j + 3]), sc2, m4.w));
-            mx4[0] = fmaxf(mx4[0], __uint_as_float(v[c][j + 0]));
-            mx4[1] = fmaxf(mx4[1], __uint_as_float(v[c][j + 1]));
-            mx4[2] = fmaxf(mx4[2], __uint_as_float(v[c][j + 2]));
-            mx4[3] = fmaxf(mx4[3], __uint_as_float(v[c][j + 3]));
+            float t0, t1, t2, t3;
+            unpack_f2(fma_f2(pack_f2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc22, pack_f2(m4.x, m4.y)), t0, t1);
+            unpack_f2(fma_f2(pack_f2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc22, pack_f2(m4.z, m4.w)), t2,
+                      t3);
+            mx4[0] = fmaxf(mx4[0], t0);
+            mx4[1] = fmaxf(mx4[1], t1);
+            mx4[2] = fmaxf(mx4[2], t2);
+            mx4[3] = fmaxf(mx4[3], t3);
           }
         }
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       lap(3);  // scale + mask + max
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const f32x2 nmx2 = pack_f2(-mx, -mx);
+      f32x2 sum01 = pack_f2(0.f, 0.f), sum23 = pack_f2(0.f, 0.f);
       uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nchunk) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, v);
+          tmem_ld_wait();
           uint8_t* prow = p_gen + (c >> 1) * 16384 + r * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             float e[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              e[j] = ex2_approx(__uint_as_float(v[c][8 * k + j]) - mx);
-              sum4[j & 3] += e[j];
+            for (int j = 0; j < 8; j += 4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(gmask + c * 32 + 8 * k + j);
+              // (v * sc2 + (mask - max)) -> ex2
+              float t0, t1, t2, t3;
+              unpack_f2(fma_f2(pack_f2(__uint_as_float(v[8 * k + j]), __uint_as_float(v[8 * k + j + 1])), sc22,
+                               add_f2(pack_f2(m4.x, m4.y), nmx2)), t0, t1);
+              unpack_f2(fma_f2(pack_f2(__uint_as_float(v[8 * k + j + 2]), __uint_as_float(v[8 * k + j + 3])), sc22,
+                               add_f2(pack_f2(m4.z, m4.w), nmx2)), t2, t3);
+              e[j] = ex2_approx(t0);
+              e[j + 1] = ex2_approx(t1);
+              e[j + 2] = ex2_approx(t2);
+              e[j + 3] = ex2_approx(t3);
+              sum01 = add_f2(sum01, pack_f2(e[j], e[j + 1]));
+              sum23 = add_f2(sum23, pack_f2(e[j + 2], e[j + 3]));
             }
             uint4 u;
             u.x = Cvt<T16>::pack2(e[0], e[1]);
@@ -680,6 +694,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
           }
         }
       }
+      float sum4[4];
+      unpack_f2(sum01, sum4[0], sum4[1]);
+      unpack_f2(sum23, sum4[2], sum4[3]);
       lap(4);  // exp + P -> smem
       fence_proxy_async_smem();
       tc_fence_before();

@@ -266,6 +266,36 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (FFMA2 on sm_100)
+// Two fp32 lanes per instruction on the FMA pipe: the softmax / GELU phases of the epilogues are bound by FMA-pipe
+// issue (one warp instruction per two cycles per scheduler), so halving their instruction count is a direct win.
+struct f32x2 {
+  uint64_t v;
+};
+__device__ __forceinline__ f32x2 pack_f2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(f32x2 p, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+}
+__device__ __forceinline__ f32x2 fma_f2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add_f2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
