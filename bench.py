@@ -206,6 +206,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group(backend="nccl", device_id=dev)
 
     from cpt_b200.modeling_bert import BertImgForPreTraining

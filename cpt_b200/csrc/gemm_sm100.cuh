@@ -93,18 +93,31 @@ __device__ __forceinline__ float gelu_exp_arg(float x) {  // q(x): gelu(x) = x /
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * rcp_approx(1.0f + ex2_approx(gelu_exp_arg(x))); }
 // Four at once with ONE reciprocal: the epilogue is MUFU-bound (2 MUFU ops per element at 4 lanes/clk/SMSP), and
-// 1/a, 1/b, 1/c, 1/d = r*(b*cd), r*(a*cd), r*(ab*d), r*(ab*c) with r = 1/(ab*cd) trades 3 MUFU.RCP for 8 FMULs.
-// Each denominator is 1 + 2^q <= 1 + 2^29 (q is clamped), so the product stays far below 2^127.
+// 1/a, 1/b, 1/c, 1/d = r*(b*cd), r*(a*cd), r*(ab*d), r*(ab*c) with r = 1/(ab*cd) trades 3 MUFU.RCP for FMULs.
+// Each denominator is 1 + 2^q <= 1 + 2^29 (q is clamped), so the product stays far below 2^127.  The polynomial
+// and the products run as packed fp32x2 instructions (FFMA2): half the FMA-pipe issue slots.
 __device__ __forceinline__ void gelu_erf4(float& x0, float& x1, float& x2, float& x3) {
-  const float a = 1.0f + ex2_approx(gelu_exp_arg(x0)), b = 1.0f + ex2_approx(gelu_exp_arg(x1));
-  const float c = 1.0f + ex2_approx(gelu_exp_arg(x2)), d = 1.0f + ex2_approx(gelu_exp_arg(x3));
-  const float ab = a * b, cd = c * d;
+  const float c0 = fminf(fmaxf(x0, -6.0f), 6.0f), c1 = fminf(fmaxf(x1, -6.0f), 6.0f);
+  const float c2 = fminf(fmaxf(x2, -6.0f), 6.0f), c3 = fminf(fmaxf(x3, -6.0f), 6.0f);
+  const f32x2 xc01 = pack_f2(c0, c1), xc23 = pack_f2(c2, c3);
+  const f32x2 k2 = pack_f2(0.0010142651153728366f, 0.0010142651153728366f);
+  const f32x2 k1 = pack_f2(-0.10677573829889297f, -0.10677573829889297f);
+  const f32x2 k0 = pack_f2(-2.301121234893799f, -2.301121234893799f);
+  const f32x2 u01 = mul_f2(xc01, xc01), u23 = mul_f2(xc23, xc23);
+  const f32x2 q01 = mul_f2(fma_f2(u01, fma_f2(u01, k2, k1), k0), xc01);
+  const f32x2 q23 = mul_f2(fma_f2(u23, fma_f2(u23, k2, k1), k0), xc23);
+  float q0, q1, q2, q3;
+  unpack_f2(q01, q0, q1);
+  unpack_f2(q23, q2, q3);
+  const float a = 1.0f + ex2_approx(q0), b = 1.0f + ex2_approx(q1);
+  const float c = 1.0f + ex2_approx(q2), d = 1.0f + ex2_approx(q3);
+  float ab, cd;
+  unpack_f2(mul_f2(pack_f2(a, c), pack_f2(b, d)), ab, cd);
   const float r = rcp_approx(ab * cd);
-  const float rab = r * ab, rcd = r * cd;
-  x0 *= rcd * b;
-  x1 *= rcd * a;
-  x2 *= rab * d;
-  x3 *= rab * c;
+  float rab, rcd;
+  unpack_f2(mul_f2(pack_f2(r, r), pack_f2(ab, cd)), rab, rcd);
+  unpack_f2(mul_f2(mul_f2(pack_f2(x0, x1), pack_f2(rcd, rcd)), pack_f2(b, a)), x0, x1);
+  unpack_f2(mul_f2(mul_f2(pack_f2(x2, x3), pack_f2(rab, rab)), pack_f2(d, c)), x2, x3);
 }
 
 template <int BN, bool PAIR, int EPI, typename OutT, typename T16>
