@@ -372,9 +372,18 @@ static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long l
                      const float* resid = nullptr, const void* x16 = nullptr) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN);
-  CK(launch_k(ln_rows_kernel<T16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, reinterpret_cast<const T16*>(x16), ldx,
-              resid, M, H, g, b, eps, do_ln ? 1 : 0, o32,
-              reinterpret_cast<T16*>(o16), rin, rout, roff));
+  // persistent: 2 CTAs of 8 warps per SM, each warp walks rows with the next row's loads in flight
+  const int ln_grid = (M + 7) / 8 < 2 * h->num_sms ? (M + 7) / 8 : 2 * h->num_sms;
+#define CPT_LN_CASE(NV_)                                                                                             \
+  case NV_:                                                                                                          \
+    CK(launch_k(ln_rows_kernel<T16, NV_>, dim3(ln_grid), dim3(256), 0, st, 1, x, reinterpret_cast<const T16*>(x16), ldx, \
+                resid, M, H, g, b, eps, do_ln ? 1 : 0, o32, reinterpret_cast<T16*>(o16), rin, rout, roff));          \
+    break;
+  switch (H / 128) {
+    CPT_LN_CASE(1) CPT_LN_CASE(2) CPT_LN_CASE(3) CPT_LN_CASE(4) CPT_LN_CASE(5) CPT_LN_CASE(6) CPT_LN_CASE(7) CPT_LN_CASE(8)
+    default: return fail("layernorm: unsupported hidden size %d", H);
+  }
+#undef CPT_LN_CASE
   return 0;
 }
 
@@ -580,16 +589,24 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   }
   {  // K1: text rows
     ProfScope ps(h, st, CPT_K_EMBED);
-    CK(launch_k(embed_text_ln_kernel<T16>, dim3((B * T + 7) / 8), dim3(256), 0, st, 1, (const long long*)ids,
-                (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, (const float*)h->emb_g,
-                (const float*)h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings,
-                c.type_vocab_size, w.h32, reinterpret_cast<T16*>(w.h16), h->err_flag));
+#define CPT_EMB_CASE(NV_)                                                                                            \
+  case NV_:                                                                                                          \
+    CK(launch_k(embed_text_ln_kernel<T16, NV_>, dim3((B * T + 7) / 8), dim3(256), 0, st, 1, (const long long*)ids,    \
+                (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, (const float*)h->emb_g,  \
+                (const float*)h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings,       \
+                c.type_vocab_size, w.h32, reinterpret_cast<T16*>(w.h16), h->err_flag));                              \
+    break;
+    switch (H / 128) {
+      CPT_EMB_CASE(1) CPT_EMB_CASE(2) CPT_EMB_CASE(3) CPT_EMB_CASE(4) CPT_EMB_CASE(5) CPT_EMB_CASE(6) CPT_EMB_CASE(7)
+      CPT_EMB_CASE(8)
+      default: return fail("unsupported hidden size %d", H);
+    }
+#undef CPT_EMB_CASE
   }
   // K2+K3: region rows
   if (R > 0) {
     const int F = c.img_feature_dim, Mi = B * R;
-    const long long pairs = (long long)Mi * (h->Fp / 2);
-    const int grid = (int)((pairs + 255) / 256 < 8192 ? (pairs + 255) / 256 : 8192);
+    const int grid = (Mi + 7) / 8 < 8 * h->num_sms ? (Mi + 7) / 8 : 8 * h->num_sms;
     {
       ProfScope ps(h, st, CPT_K_CAST);
       CK(launch_k(cast_pad_kernel<T16>, dim3(grid), dim3(256), 0, st, 1, img, Mi, F, h->Fp,

@@ -16,29 +16,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // BertLayerNorm on a row held as nv float4 per lane: biased variance, eps inside the sqrt, two-pass.
-template <typename T16>
-__device__ __forceinline__ void ln_store_row(float4* x, int nv, int H, const float* __restrict__ gamma,
+template <typename T16, int NV>
+__device__ __forceinline__ void ln_store_row(float4* x, int H, const float* __restrict__ gamma,
                                              const float* __restrict__ beta, float eps, float* __restrict__ out32,
                                              T16* __restrict__ out16, int lane, bool do_ln) {
   float mean = 0.f, rstd = 1.f;
   if (do_ln) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
     mean = warp_sum(s) / (float)H;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) {
-        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
-      }
+    for (int i = 0; i < NV; ++i) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
     rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
   }
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) {
+  for (int i = 0; i < NV; ++i) {
+    {
       const int col = (i * 32 + lane) * 4;
       float4 y = x[i];
       if (do_ln) {
@@ -57,10 +55,11 @@ __device__ __forceinline__ void ln_store_row(float4* x, int nv, int H, const flo
         *reinterpret_cast<uint2*>(out16 + col) = u;
       }
     }
+  }
 }
 
 // K1: LN(word[ids] + pos[t or position_ids] + type[seg]) -> rows [b*S + t] of the [B,S,H] stream.
-template <typename T16>
+template <typename T16, int NV>
 __global__ void __launch_bounds__(256) embed_text_ln_kernel(
     const long long* __restrict__ ids, const long long* __restrict__ seg, const long long* __restrict__ pos_ids,
     const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
@@ -81,88 +80,109 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(
     sg = min(max(sg, 0ll), (long long)n_type - 1);
     ps = min(max(ps, 0ll), (long long)max_pos - 1);
   }
-  const int nv = H >> 7;
-  float4 x[kMaxVec];
+  float4 x[NV];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) {
-      const int col = (i * 32 + lane) * 4;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
-      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
-      const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
-      x[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
+    const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
+    x[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
+  }
   const long long orow = (long long)b * S + t;
-  ln_store_row<T16>(x, nv, H, gamma, beta, eps, out32 + orow * H, out16 + orow * H, lane, true);
+  ln_store_row<T16, NV>(x, H, gamma, beta, eps, out32 + orow * H, out16 + orow * H, lane, true);
 }
 
-// LayerNorm of fp32 rows (already bias+residual-added by the GEMM epilogue) -> fp32 stream + 16-bit shadow.
-// Row remap as in GemmParams (used to drop the region embeddings behind the text rows: the `cat` of
-// modeling_bert.py:269 is never materialised).
-template <typename T16>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, const T16* __restrict__ in16,
-                                                      long long ld_in, const float* __restrict__ resid, int M, int H,
-                                                      const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float eps, int do_ln,
-                                                      float* __restrict__ out32, T16* __restrict__ out16, int rin,
-                                                      int rout, int roff) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// LayerNorm of fp32 (or 16-bit) rows + optional fp32 residual -> fp32 stream + 16-bit shadow.  Row remap as in
+// the region-embedding path (drops the region rows behind the text rows: the `cat` of modeling_bert.py:269 is never
+// materialised).  Persistent: a warp walks rows with stride gridDim * warps and has the NEXT row's loads in flight
+// while it reduces the current one (ncu: the one-row-per-warp version sat at 34 % of DRAM bandwidth, latency bound).
+template <typename T16, int NV>
+__device__ __forceinline__ void ln_load_row(float4* x, float4* rs, const float* __restrict__ in,
+                                            const T16* __restrict__ in16, long long ld_in,
+                                            const float* __restrict__ resid, int H, int row, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    if (in16 != nullptr) {  // 16-bit GEMM output (the dense+bias delta); the fp32 residual is added by the caller
+      const uint2 u = *reinterpret_cast<const uint2*>(in16 + (long long)row * ld_in + col);
+      const T16* e = reinterpret_cast<const T16*>(&u);
+      x[i] = make_float4(Cvt<T16>::to(e[0]), Cvt<T16>::to(e[1]), Cvt<T16>::to(e[2]), Cvt<T16>::to(e[3]));
+    } else {
+      x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + col);
+    }
+    if (resid != nullptr) rs[i] = *reinterpret_cast<const float4*>(resid + (long long)row * H + col);
+  }
+}
+
+// NV = H / 128 float4 per lane (compile-time so the double-buffered row fits the register file at 2 CTAs / SM)
+template <typename T16, int NV>
+__global__ void __launch_bounds__(256, 2) ln_rows_kernel(const float* __restrict__ in, const T16* __restrict__ in16,
+                                                         long long ld_in, const float* __restrict__ resid, int M, int H,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int do_ln,
+                                                         float* __restrict__ out32, T16* __restrict__ out16, int rin,
+                                                         int rout, int roff) {
   const int lane = threadIdx.x & 31;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   pdl_launch_dependents();
   pdl_wait();
-  if (row >= M) return;
-  const int nv = H >> 7;
-  float4 x[kMaxVec];
+  float4 x[NV], rs[NV], nx[NV], nrs[NV];
+  if (row < M) ln_load_row<T16, NV>(x, rs, in, in16, ld_in, resid, H, row, lane);
+  for (; row < M; row += wstride) {
+    const int next = row + wstride;
+    if (next < M) ln_load_row<T16, NV>(nx, nrs, in, in16, ld_in, resid, H, next, lane);
+    if (resid != nullptr) {  // residual added here (a streaming kernel) rather than in the GEMM epilogue
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) {
-      if (in16 != nullptr) {  // 16-bit GEMM output (the dense+bias delta); the fp32 residual is added below
-        const uint2 u = *reinterpret_cast<const uint2*>(in16 + (long long)row * ld_in + (i * 32 + lane) * 4);
-        const T16* e = reinterpret_cast<const T16*>(&u);
-        x[i] = make_float4(Cvt<T16>::to(e[0]), Cvt<T16>::to(e[1]), Cvt<T16>::to(e[2]), Cvt<T16>::to(e[3]));
-      } else {
-        x[i] = *reinterpret_cast<const float4*>(in + (long long)row * ld_in + (i * 32 + lane) * 4);
+      for (int i = 0; i < NV; ++i) {
+        x[i].x += rs[i].x; x[i].y += rs[i].y; x[i].z += rs[i].z; x[i].w += rs[i].w;
       }
     }
-  if (resid != nullptr) {  // residual added here (a streaming kernel) rather than in the GEMM epilogue
+    long long orow = row;
+    if (rin > 0) orow = (long long)(row / rin) * rout + roff + (row % rin);
+    ln_store_row<T16, NV>(x, H, gamma, beta, eps, out32 ? out32 + orow * H : nullptr,
+                          out16 ? out16 + orow * H : nullptr, lane, do_ln != 0);
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) {
-        const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * H + (i * 32 + lane) * 4);
-        x[i].x += r.x; x[i].y += r.y; x[i].z += r.z; x[i].w += r.w;
-      }
+    for (int i = 0; i < NV; ++i) {
+      x[i] = nx[i];
+      rs[i] = nrs[i];
+    }
   }
-  long long orow = row;
-  if (rin > 0) orow = (long long)(row / rin) * rout + roff + (row % rin);
-  ln_store_row<T16>(x, nv, H, gamma, beta, eps, out32 ? out32 + orow * H : nullptr,
-                    out16 ? out16 + orow * H : nullptr, lane, do_ln != 0);
 }
 
 // fp32 [rows, F] -> 16-bit [rows, Fp] (Fp = F rounded up to 8, zero padded) so the row pitch is a legal TMA stride.
 template <typename T16>
 __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ in, int rows, int F, int Fp,
                                                        T16* __restrict__ out) {
-  const long long pairs_per_row = Fp >> 1;
-  const long long total = (long long)rows * pairs_per_row;
+  // one warp per row, 8 independent 8-byte loads in flight per lane (the element-per-thread version was latency bound)
+  const int lane = threadIdx.x & 31;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
   pdl_launch_dependents();
   pdl_wait();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / pairs_per_row;
-    const int c = int(i % pairs_per_row) * 2;
-    float a = 0.f, b = 0.f;
-    const float* src = in + r * F + c;
-    if (c + 1 < F) {
-      if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(src));
-        a = v.x; b = v.y;
-      } else {
-        a = __ldg(src); b = __ldg(src + 1);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+    const float* src = in + (long long)r * F;
+    T16* dst = out + (long long)r * Fp;
+    const bool al8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    for (int c0 = lane * 2; c0 < Fp; c0 += 64 * 8) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * 64;
+        v[u] = make_float2(0.f, 0.f);
+        if (c + 1 < F) {
+          if (al8) v[u] = __ldg(reinterpret_cast<const float2*>(src + c));
+          else v[u] = make_float2(__ldg(src + c), __ldg(src + c + 1));
+        } else if (c < F) {
+          v[u].x = __ldg(src + c);
+        }
       }
-    } else if (c < F) {
-      a = __ldg(src);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * 64;
+        if (c < Fp) *reinterpret_cast<uint32_t*>(dst + c) = Cvt<T16>::pack2(v[u].x, v[u].y);
+      }
     }
-    *reinterpret_cast<uint32_t*>(out + r * Fp + c) = Cvt<T16>::pack2(a, b);
   }
 }
 
