@@ -135,6 +135,7 @@ struct cpt_handle {
   int attn_impl = 0;
   int fold_ln = 0;       // CPT_B200_FOLD_LN=1: LayerNorm folded into the neighbouring GEMM epilogues (slower, kept for study)
   int resid_in_ln = 1;   // residual added by the (streaming) LayerNorm kernel instead of the GEMM epilogue
+  int reduce_resid = 1;  // ... or, better, by the GEMM's TMA store itself (cp.reduce .add at L2): CPT_B200_REDUCE_RESID=0 off
   int tma_store = 1;     // CPT_B200_TMA_STORE=0: LSU stores in the GEMM epilogue (A/B experiments)
   int delta16 = 0;       // CPT_B200_DELTA16=1: hand the dense+bias delta to it as 16 bits (2% faster, ~1.8x the logit error)
   struct { int bn, pair; } gemm_choice[16] = {};  // per kernel class, bn 0 = default (CPT_B200_GEMM overrides)
@@ -287,12 +288,16 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
   // otherwise (e.g. the [rows, 30522] fp32 score matrix) through the LSU path
   const unsigned osz = out_fp32 ? 4 : 2;
   CUtensorMap to = ta;
+  const int want_reduce = p.tma_reduce;
   p.tma_store = 0;
+  p.tma_reduce = 0;
   if (epi != EPI_BIAS_RESID && h->tma_store && !(reinterpret_cast<uintptr_t>(p.out) & 15) && !((p.ldo * osz) & 15)) {
     TRY(make_tmap_ex(&to, p.out, out_fp32 ? 2 : dt, p.M, p.N, p.ldo, 32, 32,
                      out_fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
     p.tma_store = 1;
+    p.tma_reduce = want_reduce && out_fp32;
   }
+  if (want_reduce && !p.tma_reduce) return fail("GEMM: accumulate-into-output needs an aligned fp32 destination");
   if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, to, p);
   if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, to, p);
   if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, to, p);
@@ -679,7 +684,13 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
       {  // K10
         GemmParams p{};
         p.M = M; p.N = H; p.K = H; p.out = w.pre32; p.ldo = H; p.bias = d.b_ao;
-        if (h->resid_in_ln && h->delta16) {
+        if (h->reduce_resid && h->tma_store) {
+          // x1 = h + (ctx Wo^T + b): the epilogue's bulk tensor stores ADD into the residual buffer at L2; LayerNorm
+          // then reads one fp32 tensor instead of two
+          p.out = w.h32; p.tma_reduce = 1;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS, true));
+          TRY(layernorm<T16>(h, st, w.h32, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16));
+        } else if (h->resid_in_ln && h->delta16) {
           p.out = w.pre16;
           TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, w.ctx16, H, d.w_ao, H, p, EPI_BIAS, false));
           TRY(layernorm<T16>(h, st, nullptr, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, w.a32, w.a16, 0, 0, 0,
@@ -703,7 +714,12 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
         GemmParams p{};
         p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o;
         float* o32 = (l == L - 1) ? seq_out : w.h32;
-        if (h->resid_in_ln && h->delta16) {
+        if (h->reduce_resid && h->tma_store) {
+          p.out = w.a32; p.tma_reduce = 1;
+          TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, true));
+          TRY(layernorm<T16>(h, st, w.a32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
+                             (l == L - 1) ? nullptr : w.h16));
+        } else if (h->resid_in_ln && h->delta16) {
           p.out = w.pre16;
           TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, false));
           TRY(layernorm<T16>(h, st, nullptr, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
@@ -802,6 +818,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_DELTA16")) h->delta16 = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_TMA_STORE")) h->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
       cudaMemset(h->trace, 0, (size_t)h->num_sms * 128);

@@ -32,6 +32,7 @@ struct GemmParams {
   const float* resid; // fp32 [M, ldr] (EPI_BIAS_RESID)
   long long ldr;
   int tma_store;        // outputs leave through tmap_out (set by the host when `out` is 16-byte aligned and pitched)
+  int tma_reduce;       // ... as out += tile (cp.reduce.async.bulk .add at L2): `out` already holds the residual
   long long* trace;     // optional [gridDim.x][16] cycle counters (debug): see cpt_gemm_trace
   // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
   // EPI_BIAS / EPI_BIAS_GELU: the A operand is a PRE-LayerNorm tensor x (16-bit) and W already carries gamma;
@@ -440,7 +441,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&tmap_out, pad_u32 + buf * kBufBytes, nc, mrow0);
+                if (sizeof(OutT) == 4 && p.tma_reduce) tma_reduce_add_2d(&tmap_out, pad_u32 + buf * kBufBytes, nc, mrow0);
+                else tma_store_2d(&tmap_out, pad_u32 + buf * kBufBytes, nc, mrow0);
                 tma_store_commit();
               }
               ++n_stores;

@@ -98,6 +98,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(x), "r"(y)
                : "memory");
 }
+// dst[tile] += smem tile (element-wise add performed at L2): the residual add of the BertSelfOutput / BertOutput
+// blocks without the SM ever reading the residual
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int x, int y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),

@@ -1,0 +1,78 @@
+"""Throughput of the CUDA path over the BASELINE.json configs' shapes (inference, one GPU, CUDA-graph replay).
+    python tools/sweep.py"""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from cpt_b200 import config as C  # noqa: E402
+from cpt_b200.modeling_bert import BertImgForPreTraining  # noqa: E402
+from cpt_b200.modeling_rec import REC_MLM_CPT  # noqa: E402
+from cpt_b200.modeling_vcr import NSPCPT  # noqa: E402
+from cpt_b200.synthetic import synth_batch, synth_vocab_ids  # noqa: E402
+
+
+def flops(cfg, T, R, K):
+    S, H, L, F = T + R, cfg.hidden_size, cfg.num_hidden_layers, cfg.img_feature_dim
+    return L * (24 * S * H * H + 4 * S * S * H) + 2 * R * F * H + (2 * H * H + 2 * H * K)
+
+
+def build(cfg):
+    pre = BertImgForPreTraining(cfg)   # random init (no checkpoints offline)
+    for m in pre.modules():
+        if isinstance(m, torch.nn.LayerNorm):
+            torch.nn.init.uniform_(m.weight, 0.5, 1.5)
+    pre.tie_weights()
+    pre = pre.cuda().eval()
+    rec, nsp = REC_MLM_CPT(cfg), NSPCPT(cfg)
+    rec.copy_from_pretraining_model(pre)
+    nsp.copy_from_pretraining_model(pre)
+    return rec.eval(), nsp.eval()
+
+
+cases = [("config 1 shape: base, B=1,   S=120 (latency)", C.oscar_base, 1, 70, 50, 2, "mlm"),
+         ("config 2: base, B=64,  S=120, K=2 (RefCOCO)", C.oscar_base, 64, 70, 50, 2, "mlm"),
+         ("config 3 shape: base, B=64, S=210, K=1853 (GQA eval)", C.oscar_base, 64, 165, 45, 1853, "mlm"),
+         ("config 4: base, 16 rows/GPU, S=210, NSP (VCR)", C.oscar_base, 16, 165, 45, 0, "nsp"),
+         ("config 4 shape at B=128 rows, S=210, NSP", C.oscar_base, 128, 165, 45, 0, "nsp"),
+         ("config 5: large, B=256, S=200, K=2", C.oscar_large, 256, 150, 50, 2, "mlm")]
+for name, fac, B, T, R, K, head in cases:
+    cfg = fac()
+    rec, nsp = build(cfg)
+    b = {k: v.cuda() for k, v in synth_batch(cfg, B, T, R, seed=3).items()}
+    vids = synth_vocab_ids(cfg, max(K, 1), seed=3).cuda()
+
+    def step():
+        if head == "mlm":
+            return rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
+                       mask_pos=b["mask_pos"], vocab_ids=vids)[0]
+        return nsp(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"])[0]
+
+    with torch.no_grad():
+        for _ in range(4):
+            out = step()
+        if head == "nsp":  # no graph path for the NSP wrapper: capture it here
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.cuda.graph(g, stream=s):
+                out = step()
+            torch.cuda.current_stream().wait_stream(s)
+            run = g.replay
+        else:
+            run = step
+        torch.cuda.synchronize()
+        n = 30 if B * (T + R) < 30000 else 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+    fl = flops(cfg, T, R, K)
+    print("%-58s %8.3f ms/step %9.0f samples/s  %6.0f TFLOP/s (algorithmic)" % (name, ms, B / ms * 1e3, B / ms * 1e3 * fl / 1e12),
+          flush=True)
+    del rec, nsp
+    torch.cuda.empty_cache()
