@@ -473,28 +473,41 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pipe_kernel(const __gri
   }
 }
 
-constexpr int kAttnPPSmemBytes = 1024 + 4 * Attn2Cfg<2>::kSlotBytes + 4096 /*per-warp masks*/ + 256;
-
 // ------------------------------------------------------------------------------------------------------------
-// S <= 128 (RefCOCO: S = 120): ping-pong variant of the pipelined kernel.  Two softmax groups of 4 warps each take
-// alternate work items; a thread owns a WHOLE query row (128 score columns read from TMEM once into registers), so
-// there is no cross-thread max/sum exchange and no CTA-wide barrier in the loop, and while one group is in its
-// MUFU-bound exp phase the other is in its TMEM-bound load / read-out phase.  4 slots; P aliases Q/K, O aliases S.
-template <typename T16>
+// Production kernel (S <= 256): ping-pong variant of the pipelined kernel.  Two softmax groups of 4 warps each take
+// alternate work items (sample, head, 128-query tile); a thread owns a WHOLE query row, walked 32 score columns at a
+// time in two passes straight out of TMEM (max, then exp/sum/P), so there is no cross-thread exchange and no CTA-wide
+// barrier in the loop, and while one group is in its MUFU-bound exp phase the other is loading / reading out.
+// NCH = 64-key blocks: S <= 128 -> 4 slots, S <= 256 -> 2 slots.  P aliases the dead Q/K tiles, O aliases the first 64
+// TMEM columns of S, the 16-bit read-out is staged in the dead P tile and leaves as one bulk tensor store per warp
+// (a [B][S][H] map clips the rows of the tile that lie beyond S).
+template <int NCH>
+struct AttnPPCfg {
+  using Base = Attn2Cfg<NCH>;
+  static constexpr int kSlots = Base::kSlots;
+  static constexpr int kMaskBytes = 8 * NCH * 64 * 4;  // one private copy of the key mask per softmax warp
+  static constexpr int kSmemBytes = 1024 + kSlots * Base::kSlotBytes + kMaskBytes + 256;
+};
+
+template <typename T16, int NCH>
 __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                    const __grid_constant__ CUtensorMap tmap_ctx,
                                                                    const AttnParams p) {
-  using Cfg = Attn2Cfg<2>;
-  constexpr int NSLOT = 4;
+  using Cfg = Attn2Cfg<NCH>;
+  constexpr int NSLOT = Cfg::kSlots;
+  constexpr bool kDefer = NSLOT >= 4;
+  constexpr int kMaskVec = (NCH * 64 + 127) / 128;  // float4 per lane covering the key mask
   extern __shared__ uint8_t smem_raw[];
-  const int S = p.S;                      // <= 128, one query tile per (sample, head)
-  const int NK = (S + 31) & ~31;          // whole 32-column chunks (see attn_pipe_kernel)
-  const int nchunk = NK / 32;             // <= 4
-  const int n_items = p.B * p.nH;
+  const int S = p.S;
+  const int NK = (S + 31) & ~31;          // whole 32-column chunks: every score column read was written by the MMA
+  const int nchunk = NK / 32;             // <= 2 * NCH
+  const int n_mt = (S + 127) / 128;
+  const int n_items = p.B * p.nH * n_mt;
+  const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);   // [8 softmax warps][128] (3 KB region)
-  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + 4096;  // after the 8 per-warp mask copies
+  float* mask_s = reinterpret_cast<float*>(gen + NSLOT * Cfg::kSlotBytes);
+  const uint32_t bars = base + NSLOT * Cfg::kSlotBytes + AttnPPCfg<NCH>::kMaskBytes;
   enum { QK_FULL = 0, V_FULL, S_FULL, P_READY, O_FULL, SLOT_FREE };
   auto bar = [&](int which, int s) { return bars + 8u * (which * NSLOT + s); };
   const uint32_t tmem_slot = bars + 8u * 6 * NSLOT;
@@ -503,6 +516,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_ctx);
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar(QK_FULL, s), 1);
       mbar_init(bar(V_FULL, s), 1);
@@ -532,61 +546,77 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
         const int s = i % NSLOT;
         const uint32_t par = (i / NSLOT) & 1u;
-        const int h = item % p.nH, b = item / p.nH;
+        const int mt = item % n_mt, h = (item / n_mt) % p.nH, b = item / (n_mt * p.nH);
         const int row0 = b * S;
         const uint32_t sQ = base + s * Cfg::kSlotBytes, sK = sQ + 16384, sV = sQ + Cfg::kVOff;
         mbar_wait(bar(SLOT_FREE, s), par ^ 1u);
-        mbar_expect_tx(bar(QK_FULL, s), 16384 + 2 * 8192);
-        tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0);
-        tma_load_2d(sQ + 8192, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + 64);
-        tma_load_2d(sK, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0);
-        tma_load_2d(sK + 8192, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0 + 64);
-        mbar_expect_tx(bar(V_FULL, s), 2 * 8192);
-        tma_load_2d(sV, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0);
-        tma_load_2d(sV + 8192, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0 + 64);
+        mbar_expect_tx(bar(QK_FULL, s), 16384 + NCH * 8192);
+        tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128);
+        tma_load_2d(sQ + 8192, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128 + 64);
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+          tma_load_2d(sK + kb * 8192, &tmap_qkv, bar(QK_FULL, s), p.H + h * kAttnDH, row0 + kb * 64);
+        mbar_expect_tx(bar(V_FULL, s), NCH * 8192);
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+          tma_load_2d(sV + kb * 8192, &tmap_qkv, bar(V_FULL, s), 2 * p.H + h * kAttnDH, row0 + kb * 64);
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer: an event loop over the two things
+    // it can be asked to do (S = Q K^T of the next loaded item, O = P V of the next finished softmax), so that
+    // neither waits behind the other
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, NK, Cvt<T16>::kFmt, 0, 0);
       const uint32_t idesc_o = make_idesc_f16(128, kAttnDH, Cvt<T16>::kFmt, 0, 1);
-      const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      auto issue_qk = [&](int i) {
-        const int s = i % NSLOT;
-        mbar_wait(bar(QK_FULL, s), (i / NSLOT) & 1u);
-        tc_fence_after();
-        const uint32_t sQ = base + s * Cfg::kSlotBytes;
-        const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sQ + 16384, 16, 1024);
+      int next_qk = 0, next_pv = 0;
+      uint32_t spins = 0;
+      while (next_pv < n_mine) {
+        bool did = false;
+        if (next_qk < n_mine) {
+          const int s = next_qk % NSLOT;
+          if (mbar_try_wait(bar(QK_FULL, s), (next_qk / NSLOT) & 1u)) {
+            tc_fence_after();
+            const uint32_t sQ = base + s * Cfg::kSlotBytes;
+            const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sQ + 16384, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + s * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-        umma_commit(bar(S_FULL, s));
-      };
-      // both softmax groups always have a score tile waiting: S is issued two items ahead of P V
-      if (n_mine > 0) issue_qk(0);
-      if (n_mine > 1) issue_qk(1);
-      for (int i = 0; i < n_mine; ++i) {
-        const int s = i % NSLOT;
-        const uint32_t par = (i / NSLOT) & 1u;
-        mbar_wait(bar(P_READY, s), par);
-        mbar_wait(bar(V_FULL, s), par);
-        tc_fence_after();
-        const uint32_t sP = base + s * Cfg::kSlotBytes, sV = sP + Cfg::kVOff;
-        for (int k = 0; k < NK / 16; ++k) {
-          const uint64_t pd = make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          const uint64_t vd = make_smem_desc(sV + k * 2048, 1024, 1024);
-          umma_f16(tmem_base + s * 128, pd, vd, idesc_o, k != 0);
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + s * Cfg::kTmemStride, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+            umma_commit(bar(S_FULL, s));
+            ++next_qk;
+            did = true;
+          }
         }
-        umma_commit(bar(O_FULL, s));
-        if (i + 2 < n_mine) issue_qk(i + 2);
+        {
+          const int s = next_pv % NSLOT;
+          const uint32_t par = (next_pv / NSLOT) & 1u;
+          if (next_pv < next_qk && mbar_try_wait(bar(P_READY, s), par) && mbar_try_wait(bar(V_FULL, s), par)) {
+            tc_fence_after();
+            const uint32_t sP = base + s * Cfg::kSlotBytes, sV = sP + Cfg::kVOff;
+            for (int k = 0; k < NK / 16; ++k) {
+              const uint64_t pd = make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+              const uint64_t vd = make_smem_desc(sV + k * 2048, 1024, 1024);
+              umma_f16(tmem_base + s * Cfg::kTmemStride, pd, vd, idesc_o, k != 0);
+            }
+            umma_commit(bar(O_FULL, s));
+            ++next_pv;
+            did = true;
+          }
+        }
+        if (did) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("cpt_b200: attention MMA issuer stalled (block %d, qk %d pv %d of %d)\n", blockIdx.x, next_qk, next_pv,
+                 n_mine);
+          __trap();
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ two softmax groups (4 warps each)
     const int grp = (warp - 2) >> 2, q = warp & 3;
     const int r = q * 32 + lane;             // query row == TMEM lane
-    float* gmask = mask_s + (warp - 2) * 128;  // this warp's private copy of the item's key mask (no group barrier)
-    const int n_mine = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    float* gmask = mask_s + (warp - 2) * (NCH * 64);  // this warp's private copy of the item's key mask (no group barrier)
     const bool tr = p.trace != nullptr && warp == 2 && lane == 0;
     long long tq = tr ? clock64() : 0;
     auto lap = [&](int slot) {
@@ -598,11 +628,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     };
     // this thread's mask element of the group's NEXT item is fetched one item ahead (a global load at item start sat
     // on the critical path); pre-multiplied by log2(e): softmax(t) = 2^((t - max) log2 e), exp is a bare ex2.approx
-    auto fetch_mask = [&](int i) -> float4 {
+    auto fetch_mask = [&](int i, int kk) -> float4 {
       float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       if (i < n_mine) {
-        const float* src = p.ext_mask + (long long)((blockIdx.x + i * gridDim.x) / p.nH) * S;
-        const int c = lane * 4;
+        const float* src = p.ext_mask + (long long)((blockIdx.x + i * gridDim.x) / (p.nH * n_mt)) * S;
+        const int c = (kk * 32 + lane) * 4;
         if (c + 0 < S) m.x = src[c + 0];  // raw values: the scaling happens when they are consumed, one item later,
         if (c + 1 < S) m.y = src[c + 1];  // so nothing waits on these loads
         if (c + 2 < S) m.z = src[c + 2];
@@ -610,31 +640,38 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       }
       return m;
     };
-    float4 next_mask = fetch_mask(grp);
+    float4 next_mask[kMaskVec];
+#pragma unroll
+    for (int kk = 0; kk < kMaskVec; ++kk) next_mask[kk] = fetch_mask(grp, kk);
     int pending_free = -1;  // slot whose read-out store is still draining its smem reads
     const float sc2 = p.scale * 1.4426950408889634f;
     for (int i = grp; i < n_mine; i += 2) {
       const int item = blockIdx.x + i * gridDim.x;
       const int s = i % NSLOT;
       const uint32_t par = (i / NSLOT) & 1u;
-      const int h = item % p.nH, b = item / p.nH;
-      *reinterpret_cast<float4*>(gmask + lane * 4) =
-          make_float4(next_mask.x * 1.4426950408889634f, next_mask.y * 1.4426950408889634f,
-                      next_mask.z * 1.4426950408889634f, next_mask.w * 1.4426950408889634f);
-      next_mask = fetch_mask(i + 2);
+      const int mt = item % n_mt, h = (item / n_mt) % p.nH, b = item / (n_mt * p.nH);
+#pragma unroll
+      for (int kk = 0; kk < kMaskVec; ++kk) {
+        if ((kk * 32 + lane) * 4 < NCH * 64) {  // stay inside this warp's private copy
+          *reinterpret_cast<float4*>(gmask + (kk * 32 + lane) * 4) =
+              make_float4(next_mask[kk].x * 1.4426950408889634f, next_mask[kk].y * 1.4426950408889634f,
+                          next_mask[kk].z * 1.4426950408889634f, next_mask[kk].w * 1.4426950408889634f);
+          next_mask[kk] = fetch_mask(i + 2, kk);
+        }
+      }
       __syncwarp();
       lap(0);  // mask
       mbar_wait(bar(S_FULL, s), par);
       tc_fence_after();
       lap(1);  // wait S
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * 128;
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + s * Cfg::kTmemStride;
       // Two passes over the score row, 32 columns at a time, re-reading TMEM (a 32-column read costs ~30 cycles;
       // holding all 128 scores in registers spilled).  t = (s / sqrt(dH) + ext_mask) * log2(e); padded key columns
       // carry mask = -inf and are excluded outright.  Packed fp32x2 FMAs, 4 independent max / sum chains.
       const f32x2 sc22 = pack_f2(sc2, sc2);
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2 * NCH; ++c) {
         if (c < nchunk) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
@@ -659,7 +696,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       f32x2 sum01 = pack_f2(0.f, 0.f), sum23 = pack_f2(0.f, 0.f);
       uint8_t* p_gen = gen + s * Cfg::kSlotBytes;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2 * NCH; ++c) {
         if (c < nchunk) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
@@ -702,7 +739,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_READY, s));
-      if (pending_free >= 0) {  // the previous item's bulk store has long read its staging tile: release that slot
+      if (kDefer && pending_free >= 0) {  // the previous item's bulk store has long read its staging tile
         if (lane == 0) {
           tma_store_wait_read<0>();
           mbar_arrive(bar(SLOT_FREE, pending_free));
@@ -738,10 +775,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmap_ctx, stage_u32, h * kAttnDH, q * 32, b);
+          tma_store_3d(&tmap_ctx, stage_u32, h * kAttnDH, mt * 128 + q * 32, b);
           tma_store_commit();
+          if (!kDefer) {  // two slots only: the slot must be refilled as soon as possible
+            tma_store_wait_read<0>();
+            mbar_arrive(bar(SLOT_FREE, s));
+          }
         }
-        pending_free = s;  // released at the top of this group's next item (or after the loop)
+        if (kDefer) pending_free = s;  // released in the middle of this group's next item (or after the loop)
       }
       lap(7);  // read-out + store
       if (tr) p.trace[blockIdx.x * 16 + 8] += 1;

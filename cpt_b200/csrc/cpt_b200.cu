@@ -324,21 +324,33 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   }
   CUtensorMap tq;
   TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
-  if (impl == 0 && S <= 128) {  // production, S <= 128: ping-pong softmax groups, one thread per query row
-    auto* fn = attn_pp_kernel<T16>;
-    static bool attr_set[64] = {};
-    if (!attr_set[h->device & 63]) {
-      TRY(set_smem_attr(fn, kAttnPPSmemBytes));
-      attr_set[h->device & 63] = true;
-    }
-    const int items = B * nH;
+  if (impl == 0) {  // production: ping-pong softmax groups, one thread per query row
+    const int items = B * nH * ((S + 127) / 128);
+    const int grid = items < h->num_sms ? items : h->num_sms;
     CUtensorMap tc;
     TRY(make_tmap_bsh(&tc, ctx, Cvt<T16>::kFmt, B, S, H, 32));
-    CK(launch_k(fn, dim3(items < h->num_sms ? items : h->num_sms), dim3(kAttn2Threads), kAttnPPSmemBytes, st, 1, tq, tc,
-                p));
+#define CPT_ATTN_PP_CASE(N_)                                                                       \
+  case N_: {                                                                                       \
+    auto* fn = attn_pp_kernel<T16, N_>;                                                            \
+    static bool attr_set[64] = {};                                                                 \
+    if (!attr_set[h->device & 63]) {                                                               \
+      TRY(set_smem_attr(fn, AttnPPCfg<N_>::kSmemBytes));                                           \
+      attr_set[h->device & 63] = true;                                                             \
+    }                                                                                              \
+    CK(launch_k(fn, dim3(grid), dim3(kAttn2Threads), AttnPPCfg<N_>::kSmemBytes, st, 1, tq, tc, p)); \
+    break;                                                                                         \
+  }
+    switch ((S + 63) / 64) {
+      CPT_ATTN_PP_CASE(1)
+      CPT_ATTN_PP_CASE(2)
+      CPT_ATTN_PP_CASE(3)
+      CPT_ATTN_PP_CASE(4)
+      default: return fail("attention: unsupported S=%d", S);
+    }
+#undef CPT_ATTN_PP_CASE
     return 0;
   }
-  if (impl == 0 || impl == 3) {  // S > 128 (or impl 3): persistent pipelined kernel, two threads per query row
+  if (impl == 3) {  // earlier design kept as a cross-check: persistent pipelined kernel, two threads per query row
     const int items = B * nH * ((S + 127) / 128);
     const int grid = items < h->num_sms ? items : h->num_sms;
     const int nch = (S + 63) / 64;

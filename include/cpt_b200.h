@@ -130,9 +130,9 @@ int cpt_gemm(cpt_handle *h, void *stream, const void *A, long long lda, const vo
  * + PDL wait, CTA lifetime cycles, globaltimer ns at entry, at exit, 0, 0, 0}. */
 int cpt_gemm_trace(cpt_handle *h, long long *out, int max_ctas);
 /* ctx[B*S,H] = softmax(QK^T/sqrt(dH) + (1-mask)*-1e4) V from packed qkv[B*S,3H] (16-bit); ext_mask fp32 [B,S].
- * impl: 0 = production (persistent pipelined tcgen05 kernels: ping-pong one-thread-per-row for S <= 128, two-threads-per-
- * row otherwise), 1 = CUDA-core cross-check kernel, 2 = single-tile tcgen05 kernel (one CTA per (head, query tile,
- * sample)), 3 = force the two-threads-per-row pipelined kernel at any S. */
+ * impl: 0 = production (persistent ping-pong tcgen05 kernel, one thread per query row), 1 = CUDA-core cross-check
+ * kernel, 2 = single-tile tcgen05 kernel (one CTA per (head, query tile, sample)), 3 = two-threads-per-row pipelined
+ * tcgen05 kernel (earlier design, kept as a cross-check). */
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,
                   int impl);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
