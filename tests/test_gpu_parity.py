@@ -218,3 +218,27 @@ def test_layernorm_folding_agrees_with_separate_layernorm_kernels(monkeypatch):
     assert (outs[1] - ref).abs().max().item() <= RTOL * scale
     assert (outs[0] - outs[1]).abs().max().item() <= RTOL * scale
     assert not torch.equal(outs[0], outs[1])   # the flag really switched the path
+
+
+def test_bf16_operand_mode_runs_and_is_coarser(monkeypatch):
+    """cpt_config.dtype = 1: the same kernels with bf16 tensor-core operands (range over precision).  Must run, must
+    agree with the oracle at bf16's resolution (8-bit significand), and must differ from the fp16 result."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=3)
+    sd = synth_state_dict(cfg, seed=13)
+    b = synth_batch(cfg, 4, 70, 50, seed=6)
+    d = cuda(b)
+    outs = {}
+    for dt in ("fp16", "bf16"):
+        monkeypatch.setenv("CPT_B200_DTYPE", dt)
+        pre, rec, nsp = build(cfg, sd)
+        with torch.no_grad():
+            outs[dt] = rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0].cpu()
+        assert rec.bert.engine().dtype == dt
+    with torch.no_grad():
+        ref = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                               img_feats=b["img_feats"])[0]
+    scale = ref.abs().max().item()
+    e16 = (outs["fp16"] - ref).abs().max().item() / scale
+    eb16 = (outs["bf16"] - ref).abs().max().item() / scale
+    assert e16 <= RTOL and eb16 <= 1.5e-2 and eb16 > e16
