@@ -136,6 +136,9 @@ struct cpt_handle {
   int fold_ln = 0;       // CPT_B200_FOLD_LN=1: LayerNorm folded into the neighbouring GEMM epilogues (slower, kept for study)
   int resid_in_ln = 1;   // residual added by the (streaming) LayerNorm kernel instead of the GEMM epilogue
   int reduce_resid = 1;  // ... or, better, by the GEMM's TMA store itself (cp.reduce .add at L2): CPT_B200_REDUCE_RESID=0 off
+  int split = 1;         // CPT_B200_SPLIT=2: run the two halves of the batch as concurrent branches (tail filling)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int tma_store = 1;     // CPT_B200_TMA_STORE=0: LSU stores in the GEMM epilogue (A/B experiments)
   int delta16 = 0;       // CPT_B200_DELTA16=1: hand the dense+bias delta to it as 16 bits (2% faster, ~1.8x the logit error)
   struct { int bn, pair; } gemm_choice[16] = {};  // per kernel class, bn 0 = default (CPT_B200_GEMM overrides)
@@ -830,6 +833,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_DELTA16")) h->delta16 = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_TMA_STORE")) h->tma_store = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_SPLIT")) h->split = atoi(e);
   if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
@@ -864,6 +868,9 @@ int cpt_destroy(cpt_handle* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   free_owned(h);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
@@ -881,7 +888,12 @@ int cpt_set_weights(cpt_handle* h, const cpt_weights* w, void* stream) {
 
 size_t cpt_workspace_bytes(const cpt_handle* h, int B, int T, int R) {
   if (!h || B <= 0 || T <= 0 || R < 0) return 0;
-  return carve(h, B, T, R, nullptr).total;
+  size_t n = carve(h, B, T, R, nullptr).total;
+  if (B >= 2) {  // room for the split forward (two half-batch workspaces)
+    const size_t two = carve(h, B / 2, T, R, nullptr).total + carve(h, B - B / 2, T, R, nullptr).total + 1024;
+    if (two > n) n = two;
+  }
+  return n;
 }
 
 int cpt_encoder_forward(cpt_handle* h, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
@@ -890,10 +902,55 @@ int cpt_encoder_forward(cpt_handle* h, void* stream, const int64_t* input_ids, c
                         float* hidden_states) {
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
-#define CALL(T16)                                                                                             \
-  encoder_forward_impl<T16>(h, (cudaStream_t)stream, input_ids, token_type_ids, attention_mask, position_ids, \
-                            img_feats, B, T, R, workspace, workspace_bytes, seq_out, pooled, hidden_states)
-  return DISPATCH_DTYPE(h, CALL);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(T16, ST, IDS, SEG, MSK, POS, IMG, NB, WS, WSB, SEQ, POOL)                                            \
+  encoder_forward_impl<T16>(h, ST, IDS, SEG, MSK, POS, IMG, NB, T, R, WS, WSB, SEQ, POOL, hidden_states)
+  const int S = T + R, H = h->cfg.hidden_size;
+  if (h->split == 2 && B >= 16 && !hidden_states && !h->profiling && workspace) {
+    // Two half-batches as concurrent branches (fork / join on a side stream; inside a CUDA graph they become parallel
+    // branches): every kernel is a persistent grid of <= 148 CTAs, so while one branch's GEMM drains its last tiles
+    // the other branch's kernel takes the SMs that are already free.
+    if (!h->side) {
+      CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    const int B0 = B / 2, B1 = B - B0;
+    const size_t w0 = carve(h, B0, T, R, nullptr).total, w1 = carve(h, B1, T, R, nullptr).total;
+    if (workspace_bytes < w0 + w1 + 512) return fail("workspace too small for the split forward");
+    char* ws1 = (char*)workspace + ((w0 + 255) & ~size_t(255));
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    int rc;
+    if (h->cfg.dtype == 0) {
+      rc = CALL(__half, st, input_ids, token_type_ids, attention_mask, position_ids, img_feats, B0, workspace, w0,
+                seq_out, pooled);
+      if (!rc)
+        rc = CALL(__half, h->side, input_ids + (size_t)B0 * T, token_type_ids ? token_type_ids + (size_t)B0 * T : nullptr,
+                  attention_mask ? attention_mask + (size_t)B0 * S : nullptr,
+                  position_ids ? position_ids + (size_t)B0 * T : nullptr,
+                  img_feats ? img_feats + (size_t)B0 * R * h->cfg.img_feature_dim : nullptr, B1, ws1, w1,
+                  seq_out + (size_t)B0 * S * H, pooled ? pooled + (size_t)B0 * H : nullptr);
+    } else {
+      rc = CALL(__nv_bfloat16, st, input_ids, token_type_ids, attention_mask, position_ids, img_feats, B0, workspace, w0,
+                seq_out, pooled);
+      if (!rc)
+        rc = CALL(__nv_bfloat16, h->side, input_ids + (size_t)B0 * T,
+                  token_type_ids ? token_type_ids + (size_t)B0 * T : nullptr,
+                  attention_mask ? attention_mask + (size_t)B0 * S : nullptr,
+                  position_ids ? position_ids + (size_t)B0 * T : nullptr,
+                  img_feats ? img_feats + (size_t)B0 * R * h->cfg.img_feature_dim : nullptr, B1, ws1, w1,
+                  seq_out + (size_t)B0 * S * H, pooled ? pooled + (size_t)B0 * H : nullptr);
+    }
+    CK(cudaEventRecord(h->ev_join, h->side));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return rc;
+  }
+  if (h->cfg.dtype == 0)
+    return CALL(__half, st, input_ids, token_type_ids, attention_mask, position_ids, img_feats, B, workspace,
+                workspace_bytes, seq_out, pooled);
+  return CALL(__nv_bfloat16, st, input_ids, token_type_ids, attention_mask, position_ids, img_feats, B, workspace,
+              workspace_bytes, seq_out, pooled);
 #undef CALL
 }
 
