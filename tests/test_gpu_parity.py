@@ -242,3 +242,28 @@ def test_bf16_operand_mode_runs_and_is_coarser(monkeypatch):
     e16 = (outs["fp16"] - ref).abs().max().item() / scale
     eb16 = (outs["bf16"] - ref).abs().max().item() / scale
     assert e16 <= RTOL and eb16 <= 1.5e-2 and eb16 > e16
+
+
+@pytest.mark.parametrize("H,nH,I,B,T,R", [(1024, 16, 4096, 3, 150, 50), (256, 4, 1024, 9, 100, 28), (384, 6, 1536, 2, 200, 56)])
+def test_other_geometries_against_oracle(H, nH, I, B, T, R):
+    """Oscar-large width (H=1024, 16 heads, S=200) and other legal widths (H % 128 == 0, head size 64), S up to 256,
+    odd batch sizes: same kernels, different template instantiations (LayerNorm vector count, attention key blocks)."""
+    from oracle import cpt_oracle as O
+    cfg = C.BertConfig(2048, hidden_size=H, num_hidden_layers=2, num_attention_heads=nH, intermediate_size=I,
+                       max_position_embeddings=256)
+    sd = synth_state_dict(cfg, seed=17)
+    b = synth_batch(cfg, B, T, R, seed=23)
+    vids = synth_vocab_ids(cfg, 7, seed=5)
+    pre, rec, nsp = build(cfg, sd)
+    d = cuda(b)
+    with torch.no_grad():
+        seq = rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0].cpu()
+        logits = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                     mask_pos=d["mask_pos"], vocab_ids=vids.cuda())[0].cpu()
+        oseq, _, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                      img_feats=b["img_feats"])
+        rows = O.lm_head(sd, cfg, oseq[torch.arange(B), b["mask_pos"]])
+    rec.bert.engine().check()
+    assert (seq - oseq).abs().max().item() <= RTOL * oseq.abs().max().item()
+    row_max = rows.abs().max(dim=1, keepdim=True).values
+    assert ((logits - rows[:, vids]).abs() <= RTOL * row_max).all()
