@@ -8,8 +8,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcpt_b200.so")
-ABI_VERSION = 1
-K_COUNT = 13  # CPT_K_COUNT
+ABI_VERSION = 2
+K_COUNT = 17  # CPT_K_COUNT
 
 
 class CptError(RuntimeError):
@@ -41,6 +41,18 @@ class Weights(C.Structure):
     _fields_ = [(n, _fp) for n in GLOBAL_FIELDS] + [("layers", C.POINTER(LayerWeights))]
 
 
+GRAD_GLOBAL_FIELDS = ("word_emb", "pos_emb", "type_emb", "emb_ln_g", "emb_ln_b", "img_w", "img_b", "img_ln_g",
+                      "img_ln_b", "mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, _fp) for n in LAYER_FIELDS]
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, _fp) for n in GRAD_GLOBAL_FIELDS] + [("layers", C.POINTER(LayerGrads))]
+
+
 # name -> (restype, argtypes); every symbol include/cpt_b200.h declares
 _i, _ll, _sz, _p, _f = C.c_int, C.c_longlong, C.c_size_t, C.c_void_p, C.c_float
 SYMBOLS = {
@@ -55,6 +67,10 @@ SYMBOLS = {
     "cpt_mlm_scores_forward": (_i, [_p, _p, _p, _ll, _p, _sz, _p]),
     "cpt_mlm_scores_workspace_bytes": (_sz, [_p, _ll]),
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
+    "cpt_train_enable": (_i, [_p, _i]),
+    "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),
+    "cpt_train_forward_mlm": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _sz, _p]),
+    "cpt_train_backward_mlm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _sz, C.POINTER(Grads)]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),
     "cpt_launch_count": (_ll, [_p]),

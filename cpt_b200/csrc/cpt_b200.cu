@@ -20,6 +20,7 @@
 #include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
+#include "train.cuh"
 
 using namespace cptk;
 
@@ -110,8 +111,11 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int dtype, unsigned long l
 
 // ------------------------------------------------------------------------------------------------ handle
 struct LayerDev {
-  void *w_qkv, *w_ao, *w_i, *w_o;  // 16-bit [3H,H] [H,H] [I,H] [H,I]
-  float *b_qkv, *b_ao, *ao_g, *ao_b, *b_i, *b_o, *o_g, *o_b;
+  void *w_qkv = nullptr, *w_ao = nullptr, *w_i = nullptr, *w_o = nullptr;  // 16-bit [3H,H] [H,H] [I,H] [H,I]
+  float *b_qkv = nullptr, *b_ao = nullptr, *ao_g = nullptr, *ao_b = nullptr, *b_i = nullptr, *b_o = nullptr,
+        *o_g = nullptr, *o_b = nullptr;
+  // training: transposed 16-bit copies, the W operand of the dgrad GEMMs ([H,3H] [H,H] [H,I] [I,H])
+  void *w_qkv_t = nullptr, *w_ao_t = nullptr, *w_i_t = nullptr, *w_o_t = nullptr;
   // LayerNorm-folded copies (DESIGN.md "LayerNorm folding"): W .* gamma of the LayerNorm that feeds the GEMM
   void *w_qkv_f = nullptr, *w_i_f = nullptr;
   float *g_qkv = nullptr, *c_qkv = nullptr, *g_i = nullptr, *c_i = nullptr;
@@ -129,6 +133,9 @@ struct cpt_handle {
   float *pool_w = nullptr, *pool_b = nullptr;
   float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
   void *mlm_w16 = nullptr, *word16 = nullptr;
+  void *mlm_w16_t = nullptr, *word16_t = nullptr;  // training: [H,H]^T and [H, Vp] (Vp = vocab rounded up to 8)
+  int train = 0;                                   // cpt_train_enable: keep transposed copies, reuse allocations
+  unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
   float *nsp_w = nullptr, *nsp_b = nullptr;
   std::vector<LayerDev> layers;
   int* err_flag = nullptr;
@@ -466,13 +473,27 @@ static int cast_w(cudaStream_t st, const float* src, long long rows, int cols, i
   CKL("cast_weight_kernel");
   return 0;
 }
-static int copy_vec(cpt_handle* h, cudaStream_t st, const float* src, size_t n, float** dst) {
+// (re)allocation policy of cpt_set_weights: a training handle whose previous call covered the same tensors keeps
+// its device buffers and only refreshes their contents (one optimizer step later the shapes cannot have changed)
+static int walloc(cpt_handle* h, bool reuse, void** p, size_t bytes) {
+  if (reuse && *p) return 0;
+  return dev_alloc(h, p, bytes);
+}
+static int copy_vec(cpt_handle* h, bool reuse, cudaStream_t st, const float* src, size_t n, float** dst) {
   if (!src) {
     *dst = nullptr;
     return 0;
   }
-  TRY(dev_alloc(h, (void**)dst, n * 4));
+  TRY(walloc(h, reuse, (void**)dst, n * 4));
   CK(cudaMemcpyAsync(*dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+template <typename T16>
+static int transpose16(cudaStream_t st, const void* in, int R, int C, long long ld_in, void* out, long long ld_out) {
+  dim3 grid((C + 31) / 32, (int)((std::max<long long>(R, ld_out) + 31) / 32));
+  transpose16_kernel<T16><<<grid, 256, 0, st>>>(reinterpret_cast<const T16*>(in), R, C, ld_in,
+                                                 reinterpret_cast<T16*>(out), ld_out);
+  CKL("transpose16_kernel");
   return 0;
 }
 
@@ -480,32 +501,43 @@ template <typename T16>
 static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, F = c.img_feature_dim;
-  int* flag = h->err_flag;
-  h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)flag), h->owned.end());
-  h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)h->trace), h->owned.end());
-  free_owned(h);
-  h->owned.push_back(flag);
-  if (h->trace) h->owned.push_back(h->trace);
-  h->has_weights = false;
   if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b || !w->layers)
     return fail("cpt_set_weights: embedding tables / LayerNorm / layers must be non-NULL");
+  const bool has_pooler = w->pooler_w && w->pooler_b;
+  const bool has_mlm = w->mlm_dense_w && w->mlm_dense_b && w->mlm_ln_g && w->mlm_ln_b && w->mlm_bias;
+  const bool has_nsp = w->nsp_w && w->nsp_b;
+  const unsigned sig = 1u | (w->img_w ? 2u : 0u) | (w->img_ln_g ? 4u : 0u) | (has_pooler ? 8u : 0u) |
+                       (has_mlm ? 16u : 0u) | (has_nsp ? 32u : 0u) | (h->train ? 64u : 0u);
+  const bool reuse = h->train && h->has_weights && h->weights_sig == sig;
+  if (!reuse) {
+    CK(cudaDeviceSynchronize());  // no kernel may still be reading the buffers we are about to free
+    int* flag = h->err_flag;
+    h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)flag), h->owned.end());
+    h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)h->trace), h->owned.end());
+    free_owned(h);
+    h->owned.push_back(flag);
+    if (h->trace) h->owned.push_back(h->trace);
+    h->emb_g = h->emb_b = h->b_img = h->img_g = h->img_b = h->pool_w = h->pool_b = nullptr;
+    h->mlm_w = h->mlm_b = h->mlm_g = h->mlm_beta = h->mlm_bias = h->nsp_w = h->nsp_b = nullptr;
+    h->w_img = h->mlm_w16 = h->word16 = h->mlm_w16_t = h->word16_t = nullptr;
+    h->layers.assign(L, LayerDev{});
+  }
+  h->has_weights = false;
   h->word = w->word_emb;
   h->pos = w->pos_emb;
   h->type = w->type_emb;
-  TRY(copy_vec(h, st, w->emb_ln_g, H, &h->emb_g));
-  TRY(copy_vec(h, st, w->emb_ln_b, H, &h->emb_b));
-  h->w_img = nullptr;
+  TRY(copy_vec(h, reuse, st, w->emb_ln_g, H, &h->emb_g));
+  TRY(copy_vec(h, reuse, st, w->emb_ln_b, H, &h->emb_b));
   if (w->img_w) {
     if (!w->img_b) return fail("cpt_set_weights: img_w without img_b");
     if (c.use_img_layernorm && (!w->img_ln_g || !w->img_ln_b))
       return fail("cpt_set_weights: use_img_layernorm=1 needs bert.LayerNorm weights");
-    TRY(dev_alloc(h, &h->w_img, (size_t)H * h->Fp * 2));
+    TRY(walloc(h, reuse, &h->w_img, (size_t)H * h->Fp * 2));
     TRY(cast_w<T16>(st, w->img_w, H, F, h->Fp, h->w_img));
-    TRY(copy_vec(h, st, w->img_b, H, &h->b_img));
-    TRY(copy_vec(h, st, w->img_ln_g, H, &h->img_g));
-    TRY(copy_vec(h, st, w->img_ln_b, H, &h->img_b));
+    TRY(copy_vec(h, reuse, st, w->img_b, H, &h->b_img));
+    TRY(copy_vec(h, reuse, st, w->img_ln_g, H, &h->img_g));
+    TRY(copy_vec(h, reuse, st, w->img_ln_b, H, &h->img_b));
   }
-  h->layers.assign(L, LayerDev{});
   for (int l = 0; l < L; ++l) {
     const cpt_layer_weights& s = w->layers[l];
     LayerDev& d = h->layers[l];
@@ -513,27 +545,38 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
                            s.i_w, s.i_b, s.o_w, s.o_b, s.o_ln_g, s.o_ln_b};
     for (const float* q : need)
       if (!q) return fail("cpt_set_weights: layer %d has a NULL tensor", l);
-    TRY(dev_alloc(h, &d.w_qkv, (size_t)3 * H * H * 2));
+    TRY(walloc(h, reuse, &d.w_qkv, (size_t)3 * H * H * 2));
     TRY(cast_w<T16>(st, s.q_w, H, H, H, d.w_qkv));
     TRY(cast_w<T16>(st, s.k_w, H, H, H, (char*)d.w_qkv + (size_t)H * H * 2));
     TRY(cast_w<T16>(st, s.v_w, H, H, H, (char*)d.w_qkv + (size_t)2 * H * H * 2));
-    TRY(dev_alloc(h, (void**)&d.b_qkv, (size_t)3 * H * 4));
+    TRY(walloc(h, reuse, (void**)&d.b_qkv, (size_t)3 * H * 4));
     CK(cudaMemcpyAsync(d.b_qkv, s.q_b, H * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(d.b_qkv + H, s.k_b, H * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(d.b_qkv + 2 * H, s.v_b, H * 4, cudaMemcpyDeviceToDevice, st));
-    TRY(dev_alloc(h, &d.w_ao, (size_t)H * H * 2));
+    TRY(walloc(h, reuse, &d.w_ao, (size_t)H * H * 2));
     TRY(cast_w<T16>(st, s.ao_w, H, H, H, d.w_ao));
-    TRY(copy_vec(h, st, s.ao_b, H, &d.b_ao));
-    TRY(copy_vec(h, st, s.ao_ln_g, H, &d.ao_g));
-    TRY(copy_vec(h, st, s.ao_ln_b, H, &d.ao_b));
-    TRY(dev_alloc(h, &d.w_i, (size_t)I * H * 2));
+    TRY(copy_vec(h, reuse, st, s.ao_b, H, &d.b_ao));
+    TRY(copy_vec(h, reuse, st, s.ao_ln_g, H, &d.ao_g));
+    TRY(copy_vec(h, reuse, st, s.ao_ln_b, H, &d.ao_b));
+    TRY(walloc(h, reuse, &d.w_i, (size_t)I * H * 2));
     TRY(cast_w<T16>(st, s.i_w, I, H, H, d.w_i));
-    TRY(copy_vec(h, st, s.i_b, I, &d.b_i));
-    TRY(dev_alloc(h, &d.w_o, (size_t)H * I * 2));
+    TRY(copy_vec(h, reuse, st, s.i_b, I, &d.b_i));
+    TRY(walloc(h, reuse, &d.w_o, (size_t)H * I * 2));
     TRY(cast_w<T16>(st, s.o_w, H, I, I, d.w_o));
-    TRY(copy_vec(h, st, s.o_b, H, &d.b_o));
-    TRY(copy_vec(h, st, s.o_ln_g, H, &d.o_g));
-    TRY(copy_vec(h, st, s.o_ln_b, H, &d.o_b));
+    TRY(copy_vec(h, reuse, st, s.o_b, H, &d.b_o));
+    TRY(copy_vec(h, reuse, st, s.o_ln_g, H, &d.o_g));
+    TRY(copy_vec(h, reuse, st, s.o_ln_b, H, &d.o_b));
+    if (h->train) {
+      TRY(walloc(h, reuse, &d.w_qkv_t, (size_t)3 * H * H * 2));
+      TRY(transpose16<T16>(st, d.w_qkv, 3 * H, H, H, d.w_qkv_t, 3 * H));
+      TRY(walloc(h, reuse, &d.w_ao_t, (size_t)H * H * 2));
+      TRY(transpose16<T16>(st, d.w_ao, H, H, H, d.w_ao_t, H));
+      TRY(walloc(h, reuse, &d.w_i_t, (size_t)I * H * 2));
+      TRY(transpose16<T16>(st, d.w_i, I, H, H, d.w_i_t, I));
+      TRY(walloc(h, reuse, &d.w_o_t, (size_t)I * H * 2));
+      TRY(transpose16<T16>(st, d.w_o, H, I, I, d.w_o_t, H));
+      continue;  // the LayerNorm-folded copies below serve the (inference-only) folded path
+    }
     // folded copies: FFN-up reads pre-LN1 rows (gamma/beta of this layer's attention.output.LayerNorm); the QKV
     // projection of layer l >= 1 reads pre-LN2 rows of layer l-1 (gamma/beta of its output.LayerNorm)
     TRY(dev_alloc(h, &d.w_i_f, (size_t)I * H * 2));
@@ -557,30 +600,38 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
       }
     }
   }
-  h->has_pooler = w->pooler_w && w->pooler_b;
+  h->has_pooler = has_pooler;
   if (h->has_pooler) {
-    TRY(copy_vec(h, st, w->pooler_w, (size_t)H * H, &h->pool_w));
-    TRY(copy_vec(h, st, w->pooler_b, H, &h->pool_b));
+    TRY(copy_vec(h, reuse, st, w->pooler_w, (size_t)H * H, &h->pool_w));
+    TRY(copy_vec(h, reuse, st, w->pooler_b, H, &h->pool_b));
   }
-  h->has_mlm = w->mlm_dense_w && w->mlm_dense_b && w->mlm_ln_g && w->mlm_ln_b && w->mlm_bias;
+  h->has_mlm = has_mlm;
   if (h->has_mlm) {
-    TRY(copy_vec(h, st, w->mlm_dense_w, (size_t)H * H, &h->mlm_w));
-    TRY(copy_vec(h, st, w->mlm_dense_b, H, &h->mlm_b));
-    TRY(copy_vec(h, st, w->mlm_ln_g, H, &h->mlm_g));
-    TRY(copy_vec(h, st, w->mlm_ln_b, H, &h->mlm_beta));
-    TRY(copy_vec(h, st, w->mlm_bias, c.vocab_size, &h->mlm_bias));
+    TRY(copy_vec(h, reuse, st, w->mlm_dense_w, (size_t)H * H, &h->mlm_w));
+    TRY(copy_vec(h, reuse, st, w->mlm_dense_b, H, &h->mlm_b));
+    TRY(copy_vec(h, reuse, st, w->mlm_ln_g, H, &h->mlm_g));
+    TRY(copy_vec(h, reuse, st, w->mlm_ln_b, H, &h->mlm_beta));
+    TRY(copy_vec(h, reuse, st, w->mlm_bias, c.vocab_size, &h->mlm_bias));
     // 16-bit copies for the full-vocabulary scores path (tensor-core GEMM over all rows)
-    TRY(dev_alloc(h, &h->mlm_w16, (size_t)H * H * 2));
+    TRY(walloc(h, reuse, &h->mlm_w16, (size_t)H * H * 2));
     TRY(cast_w<T16>(st, w->mlm_dense_w, H, H, H, h->mlm_w16));
-    TRY(dev_alloc(h, &h->word16, (size_t)c.vocab_size * H * 2));
+    TRY(walloc(h, reuse, &h->word16, (size_t)c.vocab_size * H * 2));
     TRY(cast_w<T16>(st, w->word_emb, c.vocab_size, H, H, h->word16));
+    if (h->train) {
+      const int Vp = (c.vocab_size + 7) & ~7;
+      TRY(walloc(h, reuse, &h->mlm_w16_t, (size_t)H * H * 2));
+      TRY(transpose16<T16>(st, h->mlm_w16, H, H, H, h->mlm_w16_t, H));
+      TRY(walloc(h, reuse, &h->word16_t, (size_t)H * Vp * 2));
+      TRY(transpose16<T16>(st, h->word16, c.vocab_size, H, H, h->word16_t, Vp));
+    }
   }
-  h->has_nsp = w->nsp_w && w->nsp_b;
+  h->has_nsp = has_nsp;
   if (h->has_nsp) {
-    TRY(copy_vec(h, st, w->nsp_w, (size_t)c.num_contrast_classes * H, &h->nsp_w));
-    TRY(copy_vec(h, st, w->nsp_b, c.num_contrast_classes, &h->nsp_b));
+    TRY(copy_vec(h, reuse, st, w->nsp_w, (size_t)c.num_contrast_classes * H, &h->nsp_w));
+    TRY(copy_vec(h, reuse, st, w->nsp_b, c.num_contrast_classes, &h->nsp_b));
   }
   h->has_weights = true;
+  h->weights_sig = sig;
   return 0;
 }
 
@@ -640,7 +691,7 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   }
   if (hidden_states) CK(cudaMemcpyAsync(hidden_states, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
 
-  const bool fold = h->fold_ln && !hidden_states && L > 0;
+  const bool fold = h->fold_ln && !h->train && !hidden_states && L > 0;
   if (fold) {
     // LayerNorm folded into the GEMMs on either side of it (DESIGN.md "LayerNorm folding"): the stream buffers hold
     // PRE-LayerNorm rows (fp32 + 16-bit) plus per-row (sum, sum of squares); no LayerNorm kernel runs between GEMMs.
@@ -789,6 +840,8 @@ static int mlm_scores_impl(cpt_handle* h, cudaStream_t st, const float* seq_out,
 #define DISPATCH_DTYPE(h, CALL)                                  \
   ((h)->cfg.dtype == 0 ? CALL(__half) : CALL(__nv_bfloat16))
 
+#include "train_host.inl"
+
 // ================================================================================================ C ABI
 extern "C" {
 
@@ -880,7 +933,6 @@ int cpt_destroy(cpt_handle* h) {
 int cpt_set_weights(cpt_handle* h, const cpt_weights* w, void* stream) {
   if (!h || !w) return fail("cpt_set_weights: NULL argument");
   DeviceGuard g(h->device);
-  CK(cudaDeviceSynchronize());  // no kernel may still be reading the buffers we are about to free
 #define CALL(T) set_weights_impl<T>(h, w, (cudaStream_t)stream)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
@@ -1002,6 +1054,44 @@ int cpt_nsp_forward(cpt_handle* h, void* stream, const float* pooled, int B, flo
                      nullptr, C, B, H, C, ACT_NONE, out, C);
 }
 
+int cpt_train_enable(cpt_handle* h, int on) {
+  if (!h) return fail("NULL handle");
+  if ((h->train != 0) != (on != 0)) h->has_weights = false;  // the next cpt_set_weights rebuilds the copies
+  h->train = on != 0;
+  return 0;
+}
+
+size_t cpt_train_tape_bytes(const cpt_handle* h, int B, int T, int R, int n_rows) {
+  if (!h || B <= 0 || T <= 0 || R < 0 || n_rows <= 0) return 0;
+  return carve_tape(h, B, T, R, n_rows, nullptr).total;
+}
+
+int cpt_train_forward_mlm(cpt_handle* h, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                          const int64_t* attention_mask, const int64_t* position_ids, const float* img_feats, int B,
+                          int T, int R, const int64_t* rows, const int64_t* targets, int n_rows, void* tape,
+                          size_t tape_bytes, float* loss) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+#define CALL(T16)                                                                                                    \
+  train_forward_impl<T16>(h, (cudaStream_t)stream, input_ids, token_type_ids, attention_mask, position_ids, img_feats, \
+                          B, T, R, rows, targets, n_rows, tape, tape_bytes, loss)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_train_backward_mlm(cpt_handle* h, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                           const int64_t* position_ids, int B, int T, int R, const int64_t* rows,
+                           const int64_t* targets, int n_rows, const float* grad_loss, void* tape, size_t tape_bytes,
+                           const cpt_grads* grads) {
+  if (!h) return fail("NULL handle");
+  DeviceGuard g(h->device);
+#define CALL(T16)                                                                                                 \
+  train_backward_impl<T16>(h, (cudaStream_t)stream, input_ids, token_type_ids, position_ids, B, T, R, rows, targets, \
+                           n_rows, grad_loss, tape, tape_bytes, grads)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
 int cpt_check_async_error(cpt_handle* h, void* stream) {
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
@@ -1019,7 +1109,8 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
 
 static const char* kKernelNames[CPT_K_COUNT] = {"ext_mask", "embed_text_ln", "cast_pad", "gemm_img", "layernorm",
                                                  "gemm_qkv", "attention", "gemm_attn_out", "gemm_ffn_up",
-                                                 "gemm_ffn_down", "head_matvec", "gemm_head", "gemm_other"};
+                                                 "gemm_ffn_down", "head_matvec", "gemm_head", "gemm_other",
+                                                 "gemm_dgrad", "gemm_wgrad", "attention_bwd", "train_rowwise"};
 const char* cpt_kernel_name(int tag) { return (tag >= 0 && tag < CPT_K_COUNT) ? kKernelNames[tag] : ""; }
 long long cpt_launch_count(const cpt_handle* h) { return h ? h->launches : 0; }
 

@@ -1,0 +1,435 @@
+// Kernels of the training step (forward with a tape, backward for every parameter of
+// REC_MLM_CPT — /root/reference/Oscar/oscar/fewshot/{refcoco_cpt.py:231-250, gqa_cpt.py:428-462}).  The heavy lifting
+// (all dgrad / wgrad products) reuses the tcgen05 GEMM of gemm_sm100.cuh on transposed 16-bit operands; this file holds
+// the row-wise / element-wise pieces and a CUDA-core attention backward (few-shot batches are a handful of rows).
+#pragma once
+#include "ptx.cuh"
+#include "rowwise.cuh"
+
+namespace cptk {
+
+// out[C, ld_out] = in[R, ld_in]^T (16-bit), columns R..ld_out-1 of out zero-filled (TMA pitch padding)
+template <typename T16>
+__global__ void __launch_bounds__(256) transpose16_kernel(const T16* __restrict__ in, int R, int C, long long ld_in,
+                                                          T16* __restrict__ out, long long ld_out) {
+  __shared__ T16 tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < R && c < C) ? in[(long long)r * ld_in + c] : Cvt<T16>::from(0.f);
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;
+    if (c < C && r < ld_out) out[(long long)c * ld_out + r] = tile[tx][k];
+  }
+}
+
+// out[n] += sum_m in[m, n]   (bias gradients); T = float or a 16-bit type
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int M, int N, long long ld,
+                                                     float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += (float)in[(long long)m * ld + n];
+  if (m1 > m0) atomicAdd(out + n, s);
+}
+
+__device__ __forceinline__ float gelu_exact(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+template <typename T16>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T16* __restrict__ in, long long n, T16* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = Cvt<T16>::from(gelu_exact(Cvt<T16>::to(in[i])));
+}
+// dpre = dpost * gelu'(pre)
+template <typename T16>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T16* __restrict__ dpost, const T16* __restrict__ pre,
+                                                       long long n, T16* __restrict__ dpre) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dpre[i] = Cvt<T16>::from(Cvt<T16>::to(dpost[i]) * gelu_grad(Cvt<T16>::to(pre[i])));
+}
+// fp32 variants for the small head tensors
+__global__ void __launch_bounds__(256) gelu_fwd32_kernel(const float* __restrict__ in, long long n,
+                                                         float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = gelu_exact(in[i]);
+}
+__global__ void __launch_bounds__(256) gelu_bwd32_kernel(const float* __restrict__ dpost, const float* __restrict__ pre,
+                                                         long long n, float* __restrict__ dpre) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dpre[i] = dpost[i] * gelu_grad(pre[i]);
+}
+
+// LayerNorm backward, one warp per row (persistent over rows).  y = (x - mu) * rstd * gamma + beta.
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;   dgamma += dy * xhat;  dbeta += dy
+// dy row index = remap(m) (region rows live behind the text rows of the [B,S,H] stream); x rows are dense.
+template <typename T16, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int M,
+                                                     int H, const float* __restrict__ gamma, float eps, int do_ln,
+                                                     float* __restrict__ dx32, T16* __restrict__ dx16,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rin,
+                                                     int rout, int roff) {
+  __shared__ float red[8][NV * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wstride = gridDim.x * 8;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * 8 + warp; row < M; row += wstride) {
+    long long drow = row;
+    if (rin > 0) drow = (long long)(row / rin) * rout + roff + (row % rin);
+    float4 xv[NV], gv[NV], dv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      xv[i] = *reinterpret_cast<const float4*>(x + (long long)row * H + col);
+      dv[i] = *reinterpret_cast<const float4*>(dy + drow * H + col);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (do_ln) {
+      mean = warp_sum(s) / (float)H;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
+    }
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (do_ln) gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      // xhat in xv, g = dy * gamma in gv
+      xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
+      xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+      gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
+      m1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      m2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+      ag[i].x += dv[i].x * xv[i].x; ag[i].y += dv[i].y * xv[i].y; ag[i].z += dv[i].z * xv[i].z; ag[i].w += dv[i].w * xv[i].w;
+      ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+    }
+    m1 = warp_sum(m1) / (float)H;
+    m2 = warp_sum(m2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      float4 o;
+      if (do_ln) {
+        o.x = rstd * (gv[i].x - m1 - xv[i].x * m2); o.y = rstd * (gv[i].y - m1 - xv[i].y * m2);
+        o.z = rstd * (gv[i].z - m1 - xv[i].z * m2); o.w = rstd * (gv[i].w - m1 - xv[i].w * m2);
+      } else {
+        o = dv[i];
+      }
+      if (dx32) *reinterpret_cast<float4*>(dx32 + (long long)row * H + col) = o;
+      if (dx16) {
+        uint2 u;
+        u.x = Cvt<T16>::pack2(o.x, o.y);
+        u.y = Cvt<T16>::pack2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dx16 + (long long)row * H + col) = u;
+      }
+    }
+  }
+  if (!do_ln || dgamma == nullptr) return;
+  // block reduction of the per-warp partial dgamma / dbeta, then one atomic per column per CTA
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(&red[warp][col]) = which == 0 ? ag[i] : ab[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NV * 128; c += 256) {
+      float sg = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sg += red[w][c];
+      atomicAdd((which == 0 ? dgamma : dbeta) + c, sg);
+    }
+    __syncthreads();
+  }
+}
+
+// Text-embedding backward: recompute x = word[id] + pos[p] + type[s], LayerNorm backward, scatter-add dx into the three
+// tables' gradients (fp32 atomics; rows of the same token collide).  dy rows are b*S + t of the [B,S,H] gradient.
+template <int NV>
+__global__ void __launch_bounds__(256) embed_bwd_kernel(
+    const long long* __restrict__ ids, const long long* __restrict__ seg, const long long* __restrict__ pos_ids,
+    const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
+    const float* __restrict__ gamma, float eps, const float* __restrict__ dy, int B, int T, int S, int H, int vocab,
+    int max_pos, int n_type, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= B * T) return;
+  const int b = row / T, t = row % T;
+  long long id = min(max(ids[row], 0ll), (long long)vocab - 1);
+  long long sg = seg ? min(max(seg[row], 0ll), (long long)n_type - 1) : 0;
+  long long ps = pos_ids ? min(max(pos_ids[row], 0ll), (long long)max_pos - 1) : t;
+  float4 xv[NV], dv[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
+    const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
+    xv[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
+    dv[i] = *reinterpret_cast<const float4*>(dy + ((long long)b * S + t) * H + col);
+    s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
+  float m1 = 0.f, m2 = 0.f;
+  float4 gv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
+    xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+    gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
+    m1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+    m2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    atomicAdd(dgamma + col + 0, dv[i].x * xv[i].x); atomicAdd(dgamma + col + 1, dv[i].y * xv[i].y);
+    atomicAdd(dgamma + col + 2, dv[i].z * xv[i].z); atomicAdd(dgamma + col + 3, dv[i].w * xv[i].w);
+    atomicAdd(dbeta + col + 0, dv[i].x); atomicAdd(dbeta + col + 1, dv[i].y);
+    atomicAdd(dbeta + col + 2, dv[i].z); atomicAdd(dbeta + col + 3, dv[i].w);
+  }
+  m1 = warp_sum(m1) / (float)H;
+  m2 = warp_sum(m2) / (float)H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float o[4] = {rstd * (gv[i].x - m1 - xv[i].x * m2), rstd * (gv[i].y - m1 - xv[i].y * m2),
+                        rstd * (gv[i].z - m1 - xv[i].z * m2), rstd * (gv[i].w - m1 - xv[i].w * m2)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (id != 0) atomicAdd(dword + id * H + col + e, o[e]);  // padding_idx = 0 receives no gradient (nn.Embedding)
+      atomicAdd(dpos + ps * H + col + e, o[e]);
+      atomicAdd(dtype + sg * H + col + e, o[e]);
+    }
+  }
+}
+
+// X16[i, :] = X32[rows[i], :]  (+ fp32 copy)
+template <typename T16>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, const long long* __restrict__ rows,
+                                                          int n, int H, T16* __restrict__ out16,
+                                                          float* __restrict__ out32) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const long long r = rows[i];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float v = X[r * H + c];
+    if (out16) out16[(long long)i * H + c] = Cvt<T16>::from(v);
+    if (out32) out32[(long long)i * H + c] = v;
+  }
+}
+// dX[rows[i], :] += d[i, :]
+__global__ void __launch_bounds__(256) scatter_rows_add_kernel(const float* __restrict__ d,
+                                                               const long long* __restrict__ rows, int n, int H,
+                                                               float* __restrict__ dX) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const long long r = rows[i];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) atomicAdd(dX + r * H + c, d[(long long)i * H + c]);
+}
+
+// Cross entropy over the vocabulary at the n labelled rows (CrossEntropyLoss(ignore_index=-1) averages over them,
+// modeling_rec.py:148-149).  One CTA per row.  lse[i] saved for the backward.
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int V,
+                                                     const long long* __restrict__ targets, float* __restrict__ lse,
+                                                     float* __restrict__ loss) {
+  __shared__ float sm[8];
+  const int i = blockIdx.x;
+  const float* row = logits + (long long)i * ld;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) mx = fmaxf(mx, row[v]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sm[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sm[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) s += expf(row[v] - mx);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    const float l = mx + logf(t);
+    lse[i] = l;
+    atomicAdd(loss, (l - row[targets[i]]) / (float)n);
+  }
+}
+// dlogits[i, v] = g * (softmax - onehot) / n   (16-bit, row pitch ld16, zero padded)
+template <typename T16>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, long long ld, int n, int V,
+                                                     const long long* __restrict__ targets,
+                                                     const float* __restrict__ lse, const float* __restrict__ g,
+                                                     T16* __restrict__ dlogits, long long ld16) {
+  const int i = blockIdx.x;
+  const float* row = logits + (long long)i * ld;
+  const float scale = g[0] / (float)n, l = lse[i];
+  const long long tgt = targets[i];
+  for (int v = threadIdx.x; v < ld16; v += 256) {
+    float d = 0.f;
+    if (v < V) d = scale * (expf(row[v] - l) - (v == tgt ? 1.f : 0.f));
+    dlogits[(long long)i * ld16 + v] = Cvt<T16>::from(d);
+  }
+}
+
+// out[i] (+)= a[i]   (fp32, strided rows: copies a padded [rows, ld_a] gradient into its [rows, cols] home)
+__global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ a, long long ld_a, int rows, int cols,
+                                                       float* __restrict__ out, long long ld_out) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    out[r * ld_out + c] += a[r * ld_a + c];
+  }
+}
+__global__ void __launch_bounds__(256) cast32to16_kernel(const float* __restrict__ in, long long n, __half* o16,
+                                                         __nv_bfloat16* ob16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (o16) o16[i] = __float2half_rn(in[i]);
+    if (ob16) ob16[i] = __float2bfloat16_rn(in[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Attention backward on CUDA cores, one CTA per (head, sample); P is recomputed from Q, K (never stored).
+//   phase A (thread = query i): m_i, l_i, D_i = sum_j p_ij (dO_i . v_j), dQ_i = sum_j dS_ij k_j / sqrt(dH)
+//   phase B (thread = key j)  : dK_j = sum_i dS_ij q_i / sqrt(dH), dV_j = sum_i p_ij dO_i
+// with dS_ij = p_ij (dO_i . v_j - D_i).  No atomics.  Few-shot tuning runs 4-16 rows per GPU; this kernel is not
+// meant for large batches.
+template <typename T16>
+__global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restrict__ qkv, const T16* __restrict__ dctx,
+                                                            const float* __restrict__ ext_mask, int S, int H,
+                                                            float scale, T16* __restrict__ dqkv) {
+  extern __shared__ uint8_t smem_raw[];
+  T16* sQ = reinterpret_cast<T16*>(smem_raw);
+  T16* sK = sQ + (size_t)S * kAttnDH;
+  T16* sV = sK + (size_t)S * kAttnDH;
+  T16* sdO = sV + (size_t)S * kAttnDH;
+  float* sM = reinterpret_cast<float*>(sdO + (size_t)S * kAttnDH);  // mask[S], m[S], l[S], D[S]
+  float* sMx = sM + S;
+  float* sL = sMx + S;
+  float* sD = sL + S;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const T16* base = qkv + (long long)b * S * 3 * H;
+  const T16* dob = dctx + (long long)b * S * H;
+  for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
+    const int j = i >> 3, c = (i & 7) * 8;
+    *reinterpret_cast<uint4*>(sQ + j * kAttnDH + c) = *reinterpret_cast<const uint4*>(base + (long long)j * 3 * H + h * kAttnDH + c);
+    *reinterpret_cast<uint4*>(sK + j * kAttnDH + c) = *reinterpret_cast<const uint4*>(base + (long long)j * 3 * H + H + h * kAttnDH + c);
+    *reinterpret_cast<uint4*>(sV + j * kAttnDH + c) = *reinterpret_cast<const uint4*>(base + (long long)j * 3 * H + 2 * H + h * kAttnDH + c);
+    *reinterpret_cast<uint4*>(sdO + j * kAttnDH + c) = *reinterpret_cast<const uint4*>(dob + (long long)j * H + h * kAttnDH + c);
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) sM[j] = ext_mask[(long long)b * S + j];
+  __syncthreads();
+  T16* dq_out = dqkv + (long long)b * S * 3 * H + h * kAttnDH;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    float q[kAttnDH], dO[kAttnDH];
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) {
+      q[d] = Cvt<T16>::to(sQ[i * kAttnDH + d]);
+      dO[d] = Cvt<T16>::to(sdO[i * kAttnDH + d]);
+    }
+    float mx = -INFINITY;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) s = fmaf(q[d], Cvt<T16>::to(sK[j * kAttnDH + d]), s);
+      mx = fmaxf(mx, fmaf(s, scale, sM[j]));
+    }
+    float l = 0.f, D = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) {
+        s = fmaf(q[d], Cvt<T16>::to(sK[j * kAttnDH + d]), s);
+        dp = fmaf(dO[d], Cvt<T16>::to(sV[j * kAttnDH + d]), dp);
+      }
+      const float e = expf(fmaf(s, scale, sM[j]) - mx);
+      l += e;
+      D += e * dp;
+    }
+    D /= l;
+    sMx[i] = mx; sL[i] = l; sD[i] = D;
+    float dq[kAttnDH];
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) dq[d] = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) {
+        s = fmaf(q[d], Cvt<T16>::to(sK[j * kAttnDH + d]), s);
+        dp = fmaf(dO[d], Cvt<T16>::to(sV[j * kAttnDH + d]), dp);
+      }
+      const float pij = expf(fmaf(s, scale, sM[j]) - mx) / l;
+      const float ds = pij * (dp - D) * scale;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) dq[d] = fmaf(ds, Cvt<T16>::to(sK[j * kAttnDH + d]), dq[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) dq_out[(long long)i * 3 * H + d] = Cvt<T16>::from(dq[d]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    float k[kAttnDH], v[kAttnDH], dk[kAttnDH], dv[kAttnDH];
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) {
+      k[d] = Cvt<T16>::to(sK[j * kAttnDH + d]);
+      v[d] = Cvt<T16>::to(sV[j * kAttnDH + d]);
+      dk[d] = 0.f;
+      dv[d] = 0.f;
+    }
+    const float mj = sM[j];
+    for (int i = 0; i < S; ++i) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) {
+        s = fmaf(Cvt<T16>::to(sQ[i * kAttnDH + d]), k[d], s);
+        dp = fmaf(Cvt<T16>::to(sdO[i * kAttnDH + d]), v[d], dp);
+      }
+      const float pij = expf(fmaf(s, scale, mj) - sMx[i]) / sL[i];
+      const float ds = pij * (dp - sD[i]) * scale;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) {
+        dk[d] = fmaf(ds, Cvt<T16>::to(sQ[i * kAttnDH + d]), dk[d]);
+        dv[d] = fmaf(pij, Cvt<T16>::to(sdO[i * kAttnDH + d]), dv[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) {
+      dq_out[(long long)j * 3 * H + H + d] = Cvt<T16>::from(dk[d]);
+      dq_out[(long long)j * 3 * H + 2 * H + d] = Cvt<T16>::from(dv[d]);
+    }
+  }
+}
+
+}  // namespace cptk

@@ -1,0 +1,424 @@
+// Host orchestration of the training step (included by cpt_b200.cu; see include/cpt_b200.h "training step").
+//
+// Forward = the inference kernel sequence, except that every tensor the backward needs lands in the tape instead of a
+// reused workspace buffer, and FFN-up keeps its pre-activation (GELU is a separate pass).  Backward walks the layers
+// in reverse.  Every matrix product is the tcgen05 GEMM of gemm_sm100.cuh in its out = A . W^T form:
+//   dgrad  dX[M,Kin]    = dY[M,Nout] . (W^T)[Kin,Nout]^T      W^T = transposed 16-bit weights kept by the handle
+//   wgrad  dW[Nout,Kin] = (dY^T)[Nout,Mp] . (X^T)[Kin,Mp]^T   both operands transposed into scratch (zero padded to
+//                                                              Mp = M rounded up to 64), fp32 result ADDED into the
+//                                                              caller's gradient tensor by the TMA reduce-add store
+// The residual branches are summed the same way (dgrad results reduce-added into the fp32 gradient stream).
+
+struct TapeLayer {
+  char *h16, *qkv16, *ctx16, *a16, *preup16, *inter16;
+  float *x1, *x2;
+};
+struct Tape {
+  float *ext_mask, *imgpre32, *h32, *a32, *seq32;
+  char* img16;
+  std::vector<TapeLayer> layers;
+  // head (n labelled rows)
+  char *hx16, *ht16;
+  float *htd32, *htg32, *logits, *lse;
+  long long ldl;
+  // backward scratch
+  float *dH, *dx32, *hd32a, *hd32b, *hdx32, *dimg32, *dwimg;
+  char *dx16, *dxT16, *big16, *big16b, *bigT16, *actT16, *dctx16;
+  char *dlog16, *dlogT16, *htT16, *hxT16, *hd16, *hdT16, *dimg16, *dimgT16, *imgT16;
+  int Mp, np, Mip, Vp;
+  size_t total;
+};
+
+static int round64(int x) { return (x + 63) & ~63; }
+
+static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* base) {
+  const cpt_config& c = h->cfg;
+  const size_t S = T + R, M = (size_t)B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers;
+  const size_t Mi = (size_t)B * R, V = c.vocab_size, W = std::max(I, 3 * H);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += al(bytes);
+    return p;
+  };
+  Tape t;
+  t.Mp = round64((int)M); t.np = round64(n); t.Mip = round64((int)Mi); t.Vp = (int)((V + 7) & ~size_t(7));
+  t.ldl = (long long)((V + 3) & ~size_t(3));
+  t.ext_mask = (float*)take(M * 4);
+  t.img16 = take(Mi * h->Fp * 2);
+  t.imgpre32 = (float*)take(Mi * H * 4);
+  t.h32 = (float*)take(M * H * 4);
+  t.a32 = (float*)take(M * H * 4);
+  t.seq32 = (float*)take(M * H * 4);
+  t.layers.resize(L);
+  for (auto& l : t.layers) {
+    l.h16 = take(M * H * 2);
+    l.qkv16 = take(M * 3 * H * 2);
+    l.ctx16 = take(M * H * 2);
+    l.a16 = take(M * H * 2);
+    l.preup16 = take(M * I * 2);
+    l.inter16 = take(M * I * 2);
+    l.x1 = (float*)take(M * H * 4);
+    l.x2 = (float*)take(M * H * 4);
+  }
+  t.hx16 = take((size_t)n * H * 2);
+  t.ht16 = take((size_t)n * H * 2);
+  t.htd32 = (float*)take((size_t)n * H * 4);
+  t.htg32 = (float*)take((size_t)n * H * 4);
+  t.logits = (float*)take((size_t)n * t.ldl * 4);
+  t.lse = (float*)take((size_t)n * 4);
+  // backward scratch
+  t.dH = (float*)take(M * H * 4);
+  t.dx32 = (float*)take(M * H * 4);
+  t.dx16 = take(M * H * 2);
+  t.dxT16 = take(H * t.Mp * 2);
+  t.big16 = take(M * W * 2);
+  t.big16b = take(M * W * 2);
+  t.bigT16 = take(W * t.Mp * 2);
+  t.actT16 = take(W * t.Mp * 2);
+  t.dctx16 = take(M * H * 2);
+  t.dlog16 = take((size_t)n * t.Vp * 2);
+  t.dlogT16 = take(V * t.np * 2);
+  t.htT16 = take(H * t.np * 2);
+  t.hxT16 = take(H * t.np * 2);
+  t.hd16 = take((size_t)n * H * 2);
+  t.hdT16 = take(H * t.np * 2);
+  t.hd32a = (float*)take((size_t)n * H * 4);
+  t.hd32b = (float*)take((size_t)n * H * 4);
+  t.hdx32 = (float*)take((size_t)n * H * 4);
+  t.dimg32 = (float*)take(Mi * H * 4);
+  t.dimg16 = take(Mi * H * 2);
+  t.dimgT16 = take(H * t.Mip * 2);
+  t.imgT16 = take((size_t)h->Fp * t.Mip * 2);
+  t.dwimg = (float*)take(H * (size_t)h->Fp * 4);
+  t.total = off + 256;
+  return t;
+}
+
+static int ew_grid(const cpt_handle* h, long long n) {
+  const long long g = (n + 255) / 256;
+  return (int)std::max<long long>(1, std::min<long long>(g, 8ll * h->num_sms));
+}
+
+template <typename T>
+static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, long long ld, float* out) {
+  if (M <= 0 || !out) return 0;
+  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  const int gy = std::max(1, std::min((M + 63) / 64, 4 * h->num_sms / std::max(1, (N + 255) / 256)));
+  colsum_kernel<T><<<dim3((N + 255) / 256, gy), 256, 0, st>>>(in, M, N, ld, out);
+  CKL("colsum_kernel");
+  return 0;
+}
+
+template <typename T16>
+static int transpose_t(cpt_handle* h, cudaStream_t st, const void* in, int R, int C, long long ld_in, void* out,
+                       long long ld_out) {
+  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  return transpose16<T16>(st, in, R, C, ld_in, out, ld_out);
+}
+
+template <typename T16>
+static int ln_bwd(cpt_handle* h, cudaStream_t st, const float* dy, const float* x, int M, int H, const float* gamma,
+                  float eps, bool do_ln, float* dx32, void* dx16, float* dgamma, float* dbeta, int rin = 0,
+                  int rout = 0, int roff = 0) {
+  if (M <= 0) return 0;
+  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  const int grid = std::min((M + 7) / 8, 2 * h->num_sms);
+#define CPT_LNB_CASE(NV_)                                                                                         \
+  case NV_:                                                                                                       \
+    ln_bwd_kernel<T16, NV_><<<grid, 256, 0, st>>>(dy, x, M, H, gamma, eps, do_ln ? 1 : 0, dx32,                   \
+                                                  reinterpret_cast<T16*>(dx16), dgamma, dbeta, rin, rout, roff);  \
+    break;
+  switch (H / 128) {
+    CPT_LNB_CASE(1) CPT_LNB_CASE(2) CPT_LNB_CASE(3) CPT_LNB_CASE(4) CPT_LNB_CASE(5) CPT_LNB_CASE(6) CPT_LNB_CASE(7)
+    CPT_LNB_CASE(8)
+    default: return fail("layernorm backward: unsupported hidden size %d", H);
+  }
+#undef CPT_LNB_CASE
+  CKL("ln_bwd_kernel");
+  return 0;
+}
+
+// out(+)= A[M,K] . W[N,K]^T, no bias.  accumulate -> fp32 reduce-add into `out`.
+template <typename T16>
+static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W,
+                      long long ldw, int M, int N, int K, void* out, long long ldo, bool out_fp32, bool accumulate) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = nullptr;
+  p.tma_reduce = accumulate ? 1 : 0;
+  return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
+}
+
+template <typename T16>
+static int train_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids, const int64_t* seg,
+                              const int64_t* mask, const int64_t* pos_ids, const float* img, int B, int T, int R,
+                              const int64_t* rows, const int64_t* targets, int n, void* tape_ptr, size_t tape_bytes,
+                              float* loss) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
+  if (!h->train) return fail("cpt_train_forward_mlm: call cpt_train_enable(h, 1) before cpt_set_weights");
+  if (!h->has_weights || !h->has_mlm) return fail("cpt_train_forward_mlm needs weights including the cls.* head");
+  if (B <= 0 || T <= 0 || R < 0 || n <= 0) return fail("bad shape B=%d T=%d R=%d n_rows=%d", B, T, R, n);
+  if (T > c.max_position_embeddings) return fail("T=%d exceeds max_position_embeddings=%d", T, c.max_position_embeddings);
+  if (R > 0 && (!img || !h->w_img)) return fail("img_feats given but no img_embedding weights (or NULL img_feats)");
+  if (S > 256) return fail("sequence length T+R=%d exceeds the 256 this build's attention kernel supports", S);
+  if (!h->tma_store || !h->reduce_resid) return fail("the training path needs the TMA reduce-add stores (unset CPT_B200_TMA_STORE / CPT_B200_REDUCE_RESID)");
+  if (!ids || !rows || !targets || !loss) return fail("input_ids, rows, targets and loss must be non-NULL");
+  Tape t = carve_tape(h, B, T, R, n, (char*)(((uintptr_t)tape_ptr + 255) & ~uintptr_t(255)));
+  if (!tape_ptr || tape_bytes < t.total) return fail("tape too small: need %zu bytes, got %zu", t.total, tape_bytes);
+  const size_t act = (size_t)M * H * 4;
+
+  if (mask) {
+    ProfScope ps(h, st, CPT_K_EXTMASK);
+    CK(launch_k(ext_mask_kernel, dim3((M + 255) / 256), dim3(256), 0, st, 1, (const long long*)mask, M, t.ext_mask));
+  } else {
+    CK(cudaMemsetAsync(t.ext_mask, 0, (size_t)M * 4, st));
+  }
+  char* h16_0 = L > 0 ? t.layers[0].h16 : t.dx16;
+  {
+    ProfScope ps(h, st, CPT_K_EMBED);
+#define CPT_EMB_CASE(NV_)                                                                                            \
+  case NV_:                                                                                                          \
+    CK(launch_k(embed_text_ln_kernel<T16, NV_>, dim3((B * T + 7) / 8), dim3(256), 0, st, 1, (const long long*)ids,    \
+                (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, (const float*)h->emb_g,  \
+                (const float*)h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings,       \
+                c.type_vocab_size, t.h32, reinterpret_cast<T16*>(h16_0), h->err_flag));                              \
+    break;
+    switch (H / 128) {
+      CPT_EMB_CASE(1) CPT_EMB_CASE(2) CPT_EMB_CASE(3) CPT_EMB_CASE(4) CPT_EMB_CASE(5) CPT_EMB_CASE(6) CPT_EMB_CASE(7)
+      CPT_EMB_CASE(8)
+      default: return fail("unsupported hidden size %d", H);
+    }
+#undef CPT_EMB_CASE
+  }
+  if (R > 0) {
+    const int F = c.img_feature_dim, Mi = B * R;
+    const int grid = (Mi + 7) / 8 < 8 * h->num_sms ? (Mi + 7) / 8 : 8 * h->num_sms;
+    {
+      ProfScope ps(h, st, CPT_K_CAST);
+      CK(launch_k(cast_pad_kernel<T16>, dim3(grid), dim3(256), 0, st, 1, img, Mi, F, h->Fp,
+                  reinterpret_cast<T16*>(t.img16)));
+    }
+    GemmParams p{};
+    p.M = Mi; p.N = H; p.K = F; p.out = t.imgpre32; p.ldo = H; p.bias = h->b_img;
+    TRY(gemm<T16>(h, st, CPT_K_GEMM_IMG, t.img16, h->Fp, h->w_img, h->Fp, p, EPI_BIAS, true));
+    TRY(layernorm<T16>(h, st, t.imgpre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps,
+                       c.use_img_layernorm != 0, t.h32, h16_0, R, S, T));
+  }
+  for (int l = 0; l < L; ++l) {
+    const LayerDev& d = h->layers[l];
+    TapeLayer& tl = t.layers[l];
+    {
+      GemmParams p{};
+      p.M = M; p.N = 3 * H; p.K = H; p.out = tl.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, tl.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
+    }
+    TRY(attention<T16>(h, st, tl.qkv16, t.ext_mask, B, S, tl.ctx16, h->attn_impl));
+    {
+      CK(cudaMemcpyAsync(tl.x1, t.h32, act, cudaMemcpyDeviceToDevice, st));
+      GemmParams p{};
+      p.M = M; p.N = H; p.K = H; p.out = tl.x1; p.ldo = H; p.bias = d.b_ao; p.tma_reduce = 1;
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, tl.ctx16, H, d.w_ao, H, p, EPI_BIAS, true));
+      TRY(layernorm<T16>(h, st, tl.x1, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, t.a32, tl.a16));
+    }
+    {
+      GemmParams p{};
+      p.M = M; p.N = I; p.K = H; p.out = tl.preup16; p.ldo = I; p.bias = d.b_i;
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, tl.a16, H, d.w_i, H, p, EPI_BIAS, false));
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      const long long ne = (long long)M * I;
+      gelu_fwd_kernel<T16><<<ew_grid(h, ne), 256, 0, st>>>(reinterpret_cast<const T16*>(tl.preup16), ne,
+                                                          reinterpret_cast<T16*>(tl.inter16));
+      CKL("gelu_fwd_kernel");
+    }
+    {
+      CK(cudaMemcpyAsync(tl.x2, t.a32, act, cudaMemcpyDeviceToDevice, st));
+      GemmParams p{};
+      p.M = M; p.N = H; p.K = I; p.out = tl.x2; p.ldo = H; p.bias = d.b_o; p.tma_reduce = 1;
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, tl.inter16, I, d.w_o, I, p, EPI_BIAS, true));
+      TRY(layernorm<T16>(h, st, tl.x2, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, (l == L - 1) ? t.seq32 : t.h32,
+                         (l == L - 1) ? nullptr : t.layers[l + 1].h16));
+    }
+  }
+  if (L == 0) CK(cudaMemcpyAsync(t.seq32, t.h32, act, cudaMemcpyDeviceToDevice, st));
+  // head at the labelled rows: cls.predictions.transform (dense, GELU, LayerNorm) and the tied decoder
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    gather_rows_kernel<T16><<<n, 256, 0, st>>>(t.seq32, (const long long*)rows, n, H, reinterpret_cast<T16*>(t.hx16),
+                                               (float*)nullptr);
+    CKL("gather_rows_kernel");
+  }
+  {
+    GemmParams p{};
+    p.M = n; p.N = H; p.K = H; p.out = t.htd32; p.ldo = H; p.bias = h->mlm_b;
+    TRY(gemm<T16>(h, st, CPT_K_GEMM_HEAD, t.hx16, H, h->mlm_w16, H, p, EPI_BIAS, true));
+    {
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      gelu_fwd32_kernel<<<ew_grid(h, (long long)n * H), 256, 0, st>>>(t.htd32, (long long)n * H, t.htg32);
+      CKL("gelu_fwd32_kernel");
+    }
+    TRY(layernorm<T16>(h, st, t.htg32, H, n, H, h->mlm_g, h->mlm_beta, c.layer_norm_eps, true, nullptr, t.ht16));
+    GemmParams q{};
+    q.M = n; q.N = V; q.K = H; q.out = t.logits; q.ldo = t.ldl; q.bias = h->mlm_bias;
+    TRY(gemm<T16>(h, st, CPT_K_GEMM_HEAD, t.ht16, H, h->word16, H, q, EPI_BIAS, true));
+  }
+  CK(cudaMemsetAsync(loss, 0, 4, st));
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    ce_fwd_kernel<<<n, 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, loss);
+    CKL("ce_fwd_kernel");
+  }
+  return 0;
+}
+
+template <typename T16>
+static int train_backward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids, const int64_t* seg,
+                               const int64_t* pos_ids, int B, int T, int R, const int64_t* rows,
+                               const int64_t* targets, int n, const float* grad_loss, void* tape_ptr,
+                               size_t tape_bytes, const cpt_grads* g) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
+  if (!h->train || !h->has_weights || !h->has_mlm) return fail("cpt_train_backward_mlm: handle is not set up for training");
+  if (B <= 0 || T <= 0 || R < 0 || n <= 0 || S > 256) return fail("bad shape B=%d T=%d R=%d n_rows=%d", B, T, R, n);
+  if (!g || !g->word_emb || !g->pos_emb || !g->type_emb || !g->emb_ln_g || !g->emb_ln_b || !g->mlm_dense_w ||
+      !g->mlm_dense_b || !g->mlm_ln_g || !g->mlm_ln_b || !g->mlm_bias || (L > 0 && !g->layers))
+    return fail("cpt_train_backward_mlm: NULL gradient tensor");
+  if (R > 0 && (!g->img_w || !g->img_b || (c.use_img_layernorm && (!g->img_ln_g || !g->img_ln_b))))
+    return fail("cpt_train_backward_mlm: NULL img_* gradient tensor");
+  if (!ids || !rows || !targets || !grad_loss) return fail("NULL argument");
+  Tape t = carve_tape(h, B, T, R, n, (char*)(((uintptr_t)tape_ptr + 255) & ~uintptr_t(255)));
+  if (!tape_ptr || tape_bytes < t.total) return fail("tape too small: need %zu bytes, got %zu", t.total, tape_bytes);
+  const int Mp = t.Mp, np = t.np, Vp = t.Vp;
+  const int DG = CPT_K_GEMM_DGRAD, WG = CPT_K_GEMM_WGRAD;
+
+  // ---- head
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    ce_bwd_kernel<T16><<<n, 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, grad_loss,
+                                          reinterpret_cast<T16*>(t.dlog16), Vp);
+    CKL("ce_bwd_kernel");
+  }
+  TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dlog16), n, V, Vp, g->mlm_bias));
+  TRY(transpose_t<T16>(h, st, t.dlog16, n, V, Vp, t.dlogT16, np));
+  TRY(transpose_t<T16>(h, st, t.ht16, n, H, H, t.htT16, np));
+  TRY(gemm_plain<T16>(h, st, WG, t.dlogT16, np, t.htT16, np, V, H, np, g->word_emb, H, true, true));
+  TRY(gemm_plain<T16>(h, st, DG, t.dlog16, Vp, h->word16_t, Vp, n, H, Vp, t.hd32a, H, true, false));
+  TRY(ln_bwd<T16>(h, st, t.hd32a, t.htg32, n, H, h->mlm_g, c.layer_norm_eps, true, t.hd32b, nullptr, g->mlm_ln_g,
+                  g->mlm_ln_b));
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    const long long ne = (long long)n * H;
+    gelu_bwd32_kernel<<<ew_grid(h, ne), 256, 0, st>>>(t.hd32b, t.htd32, ne, t.hd32a);
+    CKL("gelu_bwd32_kernel");
+  }
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    const long long ne = (long long)n * H;
+    cast32to16_kernel<<<ew_grid(h, ne), 256, 0, st>>>(
+        t.hd32a, ne, c.dtype == 0 ? reinterpret_cast<__half*>(t.hd16) : nullptr,
+        c.dtype == 0 ? nullptr : reinterpret_cast<__nv_bfloat16*>(t.hd16));
+    CKL("cast32to16_kernel");
+  }
+  TRY(colsum<float>(h, st, t.hd32a, n, H, H, g->mlm_dense_b));
+  TRY(transpose_t<T16>(h, st, t.hd16, n, H, H, t.hdT16, np));
+  TRY(transpose_t<T16>(h, st, t.hx16, n, H, H, t.hxT16, np));
+  TRY(gemm_plain<T16>(h, st, WG, t.hdT16, np, t.hxT16, np, H, H, np, g->mlm_dense_w, H, true, true));
+  TRY(gemm_plain<T16>(h, st, DG, t.hd16, H, h->mlm_w16_t, H, n, H, H, t.hdx32, H, true, false));
+  CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    scatter_rows_add_kernel<<<n, 256, 0, st>>>(t.hdx32, (const long long*)rows, n, H, t.dH);
+    CKL("scatter_rows_add_kernel");
+  }
+
+  // ---- encoder layers, last to first.  t.dH = gradient of the layer's output
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerDev& d = h->layers[l];
+    const TapeLayer& tl = t.layers[l];
+    const cpt_layer_grads& gl = g->layers[l];
+    // output.LayerNorm
+    TRY(ln_bwd<T16>(h, st, t.dH, tl.x2, M, H, d.o_g, c.layer_norm_eps, true, t.dx32, t.dx16, gl.o_ln_g, gl.o_ln_b));
+    // output.dense: x2 = a + inter W2^T + b2
+    TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
+    TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
+    TRY(transpose_t<T16>(h, st, tl.inter16, M, I, I, t.actT16, Mp));
+    TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, I, Mp, gl.o_w, I, true, true));
+    TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_o_t, H, M, I, H, t.big16, I, false, false));
+    {  // GELU
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      const long long ne = (long long)M * I;
+      gelu_bwd_kernel<T16><<<ew_grid(h, ne), 256, 0, st>>>(reinterpret_cast<const T16*>(t.big16),
+                                                          reinterpret_cast<const T16*>(tl.preup16), ne,
+                                                          reinterpret_cast<T16*>(t.big16b));
+      CKL("gelu_bwd_kernel");
+    }
+    // intermediate.dense
+    TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16b), M, I, I, gl.i_b));
+    TRY(transpose_t<T16>(h, st, t.big16b, M, I, I, t.bigT16, Mp));
+    TRY(transpose_t<T16>(h, st, tl.a16, M, H, H, t.actT16, Mp));
+    TRY(gemm_plain<T16>(h, st, WG, t.bigT16, Mp, t.actT16, Mp, I, H, Mp, gl.i_w, H, true, true));
+    TRY(gemm_plain<T16>(h, st, DG, t.big16b, I, d.w_i_t, I, M, H, I, t.dx32, H, true, true));  // += residual branch
+    // attention.output.LayerNorm  (dx1 -> t.dH)
+    TRY(ln_bwd<T16>(h, st, t.dx32, tl.x1, M, H, d.ao_g, c.layer_norm_eps, true, t.dH, t.dx16, gl.ao_ln_g,
+                    gl.ao_ln_b));
+    // attention.output.dense
+    TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
+    TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
+    TRY(transpose_t<T16>(h, st, tl.ctx16, M, H, H, t.actT16, Mp));
+    TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, H, Mp, gl.ao_w, H, true, true));
+    TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_ao_t, H, M, H, H, t.dctx16, H, false, false));
+    {  // attention
+      ProfScope ps(h, st, CPT_K_ATTN_BWD);
+      auto* fn = attn_bwd_simt_kernel<T16>;
+      const size_t smem = (size_t)S * kAttnDH * 2 * 4 + (size_t)S * 4 * 4;
+      TRY(set_smem_attr(fn, smem));
+      fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16),
+                                                            reinterpret_cast<const T16*>(t.dctx16), t.ext_mask, S, H,
+                                                            0.125f, reinterpret_cast<T16*>(t.big16));
+      CKL("attn_bwd_simt_kernel");
+    }
+    // query / key / value
+    float* qkv_b[3] = {gl.q_b, gl.k_b, gl.v_b};
+    float* qkv_w[3] = {gl.q_w, gl.k_w, gl.v_w};
+    TRY(transpose_t<T16>(h, st, t.big16, M, 3 * H, 3 * H, t.bigT16, Mp));
+    TRY(transpose_t<T16>(h, st, tl.h16, M, H, H, t.actT16, Mp));
+    for (int j = 0; j < 3; ++j) {
+      TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16) + j * H, M, H, 3 * H, qkv_b[j]));
+      TRY(gemm_plain<T16>(h, st, WG, t.bigT16 + (size_t)j * H * Mp * 2, Mp, t.actT16, Mp, H, H, Mp, qkv_w[j], H, true,
+                          true));
+    }
+    TRY(gemm_plain<T16>(h, st, DG, t.big16, 3 * H, d.w_qkv_t, 3 * H, M, H, 3 * H, t.dH, H, true, true));  // += residual
+  }
+
+  // ---- embeddings
+  {
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+#define CPT_EMBB_CASE(NV_)                                                                                           \
+  case NV_:                                                                                                          \
+    embed_bwd_kernel<NV_><<<(B * T + 7) / 8, 256, 0, st>>>(                                                          \
+        (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g, \
+        c.layer_norm_eps, t.dH, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, g->word_emb, \
+        g->pos_emb, g->type_emb, g->emb_ln_g, g->emb_ln_b);                                                          \
+    break;
+    switch (H / 128) {
+      CPT_EMBB_CASE(1) CPT_EMBB_CASE(2) CPT_EMBB_CASE(3) CPT_EMBB_CASE(4) CPT_EMBB_CASE(5) CPT_EMBB_CASE(6)
+      CPT_EMBB_CASE(7) CPT_EMBB_CASE(8)
+      default: return fail("unsupported hidden size %d", H);
+    }
+#undef CPT_EMBB_CASE
+    CKL("embed_bwd_kernel");
+  }
+  if (R > 0) {
+    const int F = c.img_feature_dim, Mi = B * R, Mip = t.Mip;
+    TRY(ln_bwd<T16>(h, st, t.dH, t.imgpre32, Mi, H, h->img_g, c.img_layer_norm_eps, c.use_img_layernorm != 0,
+                    t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, R, S, T));
+    TRY(colsum<float>(h, st, t.dimg32, Mi, H, H, g->img_b));
+    TRY(transpose_t<T16>(h, st, t.dimg16, Mi, H, H, t.dimgT16, Mip));
+    TRY(transpose_t<T16>(h, st, t.img16, Mi, h->Fp, h->Fp, t.imgT16, Mip));
+    TRY(gemm_plain<T16>(h, st, WG, t.dimgT16, Mip, t.imgT16, Mip, H, h->Fp, Mip, t.dwimg, h->Fp, true, false));
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    add_rows_kernel<<<ew_grid(h, (long long)H * F), 256, 0, st>>>(t.dwimg, h->Fp, H, F, g->img_w, F);
+    CKL("add_rows_kernel");
+  }
+  return 0;
+}

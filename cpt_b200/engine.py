@@ -64,7 +64,7 @@ class Engine(object):
     """One handle on one device.  `load_state_dict` takes tensors keyed like BertImgForPreTraining's
     state_dict; fp32, on `device`."""
 
-    def __init__(self, cfg, device, dtype="fp16"):
+    def __init__(self, cfg, device, dtype="fp16", train=False):
         self.lib = _lib.load()
         device = torch.device(device)
         if device.type != "cuda":
@@ -86,6 +86,10 @@ class Engine(object):
         _lib.check(self.lib.cpt_create(C.byref(c), device.index, C.byref(h)))
         self._h = h
         self._ws = None
+        self.train = bool(train)
+        self.weights_version = 0  # bumped by load_state_dict; a training tape is only valid for the version it saw
+        if train:
+            _lib.check(self.lib.cpt_train_enable(h, 1))
         self._keep = None  # tensors the handle references in place (embedding tables)
         # CUDA-graph cache of the fused encoder+head call (one graph per distinct set of input buffers): the 91
         # launches of a forward cost ~1.8 ms of host time enqueued one by one, 3 us replayed
@@ -136,6 +140,7 @@ class Engine(object):
         self._seen.clear()
         with torch.cuda.device(dev):
             _lib.check(self.lib.cpt_set_weights(self._h, C.byref(w), _stream()))
+        self.weights_version += 1
         # only the embedding tables are referenced in place by the handle; keep them alive
         self._keep = [sd[GLOBAL_KEYS[k]] for k in ("word_emb", "pos_emb", "type_emb")]
 
@@ -176,6 +181,84 @@ class Engine(object):
                                                     _ptr(img), B, T, R, _ptr(ws), ws.numel(), _ptr(seq),
                                                     _ptr(pooled), _ptr(hidden)))
         return seq, pooled, hidden
+
+    # ------------------------------------------------------------------ training step (MLM loss)
+    def _train_inputs(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats):
+        dev, i64 = self.device, torch.int64
+        if input_ids.dim() != 2:
+            raise CptError("cpt_b200: input_ids must be [B,T]")
+        B, T = input_ids.shape
+        R = 0 if img_feats is None else img_feats.shape[1]
+        ids = _chk_tensor("input_ids", input_ids, i64, dev)
+        seg = None if token_type_ids is None else _chk_tensor("token_type_ids", token_type_ids, i64, dev, (B, T))
+        msk = None if attention_mask is None else _chk_tensor("attention_mask", attention_mask, i64, dev, (B, T + R))
+        pos = None
+        if position_ids is not None:
+            pos = _chk_tensor("position_ids", position_ids.expand(B, T) if position_ids.dim() == 2 else position_ids,
+                              i64, dev, (B, T))
+        img = None
+        if img_feats is not None:
+            img = _chk_tensor("img_feats", img_feats, torch.float32, dev, (B, R, self.cfg.img_feature_dim))
+        return B, T, R, ids, seg, msk, pos, img
+
+    def train_forward_mlm(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets):
+        """loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled positions
+        `rows` (flat b*S+s indices) with labels `targets`.  Returns (loss, saved) — `saved` feeds
+        train_backward_mlm."""
+        if not self.train:
+            raise CptError("cpt_b200: this engine was not created with train=True")
+        B, T, R, ids, seg, msk, pos, img = self._train_inputs(input_ids, token_type_ids, attention_mask,
+                                                               position_ids, img_feats)
+        dev = self.device
+        rows = _chk_tensor("rows", rows, torch.int64, dev)
+        targets = _chk_tensor("targets", targets, torch.int64, dev, tuple(rows.shape))
+        n = int(rows.numel())
+        with torch.cuda.device(dev):
+            nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
+            tape = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            _lib.check(self.lib.cpt_train_forward_mlm(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos),
+                                                      _ptr(img), B, T, R, _ptr(rows), _ptr(targets), n, _ptr(tape),
+                                                      tape.numel(), _ptr(loss)))
+        saved = dict(B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
+                     version=self.weights_version)
+        return loss, saved
+
+    def train_backward_mlm(self, saved, grad_loss, grads):
+        """Adds d(grad_loss * loss)/d(param) into `grads` (dict keyed like the state_dict, fp32 tensors shaped
+        like the parameters)."""
+        if saved["version"] != self.weights_version:
+            raise CptError("cpt_b200: weights were reloaded between the training forward and its backward")
+        dev = self.device
+        keep = []
+
+        def gp(key, optional=False):
+            t = grads.get(key)
+            if t is None:
+                if optional:
+                    return C.c_void_p(0)
+                raise CptError("cpt_b200: gradient buffer for '%s' is missing" % key)
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                raise CptError("cpt_b200: gradient buffer '%s' must be contiguous float32 on %s" % (key, dev))
+            keep.append(t)
+            return _ptr(t)
+
+        g = _lib.Grads()
+        for f in _lib.GRAD_GLOBAL_FIELDS:
+            setattr(g, f, gp(GLOBAL_KEYS[f], f.startswith("img_")))
+        L = self.cfg.num_hidden_layers
+        layers = (_lib.LayerGrads * max(L, 1))()
+        for i in range(L):
+            for f, key in layer_keys(i).items():
+                setattr(layers[i], f, gp(key))
+        g.layers = C.cast(layers, C.POINTER(_lib.LayerGrads))
+        gl = _chk_tensor("grad_loss", grad_loss.reshape(()), torch.float32, dev)
+        s = saved
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.cpt_train_backward_mlm(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]),
+                                                       _ptr(s["pos"]), s["B"], s["T"], s["R"], _ptr(s["rows"]),
+                                                       _ptr(s["targets"]), s["n"], _ptr(gl), _ptr(s["tape"]),
+                                                       s["tape"].numel(), C.byref(g)))
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

@@ -134,6 +134,7 @@ class _EngineSlot(object):
 
     def __init__(self):
         self.engine, self.sig, self.heads, self.frozen = None, None, {}, False
+        self.train_engine, self.train_sig = None, None
 
     def __deepcopy__(self, memo):
         return _EngineSlot()
@@ -277,10 +278,37 @@ class BertImgModel(BertPreTrainedModel):
             slot.sig = sig
         return slot.engine
 
+    def train_engine(self):
+        """The handle of the training step: 16-bit GEMM copies in bf16 by default (gradients span more binades than
+        fp16 holds without loss scaling; config.cpt_b200_train_dtype / CPT_B200_TRAIN_DTYPE override), transposed
+        copies for the dgrad GEMMs, refreshed in place from the fp32 parameters whenever one of them changed."""
+        slot = self._slot
+        sd = self._named_tensors()
+        dev = self.embeddings.word_embeddings.weight.device
+        if dev.type != "cuda":
+            raise CptError("cpt_b200: the model is on '%s'; this implementation runs on a CUDA sm_100a device only "
+                           "(no CPU path) — call model.to('cuda') first" % dev)
+        sig = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
+        if slot.train_engine is None or slot.train_engine.device != dev:
+            if slot.train_engine is not None:
+                slot.train_engine.close()
+            dtype = (getattr(self.config, "cpt_b200_train_dtype", None)
+                     or os.environ.get("CPT_B200_TRAIN_DTYPE", "bf16"))
+            slot.train_engine = Engine(self.config, dev, dtype=dtype, train=True)
+            slot.train_sig = None
+        if sig != slot.train_sig:
+            slot.train_engine.load_state_dict(sd)
+            slot.train_sig = sig
+        return slot.train_engine, sd
+
+    def _dropout_active(self):
+        return self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0)
+
     def _check_mode(self):
-        if self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
-            raise NotImplementedError("cpt_b200: forward in training mode with active dropout is not built yet "
-                                      "(inference path only this round) — call model.eval()")
+        if self._dropout_active():
+            raise NotImplementedError("cpt_b200: forward in training mode with active dropout is not built yet — "
+                                      "set hidden_dropout_prob = attention_probs_dropout_prob = 0 or call "
+                                      "model.eval()")
 
     # -- forward ------------------------------------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,
@@ -294,8 +322,6 @@ class BertImgModel(BertPreTrainedModel):
         if attention_mask is not None and attention_mask.dim() != 2:
             raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
         self._check_mode()
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("cpt_b200: backward is not built yet (inference path only this round)")
         if attention_mask is not None and attention_mask.dtype != torch.int64:
             attention_mask = attention_mask.to(torch.int64)
         return self.engine().cpt_logits(input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
@@ -315,8 +341,6 @@ class BertImgModel(BertPreTrainedModel):
             # the reference accepts 3-D masks (captioning) and raises NotImplementedError for anything else
             raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
         self._check_mode()
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("cpt_b200: backward is not built yet (inference path only this round)")
         eng = self.engine()
         if attention_mask is not None and attention_mask.dtype != torch.int64:
             attention_mask = attention_mask.to(torch.int64)

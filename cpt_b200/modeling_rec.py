@@ -10,6 +10,7 @@ arguments expose what every CPT caller does right after the call
 
 so the [B,S,V] score tensor (937 MB at B=64) is never formed.  Without them the full tensor is returned.
 """
+import torch
 from torch import nn
 
 from .modeling_bert import BertImgModel, BertLMPredictionHead, BertPreTrainedModel
@@ -38,6 +39,9 @@ class REC_MLM_CPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
         self.bert.register_head_tensors(self.cls.head_tensors())
+        if masked_lm_labels is not None and torch.is_grad_enabled() and self._any_requires_grad():
+            return self._train_step(input_ids, token_type_ids, attention_mask, masked_lm_labels, position_ids,
+                                    head_mask, img_feats, mask_pos)
         if (mask_pos is not None and masked_lm_labels is None and head_mask is None
                 and not getattr(self.config, "output_hidden_states", False)):
             # the CPT inference call: one fused (and CUDA-graph-cached) encoder + gathered-head launch sequence
@@ -58,3 +62,27 @@ class REC_MLM_CPT(BertPreTrainedModel):
                                                ignore_index=-1)
             out = (loss,) + out
         return out
+
+    # -- training step (fewshot/refcoco_cpt.py:243-248, gqa_cpt.py:437-462) --------------------------------------
+    def _any_requires_grad(self):
+        return any(p.requires_grad for p in self.parameters())
+
+    def _train_step(self, input_ids, token_type_ids, attention_mask, masked_lm_labels, position_ids, head_mask,
+                    img_feats, mask_pos):
+        """(loss, None): the loss is differentiable with respect to every parameter (native forward + backward,
+        cpt_b200/training.py).  The reference also returns the [B,S,V] prediction_scores next to the loss; no
+        caller reads them on this path (`loss, output = model(...)`), so they are not materialised."""
+        from .training import mlm_loss
+        if head_mask is not None or mask_pos is not None:
+            raise NotImplementedError("cpt_b200: head_mask / mask_pos are not supported together with masked_lm_labels")
+        if getattr(self.config, "output_hidden_states", False) or getattr(self.config, "output_attentions", False):
+            raise NotImplementedError("cpt_b200: output_hidden_states / output_attentions in the training step")
+        if attention_mask is not None and attention_mask.dim() != 2:
+            raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
+        self.bert._check_mode()
+        if attention_mask is not None and attention_mask.dtype != torch.int64:
+            attention_mask = attention_mask.to(torch.int64)
+        eng, named = self.bert.train_engine()
+        loss, _ = mlm_loss(eng, named, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
+                           masked_lm_labels)
+        return (loss, None)

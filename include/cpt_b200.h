@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CPT_B200_ABI_VERSION 1
+#define CPT_B200_ABI_VERSION 2
 
 typedef struct cpt_handle cpt_handle;
 
@@ -97,6 +97,49 @@ size_t cpt_mlm_scores_workspace_bytes(const cpt_handle *h, long long rows);
 /* NSPCPT head: cls.seq_relationship(pooled) — Oscar/oscar/modeling/modeling_vcr.py:120-121.  out fp32 [B,C]. */
 int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, float *out);
 
+/* ---- training step ------------------------------------------------------------------
+ * loss = CrossEntropyLoss(ignore_index=-1)(cls(bert(...)).view(-1, V), masked_lm_labels.view(-1)) and its gradient
+ * with respect to every parameter — REC_MLM_CPT.forward with masked_lm_labels, modeling_rec.py:137-150, as the
+ * few-shot loops call it (Oscar/oscar/fewshot/refcoco_cpt.py:231-250, gqa_cpt.py:428-462: forward, loss.backward(),
+ * optimizer.step()).  Dropout is not applied (the handle computes the p = 0 function; the Python module refuses
+ * .train() with p > 0 until the masks are implemented).
+ *
+ * cpt_train_enable(h, 1) before cpt_set_weights: the handle also keeps transposed 16-bit weights (the W operand of
+ * the dgrad GEMMs) and later cpt_set_weights calls refresh the existing buffers in stream order instead of
+ * reallocating (call it after every optimizer step). */
+int cpt_train_enable(cpt_handle *h, int on);
+
+/* Gradient buffers, fp32, same shapes as the cpt_weights tensors of the same name.  The backward ADDS into them
+ * (zero them, or keep accumulating over micro-batches as `gradient_accumulation_steps` does).  All non-NULL except
+ * the img_* group when the batch has no regions. */
+typedef struct {
+  float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *ao_w, *ao_b, *ao_ln_g, *ao_ln_b, *i_w, *i_b, *o_w, *o_b, *o_ln_g,
+      *o_ln_b;
+} cpt_layer_grads;
+typedef struct {
+  float *word_emb, *pos_emb, *type_emb, *emb_ln_g, *emb_ln_b;
+  float *img_w, *img_b, *img_ln_g, *img_ln_b;
+  float *mlm_dense_w, *mlm_dense_b, *mlm_ln_g, *mlm_ln_b, *mlm_bias;
+  const cpt_layer_grads *layers; /* host array [num_hidden_layers] */
+} cpt_grads;
+
+/* Bytes of the tape: activations the forward saves for the backward plus the backward's scratch.  n_rows = number
+ * of labelled positions (masked_lm_labels != -1) in the batch. */
+size_t cpt_train_tape_bytes(const cpt_handle *h, int B, int T, int R, int n_rows);
+
+/* Forward with a tape.  rows int64 [n_rows]: flat indices b*(T+R)+s of the labelled positions, ascending;
+ * targets int64 [n_rows]: their labels.  loss: fp32 scalar (device).  Inputs as cpt_encoder_forward. */
+int cpt_train_forward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
+                          const int64_t *attention_mask, const int64_t *position_ids, const float *img_feats, int B,
+                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows, void *tape,
+                          size_t tape_bytes, float *loss);
+/* Backward of the forward that filled `tape` (same inputs, same weights).  grad_loss: fp32 scalar (device),
+ * d(objective)/d(loss) — autograd's grad_output. */
+int cpt_train_backward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
+                           const int64_t *position_ids, int B, int T, int R, const int64_t *rows,
+                           const int64_t *targets, int n_rows, const float *grad_loss, void *tape, size_t tape_bytes,
+                           const cpt_grads *grads);
+
 /* Blocks until `stream` drains; reports device-side input errors (token id / position out of range, the
  * IndexError the reference's nn.Embedding would raise) and launch failures. */
 int cpt_check_async_error(cpt_handle *h, void *stream);
@@ -104,7 +147,8 @@ int cpt_check_async_error(cpt_handle *h, void *stream);
 /* ---- launch accounting and per-kernel-class timing (bench.py roofline leg) ------------------------------- */
 enum {
   CPT_K_EXTMASK = 0, CPT_K_EMBED, CPT_K_CAST, CPT_K_GEMM_IMG, CPT_K_LN, CPT_K_GEMM_QKV, CPT_K_ATTN,
-  CPT_K_GEMM_AO, CPT_K_GEMM_UP, CPT_K_GEMM_DOWN, CPT_K_HEAD, CPT_K_GEMM_HEAD, CPT_K_GEMM_OTHER, CPT_K_COUNT
+  CPT_K_GEMM_AO, CPT_K_GEMM_UP, CPT_K_GEMM_DOWN, CPT_K_HEAD, CPT_K_GEMM_HEAD, CPT_K_GEMM_OTHER,
+  CPT_K_GEMM_DGRAD, CPT_K_GEMM_WGRAD, CPT_K_ATTN_BWD, CPT_K_TRAIN_ROWWISE, CPT_K_COUNT
 };
 const char *cpt_kernel_name(int tag);
 /* kernels launched by this handle since cpt_create */
