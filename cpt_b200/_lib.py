@@ -42,7 +42,8 @@ class Weights(C.Structure):
 
 
 GRAD_GLOBAL_FIELDS = ("word_emb", "pos_emb", "type_emb", "emb_ln_g", "emb_ln_b", "img_w", "img_b", "img_ln_g",
-                      "img_ln_b", "mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")
+                      "img_ln_b", "mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias", "pooler_w",
+                      "pooler_b", "nsp_w", "nsp_b")
 
 
 class LayerGrads(C.Structure):
@@ -71,6 +72,8 @@ SYMBOLS = {
     "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),
     "cpt_train_forward_mlm": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _sz, _p]),
     "cpt_train_backward_mlm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _sz, C.POINTER(Grads)]),
+    "cpt_train_forward_nsp": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _sz, _p]),
+    "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _sz, C.POINTER(Grads)]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),
     "cpt_launch_count": (_ll, [_p]),

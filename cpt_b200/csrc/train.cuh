@@ -302,6 +302,35 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
   }
 }
 
+// fp32 dlogits for the (tiny) NSP head: d[i, c] = g * (softmax - onehot) / n
+__global__ void __launch_bounds__(128) ce_bwd32_kernel(const float* __restrict__ logits, int n, int Cn,
+                                                       const long long* __restrict__ targets,
+                                                       const float* __restrict__ lse, const float* __restrict__ g,
+                                                       float* __restrict__ d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * Cn) return;
+  const int r = i / Cn, c = i % Cn;
+  d[i] = g[0] / (float)n * (expf(logits[i] - lse[r]) - (c == targets[r] ? 1.f : 0.f));
+}
+// Generic strided fp32 product on CUDA cores for the NSP head (a few hundred rows at most):
+//   C[i*sc0 + j] (+)= act'( sum_k A[i*sa0 + k*sa1] * B[k*sb0 + j*sb1] )     act' : 0 none, 1 multiply by (1 - t^2), t = T[i*N+j]
+__global__ void __launch_bounds__(256) small_matmul_kernel(const float* __restrict__ A, long long sa0, long long sa1,
+                                                           const float* __restrict__ B, long long sb0, long long sb1,
+                                                           int M, int N, int K, float* __restrict__ Cm, long long sc0,
+                                                           int accumulate, const float* __restrict__ tanh_out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int i = (int)(idx / N), j = (int)(idx % N);
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(A[i * sa0 + k * sa1], B[k * sb0 + j * sb1], s);
+  if (tanh_out) {
+    const float t = tanh_out[(long long)i * N + j];
+    s *= 1.f - t * t;
+  }
+  if (accumulate) Cm[i * sc0 + j] += s;
+  else Cm[i * sc0 + j] = s;
+}
+
 // out[i] (+)= a[i]   (fp32, strided rows: copies a padded [rows, ld_a] gradient into its [rows, cols] home)
 __global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ a, long long ld_a, int rows, int cols,
                                                        float* __restrict__ out, long long ld_out) {

@@ -21,6 +21,8 @@ struct Tape {
   char *hx16, *ht16;
   float *htd32, *htg32, *logits, *lse;
   long long ldl;
+  // NSP head (n labelled samples): [CLS] rows, pooled, logits; backward scratch
+  float *nx32, *npool, *nlog, *ndlog, *ndpre, *ndx;
   // backward scratch
   float *dH, *dx32, *hd32a, *hd32b, *hdx32, *dimg32, *dwimg;
   char *dx16, *dxT16, *big16, *big16b, *bigT16, *actT16, *dctx16;
@@ -67,6 +69,13 @@ static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* ba
   t.htg32 = (float*)take((size_t)n * H * 4);
   t.logits = (float*)take((size_t)n * t.ldl * 4);
   t.lse = (float*)take((size_t)n * 4);
+  const size_t Cn = std::max(1, c.num_contrast_classes);
+  t.nx32 = (float*)take((size_t)n * H * 4);
+  t.npool = (float*)take((size_t)n * H * 4);
+  t.nlog = (float*)take((size_t)n * Cn * 4);
+  t.ndlog = (float*)take((size_t)n * Cn * 4);
+  t.ndpre = (float*)take((size_t)n * H * 4);
+  t.ndx = (float*)take((size_t)n * H * 4);
   // backward scratch
   t.dH = (float*)take(M * H * 4);
   t.dx32 = (float*)take(M * H * 4);
@@ -149,15 +158,29 @@ static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, lo
   return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
 }
 
+static int small_matmul(cpt_handle* h, cudaStream_t st, const float* A, long long sa0, long long sa1, const float* B,
+                        long long sb0, long long sb1, int M, int N, int K, float* Cm, long long sc0, bool accumulate,
+                        const float* tanh_out = nullptr) {
+  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  const long long total = (long long)M * N;
+  small_matmul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, sa0, sa1, B, sb0, sb1, M, N, K, Cm, sc0,
+                                                                        accumulate ? 1 : 0, tanh_out);
+  CKL("small_matmul_kernel");
+  return 0;
+}
+
 template <typename T16>
-static int train_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids, const int64_t* seg,
+static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const int64_t* ids, const int64_t* seg,
                               const int64_t* mask, const int64_t* pos_ids, const float* img, int B, int T, int R,
                               const int64_t* rows, const int64_t* targets, int n, void* tape_ptr, size_t tape_bytes,
                               float* loss) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
   if (!h->train) return fail("cpt_train_forward_mlm: call cpt_train_enable(h, 1) before cpt_set_weights");
-  if (!h->has_weights || !h->has_mlm) return fail("cpt_train_forward_mlm needs weights including the cls.* head");
+  if (!h->has_weights) return fail("cpt_train_forward called before cpt_set_weights");
+  if (head == CPT_HEAD_MLM && !h->has_mlm) return fail("cpt_train_forward_mlm needs the cls.predictions.* weights");
+  if (head == CPT_HEAD_NSP && (!h->has_pooler || !h->has_nsp))
+    return fail("cpt_train_forward_nsp needs the bert.pooler and cls.seq_relationship weights");
   if (B <= 0 || T <= 0 || R < 0 || n <= 0) return fail("bad shape B=%d T=%d R=%d n_rows=%d", B, T, R, n);
   if (T > c.max_position_embeddings) return fail("T=%d exceeds max_position_embeddings=%d", T, c.max_position_embeddings);
   if (R > 0 && (!img || !h->w_img)) return fail("img_feats given but no img_embedding weights (or NULL img_feats)");
@@ -241,6 +264,24 @@ static int train_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids
     }
   }
   if (L == 0) CK(cudaMemcpyAsync(t.seq32, t.h32, act, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(loss, 0, 4, st));
+  if (head == CPT_HEAD_NSP) {
+    // BertPooler on the [CLS] rows of the labelled samples, then cls.seq_relationship; fp32 throughout
+    const int Cn = c.num_contrast_classes;
+    {
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      gather_rows_kernel<T16><<<n, 256, 0, st>>>(t.seq32, (const long long*)rows, n, H, (T16*)nullptr, t.nx32);
+      CKL("gather_rows_kernel");
+    }
+    TRY(head_matvec(h, st, t.nx32, H, 1, nullptr, nullptr, nullptr, 0.f, h->pool_w, H, h->pool_b, nullptr, H, n, H, H,
+                    ACT_TANH, t.npool, H));
+    TRY(head_matvec(h, st, t.npool, H, 1, nullptr, nullptr, nullptr, 0.f, h->nsp_w, H, h->nsp_b, nullptr, Cn, n, H,
+                    Cn, ACT_NONE, t.nlog, Cn));
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    ce_fwd_kernel<<<n, 256, 0, st>>>(t.nlog, Cn, n, Cn, (const long long*)targets, t.lse, loss);
+    CKL("ce_fwd_kernel");
+    return 0;
+  }
   // head at the labelled rows: cls.predictions.transform (dense, GELU, LayerNorm) and the tied decoder
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
@@ -262,7 +303,6 @@ static int train_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids
     q.M = n; q.N = V; q.K = H; q.out = t.logits; q.ldo = t.ldl; q.bias = h->mlm_bias;
     TRY(gemm<T16>(h, st, CPT_K_GEMM_HEAD, t.ht16, H, h->word16, H, q, EPI_BIAS, true));
   }
-  CK(cudaMemsetAsync(loss, 0, 4, st));
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     ce_fwd_kernel<<<n, 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, loss);
@@ -272,17 +312,21 @@ static int train_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids
 }
 
 template <typename T16>
-static int train_backward_impl(cpt_handle* h, cudaStream_t st, const int64_t* ids, const int64_t* seg,
+static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const int64_t* ids, const int64_t* seg,
                                const int64_t* pos_ids, int B, int T, int R, const int64_t* rows,
                                const int64_t* targets, int n, const float* grad_loss, void* tape_ptr,
                                size_t tape_bytes, const cpt_grads* g) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
-  if (!h->train || !h->has_weights || !h->has_mlm) return fail("cpt_train_backward_mlm: handle is not set up for training");
+  if (!h->train || !h->has_weights) return fail("cpt_train_backward: handle is not set up for training");
   if (B <= 0 || T <= 0 || R < 0 || n <= 0 || S > 256) return fail("bad shape B=%d T=%d R=%d n_rows=%d", B, T, R, n);
-  if (!g || !g->word_emb || !g->pos_emb || !g->type_emb || !g->emb_ln_g || !g->emb_ln_b || !g->mlm_dense_w ||
-      !g->mlm_dense_b || !g->mlm_ln_g || !g->mlm_ln_b || !g->mlm_bias || (L > 0 && !g->layers))
-    return fail("cpt_train_backward_mlm: NULL gradient tensor");
+  if (!g || !g->word_emb || !g->pos_emb || !g->type_emb || !g->emb_ln_g || !g->emb_ln_b || (L > 0 && !g->layers))
+    return fail("cpt_train_backward: NULL gradient tensor");
+  if (head == CPT_HEAD_MLM &&
+      (!h->has_mlm || !g->mlm_dense_w || !g->mlm_dense_b || !g->mlm_ln_g || !g->mlm_ln_b || !g->mlm_bias))
+    return fail("cpt_train_backward_mlm: NULL cls.predictions.* gradient tensor");
+  if (head == CPT_HEAD_NSP && (!h->has_pooler || !h->has_nsp || !g->pooler_w || !g->pooler_b || !g->nsp_w || !g->nsp_b))
+    return fail("cpt_train_backward_nsp: NULL pooler / seq_relationship gradient tensor");
   if (R > 0 && (!g->img_w || !g->img_b || (c.use_img_layernorm && (!g->img_ln_g || !g->img_ln_b))))
     return fail("cpt_train_backward_mlm: NULL img_* gradient tensor");
   if (!ids || !rows || !targets || !grad_loss) return fail("NULL argument");
@@ -291,7 +335,28 @@ static int train_backward_impl(cpt_handle* h, cudaStream_t st, const int64_t* id
   const int Mp = t.Mp, np = t.np, Vp = t.Vp;
   const int DG = CPT_K_GEMM_DGRAD, WG = CPT_K_GEMM_WGRAD;
 
-  // ---- head
+  CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
+  if (head == CPT_HEAD_NSP) {
+    const int Cn = c.num_contrast_classes;
+    {
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      ce_bwd32_kernel<<<(n * Cn + 127) / 128, 128, 0, st>>>(t.nlog, n, Cn, (const long long*)targets, t.lse, grad_loss,
+                                                           t.ndlog);
+      CKL("ce_bwd32_kernel");
+    }
+    TRY(colsum<float>(h, st, t.ndlog, n, Cn, Cn, g->nsp_b));
+    // dW_nsp[C,H] += dlogits^T pooled ; dpre[n,H] = (dlogits W_nsp) * (1 - pooled^2)
+    TRY(small_matmul(h, st, t.ndlog, 1, Cn, t.npool, H, 1, Cn, H, n, g->nsp_w, H, true));
+    TRY(small_matmul(h, st, t.ndlog, Cn, 1, h->nsp_w, H, 1, n, H, Cn, t.ndpre, H, false, t.npool));
+    TRY(colsum<float>(h, st, t.ndpre, n, H, H, g->pooler_b));
+    // dW_pool[H,H] += dpre^T x ; dx[n,H] = dpre W_pool
+    TRY(small_matmul(h, st, t.ndpre, 1, H, t.nx32, H, 1, H, H, n, g->pooler_w, H, true));
+    TRY(small_matmul(h, st, t.ndpre, H, 1, h->pool_w, H, 1, n, H, H, t.ndx, H, false));
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    scatter_rows_add_kernel<<<n, 256, 0, st>>>(t.ndx, (const long long*)rows, n, H, t.dH);
+    CKL("scatter_rows_add_kernel");
+  } else {
+  // ---- MLM head
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     ce_bwd_kernel<T16><<<n, 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, grad_loss,
@@ -324,11 +389,11 @@ static int train_backward_impl(cpt_handle* h, cudaStream_t st, const int64_t* id
   TRY(transpose_t<T16>(h, st, t.hx16, n, H, H, t.hxT16, np));
   TRY(gemm_plain<T16>(h, st, WG, t.hdT16, np, t.hxT16, np, H, H, np, g->mlm_dense_w, H, true, true));
   TRY(gemm_plain<T16>(h, st, DG, t.hd16, H, h->mlm_w16_t, H, n, H, H, t.hdx32, H, true, false));
-  CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     scatter_rows_add_kernel<<<n, 256, 0, st>>>(t.hdx32, (const long long*)rows, n, H, t.dH);
     CKL("scatter_rows_add_kernel");
+  }
   }
 
   // ---- encoder layers, last to first.  t.dH = gradient of the layer's output

@@ -201,10 +201,11 @@ class Engine(object):
             img = _chk_tensor("img_feats", img_feats, torch.float32, dev, (B, R, self.cfg.img_feature_dim))
         return B, T, R, ids, seg, msk, pos, img
 
-    def train_forward_mlm(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets):
-        """loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled positions
-        `rows` (flat b*S+s indices) with labels `targets`.  Returns (loss, saved) — `saved` feeds
-        train_backward_mlm."""
+    def train_forward(self, head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets):
+        """head "mlm": loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled
+        positions `rows` (flat b*S+s indices) with labels `targets`; head "nsp": loss of
+        NSPCPT.forward(next_sentence_label=...) (modeling_vcr.py:120-127), rows = b*S of the labelled samples.
+        Returns (loss, saved) — `saved` feeds train_backward."""
         if not self.train:
             raise CptError("cpt_b200: this engine was not created with train=True")
         B, T, R, ids, seg, msk, pos, img = self._train_inputs(input_ids, token_type_ids, attention_mask,
@@ -217,14 +218,14 @@ class Engine(object):
             nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
             tape = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            _lib.check(self.lib.cpt_train_forward_mlm(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos),
-                                                      _ptr(img), B, T, R, _ptr(rows), _ptr(targets), n, _ptr(tape),
-                                                      tape.numel(), _ptr(loss)))
-        saved = dict(B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
+            fwd = self.lib.cpt_train_forward_mlm if head == "mlm" else self.lib.cpt_train_forward_nsp
+            _lib.check(fwd(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos), _ptr(img), B, T, R,
+                           _ptr(rows), _ptr(targets), n, _ptr(tape), tape.numel(), _ptr(loss)))
+        saved = dict(head=head, B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
                      version=self.weights_version)
         return loss, saved
 
-    def train_backward_mlm(self, saved, grad_loss, grads):
+    def train_backward(self, saved, grad_loss, grads):
         """Adds d(grad_loss * loss)/d(param) into `grads` (dict keyed like the state_dict, fp32 tensors shaped
         like the parameters)."""
         if saved["version"] != self.weights_version:
@@ -244,8 +245,10 @@ class Engine(object):
             return _ptr(t)
 
         g = _lib.Grads()
+        unused = ("pooler_w", "pooler_b", "nsp_w", "nsp_b") if saved["head"] == "mlm" else \
+            ("mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")
         for f in _lib.GRAD_GLOBAL_FIELDS:
-            setattr(g, f, gp(GLOBAL_KEYS[f], f.startswith("img_")))
+            setattr(g, f, gp(GLOBAL_KEYS[f], f.startswith("img_") or f in unused))
         L = self.cfg.num_hidden_layers
         layers = (_lib.LayerGrads * max(L, 1))()
         for i in range(L):
@@ -255,10 +258,10 @@ class Engine(object):
         gl = _chk_tensor("grad_loss", grad_loss.reshape(()), torch.float32, dev)
         s = saved
         with torch.cuda.device(dev):
-            _lib.check(self.lib.cpt_train_backward_mlm(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]),
-                                                       _ptr(s["pos"]), s["B"], s["T"], s["R"], _ptr(s["rows"]),
-                                                       _ptr(s["targets"]), s["n"], _ptr(gl), _ptr(s["tape"]),
-                                                       s["tape"].numel(), C.byref(g)))
+            bwd = self.lib.cpt_train_backward_mlm if s["head"] == "mlm" else self.lib.cpt_train_backward_nsp
+            _lib.check(bwd(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]), _ptr(s["pos"]), s["B"], s["T"], s["R"],
+                           _ptr(s["rows"]), _ptr(s["targets"]), s["n"], _ptr(gl), _ptr(s["tape"]), s["tape"].numel(),
+                           C.byref(g)))
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

@@ -4,6 +4,7 @@ Reference: /root/reference/Oscar/oscar/modeling/modeling_vcr.py:79-129: the pool
 pre-training `seq_relationship` Linear(H, num_contrast_classes); the caller scores a choice as
 1 - softmax(out)[:, 1] (fewshot/vcr_nsp_cpt.py:600).
 """
+import torch
 from torch import nn
 
 from .modeling_bert import BertImgModel, BertLMPredictionHead, BertPreTrainedModel, nsp_head_tensors
@@ -32,6 +33,10 @@ class NSPCPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: NSPCPT scores with the pre-training seq_relationship head; call "
                                "copy_from_pretraining_model(BertImgForPreTraining) first (modeling_vcr.py:90-92)")
         self.bert.register_head_tensors(nsp_head_tensors(self.cls))
+        if (next_sentence_label is not None and torch.is_grad_enabled()
+                and any(p.requires_grad for p in self.parameters())):
+            return self._train_step(input_ids, token_type_ids, attention_mask, next_sentence_label, position_ids,
+                                    head_mask, img_feats)
         outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
                             attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
         score = self.bert.engine().nsp(outputs[1])
@@ -41,3 +46,22 @@ class NSPCPT(BertPreTrainedModel):
                                                ignore_index=-1)
             out = (loss,) + out
         return out
+
+    def _train_step(self, input_ids, token_type_ids, attention_mask, next_sentence_label, position_ids, head_mask,
+                    img_feats):
+        """(loss, None) — vcr_nsp_cpt.py:445-461 reads `loss, logits = outputs[:2]` and only uses the loss.  Native
+        forward + backward behind autograd (cpt_b200/training.py)."""
+        from .training import nsp_loss
+        if head_mask is not None:
+            raise NotImplementedError("cpt_b200: head_mask is never used on the CPT path")
+        if getattr(self.config, "output_hidden_states", False) or getattr(self.config, "output_attentions", False):
+            raise NotImplementedError("cpt_b200: output_hidden_states / output_attentions in the training step")
+        if attention_mask is not None and attention_mask.dim() != 2:
+            raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
+        self.bert._check_mode()
+        if attention_mask is not None and attention_mask.dtype != torch.int64:
+            attention_mask = attention_mask.to(torch.int64)
+        eng, named = self.bert.train_engine()
+        loss, _ = nsp_loss(eng, named, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
+                           next_sentence_label)
+        return (loss, None)

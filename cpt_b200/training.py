@@ -15,23 +15,24 @@ import torch
 
 from .engine import GLOBAL_KEYS, layer_keys
 
-# parameters the MLM loss does not depend on (their .grad stays None, as in the reference)
-_UNUSED = ("pooler_w", "pooler_b", "nsp_w", "nsp_b")
+# parameters each loss does not depend on (their .grad stays None, as in the reference)
+_UNUSED = {"mlm": ("pooler_w", "pooler_b", "nsp_w", "nsp_b"),
+           "nsp": ("mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")}
 
 
-def trainable_keys(cfg, has_img=True):
-    keys = [k for f, k in GLOBAL_KEYS.items() if f not in _UNUSED and (has_img or not f.startswith("img_"))]
+def trainable_keys(cfg, head, has_img=True):
+    keys = [k for f, k in GLOBAL_KEYS.items() if f not in _UNUSED[head] and (has_img or not f.startswith("img_"))]
     for i in range(cfg.num_hidden_layers):
         keys.extend(layer_keys(i).values())
     return keys
 
 
-class _MlmLoss(torch.autograd.Function):
+class _Loss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, keys, inputs, *params):
-        input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets = inputs
-        loss, saved = engine.train_forward_mlm(input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                                               rows, targets)
+        head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets = inputs
+        loss, saved = engine.train_forward(head, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
+                                           rows, targets)
         ctx.engine, ctx.keys, ctx.saved = engine, keys, saved
         ctx.shapes = [tuple(p.shape) for p in params]
         return loss
@@ -40,7 +41,7 @@ class _MlmLoss(torch.autograd.Function):
     def backward(ctx, grad_loss):
         eng = ctx.engine
         grads = {k: torch.zeros(s, dtype=torch.float32, device=eng.device) for k, s in zip(ctx.keys, ctx.shapes)}
-        eng.train_backward_mlm(ctx.saved, grad_loss.to(torch.float32), grads)
+        eng.train_backward(ctx.saved, grad_loss.to(torch.float32), grads)
         ctx.saved = None  # drop the tape
         out = tuple(grads[k] if ctx.needs_input_grad[3 + i] else None for i, k in enumerate(ctx.keys))
         return (None, None, None) + out
@@ -57,7 +58,25 @@ def mlm_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
         raise RuntimeError("cpt_b200: masked_lm_labels has no labelled position (the reference returns NaN here)")
     targets = flat[rows].contiguous()
     has_img = img_feats is not None and img_feats.shape[1] > 0
-    keys = [k for k in trainable_keys(engine.cfg, has_img) if k in named_params]
+    keys = [k for k in trainable_keys(engine.cfg, "mlm", has_img) if k in named_params]
     params = [named_params[k] for k in keys]
-    inputs = (input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets)
-    return _MlmLoss.apply(engine, keys, inputs, *params), rows
+    inputs = ("mlm", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets)
+    return _Loss.apply(engine, keys, inputs, *params), rows
+
+
+def nsp_loss(engine, named_params, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
+             next_sentence_label):
+    """CrossEntropyLoss(ignore_index=-1) of cls.seq_relationship(pooled) against next_sentence_label [B]
+    (modeling_vcr.py:120-127), differentiable with respect to `named_params`."""
+    flat = next_sentence_label.reshape(-1)
+    S = input_ids.shape[1] + (0 if img_feats is None else img_feats.shape[1])
+    keep = torch.nonzero(flat != -1, as_tuple=False).squeeze(1)
+    if keep.numel() == 0:
+        raise RuntimeError("cpt_b200: next_sentence_label has no labelled sample (the reference returns NaN here)")
+    targets = flat[keep].contiguous()
+    rows = (keep * S).contiguous()  # the [CLS] row of every labelled sample
+    has_img = img_feats is not None and img_feats.shape[1] > 0
+    keys = [k for k in trainable_keys(engine.cfg, "nsp", has_img) if k in named_params]
+    params = [named_params[k] for k in keys]
+    inputs = ("nsp", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets)
+    return _Loss.apply(engine, keys, inputs, *params), rows

@@ -119,9 +119,13 @@ typedef struct {
 typedef struct {
   float *word_emb, *pos_emb, *type_emb, *emb_ln_g, *emb_ln_b;
   float *img_w, *img_b, *img_ln_g, *img_ln_b;
-  float *mlm_dense_w, *mlm_dense_b, *mlm_ln_g, *mlm_ln_b, *mlm_bias;
+  float *mlm_dense_w, *mlm_dense_b, *mlm_ln_g, *mlm_ln_b, *mlm_bias; /* MLM loss only (else may be NULL) */
+  float *pooler_w, *pooler_b, *nsp_w, *nsp_b;                        /* NSP loss only (else may be NULL) */
   const cpt_layer_grads *layers; /* host array [num_hidden_layers] */
 } cpt_grads;
+
+/* Which loss head a training call runs. */
+enum { CPT_HEAD_MLM = 0, CPT_HEAD_NSP = 1 };
 
 /* Bytes of the tape: activations the forward saves for the backward plus the backward's scratch.  n_rows = number
  * of labelled positions (masked_lm_labels != -1) in the batch. */
@@ -136,6 +140,18 @@ int cpt_train_forward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids,
 /* Backward of the forward that filled `tape` (same inputs, same weights).  grad_loss: fp32 scalar (device),
  * d(objective)/d(loss) — autograd's grad_output. */
 int cpt_train_backward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
+                           const int64_t *position_ids, int B, int T, int R, const int64_t *rows,
+                           const int64_t *targets, int n_rows, const float *grad_loss, void *tape, size_t tape_bytes,
+                           const cpt_grads *grads);
+
+/* The VCR few-shot loss: CrossEntropyLoss(ignore_index=-1)(cls.seq_relationship(pooled), next_sentence_label) —
+ * NSPCPT.forward, Oscar/oscar/modeling/modeling_vcr.py:115-129, as vcr_nsp_cpt.py:434-473 trains it.
+ * rows int64 [n_rows]: b*(T+R) of the samples whose label is not -1 (the [CLS] rows); targets their labels. */
+int cpt_train_forward_nsp(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
+                          const int64_t *attention_mask, const int64_t *position_ids, const float *img_feats, int B,
+                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows, void *tape,
+                          size_t tape_bytes, float *loss);
+int cpt_train_backward_nsp(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
                            const int64_t *position_ids, int B, int T, int R, const int64_t *rows,
                            const int64_t *targets, int n_rows, const float *grad_loss, void *tape, size_t tape_bytes,
                            const cpt_grads *grads);
