@@ -54,6 +54,10 @@ class Grads(C.Structure):
     _fields_ = [(n, _fp) for n in GRAD_GLOBAL_FIELDS] + [("layers", C.POINTER(LayerGrads))]
 
 
+class Dropout(C.Structure):
+    _fields_ = [("p_hidden", C.c_float), ("p_attn", C.c_float), ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/cpt_b200.h declares
 _i, _ll, _sz, _p, _f = C.c_int, C.c_longlong, C.c_size_t, C.c_void_p, C.c_float
 SYMBOLS = {
@@ -70,10 +74,14 @@ SYMBOLS = {
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
     "cpt_train_enable": (_i, [_p, _i]),
     "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),
-    "cpt_train_forward_mlm": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _sz, _p]),
-    "cpt_train_backward_mlm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _sz, C.POINTER(Grads)]),
-    "cpt_train_forward_nsp": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _sz, _p]),
-    "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _sz, C.POINTER(Grads)]),
+    "cpt_train_forward_mlm": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _sz,
+                                   _p]),
+    "cpt_train_backward_mlm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _p, _sz,
+                                    C.POINTER(Grads)]),
+    "cpt_train_forward_nsp": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _sz,
+                                   _p]),
+    "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _p, _sz,
+                                    C.POINTER(Grads)]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),
     "cpt_launch_count": (_ll, [_p]),

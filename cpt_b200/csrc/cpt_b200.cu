@@ -1070,28 +1070,28 @@ size_t cpt_train_tape_bytes(const cpt_handle* h, int B, int T, int R, int n_rows
   int cpt_train_forward_##NAME(cpt_handle* h, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,  \
                                const int64_t* attention_mask, const int64_t* position_ids, const float* img_feats,    \
                                int B, int T, int R, const int64_t* rows, const int64_t* targets, int n_rows,          \
-                               void* tape, size_t tape_bytes, float* loss) {                                          \
+                               const cpt_dropout* dropout, void* tape, size_t tape_bytes, float* loss) {                                          \
     if (!h) return fail("NULL handle");                                                                               \
     DeviceGuard g(h->device);                                                                                         \
     if (h->cfg.dtype == 0)                                                                                            \
       return train_forward_impl<__half>(h, HEAD, (cudaStream_t)stream, input_ids, token_type_ids, attention_mask,     \
-                                        position_ids, img_feats, B, T, R, rows, targets, n_rows, tape, tape_bytes,    \
-                                        loss);                                                                        \
+                                        position_ids, img_feats, B, T, R, rows, targets, n_rows, dropout, tape,       \
+                                        tape_bytes, loss);                                                                        \
     return train_forward_impl<__nv_bfloat16>(h, HEAD, (cudaStream_t)stream, input_ids, token_type_ids,                \
                                              attention_mask, position_ids, img_feats, B, T, R, rows, targets, n_rows, \
-                                             tape, tape_bytes, loss);                                                 \
+                                             dropout, tape, tape_bytes, loss);                                                 \
   }                                                                                                                   \
   int cpt_train_backward_##NAME(cpt_handle* h, void* stream, const int64_t* input_ids,                                \
                                 const int64_t* token_type_ids, const int64_t* position_ids, int B, int T, int R,      \
-                                const int64_t* rows, const int64_t* targets, int n_rows, const float* grad_loss,      \
-                                void* tape, size_t tape_bytes, const cpt_grads* grads) {                              \
+                                const int64_t* rows, const int64_t* targets, int n_rows, const cpt_dropout* dropout,  \
+                                const float* grad_loss, void* tape, size_t tape_bytes, const cpt_grads* grads) {                              \
     if (!h) return fail("NULL handle");                                                                               \
     DeviceGuard g(h->device);                                                                                         \
     if (h->cfg.dtype == 0)                                                                                            \
       return train_backward_impl<__half>(h, HEAD, (cudaStream_t)stream, input_ids, token_type_ids, position_ids, B,   \
-                                         T, R, rows, targets, n_rows, grad_loss, tape, tape_bytes, grads);            \
+                                         T, R, rows, targets, n_rows, dropout, grad_loss, tape, tape_bytes, grads);   \
     return train_backward_impl<__nv_bfloat16>(h, HEAD, (cudaStream_t)stream, input_ids, token_type_ids,               \
-                                              position_ids, B, T, R, rows, targets, n_rows, grad_loss, tape,          \
+                                              position_ids, B, T, R, rows, targets, n_rows, dropout, grad_loss, tape, \
                                               tape_bytes, grads);                                                     \
   }
 CPT_TRAIN_ENTRY(mlm, CPT_HEAD_MLM)

@@ -8,6 +8,54 @@
 
 namespace cptk {
 
+// Dropout masks are a pure function of (seed, site, element index): the backward regenerates them instead of storing
+// them.  keep(idx) <=> mix32(idx, seed, site) >= p * 2^32; kept values are scaled by 1 / (1 - p).  thresh = 0 = off.
+// Element index: hidden-state sites (row * H + col) with row = b*S + s; attention site ((b*nH + h)*S + i)*S + j.
+// Sites: layer*4 + {0: attention probabilities, 1: attention.output.dense, 2: output.dense}; 0xFFFF0 text embeddings,
+// 0xFFFF1 region embeddings.  (tests/test_gpu_train.py restates this function in torch integer arithmetic.)
+struct Drop {
+  unsigned seed_lo, seed_hi, site, thresh;
+  float scale;
+};
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  unsigned x = (unsigned)idx ^ ((unsigned)(idx >> 32) * 0x9E3779B1u);
+  x ^= d.seed_lo;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x += d.site * 0xC2B2AE35u + d.seed_hi;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x >= d.thresh;
+}
+__device__ __forceinline__ float drop_apply(const Drop& d, unsigned long long idx, float v) {
+  return d.thresh == 0u ? v : (drop_keep(d, idx) ? v * d.scale : 0.f);
+}
+
+// h32 / h16 rows <- dropout(rows) in place (embedding outputs).  Row m of the site lives at stream row remap(m).
+template <typename T16>
+__global__ void __launch_bounds__(256) dropout_rows_kernel(float* __restrict__ h32, T16* __restrict__ h16, int n_rows,
+                                                           int H, int rin, int rout, int roff, Drop d) {
+  const long long total = (long long)n_rows * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / H;
+    const int c = (int)(i % H);
+    const long long row = (m / rin) * rout + roff + (m % rin);
+    const long long e = row * H + c;
+    const float v = drop_apply(d, (unsigned long long)e, h32[e]);
+    h32[e] = v;
+    if (h16) h16[e] = Cvt<T16>::from(v);
+  }
+}
+// x = resid + dropout(delta)   (BertSelfOutput / BertOutput: dropout on the dense output, then the residual add)
+__global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restrict__ resid, const float* __restrict__ delta,
+                                                          long long n, float* __restrict__ x, Drop d) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = resid[i] + drop_apply(d, (unsigned long long)i, delta[i]);
+}
+
 // out[C, ld_out] = in[R, ld_in]^T (16-bit), columns R..ld_out-1 of out zero-filled (TMA pitch padding)
 template <typename T16>
 __global__ void __launch_bounds__(256) transpose16_kernel(const T16* __restrict__ in, int R, int C, long long ld_in,
@@ -75,7 +123,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      int H, const float* __restrict__ gamma, float eps, int do_ln,
                                                      float* __restrict__ dx32, T16* __restrict__ dx16,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rin,
-                                                     int rout, int roff) {
+                                                     int rout, int roff, Drop drop_dy, Drop drop16) {
+  // drop_dy: dropout that sat between this LayerNorm's output and its consumer (embedding sites): masks dy on load.
+  // drop16 : dropout that sat on the dense output feeding this LayerNorm's input: the 16-bit copy of dx (the operand
+  //          of that dense layer's dgrad / wgrad GEMMs) is masked; the fp32 dx (residual branch) is not.
   __shared__ float red[8][NV * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wstride = gridDim.x * 8;
@@ -92,6 +143,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       const int col = (i * 32 + lane) * 4;
       xv[i] = *reinterpret_cast<const float4*>(x + (long long)row * H + col);
       dv[i] = *reinterpret_cast<const float4*>(dy + drow * H + col);
+      if (drop_dy.thresh) {
+        const unsigned long long e = (unsigned long long)(drow * H + col);
+        dv[i].x = drop_apply(drop_dy, e, dv[i].x); dv[i].y = drop_apply(drop_dy, e + 1, dv[i].y);
+        dv[i].z = drop_apply(drop_dy, e + 2, dv[i].z); dv[i].w = drop_apply(drop_dy, e + 3, dv[i].w);
+      }
       s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
     }
     float mean = 0.f, rstd = 1.f;
@@ -134,6 +190,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       }
       if (dx32) *reinterpret_cast<float4*>(dx32 + (long long)row * H + col) = o;
       if (dx16) {
+        if (drop16.thresh) {
+          const unsigned long long e = (unsigned long long)((long long)row * H + col);
+          o.x = drop_apply(drop16, e, o.x); o.y = drop_apply(drop16, e + 1, o.y);
+          o.z = drop_apply(drop16, e + 2, o.z); o.w = drop_apply(drop16, e + 3, o.w);
+        }
         uint2 u;
         u.x = Cvt<T16>::pack2(o.x, o.y);
         u.y = Cvt<T16>::pack2(o.z, o.w);
@@ -169,7 +230,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(
     const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
     const float* __restrict__ gamma, float eps, const float* __restrict__ dy, int B, int T, int S, int H, int vocab,
     int max_pos, int n_type, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
-    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, Drop drop_dy) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B * T) return;
@@ -187,6 +248,11 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(
     const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
     xv[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
     dv[i] = *reinterpret_cast<const float4*>(dy + ((long long)b * S + t) * H + col);
+    if (drop_dy.thresh) {
+      const unsigned long long e = (unsigned long long)(((long long)b * S + t) * H + col);
+      dv[i].x = drop_apply(drop_dy, e, dv[i].x); dv[i].y = drop_apply(drop_dy, e + 1, dv[i].y);
+      dv[i].z = drop_apply(drop_dy, e + 2, dv[i].z); dv[i].w = drop_apply(drop_dy, e + 3, dv[i].w);
+    }
     s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
   }
   const float mean = warp_sum(s) / (float)H;
@@ -358,7 +424,8 @@ __global__ void __launch_bounds__(256) cast32to16_kernel(const float* __restrict
 template <typename T16>
 __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restrict__ qkv, const T16* __restrict__ dctx,
                                                             const float* __restrict__ ext_mask, int S, int H,
-                                                            float scale, T16* __restrict__ dqkv) {
+                                                            float scale, T16* __restrict__ dqkv, Drop drop) {
+  // with dropout on the probabilities (P~ = mask * P / (1-p) multiplies V): dV uses P~, and dP = mask/(1-p) * (dO . v)
   extern __shared__ uint8_t smem_raw[];
   T16* sQ = reinterpret_cast<T16*>(smem_raw);
   T16* sK = sQ + (size_t)S * kAttnDH;
@@ -369,6 +436,7 @@ __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restric
   float* sL = sMx + S;
   float* sD = sL + S;
   const int h = blockIdx.x, b = blockIdx.y;
+  const unsigned long long pbase = ((unsigned long long)b * gridDim.x + h) * S * S;  // index of P[b, h, 0, 0]
   const T16* base = qkv + (long long)b * S * 3 * H;
   const T16* dob = dctx + (long long)b * S * H;
   for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
@@ -405,7 +473,7 @@ __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restric
       }
       const float e = expf(fmaf(s, scale, sM[j]) - mx);
       l += e;
-      D += e * dp;
+      D += e * drop_apply(drop, pbase + (unsigned long long)i * S + j, dp);
     }
     D /= l;
     sMx[i] = mx; sL[i] = l; sD[i] = D;
@@ -420,7 +488,7 @@ __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restric
         dp = fmaf(dO[d], Cvt<T16>::to(sV[j * kAttnDH + d]), dp);
       }
       const float pij = expf(fmaf(s, scale, sM[j]) - mx) / l;
-      const float ds = pij * (dp - D) * scale;
+      const float ds = pij * (drop_apply(drop, pbase + (unsigned long long)i * S + j, dp) - D) * scale;
 #pragma unroll
       for (int d = 0; d < kAttnDH; ++d) dq[d] = fmaf(ds, Cvt<T16>::to(sK[j * kAttnDH + d]), dq[d]);
     }
@@ -446,11 +514,13 @@ __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restric
         dp = fmaf(Cvt<T16>::to(sdO[i * kAttnDH + d]), v[d], dp);
       }
       const float pij = expf(fmaf(s, scale, mj) - sMx[i]) / sL[i];
-      const float ds = pij * (dp - sD[i]) * scale;
+      const unsigned long long e = pbase + (unsigned long long)i * S + j;
+      const float ds = pij * (drop_apply(drop, e, dp) - sD[i]) * scale;
+      const float pdrop = drop_apply(drop, e, pij);
 #pragma unroll
       for (int d = 0; d < kAttnDH; ++d) {
         dk[d] = fmaf(ds, Cvt<T16>::to(sQ[i * kAttnDH + d]), dk[d]);
-        dv[d] = fmaf(pij, Cvt<T16>::to(sdO[i * kAttnDH + d]), dv[d]);
+        dv[d] = fmaf(pdrop, Cvt<T16>::to(sdO[i * kAttnDH + d]), dv[d]);
       }
     }
 #pragma unroll
@@ -458,6 +528,61 @@ __global__ void __launch_bounds__(128) attn_bwd_simt_kernel(const T16* __restric
       dq_out[(long long)j * 3 * H + H + d] = Cvt<T16>::from(dk[d]);
       dq_out[(long long)j * 3 * H + 2 * H + d] = Cvt<T16>::from(dv[d]);
     }
+  }
+}
+
+// Attention forward with dropout on the probabilities (training with attention_probs_dropout_prob > 0), CUDA cores,
+// one CTA per (head, sample): ctx_i = sum_j mask_ij / (1-p) * softmax_j(q_i . k_j / sqrt(dH) + ext_mask_j) v_j.
+template <typename T16>
+__global__ void __launch_bounds__(128) attn_fwd_drop_kernel(const T16* __restrict__ qkv,
+                                                            const float* __restrict__ ext_mask, int S, int H,
+                                                            float scale, T16* __restrict__ ctx, Drop drop) {
+  extern __shared__ uint8_t smem_raw[];
+  T16* sK = reinterpret_cast<T16*>(smem_raw);
+  T16* sV = sK + (size_t)S * kAttnDH;
+  float* sM = reinterpret_cast<float*>(sV + (size_t)S * kAttnDH);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const unsigned long long pbase = ((unsigned long long)b * gridDim.x + h) * S * S;
+  const T16* base = qkv + (long long)b * S * 3 * H;
+  for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
+    const int j = i >> 3, c = (i & 7) * 8;
+    *reinterpret_cast<uint4*>(sK + j * kAttnDH + c) =
+        *reinterpret_cast<const uint4*>(base + (long long)j * 3 * H + H + h * kAttnDH + c);
+    *reinterpret_cast<uint4*>(sV + j * kAttnDH + c) =
+        *reinterpret_cast<const uint4*>(base + (long long)j * 3 * H + 2 * H + h * kAttnDH + c);
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) sM[j] = ext_mask[(long long)b * S + j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    float q[kAttnDH], o[kAttnDH];
+    const T16* qp = base + (long long)i * 3 * H + h * kAttnDH;
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) {
+      q[d] = Cvt<T16>::to(qp[d]);
+      o[d] = 0.f;
+    }
+    float mx = -INFINITY;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) s = fmaf(q[d], Cvt<T16>::to(sK[j * kAttnDH + d]), s);
+      mx = fmaxf(mx, fmaf(s, scale, sM[j]));
+    }
+    float sum = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) s = fmaf(q[d], Cvt<T16>::to(sK[j * kAttnDH + d]), s);
+      const float e = expf(fmaf(s, scale, sM[j]) - mx);
+      sum += e;
+      const float ed = drop_apply(drop, pbase + (unsigned long long)i * S + j, e);
+#pragma unroll
+      for (int d = 0; d < kAttnDH; ++d) o[d] = fmaf(ed, Cvt<T16>::to(sV[j * kAttnDH + d]), o[d]);
+    }
+    const float inv = 1.0f / sum;
+    T16* dst = ctx + ((long long)b * S + i) * H + h * kAttnDH;
+#pragma unroll
+    for (int d = 0; d < kAttnDH; ++d) dst[d] = Cvt<T16>::from(o[d] * inv);
   }
 }
 

@@ -104,6 +104,20 @@ static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* ba
   return t;
 }
 
+// Drop of one site (train.cuh); p <= 0 -> off
+static Drop make_drop(const cpt_dropout* d, float p, unsigned site) {
+  Drop r{0u, 0u, site, 0u, 1.f};
+  if (!d || !(p > 0.f)) return r;
+  r.seed_lo = (unsigned)(d->seed & 0xffffffffull);
+  r.seed_hi = (unsigned)(d->seed >> 32);
+  const double t = (double)p * 4294967296.0;
+  r.thresh = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+  if (r.thresh == 0u) r.thresh = 1u;
+  r.scale = 1.0f / (1.0f - p);
+  return r;
+}
+enum { SITE_ATTN = 0, SITE_AO = 1, SITE_DOWN = 2, SITE_EMB_TEXT = 0xFFFF0, SITE_EMB_IMG = 0xFFFF1 };
+
 static int ew_grid(const cpt_handle* h, long long n) {
   const long long g = (n + 255) / 256;
   return (int)std::max<long long>(1, std::min<long long>(g, 8ll * h->num_sms));
@@ -129,14 +143,15 @@ static int transpose_t(cpt_handle* h, cudaStream_t st, const void* in, int R, in
 template <typename T16>
 static int ln_bwd(cpt_handle* h, cudaStream_t st, const float* dy, const float* x, int M, int H, const float* gamma,
                   float eps, bool do_ln, float* dx32, void* dx16, float* dgamma, float* dbeta, int rin = 0,
-                  int rout = 0, int roff = 0) {
+                  int rout = 0, int roff = 0, Drop drop_dy = Drop{0, 0, 0, 0, 1.f}, Drop drop16 = Drop{0, 0, 0, 0, 1.f}) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
   const int grid = std::min((M + 7) / 8, 2 * h->num_sms);
 #define CPT_LNB_CASE(NV_)                                                                                         \
   case NV_:                                                                                                       \
     ln_bwd_kernel<T16, NV_><<<grid, 256, 0, st>>>(dy, x, M, H, gamma, eps, do_ln ? 1 : 0, dx32,                   \
-                                                  reinterpret_cast<T16*>(dx16), dgamma, dbeta, rin, rout, roff);  \
+                                                  reinterpret_cast<T16*>(dx16), dgamma, dbeta, rin, rout, roff,   \
+                                                  drop_dy, drop16);                                               \
     break;
   switch (H / 128) {
     CPT_LNB_CASE(1) CPT_LNB_CASE(2) CPT_LNB_CASE(3) CPT_LNB_CASE(4) CPT_LNB_CASE(5) CPT_LNB_CASE(6) CPT_LNB_CASE(7)
@@ -172,8 +187,8 @@ static int small_matmul(cpt_handle* h, cudaStream_t st, const float* A, long lon
 template <typename T16>
 static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const int64_t* ids, const int64_t* seg,
                               const int64_t* mask, const int64_t* pos_ids, const float* img, int B, int T, int R,
-                              const int64_t* rows, const int64_t* targets, int n, void* tape_ptr, size_t tape_bytes,
-                              float* loss) {
+                              const int64_t* rows, const int64_t* targets, int n, const cpt_dropout* dropout,
+                              void* tape_ptr, size_t tape_bytes, float* loss) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
   if (!h->train) return fail("cpt_train_forward_mlm: call cpt_train_enable(h, 1) before cpt_set_weights");
@@ -190,6 +205,8 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
   Tape t = carve_tape(h, B, T, R, n, (char*)(((uintptr_t)tape_ptr + 255) & ~uintptr_t(255)));
   if (!tape_ptr || tape_bytes < t.total) return fail("tape too small: need %zu bytes, got %zu", t.total, tape_bytes);
   const size_t act = (size_t)M * H * 4;
+  const float p_h = dropout ? dropout->p_hidden : 0.f, p_a = dropout ? dropout->p_attn : 0.f;
+  if (p_h < 0.f || p_h >= 1.f || p_a < 0.f || p_a >= 1.f) return fail("dropout probabilities must be in [0, 1)");
 
   if (mask) {
     ProfScope ps(h, st, CPT_K_EXTMASK);
@@ -228,6 +245,36 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
     TRY(layernorm<T16>(h, st, t.imgpre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps,
                        c.use_img_layernorm != 0, t.h32, h16_0, R, S, T));
   }
+  if (p_h > 0.f) {  // dropout on the embedding outputs (BertEmbeddings.dropout; modeling_bert.py:266 for regions)
+    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    dropout_rows_kernel<T16><<<ew_grid(h, (long long)B * T * H), 256, 0, st>>>(
+        t.h32, reinterpret_cast<T16*>(h16_0), B * T, H, T, S, 0, make_drop(dropout, p_h, SITE_EMB_TEXT));
+    CKL("dropout_rows_kernel");
+    if (R > 0) {
+      dropout_rows_kernel<T16><<<ew_grid(h, (long long)B * R * H), 256, 0, st>>>(
+          t.h32, reinterpret_cast<T16*>(h16_0), B * R, H, R, S, T, make_drop(dropout, p_h, SITE_EMB_IMG));
+      CKL("dropout_rows_kernel");
+    }
+  }
+  // x = resid + dropout(A W^T + b): without dropout the GEMM's TMA stores add into a copy of the residual; with it the
+  // dense output goes to scratch first and one elementwise pass masks, scales and adds
+  auto dense_residual = [&](int tag, const void* A, int K, const void* W, const float* bias, const float* resid,
+                            float* x, unsigned site) -> int {
+    GemmParams p{};
+    p.M = M; p.N = H; p.K = K; p.ldo = H; p.bias = bias;
+    if (p_h > 0.f) {
+      p.out = t.dx32;
+      TRY(gemm<T16>(h, st, tag, A, K, W, K, p, EPI_BIAS, true));
+      ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+      dropout_add_kernel<<<ew_grid(h, (long long)M * H), 256, 0, st>>>(resid, t.dx32, (long long)M * H, x,
+                                                                      make_drop(dropout, p_h, site));
+      CKL("dropout_add_kernel");
+      return 0;
+    }
+    CK(cudaMemcpyAsync(x, resid, act, cudaMemcpyDeviceToDevice, st));
+    p.out = x; p.tma_reduce = 1;
+    return gemm<T16>(h, st, tag, A, K, W, K, p, EPI_BIAS, true);
+  };
   for (int l = 0; l < L; ++l) {
     const LayerDev& d = h->layers[l];
     TapeLayer& tl = t.layers[l];
@@ -236,14 +283,20 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
       p.M = M; p.N = 3 * H; p.K = H; p.out = tl.qkv16; p.ldo = 3 * H; p.bias = d.b_qkv;
       TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, tl.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
     }
-    TRY(attention<T16>(h, st, tl.qkv16, t.ext_mask, B, S, tl.ctx16, h->attn_impl));
-    {
-      CK(cudaMemcpyAsync(tl.x1, t.h32, act, cudaMemcpyDeviceToDevice, st));
-      GemmParams p{};
-      p.M = M; p.N = H; p.K = H; p.out = tl.x1; p.ldo = H; p.bias = d.b_ao; p.tma_reduce = 1;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_AO, tl.ctx16, H, d.w_ao, H, p, EPI_BIAS, true));
-      TRY(layernorm<T16>(h, st, tl.x1, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, t.a32, tl.a16));
+    if (p_a > 0.f) {
+      ProfScope ps(h, st, CPT_K_ATTN);
+      auto* fn = attn_fwd_drop_kernel<T16>;
+      const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
+      TRY(set_smem_attr(fn, smem));
+      fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16), t.ext_mask, S, H,
+                                                            0.125f, reinterpret_cast<T16*>(tl.ctx16),
+                                                            make_drop(dropout, p_a, l * 4 + SITE_ATTN));
+      CKL("attn_fwd_drop_kernel");
+    } else {
+      TRY(attention<T16>(h, st, tl.qkv16, t.ext_mask, B, S, tl.ctx16, h->attn_impl));
     }
+    TRY(dense_residual(CPT_K_GEMM_AO, tl.ctx16, H, d.w_ao, d.b_ao, t.h32, tl.x1, l * 4 + SITE_AO));
+    TRY(layernorm<T16>(h, st, tl.x1, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, t.a32, tl.a16));
     {
       GemmParams p{};
       p.M = M; p.N = I; p.K = H; p.out = tl.preup16; p.ldo = I; p.bias = d.b_i;
@@ -254,14 +307,9 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
                                                           reinterpret_cast<T16*>(tl.inter16));
       CKL("gelu_fwd_kernel");
     }
-    {
-      CK(cudaMemcpyAsync(tl.x2, t.a32, act, cudaMemcpyDeviceToDevice, st));
-      GemmParams p{};
-      p.M = M; p.N = H; p.K = I; p.out = tl.x2; p.ldo = H; p.bias = d.b_o; p.tma_reduce = 1;
-      TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, tl.inter16, I, d.w_o, I, p, EPI_BIAS, true));
-      TRY(layernorm<T16>(h, st, tl.x2, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, (l == L - 1) ? t.seq32 : t.h32,
-                         (l == L - 1) ? nullptr : t.layers[l + 1].h16));
-    }
+    TRY(dense_residual(CPT_K_GEMM_DOWN, tl.inter16, I, d.w_o, d.b_o, t.a32, tl.x2, l * 4 + SITE_DOWN));
+    TRY(layernorm<T16>(h, st, tl.x2, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, (l == L - 1) ? t.seq32 : t.h32,
+                       (l == L - 1) ? nullptr : t.layers[l + 1].h16));
   }
   if (L == 0) CK(cudaMemcpyAsync(t.seq32, t.h32, act, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(loss, 0, 4, st));
@@ -314,8 +362,8 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
 template <typename T16>
 static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const int64_t* ids, const int64_t* seg,
                                const int64_t* pos_ids, int B, int T, int R, const int64_t* rows,
-                               const int64_t* targets, int n, const float* grad_loss, void* tape_ptr,
-                               size_t tape_bytes, const cpt_grads* g) {
+                               const int64_t* targets, int n, const cpt_dropout* dropout, const float* grad_loss,
+                               void* tape_ptr, size_t tape_bytes, const cpt_grads* g) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, S = T + R, M = B * S, V = c.vocab_size;
   if (!h->train || !h->has_weights) return fail("cpt_train_backward: handle is not set up for training");
@@ -333,6 +381,8 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   Tape t = carve_tape(h, B, T, R, n, (char*)(((uintptr_t)tape_ptr + 255) & ~uintptr_t(255)));
   if (!tape_ptr || tape_bytes < t.total) return fail("tape too small: need %zu bytes, got %zu", t.total, tape_bytes);
   const int Mp = t.Mp, np = t.np, Vp = t.Vp;
+  const float p_h = dropout ? dropout->p_hidden : 0.f, p_a = dropout ? dropout->p_attn : 0.f;
+  const Drop no_drop{0u, 0u, 0u, 0u, 1.f};
   const int DG = CPT_K_GEMM_DGRAD, WG = CPT_K_GEMM_WGRAD;
 
   CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
@@ -402,9 +452,11 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     const TapeLayer& tl = t.layers[l];
     const cpt_layer_grads& gl = g->layers[l];
     // output.LayerNorm
-    TRY(ln_bwd<T16>(h, st, t.dH, tl.x2, M, H, d.o_g, c.layer_norm_eps, true, t.dx32, t.dx16, gl.o_ln_g, gl.o_ln_b));
-    // output.dense: x2 = a + inter W2^T + b2
-    TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
+    TRY(ln_bwd<T16>(h, st, t.dH, tl.x2, M, H, d.o_g, c.layer_norm_eps, true, t.dx32, t.dx16, gl.o_ln_g, gl.o_ln_b, 0, 0,
+                    0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_DOWN)));
+    // output.dense: x2 = a + dropout(inter W2^T + b2); t.dx16 carries the masked gradient of the dense output
+    if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.o_b));
+    else TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
     TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
     TRY(transpose_t<T16>(h, st, tl.inter16, M, I, I, t.actT16, Mp));
     TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, I, Mp, gl.o_w, I, true, true));
@@ -425,9 +477,10 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     TRY(gemm_plain<T16>(h, st, DG, t.big16b, I, d.w_i_t, I, M, H, I, t.dx32, H, true, true));  // += residual branch
     // attention.output.LayerNorm  (dx1 -> t.dH)
     TRY(ln_bwd<T16>(h, st, t.dx32, tl.x1, M, H, d.ao_g, c.layer_norm_eps, true, t.dH, t.dx16, gl.ao_ln_g,
-                    gl.ao_ln_b));
+                    gl.ao_ln_b, 0, 0, 0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_AO)));
     // attention.output.dense
-    TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
+    if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.ao_b));
+    else TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
     TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
     TRY(transpose_t<T16>(h, st, tl.ctx16, M, H, H, t.actT16, Mp));
     TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, H, Mp, gl.ao_w, H, true, true));
@@ -439,7 +492,8 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
       TRY(set_smem_attr(fn, smem));
       fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16),
                                                             reinterpret_cast<const T16*>(t.dctx16), t.ext_mask, S, H,
-                                                            0.125f, reinterpret_cast<T16*>(t.big16));
+                                                            0.125f, reinterpret_cast<T16*>(t.big16),
+                                                            make_drop(dropout, p_a, l * 4 + SITE_ATTN));
       CKL("attn_bwd_simt_kernel");
     }
     // query / key / value
@@ -463,7 +517,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     embed_bwd_kernel<NV_><<<(B * T + 7) / 8, 256, 0, st>>>(                                                          \
         (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g, \
         c.layer_norm_eps, t.dH, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, g->word_emb, \
-        g->pos_emb, g->type_emb, g->emb_ln_g, g->emb_ln_b);                                                          \
+        g->pos_emb, g->type_emb, g->emb_ln_g, g->emb_ln_b, make_drop(dropout, p_h, SITE_EMB_TEXT));                  \
     break;
     switch (H / 128) {
       CPT_EMBB_CASE(1) CPT_EMBB_CASE(2) CPT_EMBB_CASE(3) CPT_EMBB_CASE(4) CPT_EMBB_CASE(5) CPT_EMBB_CASE(6)
@@ -476,7 +530,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   if (R > 0) {
     const int F = c.img_feature_dim, Mi = B * R, Mip = t.Mip;
     TRY(ln_bwd<T16>(h, st, t.dH, t.imgpre32, Mi, H, h->img_g, c.img_layer_norm_eps, c.use_img_layernorm != 0,
-                    t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, R, S, T));
+                    t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, R, S, T, make_drop(dropout, p_h, SITE_EMB_IMG)));
     TRY(colsum<float>(h, st, t.dimg32, Mi, H, H, g->img_b));
     TRY(transpose_t<T16>(h, st, t.dimg16, Mi, H, H, t.dimgT16, Mip));
     TRY(transpose_t<T16>(h, st, t.img16, Mi, h->Fp, h->Fp, t.imgT16, Mip));

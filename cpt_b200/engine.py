@@ -201,11 +201,12 @@ class Engine(object):
             img = _chk_tensor("img_feats", img_feats, torch.float32, dev, (B, R, self.cfg.img_feature_dim))
         return B, T, R, ids, seg, msk, pos, img
 
-    def train_forward(self, head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets):
+    def train_forward(self, head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets,
+                      dropout=None):
         """head "mlm": loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled
         positions `rows` (flat b*S+s indices) with labels `targets`; head "nsp": loss of
         NSPCPT.forward(next_sentence_label=...) (modeling_vcr.py:120-127), rows = b*S of the labelled samples.
-        Returns (loss, saved) — `saved` feeds train_backward."""
+        dropout = (p_hidden, p_attn, seed) or None.  Returns (loss, saved) — `saved` feeds train_backward."""
         if not self.train:
             raise CptError("cpt_b200: this engine was not created with train=True")
         B, T, R, ids, seg, msk, pos, img = self._train_inputs(input_ids, token_type_ids, attention_mask,
@@ -214,14 +215,17 @@ class Engine(object):
         rows = _chk_tensor("rows", rows, torch.int64, dev)
         targets = _chk_tensor("targets", targets, torch.int64, dev, tuple(rows.shape))
         n = int(rows.numel())
+        drop = _lib.Dropout(0.0, 0.0, 0)
+        if dropout is not None:
+            drop = _lib.Dropout(float(dropout[0]), float(dropout[1]), int(dropout[2]) & 0xFFFFFFFFFFFFFFFF)
         with torch.cuda.device(dev):
             nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
             tape = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             fwd = self.lib.cpt_train_forward_mlm if head == "mlm" else self.lib.cpt_train_forward_nsp
             _lib.check(fwd(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos), _ptr(img), B, T, R,
-                           _ptr(rows), _ptr(targets), n, _ptr(tape), tape.numel(), _ptr(loss)))
-        saved = dict(head=head, B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
+                           _ptr(rows), _ptr(targets), n, C.byref(drop), _ptr(tape), tape.numel(), _ptr(loss)))
+        saved = dict(head=head, drop=drop, B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
                      version=self.weights_version)
         return loss, saved
 
@@ -260,8 +264,8 @@ class Engine(object):
         with torch.cuda.device(dev):
             bwd = self.lib.cpt_train_backward_mlm if s["head"] == "mlm" else self.lib.cpt_train_backward_nsp
             _lib.check(bwd(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]), _ptr(s["pos"]), s["B"], s["T"], s["R"],
-                           _ptr(s["rows"]), _ptr(s["targets"]), s["n"], _ptr(gl), _ptr(s["tape"]), s["tape"].numel(),
-                           C.byref(g)))
+                           _ptr(s["rows"]), _ptr(s["targets"]), s["n"], C.byref(s["drop"]), _ptr(gl), _ptr(s["tape"]),
+                           s["tape"].numel(), C.byref(g)))
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

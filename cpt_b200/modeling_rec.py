@@ -72,17 +72,17 @@ class REC_MLM_CPT(BertPreTrainedModel):
         """(loss, None): the loss is differentiable with respect to every parameter (native forward + backward,
         cpt_b200/training.py).  The reference also returns the [B,S,V] prediction_scores next to the loss; no
         caller reads them on this path (`loss, output = model(...)`), so they are not materialised."""
-        from .training import mlm_loss
+        from .training import draw_dropout, mlm_loss
         if head_mask is not None or mask_pos is not None:
             raise NotImplementedError("cpt_b200: head_mask / mask_pos are not supported together with masked_lm_labels")
         if getattr(self.config, "output_hidden_states", False) or getattr(self.config, "output_attentions", False):
             raise NotImplementedError("cpt_b200: output_hidden_states / output_attentions in the training step")
         if attention_mask is not None and attention_mask.dim() != 2:
             raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
-        self.bert._check_mode()
         if attention_mask is not None and attention_mask.dtype != torch.int64:
             attention_mask = attention_mask.to(torch.int64)
         eng, named = self.bert.train_engine()
+        self.last_dropout = draw_dropout(self.config, self.training)
         loss, _ = mlm_loss(eng, named, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                           masked_lm_labels)
+                           masked_lm_labels, self.last_dropout)
         return (loss, None)

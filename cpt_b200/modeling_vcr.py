@@ -51,17 +51,17 @@ class NSPCPT(BertPreTrainedModel):
                     img_feats):
         """(loss, None) — vcr_nsp_cpt.py:445-461 reads `loss, logits = outputs[:2]` and only uses the loss.  Native
         forward + backward behind autograd (cpt_b200/training.py)."""
-        from .training import nsp_loss
+        from .training import draw_dropout, nsp_loss
         if head_mask is not None:
             raise NotImplementedError("cpt_b200: head_mask is never used on the CPT path")
         if getattr(self.config, "output_hidden_states", False) or getattr(self.config, "output_attentions", False):
             raise NotImplementedError("cpt_b200: output_hidden_states / output_attentions in the training step")
         if attention_mask is not None and attention_mask.dim() != 2:
             raise NotImplementedError("cpt_b200: only 2-D attention masks are supported")
-        self.bert._check_mode()
         if attention_mask is not None and attention_mask.dtype != torch.int64:
             attention_mask = attention_mask.to(torch.int64)
         eng, named = self.bert.train_engine()
+        self.last_dropout = draw_dropout(self.config, self.training)
         loss, _ = nsp_loss(eng, named, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                           next_sentence_label)
+                           next_sentence_label, self.last_dropout)
         return (loss, None)

@@ -30,9 +30,9 @@ def trainable_keys(cfg, head, has_img=True):
 class _Loss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, keys, inputs, *params):
-        head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets = inputs
+        head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets, dropout = inputs
         loss, saved = engine.train_forward(head, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                                           rows, targets)
+                                           rows, targets, dropout)
         ctx.engine, ctx.keys, ctx.saved = engine, keys, saved
         ctx.shapes = [tuple(p.shape) for p in params]
         return loss
@@ -47,8 +47,17 @@ class _Loss(torch.autograd.Function):
         return (None, None, None) + out
 
 
+def draw_dropout(cfg, training):
+    """(p_hidden, p_attn, seed) for one forward, or None.  The seed comes from torch's default CPU generator, so
+    torch.manual_seed() makes a run reproducible (the masks themselves are this library's, include/cpt_b200.h)."""
+    p_h, p_a = float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob)
+    if not training or (p_h <= 0 and p_a <= 0):
+        return None
+    return (p_h, p_a, int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
 def mlm_loss(engine, named_params, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-             masked_lm_labels):
+             masked_lm_labels, dropout=None):
     """CrossEntropyLoss(ignore_index=-1) of the MLM scores against masked_lm_labels [B,S], differentiable with
     respect to `named_params` (dict keyed like the state_dict).  Returns (loss, rows): rows = flat indices of the
     labelled positions."""
@@ -60,12 +69,12 @@ def mlm_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     has_img = img_feats is not None and img_feats.shape[1] > 0
     keys = [k for k in trainable_keys(engine.cfg, "mlm", has_img) if k in named_params]
     params = [named_params[k] for k in keys]
-    inputs = ("mlm", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets)
+    inputs = ("mlm", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets, dropout)
     return _Loss.apply(engine, keys, inputs, *params), rows
 
 
 def nsp_loss(engine, named_params, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-             next_sentence_label):
+             next_sentence_label, dropout=None):
     """CrossEntropyLoss(ignore_index=-1) of cls.seq_relationship(pooled) against next_sentence_label [B]
     (modeling_vcr.py:120-127), differentiable with respect to `named_params`."""
     flat = next_sentence_label.reshape(-1)
@@ -78,5 +87,5 @@ def nsp_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     has_img = img_feats is not None and img_feats.shape[1] > 0
     keys = [k for k in trainable_keys(engine.cfg, "nsp", has_img) if k in named_params]
     params = [named_params[k] for k in keys]
-    inputs = ("nsp", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets)
+    inputs = ("nsp", input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets, dropout)
     return _Loss.apply(engine, keys, inputs, *params), rows

@@ -101,8 +101,10 @@ int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, flo
  * loss = CrossEntropyLoss(ignore_index=-1)(cls(bert(...)).view(-1, V), masked_lm_labels.view(-1)) and its gradient
  * with respect to every parameter — REC_MLM_CPT.forward with masked_lm_labels, modeling_rec.py:137-150, as the
  * few-shot loops call it (Oscar/oscar/fewshot/refcoco_cpt.py:231-250, gqa_cpt.py:428-462: forward, loss.backward(),
- * optimizer.step()).  Dropout is not applied (the handle computes the p = 0 function; the Python module refuses
- * .train() with p > 0 until the masks are implemented).
+ * optimizer.step()).  Dropout (cpt_dropout) sits where the reference has it: on the embedding outputs, the attention
+ * probabilities and the two dense outputs of every layer (modeling_bert.py:57,247,266 + BertSelfOutput / BertOutput).
+ * Masks are a counter-based hash of (seed, site, element index) — regenerated by the backward, never stored — so they
+ * are reproducible from the seed but are NOT the masks torch's Philox stream would draw.
  *
  * cpt_train_enable(h, 1) before cpt_set_weights: the handle also keeps transposed 16-bit weights (the W operand of
  * the dgrad GEMMs) and later cpt_set_weights calls refresh the existing buffers in stream order instead of
@@ -124,6 +126,13 @@ typedef struct {
   const cpt_layer_grads *layers; /* host array [num_hidden_layers] */
 } cpt_grads;
 
+/* Dropout of one training step; NULL or all-zero probabilities = off.  The backward must get the same values. */
+typedef struct {
+  float p_hidden; /* config.hidden_dropout_prob            */
+  float p_attn;   /* config.attention_probs_dropout_prob   */
+  uint64_t seed;  /* fresh per forward (the binding draws it from torch's CPU generator) */
+} cpt_dropout;
+
 /* Which loss head a training call runs. */
 enum { CPT_HEAD_MLM = 0, CPT_HEAD_NSP = 1 };
 
@@ -135,26 +144,26 @@ size_t cpt_train_tape_bytes(const cpt_handle *h, int B, int T, int R, int n_rows
  * targets int64 [n_rows]: their labels.  loss: fp32 scalar (device).  Inputs as cpt_encoder_forward. */
 int cpt_train_forward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
                           const int64_t *attention_mask, const int64_t *position_ids, const float *img_feats, int B,
-                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows, void *tape,
-                          size_t tape_bytes, float *loss);
-/* Backward of the forward that filled `tape` (same inputs, same weights).  grad_loss: fp32 scalar (device),
- * d(objective)/d(loss) — autograd's grad_output. */
+                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows,
+                          const cpt_dropout *dropout, void *tape, size_t tape_bytes, float *loss);
+/* Backward of the forward that filled `tape` (same inputs, same weights, same dropout).  grad_loss: fp32 scalar
+ * (device), d(objective)/d(loss) — autograd's grad_output. */
 int cpt_train_backward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
                            const int64_t *position_ids, int B, int T, int R, const int64_t *rows,
-                           const int64_t *targets, int n_rows, const float *grad_loss, void *tape, size_t tape_bytes,
-                           const cpt_grads *grads);
+                           const int64_t *targets, int n_rows, const cpt_dropout *dropout, const float *grad_loss,
+                           void *tape, size_t tape_bytes, const cpt_grads *grads);
 
 /* The VCR few-shot loss: CrossEntropyLoss(ignore_index=-1)(cls.seq_relationship(pooled), next_sentence_label) —
  * NSPCPT.forward, Oscar/oscar/modeling/modeling_vcr.py:115-129, as vcr_nsp_cpt.py:434-473 trains it.
  * rows int64 [n_rows]: b*(T+R) of the samples whose label is not -1 (the [CLS] rows); targets their labels. */
 int cpt_train_forward_nsp(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
                           const int64_t *attention_mask, const int64_t *position_ids, const float *img_feats, int B,
-                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows, void *tape,
-                          size_t tape_bytes, float *loss);
+                          int T, int R, const int64_t *rows, const int64_t *targets, int n_rows,
+                          const cpt_dropout *dropout, void *tape, size_t tape_bytes, float *loss);
 int cpt_train_backward_nsp(cpt_handle *h, void *stream, const int64_t *input_ids, const int64_t *token_type_ids,
                            const int64_t *position_ids, int B, int T, int R, const int64_t *rows,
-                           const int64_t *targets, int n_rows, const float *grad_loss, void *tape, size_t tape_bytes,
-                           const cpt_grads *grads);
+                           const int64_t *targets, int n_rows, const cpt_dropout *dropout, const float *grad_loss,
+                           void *tape, size_t tape_bytes, const cpt_grads *grads);
 
 /* Blocks until `stream` drains; reports device-side input errors (token id / position out of range, the
  * IndexError the reference's nn.Embedding would raise) and launch failures. */

@@ -52,8 +52,19 @@ def _linear(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
 
 
-def _dropout(x, p, training):
-    return F.dropout(x, p, training) if (training and p > 0) else x
+# Optional mask source for training-mode parity tests: callable(site, x) -> {0,1} tensor shaped like x, with
+# site = ("emb_text"|"emb_img", None) or ("attn"|"ao"|"down", layer).  None -> torch's own dropout (the reference's
+# behaviour).  tests/test_gpu_train.py sets it to a restatement of the CUDA path's counter-based mask so that both
+# sides drop the same elements.
+MASK_PROVIDER = None
+
+
+def _dropout(x, p, training, site=None):
+    if not (training and p > 0):
+        return x
+    if MASK_PROVIDER is not None:
+        return x * MASK_PROVIDER(site, x).to(x.dtype) / (1.0 - p)
+    return F.dropout(x, p, training)
 
 
 def extended_attention_mask(attention_mask, dtype=torch.float32):
@@ -79,7 +90,7 @@ def text_embeddings(sd, cfg, input_ids, token_type_ids=None, position_ids=None, 
          + F.embedding(position_ids, sd[p + "position_embeddings.weight"])
          + F.embedding(token_type_ids, sd[p + "token_type_embeddings.weight"]))
     e = _ln(e, sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"], cfg.layer_norm_eps)
-    return _dropout(e, cfg.hidden_dropout_prob, training)
+    return _dropout(e, cfg.hidden_dropout_prob, training, ("emb_text", None))
 
 
 def region_embeddings(sd, cfg, img_feats, training=False):
@@ -87,10 +98,10 @@ def region_embeddings(sd, cfg, img_feats, training=False):
     x = _linear(img_feats, sd, "bert.img_embedding")
     if getattr(cfg, "use_img_layernorm", 0):
         x = _ln(x, sd["bert.LayerNorm.weight"], sd["bert.LayerNorm.bias"], cfg.img_layer_norm_eps)
-    return _dropout(x, cfg.hidden_dropout_prob, training)
+    return _dropout(x, cfg.hidden_dropout_prob, training, ("emb_img", None))
 
 
-def self_attention(sd, cfg, prefix, h, ext_mask, training=False):
+def self_attention(sd, cfg, prefix, h, ext_mask, training=False, layer=None):
     """CaptionBertSelfAttention.forward, modeling_bert.py:38-67 (history_state is None on CPT)."""
     B, S, H = h.shape
     nH = cfg.num_attention_heads
@@ -105,7 +116,7 @@ def self_attention(sd, cfg, prefix, h, ext_mask, training=False):
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dH)
     scores = scores + ext_mask
     probs = torch.softmax(scores, dim=-1)
-    probs = _dropout(probs, cfg.attention_probs_dropout_prob, training)
+    probs = _dropout(probs, cfg.attention_probs_dropout_prob, training, ("attn", layer))
     ctx = torch.matmul(probs, v)
     return ctx.permute(0, 2, 1, 3).contiguous().view(B, S, H), probs
 
@@ -113,12 +124,12 @@ def self_attention(sd, cfg, prefix, h, ext_mask, training=False):
 def encoder_layer(sd, cfg, i, h, ext_mask, training=False):
     """CaptionBertLayer.forward, modeling_bert.py:139-147 (+ BertSelfOutput/Intermediate/Output)."""
     p = "bert.encoder.layer.%d." % i
-    ctx, probs = self_attention(sd, cfg, p + "attention.self", h, ext_mask, training)
-    a = _dropout(_linear(ctx, sd, p + "attention.output.dense"), cfg.hidden_dropout_prob, training)
+    ctx, probs = self_attention(sd, cfg, p + "attention.self", h, ext_mask, training, i)
+    a = _dropout(_linear(ctx, sd, p + "attention.output.dense"), cfg.hidden_dropout_prob, training, ("ao", i))
     a = _ln(a + h, sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"],
             cfg.layer_norm_eps)
     inter = _gelu(_linear(a, sd, p + "intermediate.dense"))
-    o = _dropout(_linear(inter, sd, p + "output.dense"), cfg.hidden_dropout_prob, training)
+    o = _dropout(_linear(inter, sd, p + "output.dense"), cfg.hidden_dropout_prob, training, ("down", i))
     o = _ln(o + a, sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], cfg.layer_norm_eps)
     return o, probs
 

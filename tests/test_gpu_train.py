@@ -252,15 +252,122 @@ def test_accumulation_scaling_and_optimizer_step():
     assert abs(ce.item() - l1.item()) <= 5e-3 * max(1.0, abs(l1.item()))
 
 
-def test_training_refuses_active_dropout():
+# ---- dropout: the CUDA path's masks are a counter-based hash (cpt_b200/csrc/train.cuh drop_keep); restated here in
+# torch integer arithmetic and injected into the oracle so both sides drop exactly the same elements
+_M32 = 0xFFFFFFFF
+
+
+def _mul32(x, c):
+    return (((x & 0xFFFF) * c) + ((((x >> 16) * c) & 0xFFFF) << 16)) & _M32
+
+
+def keep_mask(idx, seed, site, p):
+    import numpy as np
+    lo, hi = idx & _M32, (idx >> 32) & _M32
+    x = lo ^ _mul32(hi, 0x9E3779B1)
+    x = x ^ (seed & _M32)
+    x = _mul32(x, 0x85EBCA6B)
+    x = x ^ (x >> 13)
+    x = (x + ((site * 0xC2B2AE35) & _M32) + (seed >> 32)) & _M32
+    x = x ^ (x >> 16)
+    x = _mul32(x, 0x7FEB352D)
+    x = x ^ (x >> 15)
+    x = _mul32(x, 0x846CA68B)
+    x = x ^ (x >> 16)
+    thresh = max(1, min(_M32, int(float(np.float32(p)) * 4294967296.0)))
+    return x >= thresh
+
+
+def make_provider(cfg, T, R, seed):
+    S, H = T + R, cfg.hidden_size
+    p_h, p_a = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob
+
+    def provider(site, x):
+        kind, layer = site
+        if kind in ("emb_text", "emb_img"):
+            B, n = x.shape[0], x.shape[1]
+            off = 0 if kind == "emb_text" else T
+            rows = (torch.arange(B)[:, None] * S + off + torch.arange(n)[None, :])  # [B, n]
+            idx = rows[:, :, None] * H + torch.arange(H)[None, None, :]
+            return keep_mask(idx, seed, 0xFFFF0 if kind == "emb_text" else 0xFFFF1, p_h)
+        idx = torch.arange(x.numel()).view(x.shape)
+        code = {"attn": 0, "ao": 1, "down": 2}[kind]
+        return keep_mask(idx, seed, layer * 4 + code, p_a if kind == "attn" else p_h)
+
+    return provider
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,T,R,p_h,p_a", [(4, 50, 30, 0.1, 0.1), (2, 70, 50, 0.3, 0.0), (3, 40, 0, 0.0, 0.2)])
+def test_dropout_step_against_oracle_with_the_same_masks(B, T, R, p_h, p_a, dtype):
+    """training mode with active dropout (the reference's few-shot configs run hidden_dropout_prob 0.1-0.3): loss and
+    every gradient against the oracle fed the same keep-masks."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=15)
+    b = synth_batch(cfg, B, T, max(R, 1), seed=60 + B)
+    if R == 0:
+        b["img_feats"] = None
+        b["attention_mask"] = b["attention_mask"][:, :T].contiguous()
+    labels = torch.full((B, T + R), -1, dtype=torch.long)
+    labels[torch.arange(B), b["mask_pos"]] = torch.arange(B) + 7
+    rec = build_rec(cfg, sd, dtype)
+    rec.config.hidden_dropout_prob, rec.config.attention_probs_dropout_prob = p_h, p_a
+    d = {k: (v.cuda() if v is not None else None) for k, v in b.items()}
+    torch.manual_seed(1234 + B)
+    loss, _ = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                  masked_lm_labels=labels.cuda())
+    (loss * LOSS_SCALE[dtype]).backward()
+    rec.bert.train_engine()[0].check()
+    seed = rec.last_dropout[2]
+    # the oracle in training mode with the same masks
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.MASK_PROVIDER = make_provider(rec.config, T, R, seed)
+    try:
+        ref_loss = O.rec_mlm_cpt(leaf, rec.config, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                 masked_lm_labels=labels, img_feats=b["img_feats"], training=True)[0]
+    finally:
+        O.MASK_PROVIDER = None
+    ref_loss.backward()
+    # dropout really happened: the p = 0 loss differs
+    base = O.rec_mlm_cpt(sd, rec.config, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                         masked_lm_labels=labels, img_feats=b["img_feats"], training=False)[0]
+    assert abs(base.item() - ref_loss.item()) > 1e-4
+    assert abs(loss.item() - ref_loss.item()) <= LTOL[dtype] * abs(ref_loss.item())
+
+    def key_of(k):
+        key = k if k.startswith("bert.") else "cls.predictions." + k[len("cls."):]
+        return None if key == "cls.predictions.decoder.weight" else key
+
+    compare_all(rec.named_parameters(), {k: v.grad for k, v in leaf.items()}, key_of, dtype, LOSS_SCALE[dtype],
+                16 * 2 + 10)
+
+
+def test_dropout_is_seeded_by_torch_and_off_in_eval():
     cfg = C.oscar_tiny(num_hidden_layers=1)
     sd = synth_state_dict(cfg, seed=1)
     rec = build_rec(cfg, sd, "bf16")
     rec.config.hidden_dropout_prob = 0.1
+    rec.config.attention_probs_dropout_prob = 0.1
     b = synth_batch(cfg, 2, 20, 8, seed=1)
     d = {k: v.cuda() for k, v in b.items()}
     labels = torch.full((2, 28), -1, dtype=torch.long)
     labels[:, 3] = 7
+    labels = labels.cuda()
+
+    def run():
+        return rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                   masked_lm_labels=labels)[0].item()
+
+    torch.manual_seed(5)
+    a = run()
+    torch.manual_seed(5)
+    assert run() == a
+    assert run() != a  # generator advanced: new masks
+    rec.eval()  # eval mode: no dropout, even through the (grad-enabled) training entry point
+    e1, e2 = run(), run()
+    assert e1 == e2
+    # a forward without labels in train mode with active dropout has no native path
+    rec.train()
     with pytest.raises(NotImplementedError):
-        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
-            masked_lm_labels=labels.cuda())
+        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])
