@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcpt_b200.so")
 ABI_VERSION = 2
-K_COUNT = 17  # CPT_K_COUNT
+K_COUNT = 21  # CPT_K_COUNT
 
 
 class CptError(RuntimeError):
@@ -90,6 +90,7 @@ SYMBOLS = {
     "cpt_gemm_trace": (_i, [_p, C.POINTER(_ll), _i]),
     "cpt_gemm": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _i, _p, _ll, _i]),
     "cpt_attention": (_i, [_p, _p, _p, _p, _i, _i, _p, _i]),
+    "cpt_attention_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),
     "cpt_cast16": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
 }

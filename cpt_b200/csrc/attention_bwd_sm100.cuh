@@ -1,0 +1,215 @@
+// Self-attention backward on the tensor cores for S <= 128 (the RefCOCO geometry, S = 120), one CTA per
+// (head, sample).  Probabilities are recomputed from Q, K (never stored by the forward):
+//     S  = Q K^T                 (tcgen05, TMEM cols   0..127)      P  = softmax(S / sqrt(dH) + ext_mask)
+//     dP = dO V^T                (tcgen05, TMEM cols 128..255)      D  = rowsum(P * dP)
+//     dS = P * (dP - D) / sqrt(dH)
+//     dQ = dS K                  (A = dS, K-major;  B = K tile, MN-major)          TMEM cols 256..319, lanes = queries
+//     dV = P^T dO                (A = P  read MN-major: M = keys; B = dO MN-major)  TMEM cols 320..383, lanes = keys
+//     dK = dS^T Q                (A = dS read MN-major;           B = Q  MN-major)  TMEM cols 384..447, lanes = keys
+// Thread r owns query row r for the softmax algebra (TMEM lane r of S, dP, dQ) and key row r for the dV / dK read-out.
+// P and dS are written once to shared memory as 16-bit [query][key] tiles in the 128B-swizzled layout; the same bytes
+// serve as the K-major A operand of dQ and, through an MN-major descriptor, as the transposed A operand of dV / dK —
+// no transpose pass.  Rows / keys beyond S are zeroed so the neighbouring sample's rows that the 128-row TMA boxes
+// pull in never contribute.
+#pragma once
+#include "attention_sm100.cuh"
+#include "ptx.cuh"
+
+namespace cptk {
+
+struct AttnBwdParams {
+  int B, S, H, nH;
+  const float* ext_mask;  // [B, S]
+  void* dqkv;             // T16 [B*S, 3H]
+  float scale;
+};
+
+constexpr int kAttnBwdSmem = 1024 + 4 * 16384 + 2 * 32768 + 512 + 64;
+
+template <typename T16>
+__global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                          const __grid_constant__ CUtensorMap tmap_do,
+                                                          const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int S = p.S;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = sQ + 16384, sV = sK + 16384, sdO = sV + 16384;
+  const uint32_t sP = sdO + 16384, sdS = sP + 32768;
+  const uint32_t sMask = sdS + 32768;
+  const uint32_t bar_ld = sMask + 512, bar_s = bar_ld + 8, bar_g = bar_ld + 16, tmem_slot = bar_ld + 32;
+  float* maskp = reinterpret_cast<float*>(smem_raw + (sMask - smem_u32(smem_raw)));
+  uint8_t* p_gen = smem_raw + (sP - smem_u32(smem_raw));
+  uint8_t* ds_gen = smem_raw + (sdS - smem_u32(smem_raw));
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_g, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 128) maskp[threadIdx.x] = (threadIdx.x < S) ? p.ext_mask[(long long)b * S + threadIdx.x] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t cS = 0, cdP = 128, cdQ = 256, cdV = 320, cdK = 384;
+
+  if (threadIdx.x == 0) {
+    const int row0 = b * S;
+    mbar_expect_tx(bar_ld, 4 * 16384);
+    for (int rb = 0; rb < 2; ++rb) {
+      tma_load_2d(sQ + rb * 8192, &tmap_qkv, bar_ld, h * kAttnDH, row0 + rb * 64);
+      tma_load_2d(sK + rb * 8192, &tmap_qkv, bar_ld, p.H + h * kAttnDH, row0 + rb * 64);
+      tma_load_2d(sV + rb * 8192, &tmap_qkv, bar_ld, 2 * p.H + h * kAttnDH, row0 + rb * 64);
+      tma_load_2d(sdO + rb * 8192, &tmap_do, bar_ld, h * kAttnDH, row0 + rb * 64);
+    }
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, 128, Cvt<T16>::kFmt, 0, 0);
+    const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd = make_smem_desc(sK, 16, 1024);
+    const uint64_t od = make_smem_desc(sdO, 16, 1024), vd = make_smem_desc(sV, 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(tmem_base + cS, qd + 2 * k, kd + 2 * k, idesc, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(tmem_base + cdP, od + 2 * k, vd + 2 * k, idesc, k != 0);
+    umma_commit(bar_s);
+  }
+
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  const int r = warp * 32 + lane;
+  const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+  float mx = -INFINITY;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float t = (col < S) ? fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) : -INFINITY;
+      mx = fmaxf(mx, t);
+    }
+  }
+  float sum = 0.f, dn = 0.f;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32], w[32];
+    tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
+    tmem_ld_32x32b_x32(t_row + cdP + c * 32, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float e = (col < S) ? __expf(fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) - mx) : 0.f;
+      sum += e;
+      dn = fmaf(e, __uint_as_float(w[j]), dn);
+    }
+  }
+  const bool valid = r < S;
+  const float inv = valid ? 1.0f / sum : 0.f;
+  const float D = dn * inv;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32], w[32];
+    tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
+    tmem_ld_32x32b_x32(t_row + cdP + c * 32, w);
+    tmem_ld_wait();
+    float pr[32], ds[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float e = (col < S) ? __expf(fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) - mx) : 0.f;
+      pr[j] = e * inv;
+      ds[j] = pr[j] * (__uint_as_float(w[j]) - D) * p.scale;
+    }
+    const int kb = c >> 1;
+    uint8_t* prow = p_gen + kb * 16384 + r * 128;
+    uint8_t* drow = ds_gen + kb * 16384 + r * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u, d;
+      u.x = Cvt<T16>::pack2(pr[8 * i + 0], pr[8 * i + 1]);
+      u.y = Cvt<T16>::pack2(pr[8 * i + 2], pr[8 * i + 3]);
+      u.z = Cvt<T16>::pack2(pr[8 * i + 4], pr[8 * i + 5]);
+      u.w = Cvt<T16>::pack2(pr[8 * i + 6], pr[8 * i + 7]);
+      d.x = Cvt<T16>::pack2(ds[8 * i + 0], ds[8 * i + 1]);
+      d.y = Cvt<T16>::pack2(ds[8 * i + 2], ds[8 * i + 3]);
+      d.z = Cvt<T16>::pack2(ds[8 * i + 4], ds[8 * i + 5]);
+      d.w = Cvt<T16>::pack2(ds[8 * i + 6], ds[8 * i + 7]);
+      const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
+      *reinterpret_cast<uint4*>(prow + chunk * 16) = u;
+      *reinterpret_cast<uint4*>(drow + chunk * 16) = d;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    // dQ = dS K : A K-major [queries x keys], B = K tile rows = keys (the product's K dim) -> MN-major
+    const uint32_t id_q = make_idesc_f16(128, kAttnDH, Cvt<T16>::kFmt, 0, 1);
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t ad = make_smem_desc(sdS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+      const uint64_t bd = make_smem_desc(sK + k * 2048, 1024, 1024);
+      umma_f16(tmem_base + cdQ, ad, bd, id_q, k != 0);
+    }
+    // dV = P^T dO, dK = dS^T Q : A read MN-major (M = keys: two 64-key blocks 16 KB apart, 8-query groups 1 KB apart)
+    const uint32_t id_t = make_idesc_f16(128, kAttnDH, Cvt<T16>::kFmt, 1, 1);
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t ad = make_smem_desc(sP + k * 2048, 16384, 1024);
+      const uint64_t bd = make_smem_desc(sdO + k * 2048, 1024, 1024);
+      umma_f16(tmem_base + cdV, ad, bd, id_t, k != 0);
+    }
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t ad = make_smem_desc(sdS + k * 2048, 16384, 1024);
+      const uint64_t bd = make_smem_desc(sQ + k * 2048, 1024, 1024);
+      umma_f16(tmem_base + cdK, ad, bd, id_t, k != 0);
+    }
+    umma_commit(bar_g);
+  }
+  mbar_wait(bar_g, 0);
+  tc_fence_after();
+  {
+    // tcgen05.ld is warp-collective: every lane reads, only rows < S store
+    T16* dst = reinterpret_cast<T16*>(p.dqkv) + ((long long)b * S + r) * 3 * p.H + h * kAttnDH;
+    const uint32_t cols[3] = {cdQ, cdK, cdV};
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + cols[which] + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = Cvt<T16>::pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+            u.y = Cvt<T16>::pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+            u.z = Cvt<T16>::pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+            u.w = Cvt<T16>::pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+            *reinterpret_cast<uint4*>(dst + which * p.H + c * 32 + i * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace cptk

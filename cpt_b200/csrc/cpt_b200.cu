@@ -18,6 +18,7 @@
 
 #include "../../include/cpt_b200.h"
 #include "attention_sm100.cuh"
+#include "attention_bwd_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
 #include "train.cuh"
@@ -134,6 +135,7 @@ struct cpt_handle {
   float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
   void *mlm_w16 = nullptr, *word16 = nullptr;
   void *mlm_w16_t = nullptr, *word16_t = nullptr;  // training: [H,H]^T and [H, Vp] (Vp = vocab rounded up to 8)
+  int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
   int train = 0;                                   // cpt_train_enable: keep transposed copies, reuse allocations
   unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
   float *nsp_w = nullptr, *nsp_b = nullptr;
@@ -882,6 +884,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   cudaMemset(h->err_flag, 0, 16);
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
+  if (const char* e = getenv("CPT_B200_ATTN_BWD")) h->attn_bwd_simt = strcmp(e, "simt") == 0;
   if (const char* e = getenv("CPT_B200_FOLD_LN")) h->fold_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_DELTA16")) h->delta16 = atoi(e) != 0;
@@ -1116,7 +1119,8 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
 static const char* kKernelNames[CPT_K_COUNT] = {"ext_mask", "embed_text_ln", "cast_pad", "gemm_img", "layernorm",
                                                  "gemm_qkv", "attention", "gemm_attn_out", "gemm_ffn_up",
                                                  "gemm_ffn_down", "head_matvec", "gemm_head", "gemm_other",
-                                                 "gemm_dgrad", "gemm_wgrad", "attention_bwd", "train_rowwise"};
+                                                 "gemm_dgrad", "gemm_wgrad", "attention_bwd", "train_rowwise",
+                                                 "transpose16", "colsum", "layernorm_bwd", "embed_bwd"};
 const char* cpt_kernel_name(int tag) { return (tag >= 0 && tag < CPT_K_COUNT) ? kKernelNames[tag] : ""; }
 long long cpt_launch_count(const cpt_handle* h) { return h ? h->launches : 0; }
 
@@ -1174,6 +1178,15 @@ int cpt_attention(cpt_handle* h, void* stream, const void* qkv, const float* ext
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
 #define CALL(T16) attention<T16>(h, (cudaStream_t)stream, qkv, ext_mask, B, S, ctx, impl)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_attention_backward(cpt_handle* h, void* stream, const void* qkv, const void* dctx, const float* ext_mask, int B,
+                           int S, void* dqkv, int impl) {
+  if (!h || !qkv || !dctx || !ext_mask || !dqkv) return fail("NULL argument");
+  DeviceGuard g(h->device);
+#define CALL(T) attention_backward<T>(h, (cudaStream_t)stream, qkv, dctx, ext_mask, B, S, dqkv, nullptr, 0.f, 0u, impl)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

@@ -126,7 +126,7 @@ static int ew_grid(const cpt_handle* h, long long n) {
 template <typename T>
 static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, long long ld, float* out) {
   if (M <= 0 || !out) return 0;
-  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  ProfScope ps(h, st, CPT_K_COLSUM);
   const int gy = std::max(1, std::min((M + 63) / 64, 4 * h->num_sms / std::max(1, (N + 255) / 256)));
   colsum_kernel<T><<<dim3((N + 255) / 256, gy), 256, 0, st>>>(in, M, N, ld, out);
   CKL("colsum_kernel");
@@ -136,7 +136,7 @@ static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, lon
 template <typename T16>
 static int transpose_t(cpt_handle* h, cudaStream_t st, const void* in, int R, int C, long long ld_in, void* out,
                        long long ld_out) {
-  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  ProfScope ps(h, st, CPT_K_TRANSPOSE);
   return transpose16<T16>(st, in, R, C, ld_in, out, ld_out);
 }
 
@@ -145,7 +145,7 @@ static int ln_bwd(cpt_handle* h, cudaStream_t st, const float* dy, const float* 
                   float eps, bool do_ln, float* dx32, void* dx16, float* dgamma, float* dbeta, int rin = 0,
                   int rout = 0, int roff = 0, Drop drop_dy = Drop{0, 0, 0, 0, 1.f}, Drop drop16 = Drop{0, 0, 0, 0, 1.f}) {
   if (M <= 0) return 0;
-  ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+  ProfScope ps(h, st, CPT_K_LN_BWD);
   const int grid = std::min((M + 7) / 8, 2 * h->num_sms);
 #define CPT_LNB_CASE(NV_)                                                                                         \
   case NV_:                                                                                                       \
@@ -164,6 +164,42 @@ static int ln_bwd(cpt_handle* h, cudaStream_t st, const float* dy, const float* 
 }
 
 // out(+)= A[M,K] . W[N,K]^T, no bias.  accumulate -> fp32 reduce-add into `out`.
+// d(qkv) from d(ctx): impl -1 = pick (tensor cores for S <= 128 without probability dropout, else CUDA cores),
+// 0 = tensor cores, 1 = CUDA cores
+template <typename T16>
+static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, const void* dctx, const float* ext_mask,
+                              int B, int S, void* dqkv, const cpt_dropout* dropout, float p_a, unsigned site,
+                              int impl) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, nH = c.num_attention_heads;
+  if (S < 1 || S > 256) return fail("attention backward supports 1 <= S <= 256 (got %d)", S);
+  if (impl < 0) impl = (S <= 128 && !(p_a > 0.f) && !h->attn_bwd_simt) ? 0 : 1;
+  ProfScope ps(h, st, CPT_K_ATTN_BWD);
+  if (impl == 0) {
+    if (S > 128 || p_a > 0.f) return fail("tensor-core attention backward: S <= 128 and no probability dropout");
+    CUtensorMap tq, td;
+    TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
+    TRY(make_tmap(&td, dctx, Cvt<T16>::kFmt, (unsigned long long)B * S, (unsigned long long)H, (unsigned long long)H, 64));
+    auto* fn = attn_bwd_tc_kernel<T16>;
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      TRY(set_smem_attr(fn, kAttnBwdSmem));
+      attr_set[h->device & 63] = true;
+    }
+    AttnBwdParams p{B, S, H, nH, ext_mask, dqkv, 0.125f};
+    fn<<<dim3(nH, B), 128, kAttnBwdSmem, st>>>(tq, td, p);
+    CKL("attn_bwd_tc_kernel");
+    return 0;
+  }
+  auto* fn = attn_bwd_simt_kernel<T16>;
+  const size_t smem = (size_t)S * kAttnDH * 2 * 4 + (size_t)S * 4 * 4;
+  TRY(set_smem_attr(fn, smem));
+  fn<<<dim3(nH, B), 128, smem, st>>>(reinterpret_cast<const T16*>(qkv), reinterpret_cast<const T16*>(dctx), ext_mask, S,
+                                     H, 0.125f, reinterpret_cast<T16*>(dqkv), make_drop(dropout, p_a, site));
+  CKL("attn_bwd_simt_kernel");
+  return 0;
+}
+
 template <typename T16>
 static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W,
                       long long ldw, int M, int N, int K, void* out, long long ldo, bool out_fp32, bool accumulate) {
@@ -485,17 +521,8 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     TRY(transpose_t<T16>(h, st, tl.ctx16, M, H, H, t.actT16, Mp));
     TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, H, Mp, gl.ao_w, H, true, true));
     TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_ao_t, H, M, H, H, t.dctx16, H, false, false));
-    {  // attention
-      ProfScope ps(h, st, CPT_K_ATTN_BWD);
-      auto* fn = attn_bwd_simt_kernel<T16>;
-      const size_t smem = (size_t)S * kAttnDH * 2 * 4 + (size_t)S * 4 * 4;
-      TRY(set_smem_attr(fn, smem));
-      fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16),
-                                                            reinterpret_cast<const T16*>(t.dctx16), t.ext_mask, S, H,
-                                                            0.125f, reinterpret_cast<T16*>(t.big16),
-                                                            make_drop(dropout, p_a, l * 4 + SITE_ATTN));
-      CKL("attn_bwd_simt_kernel");
-    }
+    TRY(attention_backward<T16>(h, st, tl.qkv16, t.dctx16, t.ext_mask, B, S, t.big16, dropout, p_a,
+                                (unsigned)(l * 4 + SITE_ATTN), -1));
     // query / key / value
     float* qkv_b[3] = {gl.q_b, gl.k_b, gl.v_b};
     float* qkv_w[3] = {gl.q_w, gl.k_w, gl.v_w};
@@ -511,7 +538,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
 
   // ---- embeddings
   {
-    ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
+    ProfScope ps(h, st, CPT_K_EMBED_BWD);
 #define CPT_EMBB_CASE(NV_)                                                                                           \
   case NV_:                                                                                                          \
     embed_bwd_kernel<NV_><<<(B * T + 7) / 8, 256, 0, st>>>(                                                          \

@@ -394,6 +394,13 @@ class Engine(object):
             _lib.check(self.lib.cpt_attention(self._h, _stream(), _ptr(qkv), _ptr(ext_mask), B, S, _ptr(ctx), impl))
         return ctx
 
+    def attention_backward(self, qkv, dctx, ext_mask, B, S, impl=-1):
+        dqkv = torch.zeros_like(qkv)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_attention_backward(self._h, _stream(), _ptr(qkv), _ptr(dctx), _ptr(ext_mask), B, S,
+                                                       _ptr(dqkv), impl))
+        return dqkv
+
     def layernorm(self, x, gamma, beta, eps):
         M, H = x.shape
         o32 = torch.empty_like(x)

@@ -173,7 +173,8 @@ int cpt_check_async_error(cpt_handle *h, void *stream);
 enum {
   CPT_K_EXTMASK = 0, CPT_K_EMBED, CPT_K_CAST, CPT_K_GEMM_IMG, CPT_K_LN, CPT_K_GEMM_QKV, CPT_K_ATTN,
   CPT_K_GEMM_AO, CPT_K_GEMM_UP, CPT_K_GEMM_DOWN, CPT_K_HEAD, CPT_K_GEMM_HEAD, CPT_K_GEMM_OTHER,
-  CPT_K_GEMM_DGRAD, CPT_K_GEMM_WGRAD, CPT_K_ATTN_BWD, CPT_K_TRAIN_ROWWISE, CPT_K_COUNT
+  CPT_K_GEMM_DGRAD, CPT_K_GEMM_WGRAD, CPT_K_ATTN_BWD, CPT_K_TRAIN_ROWWISE, CPT_K_TRANSPOSE, CPT_K_COLSUM, CPT_K_LN_BWD,
+  CPT_K_EMBED_BWD, CPT_K_COUNT
 };
 const char *cpt_kernel_name(int tag);
 /* kernels launched by this handle since cpt_create */
@@ -204,6 +205,10 @@ int cpt_gemm_trace(cpt_handle *h, long long *out, int max_ctas);
  * tcgen05 kernel (earlier design, kept as a cross-check). */
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,
                   int impl);
+/* d(qkv)[B*S,3H] from d(ctx)[B*S,H] (16-bit), probabilities recomputed from qkv.  impl: -1 = library choice, 0 =
+ * tcgen05 kernel (S <= 128), 1 = CUDA-core kernel (any S <= 256). */
+int cpt_attention_backward(cpt_handle *h, void *stream, const void *qkv, const void *dctx, const float *ext_mask,
+                           int B, int S, void *dqkv, int impl);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
 int cpt_layernorm(cpt_handle *h, void *stream, const float *x, int M, const float *gamma, const float *beta,
                   float eps, float *out32, void *out16);

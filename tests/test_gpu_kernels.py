@@ -98,6 +98,34 @@ def test_attention_against_torch_and_simt(eng, B, S):
     assert (ctx_pipe.float() - ref).abs().max().item() <= 3e-3 * scale
 
 
+@pytest.mark.parametrize("B,S", [(2, 120), (1, 128), (3, 17), (2, 64), (2, 65), (1, 1), (8, 120), (2, 210), (1, 256)])
+def test_attention_backward_against_torch_autograd(eng, B, S):
+    """d(qkv) from d(ctx): tensor-core kernel (S <= 128) and CUDA-core kernel against fp32 autograd on the same
+    16-bit-rounded inputs."""
+    H, nH, dH = 768, 12, 64
+    g = torch.Generator(device="cuda").manual_seed(S * 7 + B)
+    qkv = (torch.randn(B * S, 3 * H, device="cuda", generator=g)).half()
+    dctx = (torch.randn(B * S, H, device="cuda", generator=g) * 0.1).half()
+    mask = (torch.rand(B, S, device="cuda", generator=g) > 0.3).long()
+    mask[:, 0] = 1
+    ext = (1.0 - mask.float()) * -10000.0
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (t.view(B, S, nH, dH).permute(0, 2, 1, 3) for t in x.split(H, dim=1))
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext[:, None, None, :], -1)
+    ctx = (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    ctx.backward(dctx.float())
+    ref = x.grad
+    impls = [1] + ([0] if S <= 128 else [])
+    for impl in impls:
+        got = eng.attention_backward(qkv, dctx, ext, B, S, impl=impl).float()
+        torch.cuda.synchronize()
+        for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+            scale = ref[:, sl].abs().max().item()
+            err = (got[:, sl] - ref[:, sl]).abs().max().item()
+            # P / dS are rounded to 16 bits before the second-stage products on the tensor-core path
+            assert err <= (4e-3 if impl == 0 else 1.5e-3) * scale, (impl, name, err / scale)
+
+
 def test_attention_fully_masked_row_matches_additive_mask_semantics(eng):
     # (1 - mask) * -10000 is ADDITIVE: an all-zero mask row yields softmax over the raw scores, not NaN
     B, S, H = 1, 24, 768
