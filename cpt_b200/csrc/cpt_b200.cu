@@ -289,13 +289,19 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
                 GemmParams p, int epi, bool out_fp32, int cfg = 0) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   ProfScope ps(h, st, tag);
-  const GemmChoice c = pick_gemm(h, tag, p.N, p.K, cfg);
+  GemmChoice c = pick_gemm(h, tag, p.N, p.K, cfg);
+  if (p.trans) c.pair = 0;
   p.trace = h->trace;
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
-  TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
-  TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
+  if (p.trans) {  // A is [K, M], W is [K, N]: 64 x 64 boxes, k along the rows
+    TRY(make_tmap(&ta, A, dt, p.K, p.M, lda, 64));
+    TRY(make_tmap(&tb, W, dt, p.K, p.N, ldw, 64));
+  } else {
+    TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
+    TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
+  }
   // outputs leave through TMA bulk stores (32x32 blocks) whenever the destination is 16-byte aligned and pitched;
   // otherwise (e.g. the [rows, 30522] fp32 score matrix) through the LSU path
   const unsigned osz = out_fp32 ? 4 : 2;
@@ -1168,6 +1174,9 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
   DeviceGuard g(h->device);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
+  p.trans = (epi & 0x100) ? 1 : 0;
+  p.tma_reduce = (epi & 0x200) ? 1 : 0;
+  epi &= 0xff;
 #define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, tile_cfg)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL

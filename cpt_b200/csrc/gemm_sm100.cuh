@@ -34,6 +34,10 @@ struct GemmParams {
   int tma_store;        // outputs leave through tmap_out (set by the host when `out` is 16-byte aligned and pitched)
   int tma_reduce;       // ... as out += tile (cp.reduce.async.bulk .add at L2): `out` already holds the residual
   long long* trace;     // optional [gridDim.x][16] cycle counters (debug): see cpt_gemm_trace
+  // trans != 0: out = A^T . W, both operands given TRANSPOSED in memory — A as [K, M], W as [K, N] row-major (the
+  // weight-gradient product dW = dY^T X straight from the row-major activations).  The tiles are staged as
+  // [64-wide MN block][64 k rows][128 B] and read through MN-major UMMA descriptors.  Single-CTA tiles only.
+  int trans;
   // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
   // EPI_BIAS / EPI_BIAS_GELU: the A operand is a PRE-LayerNorm tensor x (16-bit) and W already carries gamma;
   //   out = rstd_m * (acc - mu_m * gvec_n) + bias_n, with (mu, rstd) from nstats[m] = (sum x, sum x^2) over nH
@@ -208,7 +212,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           t_wait += clock64() - t0;
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          if (!PAIR) {
+          if (!PAIR && p.trans) {
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+            for (int blk = 0; blk < kGemmBM / 64; ++blk)
+              tma_load_2d(sa + blk * 8192, &tmap_a, full_bar(stage), m0 + blk * 64, kb * kGemmBK);
+#pragma unroll
+            for (int blk = 0; blk < BN / 64; ++blk)
+              tma_load_2d(sb + blk * 8192, &tmap_b, full_bar(stage), n0 + blk * 64, kb * kGemmBK);
+          } else if (!PAIR) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kGemmBK, m0);
             tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kGemmBK, n0);
@@ -233,7 +245,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 0, 0);
+      constexpr uint32_t idesc_kmajor = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 0, 0);
+      constexpr uint32_t idesc_mnmajor = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 1, 1);
+      const bool trans = !PAIR && p.trans;
+      const uint32_t idesc = trans ? idesc_mnmajor : idesc_kmajor;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -252,13 +267,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           t_full += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + Cfg::kABytes, 16, 1024);
+          // K-major: +32 B per UMMA_K=16 step inside the 128-byte swizzle row (descriptor address is in 16-B units);
+          // MN-major: 64-wide MN blocks 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO), +2 KB per 16 k rows
+          const uint64_t adesc = trans ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc =
+              trans ? make_smem_desc(sa + Cfg::kABytes, 8192, 1024) : make_smem_desc(sa + Cfg::kABytes, 16, 1024);
+          const uint32_t kstep = trans ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
-            // +32 B per UMMA_K=16 step inside the 128-byte swizzle row (descriptor address is in 16-B units)
-            if (PAIR) umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (PAIR) umma_f16_2cta(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
+            else umma_f16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
           }
           if (PAIR) umma_commit_2cta_mc(empty_bar(stage), 3);
           else umma_commit(empty_bar(stage));

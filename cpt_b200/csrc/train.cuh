@@ -74,17 +74,69 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const T16* __restrict_
   }
 }
 
-// out[n] += sum_m in[m, n]   (bias gradients); T = float or a 16-bit type
+// out[n] += sum_m in[m, n]   (bias gradients); T = float or a 16-bit type.  A CTA covers 256 columns x kColsumRows
+// rows: thread (x, y) sums columns 4x..4x+3 over rows y, y+4, ... with 8 loads in flight, the 4 row-lanes combine in
+// shared memory, one atomic per column per CTA.  N % 4 == 0 and 8-byte (16-bit) / 16-byte (fp32) aligned rows take the
+// vector path; anything else a scalar path.
+constexpr int kColsumRows = 128;
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 f = *reinterpret_cast<const float4*>(p);
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int M, int N, long long ld,
-                                                     float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-  const int m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
-  float s = 0.f;
-  for (int m = m0; m < m1; ++m) s += (float)in[(long long)m * ld + n];
-  if (m1 > m0) atomicAdd(out + n, s);
+                                                     float* __restrict__ out, int vec) {
+  __shared__ float red[4][256];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int n0 = blockIdx.x * 256 + tx * 4;
+  const int m0 = blockIdx.y * kColsumRows, m1 = min(M, m0 + kColsumRows);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n0 < N) {
+    if (vec && n0 + 3 < N) {
+      int m = m0 + ty;
+      for (; m + 28 < m1; m += 32) {
+        float v[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) load4<T>(in + (long long)(m + 4 * u) * ld + n0, v[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc[0] += v[u][0]; acc[1] += v[u][1]; acc[2] += v[u][2]; acc[3] += v[u][3];
+        }
+      }
+      for (; m < m1; m += 4) {
+        float v[4];
+        load4<T>(in + (long long)m * ld + n0, v);
+        acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+      }
+    } else {
+      for (int m = m0 + ty; m < m1; m += 4)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n0 + e < N) acc[e] += (float)in[(long long)m * ld + n0 + e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[ty][tx * 4 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x, n = blockIdx.x * 256 + c;
+  if (n < N) atomicAdd(out + n, (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]));
 }
 
 __device__ __forceinline__ float gelu_exact(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -4,9 +4,10 @@
 // reused workspace buffer, and FFN-up keeps its pre-activation (GELU is a separate pass).  Backward walks the layers
 // in reverse.  Every matrix product is the tcgen05 GEMM of gemm_sm100.cuh in its out = A . W^T form:
 //   dgrad  dX[M,Kin]    = dY[M,Nout] . (W^T)[Kin,Nout]^T      W^T = transposed 16-bit weights kept by the handle
-//   wgrad  dW[Nout,Kin] = (dY^T)[Nout,Mp] . (X^T)[Kin,Mp]^T   both operands transposed into scratch (zero padded to
-//                                                              Mp = M rounded up to 64), fp32 result ADDED into the
-//                                                              caller's gradient tensor by the TMA reduce-add store
+//   wgrad  dW[Nout,Kin] = dY[M,Nout]^T . X[M,Kin]             both operands read where they lie, row-major, through
+//                                                              MN-major UMMA descriptors (GemmParams::trans); the fp32
+//                                                              result is ADDED into the caller's gradient tensor by the
+//                                                              TMA reduce-add store
 // The residual branches are summed the same way (dgrad results reduce-added into the fp32 gradient stream).
 
 struct TapeLayer {
@@ -25,13 +26,11 @@ struct Tape {
   float *nx32, *npool, *nlog, *ndlog, *ndpre, *ndx;
   // backward scratch
   float *dH, *dx32, *hd32a, *hd32b, *hdx32, *dimg32, *dwimg;
-  char *dx16, *dxT16, *big16, *big16b, *bigT16, *actT16, *dctx16;
-  char *dlog16, *dlogT16, *htT16, *hxT16, *hd16, *hdT16, *dimg16, *dimgT16, *imgT16;
-  int Mp, np, Mip, Vp;
+  char *dx16, *big16, *big16b, *dctx16;
+  char *dlog16, *hd16, *dimg16;
+  int Vp;
   size_t total;
 };
-
-static int round64(int x) { return (x + 63) & ~63; }
 
 static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* base) {
   const cpt_config& c = h->cfg;
@@ -44,7 +43,7 @@ static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* ba
     return p;
   };
   Tape t;
-  t.Mp = round64((int)M); t.np = round64(n); t.Mip = round64((int)Mi); t.Vp = (int)((V + 7) & ~size_t(7));
+  t.Vp = (int)((V + 7) & ~size_t(7));
   t.ldl = (long long)((V + 3) & ~size_t(3));
   t.ext_mask = (float*)take(M * 4);
   t.img16 = take(Mi * h->Fp * 2);
@@ -80,25 +79,16 @@ static Tape carve_tape(const cpt_handle* h, int B, int T, int R, int n, char* ba
   t.dH = (float*)take(M * H * 4);
   t.dx32 = (float*)take(M * H * 4);
   t.dx16 = take(M * H * 2);
-  t.dxT16 = take(H * t.Mp * 2);
   t.big16 = take(M * W * 2);
   t.big16b = take(M * W * 2);
-  t.bigT16 = take(W * t.Mp * 2);
-  t.actT16 = take(W * t.Mp * 2);
   t.dctx16 = take(M * H * 2);
   t.dlog16 = take((size_t)n * t.Vp * 2);
-  t.dlogT16 = take(V * t.np * 2);
-  t.htT16 = take(H * t.np * 2);
-  t.hxT16 = take(H * t.np * 2);
   t.hd16 = take((size_t)n * H * 2);
-  t.hdT16 = take(H * t.np * 2);
   t.hd32a = (float*)take((size_t)n * H * 4);
   t.hd32b = (float*)take((size_t)n * H * 4);
   t.hdx32 = (float*)take((size_t)n * H * 4);
   t.dimg32 = (float*)take(Mi * H * 4);
   t.dimg16 = take(Mi * H * 2);
-  t.dimgT16 = take(H * t.Mip * 2);
-  t.imgT16 = take((size_t)h->Fp * t.Mip * 2);
   t.dwimg = (float*)take(H * (size_t)h->Fp * 4);
   t.total = off + 256;
   return t;
@@ -127,17 +117,10 @@ template <typename T>
 static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, long long ld, float* out) {
   if (M <= 0 || !out) return 0;
   ProfScope ps(h, st, CPT_K_COLSUM);
-  const int gy = std::max(1, std::min((M + 63) / 64, 4 * h->num_sms / std::max(1, (N + 255) / 256)));
-  colsum_kernel<T><<<dim3((N + 255) / 256, gy), 256, 0, st>>>(in, M, N, ld, out);
+  const int vec = ((ld * sizeof(T)) % (4 * sizeof(T)) == 0) && (reinterpret_cast<uintptr_t>(in) % (4 * sizeof(T)) == 0);
+  colsum_kernel<T><<<dim3((N + 255) / 256, (M + kColsumRows - 1) / kColsumRows), 256, 0, st>>>(in, M, N, ld, out, vec);
   CKL("colsum_kernel");
   return 0;
-}
-
-template <typename T16>
-static int transpose_t(cpt_handle* h, cudaStream_t st, const void* in, int R, int C, long long ld_in, void* out,
-                       long long ld_out) {
-  ProfScope ps(h, st, CPT_K_TRANSPOSE);
-  return transpose16<T16>(st, in, R, C, ld_in, out, ld_out);
 }
 
 template <typename T16>
@@ -202,11 +185,21 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
 
 template <typename T16>
 static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W,
-                      long long ldw, int M, int N, int K, void* out, long long ldo, bool out_fp32, bool accumulate) {
+                      long long ldw, int M, int N, int K, void* out, long long ldo, bool out_fp32, bool accumulate,
+                      bool trans = false) {
+  // out(+)= A[M,K] . W[N,K]^T, no bias.  accumulate -> fp32 reduce-add into `out`.  trans: A is [K,M], W is [K,N].
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = nullptr;
   p.tma_reduce = accumulate ? 1 : 0;
+  p.trans = trans ? 1 : 0;
   return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
+}
+
+// dW[Nout,Kin] += dY[rows,Nout]^T . X[rows,Kin]  (both operands read in place through MN-major descriptors)
+template <typename T16>
+static int wgrad(cpt_handle* h, cudaStream_t st, const void* dY, long long ldy, const void* X, long long ldx, int rows,
+                 int Nout, int Kin, float* dW, long long ldw, bool accumulate = true) {
+  return gemm_plain<T16>(h, st, CPT_K_GEMM_WGRAD, dY, ldy, X, ldx, Nout, Kin, rows, dW, ldw, true, accumulate, true);
 }
 
 static int small_matmul(cpt_handle* h, cudaStream_t st, const float* A, long long sa0, long long sa1, const float* B,
@@ -416,10 +409,10 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   if (!ids || !rows || !targets || !grad_loss) return fail("NULL argument");
   Tape t = carve_tape(h, B, T, R, n, (char*)(((uintptr_t)tape_ptr + 255) & ~uintptr_t(255)));
   if (!tape_ptr || tape_bytes < t.total) return fail("tape too small: need %zu bytes, got %zu", t.total, tape_bytes);
-  const int Mp = t.Mp, np = t.np, Vp = t.Vp;
+  const int Vp = t.Vp;
   const float p_h = dropout ? dropout->p_hidden : 0.f, p_a = dropout ? dropout->p_attn : 0.f;
   const Drop no_drop{0u, 0u, 0u, 0u, 1.f};
-  const int DG = CPT_K_GEMM_DGRAD, WG = CPT_K_GEMM_WGRAD;
+  const int DG = CPT_K_GEMM_DGRAD;
 
   CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
   if (head == CPT_HEAD_NSP) {
@@ -450,9 +443,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     CKL("ce_bwd_kernel");
   }
   TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dlog16), n, V, Vp, g->mlm_bias));
-  TRY(transpose_t<T16>(h, st, t.dlog16, n, V, Vp, t.dlogT16, np));
-  TRY(transpose_t<T16>(h, st, t.ht16, n, H, H, t.htT16, np));
-  TRY(gemm_plain<T16>(h, st, WG, t.dlogT16, np, t.htT16, np, V, H, np, g->word_emb, H, true, true));
+  TRY(wgrad<T16>(h, st, t.dlog16, Vp, t.ht16, H, n, V, H, g->word_emb, H));
   TRY(gemm_plain<T16>(h, st, DG, t.dlog16, Vp, h->word16_t, Vp, n, H, Vp, t.hd32a, H, true, false));
   TRY(ln_bwd<T16>(h, st, t.hd32a, t.htg32, n, H, h->mlm_g, c.layer_norm_eps, true, t.hd32b, nullptr, g->mlm_ln_g,
                   g->mlm_ln_b));
@@ -471,9 +462,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     CKL("cast32to16_kernel");
   }
   TRY(colsum<float>(h, st, t.hd32a, n, H, H, g->mlm_dense_b));
-  TRY(transpose_t<T16>(h, st, t.hd16, n, H, H, t.hdT16, np));
-  TRY(transpose_t<T16>(h, st, t.hx16, n, H, H, t.hxT16, np));
-  TRY(gemm_plain<T16>(h, st, WG, t.hdT16, np, t.hxT16, np, H, H, np, g->mlm_dense_w, H, true, true));
+  TRY(wgrad<T16>(h, st, t.hd16, H, t.hx16, H, n, H, H, g->mlm_dense_w, H));
   TRY(gemm_plain<T16>(h, st, DG, t.hd16, H, h->mlm_w16_t, H, n, H, H, t.hdx32, H, true, false));
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
@@ -493,9 +482,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     // output.dense: x2 = a + dropout(inter W2^T + b2); t.dx16 carries the masked gradient of the dense output
     if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.o_b));
     else TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
-    TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
-    TRY(transpose_t<T16>(h, st, tl.inter16, M, I, I, t.actT16, Mp));
-    TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, I, Mp, gl.o_w, I, true, true));
+    TRY(wgrad<T16>(h, st, t.dx16, H, tl.inter16, I, M, H, I, gl.o_w, I));
     TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_o_t, H, M, I, H, t.big16, I, false, false));
     {  // GELU
       ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
@@ -507,9 +494,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     }
     // intermediate.dense
     TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16b), M, I, I, gl.i_b));
-    TRY(transpose_t<T16>(h, st, t.big16b, M, I, I, t.bigT16, Mp));
-    TRY(transpose_t<T16>(h, st, tl.a16, M, H, H, t.actT16, Mp));
-    TRY(gemm_plain<T16>(h, st, WG, t.bigT16, Mp, t.actT16, Mp, I, H, Mp, gl.i_w, H, true, true));
+    TRY(wgrad<T16>(h, st, t.big16b, I, tl.a16, H, M, I, H, gl.i_w, H));
     TRY(gemm_plain<T16>(h, st, DG, t.big16b, I, d.w_i_t, I, M, H, I, t.dx32, H, true, true));  // += residual branch
     // attention.output.LayerNorm  (dx1 -> t.dH)
     TRY(ln_bwd<T16>(h, st, t.dx32, tl.x1, M, H, d.ao_g, c.layer_norm_eps, true, t.dH, t.dx16, gl.ao_ln_g,
@@ -517,21 +502,16 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     // attention.output.dense
     if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.ao_b));
     else TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
-    TRY(transpose_t<T16>(h, st, t.dx16, M, H, H, t.dxT16, Mp));
-    TRY(transpose_t<T16>(h, st, tl.ctx16, M, H, H, t.actT16, Mp));
-    TRY(gemm_plain<T16>(h, st, WG, t.dxT16, Mp, t.actT16, Mp, H, H, Mp, gl.ao_w, H, true, true));
+    TRY(wgrad<T16>(h, st, t.dx16, H, tl.ctx16, H, M, H, H, gl.ao_w, H));
     TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_ao_t, H, M, H, H, t.dctx16, H, false, false));
     TRY(attention_backward<T16>(h, st, tl.qkv16, t.dctx16, t.ext_mask, B, S, t.big16, dropout, p_a,
                                 (unsigned)(l * 4 + SITE_ATTN), -1));
     // query / key / value
     float* qkv_b[3] = {gl.q_b, gl.k_b, gl.v_b};
     float* qkv_w[3] = {gl.q_w, gl.k_w, gl.v_w};
-    TRY(transpose_t<T16>(h, st, t.big16, M, 3 * H, 3 * H, t.bigT16, Mp));
-    TRY(transpose_t<T16>(h, st, tl.h16, M, H, H, t.actT16, Mp));
     for (int j = 0; j < 3; ++j) {
       TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16) + j * H, M, H, 3 * H, qkv_b[j]));
-      TRY(gemm_plain<T16>(h, st, WG, t.bigT16 + (size_t)j * H * Mp * 2, Mp, t.actT16, Mp, H, H, Mp, qkv_w[j], H, true,
-                          true));
+      TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
     }
     TRY(gemm_plain<T16>(h, st, DG, t.big16, 3 * H, d.w_qkv_t, 3 * H, M, H, 3 * H, t.dH, H, true, true));  // += residual
   }
@@ -555,13 +535,11 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     CKL("embed_bwd_kernel");
   }
   if (R > 0) {
-    const int F = c.img_feature_dim, Mi = B * R, Mip = t.Mip;
+    const int F = c.img_feature_dim, Mi = B * R;
     TRY(ln_bwd<T16>(h, st, t.dH, t.imgpre32, Mi, H, h->img_g, c.img_layer_norm_eps, c.use_img_layernorm != 0,
                     t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, R, S, T, make_drop(dropout, p_h, SITE_EMB_IMG)));
     TRY(colsum<float>(h, st, t.dimg32, Mi, H, H, g->img_b));
-    TRY(transpose_t<T16>(h, st, t.dimg16, Mi, H, H, t.dimgT16, Mip));
-    TRY(transpose_t<T16>(h, st, t.img16, Mi, h->Fp, h->Fp, t.imgT16, Mip));
-    TRY(gemm_plain<T16>(h, st, WG, t.dimgT16, Mip, t.imgT16, Mip, H, h->Fp, Mip, t.dwimg, h->Fp, true, false));
+    TRY(wgrad<T16>(h, st, t.dimg16, H, t.img16, h->Fp, Mi, H, h->Fp, t.dwimg, h->Fp, false));
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     add_rows_kernel<<<ew_grid(h, (long long)H * F), 256, 0, st>>>(t.dwimg, h->Fp, H, F, g->img_w, F);
     CKL("add_rows_kernel");

@@ -372,10 +372,21 @@ class Engine(object):
     def _t16(self):
         return torch.float16 if DTYPES[self.dtype] == 0 else torch.bfloat16
 
-    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, tile_cfg=0):
-        M, K = A.shape
-        N = W.shape[0]
-        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else self._t16(), device=self.device)
+    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, tile_cfg=0, trans=False, accumulate_into=None):
+        """out = epi(A . W^T); trans: A is [K,M], W is [K,N] and out = A^T . W; accumulate_into: fp32 [M,N] tensor
+        the result is added to (returned)."""
+        if trans:
+            K, M = A.shape
+            N = W.shape[1]
+            epi |= 0x100
+        else:
+            M, K = A.shape
+            N = W.shape[0]
+        if accumulate_into is not None:
+            out, out_fp32 = accumulate_into, True
+            epi |= 0x200
+        else:
+            out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else self._t16(), device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cpt_gemm(self._h, _stream(), _ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K,
                                          _ptr(bias), _ptr(resid), 0 if resid is None else resid.stride(0), epi,

@@ -98,6 +98,29 @@ def test_attention_against_torch_and_simt(eng, B, S):
     assert (ctx_pipe.float() - ref).abs().max().item() <= 3e-3 * scale
 
 
+@pytest.mark.parametrize("M,N,K,cfg", [(768, 768, 7680, 0), (768, 3072, 1920, 0), (3072, 768, 840, 1256),
+                                       (2304, 768, 75, 1128), (30522, 768, 64, 0), (128, 2056, 200, 1064),
+                                       (100, 72, 33, 0)])
+def test_gemm_transposed_operands_accumulate(eng, M, N, K, cfg):
+    """the weight-gradient form: out[M,N] += A[K,M]^T . W[K,N] with both operands read through MN-major descriptors
+    and the fp32 result added into `out` by TMA reduce-add stores"""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.randn(K, Mp, device="cuda", generator=g).half()[:, :M]
+    W = torch.randn(K, Np, device="cuda", generator=g).half()[:, :N]
+    ref = A.float().t() @ W.float()
+    out = eng.gemm(A, W, out_fp32=True, tile_cfg=cfg, trans=True)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-3 * scale
+    if N % 4 == 0:
+        acc = torch.randn(M, N, device="cuda", generator=g)
+        want = acc + ref
+        eng.gemm(A, W, tile_cfg=cfg, trans=True, accumulate_into=acc)
+        torch.cuda.synchronize()
+        assert (acc - want).abs().max().item() <= 2e-3 * scale
+
+
 @pytest.mark.parametrize("B,S", [(2, 120), (1, 128), (3, 17), (2, 64), (2, 65), (1, 1), (8, 120), (2, 210), (1, 256)])
 def test_attention_backward_against_torch_autograd(eng, B, S):
     """d(qkv) from d(ctx): tensor-core kernel (S <= 128) and CUDA-core kernel against fp32 autograd on the same
