@@ -246,7 +246,7 @@ static int launch_gemm_t(cpt_handle* h, cudaStream_t st, const CUtensorMap& ta, 
   }
   constexpr int kCluster = PAIR ? 2 : 1;
   const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM, n_tiles = (p.N + BN - 1) / BN;
-  const int ctiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles;
+  const int ctiles = ((m_tiles + kCluster - 1) / kCluster) * n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   int clusters = h->num_sms / kCluster;
   if (ctiles < clusters) clusters = ctiles;
   CK(launch_k(fn, dim3(clusters * kCluster), dim3(kGemmThreads), Cfg::kSmemBytes, st, kCluster, ta, tb, to, p));
@@ -316,6 +316,12 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
     p.tma_reduce = want_reduce && out_fp32;
   }
   if (want_reduce && !p.tma_reduce) return fail("GEMM: accumulate-into-output needs an aligned fp32 destination");
+  if (p.ksplit > 1) {
+    // split-K only where partial products can be added at the destination; pieces of at least 4 k-blocks
+    const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+    if (!p.tma_reduce || p.bias) p.ksplit = 1;
+    else p.ksplit = std::max(1, std::min(p.ksplit, num_kb / 4));
+  }
   if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, to, p);
   if (epi == EPI_BIAS && out_fp32) return launch_gemm_bn<EPI_BIAS, float, T16>(h, st, c, ta, tb, to, p);
   if (epi == EPI_BIAS_GELU && !out_fp32) return launch_gemm_bn<EPI_BIAS_GELU, T16, T16>(h, st, c, ta, tb, to, p);
@@ -1176,6 +1182,7 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
   p.trans = (epi & 0x100) ? 1 : 0;
   p.tma_reduce = (epi & 0x200) ? 1 : 0;
+  p.ksplit = (epi >> 12) & 0xff;
   epi &= 0xff;
 #define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, tile_cfg)
   return DISPATCH_DTYPE(h, CALL);

@@ -38,6 +38,10 @@ struct GemmParams {
   // weight-gradient product dW = dY^T X straight from the row-major activations).  The tiles are staged as
   // [64-wide MN block][64 k rows][128 B] and read through MN-major UMMA descriptors.  Single-CTA tiles only.
   int trans;
+  // ksplit > 1: the K range is cut into ksplit pieces handled as separate work items that all ADD their partial
+  // product into `out` (needs tma_reduce and no bias): fills the machine when M x N is a handful of tiles and K is long
+  // (weight gradients: 768 x 768 outputs over K = 7680 rows)
+  int ksplit;
   // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
   // EPI_BIAS / EPI_BIAS_GELU: the A operand is a PRE-LayerNorm tensor x (16-bit) and W already carries gamma;
   //   out = rstd_m * (acc - mu_m * gvec_n) + bias_n, with (mu, rstd) from nstats[m] = (sum x, sum x^2) over nH
@@ -150,8 +154,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int ct_m = (m_tiles + kCluster - 1) / kCluster;
-  const int num_ctiles = ct_m * n_tiles;  // cluster tiles: (kCluster*128) x BN
+  const int mn_ctiles = ct_m * n_tiles;  // cluster tiles: (kCluster*128) x BN
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_ctiles = mn_ctiles * ksplit;  // work items: (tile, K piece); piece index = ct / mn_ctiles
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
@@ -204,9 +210,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       long long t_wait = 0, t_start = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        const int m0 = ((ct / n_tiles) * kCluster + (int)crank) * kGemmBM;
-        const int n0 = (ct % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int tile = ct % mn_ctiles, ks = ct / mn_ctiles;
+        const int m0 = ((tile / n_tiles) * kCluster + (int)crank) * kGemmBM;
+        const int n0 = (tile % n_tiles) * BN;
+        const int kb_end = (int)((long long)(ks + 1) * num_kb / ksplit);
+        for (int kb = (int)((long long)ks * num_kb / ksplit); kb < kb_end; ++kb) {
           const long long t0 = clock64();
           mbar_wait(empty_bar(stage), phase ^ 1u);
           t_wait += clock64() - t0;
@@ -261,7 +269,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         t_tmem += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = ct / mn_ctiles;
+        const int kb_begin = (int)((long long)ks * num_kb / ksplit), kb_end = (int)((long long)(ks + 1) * num_kb / ksplit);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           t0 = clock64();
           mbar_wait(full_bar(stage), phase);
           t_full += clock64() - t0;
@@ -275,8 +285,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t kstep = trans ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
-            if (PAIR) umma_f16_2cta(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
-            else umma_f16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
+            if (PAIR) umma_f16_2cta(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb_begin) | k) != 0);
+            else umma_f16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb_begin) | k) != 0);
           }
           if (PAIR) umma_commit_2cta_mc(empty_bar(stage), 3);
           else umma_commit(empty_bar(stage));
@@ -334,8 +344,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = ((ct / n_tiles) * kCluster + (int)crank) * kGemmBM;
-      const int n0 = (ct % n_tiles) * BN;
+      const int tile = ct % mn_ctiles;
+      const int m0 = ((tile / n_tiles) * kCluster + (int)crank) * kGemmBM;
+      const int n0 = (tile % n_tiles) * BN;
       const int mrow0 = m0 + q * 32;  // first row of this warp's 32-row band
       const int ncol0 = n0 + half * kColsPerWarp;
 

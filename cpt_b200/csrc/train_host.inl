@@ -192,6 +192,12 @@ static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, lo
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = nullptr;
   p.tma_reduce = accumulate ? 1 : 0;
   p.trans = trans ? 1 : 0;
+  if (trans && accumulate) {
+    // weight gradients: few output tiles, long K -> cut K until the work items cover the SMs about twice
+    const int bn = N >= 2048 ? 256 : 192;
+    const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
+    p.ksplit = std::max(1, (2 * h->num_sms + tiles - 1) / tiles);
+  }
   return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
 }
 

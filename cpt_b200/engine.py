@@ -372,7 +372,8 @@ class Engine(object):
     def _t16(self):
         return torch.float16 if DTYPES[self.dtype] == 0 else torch.bfloat16
 
-    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, tile_cfg=0, trans=False, accumulate_into=None):
+    def gemm(self, A, W, bias=None, resid=None, epi=0, out_fp32=False, tile_cfg=0, trans=False, accumulate_into=None,
+             ksplit=0):
         """out = epi(A . W^T); trans: A is [K,M], W is [K,N] and out = A^T . W; accumulate_into: fp32 [M,N] tensor
         the result is added to (returned)."""
         if trans:
@@ -384,7 +385,7 @@ class Engine(object):
             N = W.shape[0]
         if accumulate_into is not None:
             out, out_fp32 = accumulate_into, True
-            epi |= 0x200
+            epi |= 0x200 | (int(ksplit) << 12)
         else:
             out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else self._t16(), device=self.device)
         with torch.cuda.device(self.device):

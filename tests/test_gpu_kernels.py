@@ -119,6 +119,23 @@ def test_gemm_transposed_operands_accumulate(eng, M, N, K, cfg):
         eng.gemm(A, W, tile_cfg=cfg, trans=True, accumulate_into=acc)
         torch.cuda.synchronize()
         assert (acc - want).abs().max().item() <= 2e-3 * scale
+        # split-K: K cut into pieces that all add into the destination
+        acc2 = want - ref
+        eng.gemm(A, W, tile_cfg=cfg, trans=True, accumulate_into=acc2, ksplit=7)
+        torch.cuda.synchronize()
+        assert (acc2 - want).abs().max().item() <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("M,N,K,ksplit", [(768, 768, 3072, 4), (100, 192, 7680, 30), (1920, 768, 768, 3)])
+def test_gemm_split_k_accumulate(eng, M, N, K, ksplit):
+    g = torch.Generator(device="cuda").manual_seed(K + ksplit)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = torch.randn(N, K, device="cuda", generator=g).half()
+    acc = torch.randn(M, N, device="cuda", generator=g)
+    want = acc + A.float() @ W.float().t()
+    eng.gemm(A, W, accumulate_into=acc, ksplit=ksplit)
+    torch.cuda.synchronize()
+    assert (acc - want).abs().max().item() <= 2e-3 * want.abs().max().item()
 
 
 @pytest.mark.parametrize("B,S", [(2, 120), (1, 128), (3, 17), (2, 64), (2, 65), (1, 1), (8, 120), (2, 210), (1, 256)])
