@@ -6,7 +6,9 @@
 //     dQ = dS K                  (A = dS, K-major;  B = K tile, MN-major)          TMEM cols 256..319, lanes = queries
 //     dV = P^T dO                (A = P  read MN-major: M = keys; B = dO MN-major)  TMEM cols 320..383, lanes = keys
 //     dK = dS^T Q                (A = dS read MN-major;           B = Q  MN-major)  TMEM cols 384..447, lanes = keys
-// Thread r owns query row r for the softmax algebra (TMEM lane r of S, dP, dQ) and key row r for the dV / dK read-out.
+// Two threads own each query row for the softmax algebra (TMEM lane r of S, dP: warps w and w+4 share a lane quadrant
+// and take 64 key columns each; row max / sum / D meet in shared memory) and each key row for the dV / dK read-out
+// — with one warp per scheduler the kernel was issue-latency bound (ncu: 7.3 cycles per instruction, 13 % issue slots).
 // P and dS are written once to shared memory as 16-bit [query][key] tiles in the 128B-swizzled layout; the same bytes
 // serve as the K-major A operand of dQ and, through an MN-major descriptor, as the transposed A operand of dV / dK —
 // no transpose pass.  Rows / keys beyond S are zeroed so the neighbouring sample's rows that the 128-row TMA boxes
@@ -24,10 +26,11 @@ struct AttnBwdParams {
   float scale;
 };
 
-constexpr int kAttnBwdSmem = 1024 + 4 * 16384 + 2 * 32768 + 512 + 64;
+constexpr int kAttnBwdThreads = 256;
+constexpr int kAttnBwdSmem = 1024 + 4 * 16384 + 2 * 32768 + 512 + 3 * 1024 + 64;
 
 template <typename T16>
-__global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+__global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                           const __grid_constant__ CUtensorMap tmap_do,
                                                           const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -36,8 +39,10 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   const uint32_t sQ = base, sK = sQ + 16384, sV = sK + 16384, sdO = sV + 16384;
   const uint32_t sP = sdO + 16384, sdS = sP + 32768;
   const uint32_t sMask = sdS + 32768;
-  const uint32_t bar_ld = sMask + 512, bar_s = bar_ld + 8, bar_g = bar_ld + 16, tmem_slot = bar_ld + 32;
+  const uint32_t sStat = sMask + 512;  // [3][2][128] fp32: partial row max, sum, sum(e * dP) of the two column halves
+  const uint32_t bar_ld = sStat + 3072, bar_s = bar_ld + 8, bar_g = bar_ld + 16, tmem_slot = bar_ld + 32;
   float* maskp = reinterpret_cast<float*>(smem_raw + (sMask - smem_u32(smem_raw)));
+  float* statp = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));
   uint8_t* p_gen = smem_raw + (sP - smem_u32(smem_raw));
   uint8_t* ds_gen = smem_raw + (sdS - smem_u32(smem_raw));
   const int h = blockIdx.x, b = blockIdx.y;
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (threadIdx.x < 128) maskp[threadIdx.x] = (threadIdx.x < S) ? p.ext_mask[(long long)b * S + threadIdx.x] : 0.f;
+  if (threadIdx.x < 128) maskp[threadIdx.x] = ((int)threadIdx.x < S) ? p.ext_mask[(long long)b * S + threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -87,10 +92,12 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
 
   mbar_wait(bar_s, 0);
   tc_fence_after();
-  const int r = warp * 32 + lane;
-  const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+  const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quadrant, column half
+  const int r = q4 * 32 + lane;
+  const uint32_t t_row = tmem_base + (uint32_t(q4 * 32) << 16);
+  const int c0 = half * 2;  // this thread's two 32-column chunks
   float mx = -INFINITY;
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c0; c < c0 + 2; ++c) {
     uint32_t v[32];
     tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
     tmem_ld_wait();
@@ -101,8 +108,11 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
       mx = fmaxf(mx, t);
     }
   }
+  statp[half * 128 + r] = mx;
+  __syncthreads();
+  mx = fmaxf(statp[r], statp[128 + r]);
   float sum = 0.f, dn = 0.f;
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c0; c < c0 + 2; ++c) {
     uint32_t v[32], w[32];
     tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
     tmem_ld_32x32b_x32(t_row + cdP + c * 32, w);
@@ -115,10 +125,15 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
       dn = fmaf(e, __uint_as_float(w[j]), dn);
     }
   }
+  statp[256 + half * 128 + r] = sum;
+  statp[512 + half * 128 + r] = dn;
+  __syncthreads();
+  sum = statp[256 + r] + statp[384 + r];
+  dn = statp[512 + r] + statp[640 + r];
   const bool valid = r < S;
   const float inv = valid ? 1.0f / sum : 0.f;
   const float D = dn * inv;
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c0; c < c0 + 2; ++c) {
     uint32_t v[32], w[32];
     tmem_ld_32x32b_x32(t_row + cS + c * 32, v);
     tmem_ld_32x32b_x32(t_row + cdP + c * 32, w);
@@ -185,8 +200,8 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
     const uint32_t cols[3] = {cdQ, cdK, cdV};
 #pragma unroll
     for (int which = 0; which < 3; ++which) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = half;  // this thread's 32 of the 64 head-dim columns
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + cols[which] + c * 32, v);
         tmem_ld_wait();

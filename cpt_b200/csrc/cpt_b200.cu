@@ -115,8 +115,6 @@ struct LayerDev {
   void *w_qkv = nullptr, *w_ao = nullptr, *w_i = nullptr, *w_o = nullptr;  // 16-bit [3H,H] [H,H] [I,H] [H,I]
   float *b_qkv = nullptr, *b_ao = nullptr, *ao_g = nullptr, *ao_b = nullptr, *b_i = nullptr, *b_o = nullptr,
         *o_g = nullptr, *o_b = nullptr;
-  // training: transposed 16-bit copies, the W operand of the dgrad GEMMs ([H,3H] [H,H] [H,I] [I,H])
-  void *w_qkv_t = nullptr, *w_ao_t = nullptr, *w_i_t = nullptr, *w_o_t = nullptr;
   // LayerNorm-folded copies (DESIGN.md "LayerNorm folding"): W .* gamma of the LayerNorm that feeds the GEMM
   void *w_qkv_f = nullptr, *w_i_f = nullptr;
   float *g_qkv = nullptr, *c_qkv = nullptr, *g_i = nullptr, *c_i = nullptr;
@@ -134,9 +132,8 @@ struct cpt_handle {
   float *pool_w = nullptr, *pool_b = nullptr;
   float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
   void *mlm_w16 = nullptr, *word16 = nullptr;
-  void *mlm_w16_t = nullptr, *word16_t = nullptr;  // training: [H,H]^T and [H, Vp] (Vp = vocab rounded up to 8)
   int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
-  int train = 0;                                   // cpt_train_enable: keep transposed copies, reuse allocations
+  int train = 0;                                   // cpt_train_enable: cpt_set_weights refreshes in place, no LN-folded copies
   unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
   float *nsp_w = nullptr, *nsp_b = nullptr;
   std::vector<LayerDev> layers;
@@ -295,13 +292,11 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   const int dt = Cvt<T16>::kFmt;
   CUtensorMap ta, tb;
-  if (p.trans) {  // A is [K, M], W is [K, N]: 64 x 64 boxes, k along the rows
-    TRY(make_tmap(&ta, A, dt, p.K, p.M, lda, 64));
-    TRY(make_tmap(&tb, W, dt, p.K, p.N, ldw, 64));
-  } else {
-    TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
-    TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
-  }
+  // a transposed operand ([K, M] / [K, N] in memory) is fetched as 64 x 64 boxes, k along the rows
+  if (p.trans & 1) TRY(make_tmap(&ta, A, dt, p.K, p.M, lda, 64));
+  else TRY(make_tmap(&ta, A, dt, p.M, p.K, lda, kGemmBM));
+  if (p.trans & 2) TRY(make_tmap(&tb, W, dt, p.K, p.N, ldw, 64));
+  else TRY(make_tmap(&tb, W, dt, p.N, p.K, ldw, c.pair ? c.bn / 2 : c.bn));
   // outputs leave through TMA bulk stores (32x32 blocks) whenever the destination is 16-byte aligned and pitched;
   // otherwise (e.g. the [rows, 30522] fp32 score matrix) through the LSU path
   const unsigned osz = out_fp32 ? 4 : 2;
@@ -533,7 +528,7 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     if (h->trace) h->owned.push_back(h->trace);
     h->emb_g = h->emb_b = h->b_img = h->img_g = h->img_b = h->pool_w = h->pool_b = nullptr;
     h->mlm_w = h->mlm_b = h->mlm_g = h->mlm_beta = h->mlm_bias = h->nsp_w = h->nsp_b = nullptr;
-    h->w_img = h->mlm_w16 = h->word16 = h->mlm_w16_t = h->word16_t = nullptr;
+    h->w_img = h->mlm_w16 = h->word16 = nullptr;
     h->layers.assign(L, LayerDev{});
   }
   h->has_weights = false;
@@ -580,17 +575,7 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     TRY(copy_vec(h, reuse, st, s.o_b, H, &d.b_o));
     TRY(copy_vec(h, reuse, st, s.o_ln_g, H, &d.o_g));
     TRY(copy_vec(h, reuse, st, s.o_ln_b, H, &d.o_b));
-    if (h->train) {
-      TRY(walloc(h, reuse, &d.w_qkv_t, (size_t)3 * H * H * 2));
-      TRY(transpose16<T16>(st, d.w_qkv, 3 * H, H, H, d.w_qkv_t, 3 * H));
-      TRY(walloc(h, reuse, &d.w_ao_t, (size_t)H * H * 2));
-      TRY(transpose16<T16>(st, d.w_ao, H, H, H, d.w_ao_t, H));
-      TRY(walloc(h, reuse, &d.w_i_t, (size_t)I * H * 2));
-      TRY(transpose16<T16>(st, d.w_i, I, H, H, d.w_i_t, I));
-      TRY(walloc(h, reuse, &d.w_o_t, (size_t)I * H * 2));
-      TRY(transpose16<T16>(st, d.w_o, H, I, I, d.w_o_t, H));
-      continue;  // the LayerNorm-folded copies below serve the (inference-only) folded path
-    }
+    if (h->train) continue;  // the LayerNorm-folded copies below serve the (inference-only) folded path
     // folded copies: FFN-up reads pre-LN1 rows (gamma/beta of this layer's attention.output.LayerNorm); the QKV
     // projection of layer l >= 1 reads pre-LN2 rows of layer l-1 (gamma/beta of its output.LayerNorm)
     TRY(dev_alloc(h, &d.w_i_f, (size_t)I * H * 2));
@@ -631,13 +616,6 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     TRY(cast_w<T16>(st, w->mlm_dense_w, H, H, H, h->mlm_w16));
     TRY(walloc(h, reuse, &h->word16, (size_t)c.vocab_size * H * 2));
     TRY(cast_w<T16>(st, w->word_emb, c.vocab_size, H, H, h->word16));
-    if (h->train) {
-      const int Vp = (c.vocab_size + 7) & ~7;
-      TRY(walloc(h, reuse, &h->mlm_w16_t, (size_t)H * H * 2));
-      TRY(transpose16<T16>(st, h->mlm_w16, H, H, H, h->mlm_w16_t, H));
-      TRY(walloc(h, reuse, &h->word16_t, (size_t)H * Vp * 2));
-      TRY(transpose16<T16>(st, h->word16, c.vocab_size, H, H, h->word16_t, Vp));
-    }
   }
   h->has_nsp = has_nsp;
   if (h->has_nsp) {
@@ -1180,7 +1158,7 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
   DeviceGuard g(h->device);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
-  p.trans = (epi & 0x100) ? 1 : 0;
+  p.trans = ((epi & 0x100) ? 3 : 0) | ((epi & 0x400) ? 2 : 0);
   p.tma_reduce = (epi & 0x200) ? 1 : 0;
   p.ksplit = (epi >> 12) & 0xff;
   epi &= 0xff;

@@ -34,9 +34,11 @@ struct GemmParams {
   int tma_store;        // outputs leave through tmap_out (set by the host when `out` is 16-byte aligned and pitched)
   int tma_reduce;       // ... as out += tile (cp.reduce.async.bulk .add at L2): `out` already holds the residual
   long long* trace;     // optional [gridDim.x][16] cycle counters (debug): see cpt_gemm_trace
-  // trans != 0: out = A^T . W, both operands given TRANSPOSED in memory — A as [K, M], W as [K, N] row-major (the
-  // weight-gradient product dW = dY^T X straight from the row-major activations).  The tiles are staged as
-  // [64-wide MN block][64 k rows][128 B] and read through MN-major UMMA descriptors.  Single-CTA tiles only.
+  // trans bit 0: A is given TRANSPOSED in memory, as [K, M] row-major; bit 1: W is given as [K, N] row-major.
+  //   3: out = A^T . W  — the weight-gradient product dW = dY^T X straight from the row-major activations;
+  //   2: out = A . W    — the data-gradient product dX = dY W straight from the nn.Linear weight [out, in].
+  // A transposed operand's tiles are staged as [64-wide MN block][64 k rows][128 B] and read through MN-major UMMA
+  // descriptors.  Single-CTA tiles only.
   int trans;
   // ksplit > 1: the K range is cut into ksplit pieces handled as separate work items that all ADD their partial
   // product into `out` (needs tma_reduce and no bias): fills the machine when M x N is a handful of tiles and K is long
@@ -222,12 +224,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + Cfg::kABytes;
           if (!PAIR && p.trans) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            if (p.trans & 1) {
 #pragma unroll
-            for (int blk = 0; blk < kGemmBM / 64; ++blk)
-              tma_load_2d(sa + blk * 8192, &tmap_a, full_bar(stage), m0 + blk * 64, kb * kGemmBK);
+              for (int blk = 0; blk < kGemmBM / 64; ++blk)
+                tma_load_2d(sa + blk * 8192, &tmap_a, full_bar(stage), m0 + blk * 64, kb * kGemmBK);
+            } else {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kGemmBK, m0);
+            }
+            if (p.trans & 2) {
 #pragma unroll
-            for (int blk = 0; blk < BN / 64; ++blk)
-              tma_load_2d(sb + blk * 8192, &tmap_b, full_bar(stage), n0 + blk * 64, kb * kGemmBK);
+              for (int blk = 0; blk < BN / 64; ++blk)
+                tma_load_2d(sb + blk * 8192, &tmap_b, full_bar(stage), n0 + blk * 64, kb * kGemmBK);
+            } else {
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kGemmBK, n0);
+            }
           } else if (!PAIR) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kGemmBK, m0);
@@ -253,10 +263,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only when PAIR)
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc_kmajor = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 0, 0);
-      constexpr uint32_t idesc_mnmajor = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, 1, 1);
-      const bool trans = !PAIR && p.trans;
-      const uint32_t idesc = trans ? idesc_mnmajor : idesc_kmajor;
+      const bool ta = !PAIR && (p.trans & 1), tb = !PAIR && (p.trans & 2);
+      const uint32_t idesc = make_idesc_f16(kGemmBM * kCluster, BN, Cvt<T16>::kFmt, ta ? 1 : 0, tb ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -279,14 +287,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           // K-major: +32 B per UMMA_K=16 step inside the 128-byte swizzle row (descriptor address is in 16-B units);
           // MN-major: 64-wide MN blocks 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO), +2 KB per 16 k rows
-          const uint64_t adesc = trans ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t adesc = ta ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc =
-              trans ? make_smem_desc(sa + Cfg::kABytes, 8192, 1024) : make_smem_desc(sa + Cfg::kABytes, 16, 1024);
-          const uint32_t kstep = trans ? 128u : 2u;
+              tb ? make_smem_desc(sa + Cfg::kABytes, 8192, 1024) : make_smem_desc(sa + Cfg::kABytes, 16, 1024);
+          const uint32_t ka = ta ? 128u : 2u, kbs = tb ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
-            if (PAIR) umma_f16_2cta(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb_begin) | k) != 0);
-            else umma_f16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb_begin) | k) != 0);
+            if (PAIR) umma_f16_2cta(d_tmem, adesc + ka * k, bdesc + kbs * k, idesc, ((kb - kb_begin) | k) != 0);
+            else umma_f16(d_tmem, adesc + ka * k, bdesc + kbs * k, idesc, ((kb - kb_begin) | k) != 0);
           }
           if (PAIR) umma_commit_2cta_mc(empty_bar(stage), 3);
           else umma_commit(empty_bar(stage));

@@ -143,17 +143,52 @@ __device__ __forceinline__ float gelu_exact(float x) { return x * 0.5f * (1.0f +
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
+// 8 elements (one 16-byte vector) per thread per step; n % 8 == 0 (intermediate_size is a multiple of 8)
+template <typename T16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    T16 lo, hi;
+    *reinterpret_cast<uint16_t*>(&lo) = (uint16_t)(w[i] & 0xffffu);
+    *reinterpret_cast<uint16_t*>(&hi) = (uint16_t)(w[i] >> 16);
+    f[2 * i] = Cvt<T16>::to(lo);
+    f[2 * i + 1] = Cvt<T16>::to(hi);
+  }
+}
+template <typename T16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = Cvt<T16>::pack2(f[0], f[1]);
+  u.y = Cvt<T16>::pack2(f[2], f[3]);
+  u.z = Cvt<T16>::pack2(f[4], f[5]);
+  u.w = Cvt<T16>::pack2(f[6], f[7]);
+  return u;
+}
 template <typename T16>
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T16* __restrict__ in, long long n, T16* __restrict__ out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = Cvt<T16>::from(gelu_exact(Cvt<T16>::to(in[i])));
+  const long long nv = n >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8<T16>(reinterpret_cast<const uint4*>(in)[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = gelu_exact(f[e]);
+    reinterpret_cast<uint4*>(out)[i] = pack8<T16>(f);
+  }
 }
 // dpre = dpost * gelu'(pre)
 template <typename T16>
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T16* __restrict__ dpost, const T16* __restrict__ pre,
                                                        long long n, T16* __restrict__ dpre) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dpre[i] = Cvt<T16>::from(Cvt<T16>::to(dpost[i]) * gelu_grad(Cvt<T16>::to(pre[i])));
+  const long long nv = n >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float d[8], x[8];
+    unpack8<T16>(reinterpret_cast<const uint4*>(dpost)[i], d);
+    unpack8<T16>(reinterpret_cast<const uint4*>(pre)[i], x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] *= gelu_grad(x[e]);
+    reinterpret_cast<uint4*>(dpre)[i] = pack8<T16>(d);
+  }
 }
 // fp32 variants for the small head tensors
 __global__ void __launch_bounds__(256) gelu_fwd32_kernel(const float* __restrict__ in, long long n,
@@ -275,7 +310,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // Text-embedding backward: recompute x = word[id] + pos[p] + type[s], LayerNorm backward, scatter-add dx into the three
-// tables' gradients (fp32 atomics; rows of the same token collide).  dy rows are b*S + t of the [B,S,H] gradient.
+// tables' gradients.  dy rows are b*S + t of the [B,S,H] gradient.  Persistent warps: dgamma / dbeta and the (two-row)
+// token-type table gradient accumulate per warp / per CTA and reach global memory once per CTA — per-row atomics on
+// those few addresses serialised at L2 (251 us at B=64 before); word / position rows take fp32 atomics (rows of the
+// same token or position collide only B-fold).
+constexpr int kEmbTypeSlots = 4;  // token-type rows accumulated in shared memory (type_vocab_size is 2)
 template <int NV>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(
     const long long* __restrict__ ids, const long long* __restrict__ seg, const long long* __restrict__ pos_ids,
@@ -283,68 +322,96 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(
     const float* __restrict__ gamma, float eps, const float* __restrict__ dy, int B, int T, int S, int H, int vocab,
     int max_pos, int n_type, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
     float* __restrict__ dgamma, float* __restrict__ dbeta, Drop drop_dy) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= B * T) return;
-  const int b = row / T, t = row % T;
-  long long id = min(max(ids[row], 0ll), (long long)vocab - 1);
-  long long sg = seg ? min(max(seg[row], 0ll), (long long)n_type - 1) : 0;
-  long long ps = pos_ids ? min(max(pos_ids[row], 0ll), (long long)max_pos - 1) : t;
-  float4 xv[NV], dv[NV];
-  float s = 0.f;
+  __shared__ float red[8][NV * 128];
+  __shared__ float stype[kEmbTypeSlots][NV * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool type_in_smem = n_type <= kEmbTypeSlots;
+  for (int c = threadIdx.x; c < kEmbTypeSlots * NV * 128; c += 256) (&stype[0][0])[c] = 0.f;
+  __syncthreads();
+  float4 ag[NV], ab[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
-    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
-    const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
-    xv[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
-    dv[i] = *reinterpret_cast<const float4*>(dy + ((long long)b * S + t) * H + col);
-    if (drop_dy.thresh) {
-      const unsigned long long e = (unsigned long long)(((long long)b * S + t) * H + col);
-      dv[i].x = drop_apply(drop_dy, e, dv[i].x); dv[i].y = drop_apply(drop_dy, e + 1, dv[i].y);
-      dv[i].z = drop_apply(drop_dy, e + 2, dv[i].z); dv[i].w = drop_apply(drop_dy, e + 3, dv[i].w);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * 8 + warp; row < B * T; row += gridDim.x * 8) {
+    const int b = row / T, t = row % T;
+    const long long id = min(max(ids[row], 0ll), (long long)vocab - 1);
+    const long long sg = seg ? min(max(seg[row], 0ll), (long long)n_type - 1) : 0;
+    const long long ps = pos_ids ? min(max(pos_ids[row], 0ll), (long long)max_pos - 1) : t;
+    float4 xv[NV], dv[NV], gv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * H + col));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + ps * H + col));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(type + sg * H + col));
+      xv[i] = make_float4((w.x + p.x) + y.x, (w.y + p.y) + y.y, (w.z + p.z) + y.z, (w.w + p.w) + y.w);
+      dv[i] = *reinterpret_cast<const float4*>(dy + ((long long)b * S + t) * H + col);
+      if (drop_dy.thresh) {
+        const unsigned long long e = (unsigned long long)(((long long)b * S + t) * H + col);
+        dv[i].x = drop_apply(drop_dy, e, dv[i].x); dv[i].y = drop_apply(drop_dy, e + 1, dv[i].y);
+        dv[i].z = drop_apply(drop_dy, e + 2, dv[i].z); dv[i].w = drop_apply(drop_dy, e + 3, dv[i].w);
+      }
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
     }
-    s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
-  }
-  const float mean = warp_sum(s) / (float)H;
-  float q = 0.f;
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
-    q += (a * a + bb * bb) + (c * c + d * d);
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
-  float m1 = 0.f, m2 = 0.f;
-  float4 gv[NV];
+    for (int i = 0; i < NV; ++i) {
+      const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
+    float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
-    xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
-    xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
-    gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
-    m1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
-    m2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
-    atomicAdd(dgamma + col + 0, dv[i].x * xv[i].x); atomicAdd(dgamma + col + 1, dv[i].y * xv[i].y);
-    atomicAdd(dgamma + col + 2, dv[i].z * xv[i].z); atomicAdd(dgamma + col + 3, dv[i].w * xv[i].w);
-    atomicAdd(dbeta + col + 0, dv[i].x); atomicAdd(dbeta + col + 1, dv[i].y);
-    atomicAdd(dbeta + col + 2, dv[i].z); atomicAdd(dbeta + col + 3, dv[i].w);
-  }
-  m1 = warp_sum(m1) / (float)H;
-  m2 = warp_sum(m2) / (float)H;
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
+      xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+      gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
+      m1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      m2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+      ag[i].x += dv[i].x * xv[i].x; ag[i].y += dv[i].y * xv[i].y; ag[i].z += dv[i].z * xv[i].z; ag[i].w += dv[i].w * xv[i].w;
+      ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+    }
+    m1 = warp_sum(m1) / (float)H;
+    m2 = warp_sum(m2) / (float)H;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const float o[4] = {rstd * (gv[i].x - m1 - xv[i].x * m2), rstd * (gv[i].y - m1 - xv[i].y * m2),
-                        rstd * (gv[i].z - m1 - xv[i].z * m2), rstd * (gv[i].w - m1 - xv[i].w * m2)};
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float o[4] = {rstd * (gv[i].x - m1 - xv[i].x * m2), rstd * (gv[i].y - m1 - xv[i].y * m2),
+                          rstd * (gv[i].z - m1 - xv[i].z * m2), rstd * (gv[i].w - m1 - xv[i].w * m2)};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (id != 0) atomicAdd(dword + id * H + col + e, o[e]);  // padding_idx = 0 receives no gradient (nn.Embedding)
-      atomicAdd(dpos + ps * H + col + e, o[e]);
-      atomicAdd(dtype + sg * H + col + e, o[e]);
+      for (int e = 0; e < 4; ++e) {
+        if (id != 0) atomicAdd(dword + id * H + col + e, o[e]);  // padding_idx = 0 receives no gradient (nn.Embedding)
+        atomicAdd(dpos + ps * H + col + e, o[e]);
+        if (type_in_smem) atomicAdd(&stype[sg][col + e], o[e]);
+        else atomicAdd(dtype + sg * H + col + e, o[e]);
+      }
     }
   }
+  // per-CTA reduction of dgamma / dbeta (and the token-type rows), one atomic per column per CTA
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(&red[warp][col]) = which == 0 ? ag[i] : ab[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NV * 128; c += 256) {
+      float sg = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sg += red[w][c];
+      atomicAdd((which == 0 ? dgamma : dbeta) + c, sg);
+    }
+    __syncthreads();
+  }
+  if (type_in_smem)
+    for (int c = threadIdx.x; c < n_type * NV * 128; c += 256) {
+      const float v = stype[c / (NV * 128)][c % (NV * 128)];
+      if (v != 0.f) atomicAdd(dtype + (long long)(c / (NV * 128)) * H + c % (NV * 128), v);
+    }
 }
 
 // X16[i, :] = X32[rows[i], :]  (+ fp32 copy)

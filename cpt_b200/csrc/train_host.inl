@@ -3,7 +3,8 @@
 // Forward = the inference kernel sequence, except that every tensor the backward needs lands in the tape instead of a
 // reused workspace buffer, and FFN-up keeps its pre-activation (GELU is a separate pass).  Backward walks the layers
 // in reverse.  Every matrix product is the tcgen05 GEMM of gemm_sm100.cuh in its out = A . W^T form:
-//   dgrad  dX[M,Kin]    = dY[M,Nout] . (W^T)[Kin,Nout]^T      W^T = transposed 16-bit weights kept by the handle
+//   dgrad  dX[M,Kin]    = dY[M,Nout] . W[Nout,Kin]             W = the handle's 16-bit nn.Linear weight, read in place as
+//                                                              the MN-major B operand (GemmParams::trans = 2)
 //   wgrad  dW[Nout,Kin] = dY[M,Nout]^T . X[M,Kin]             both operands read where they lie, row-major, through
 //                                                              MN-major UMMA descriptors (GemmParams::trans); the fp32
 //                                                              result is ADDED into the caller's gradient tensor by the
@@ -170,7 +171,7 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
       attr_set[h->device & 63] = true;
     }
     AttnBwdParams p{B, S, H, nH, ext_mask, dqkv, 0.125f};
-    fn<<<dim3(nH, B), 128, kAttnBwdSmem, st>>>(tq, td, p);
+    fn<<<dim3(nH, B), kAttnBwdThreads, kAttnBwdSmem, st>>>(tq, td, p);
     CKL("attn_bwd_tc_kernel");
     return 0;
   }
@@ -186,13 +187,14 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
 template <typename T16>
 static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, long long lda, const void* W,
                       long long ldw, int M, int N, int K, void* out, long long ldo, bool out_fp32, bool accumulate,
-                      bool trans = false) {
-  // out(+)= A[M,K] . W[N,K]^T, no bias.  accumulate -> fp32 reduce-add into `out`.  trans: A is [K,M], W is [K,N].
+                      int trans = 0) {
+  // out(+)= A[M,K] . W[N,K]^T, no bias.  accumulate -> fp32 reduce-add into `out`.  trans (GemmParams::trans): 3 = A is
+  // [K,M] and W is [K,N]; 2 = W is [K,N]
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = nullptr;
   p.tma_reduce = accumulate ? 1 : 0;
-  p.trans = trans ? 1 : 0;
-  if (trans && accumulate) {
+  p.trans = trans;
+  if (trans == 3 && accumulate) {
     // weight gradients: few output tiles, long K -> cut K until the work items cover the SMs about twice
     const int bn = N >= 2048 ? 256 : 192;
     const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
@@ -201,11 +203,18 @@ static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, lo
   return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
 }
 
+// dX[rows,Kin] (+)= dY[rows,Nout] . W[Nout,Kin]  (W read in place through an MN-major descriptor)
+template <typename T16>
+static int dgrad(cpt_handle* h, cudaStream_t st, const void* dY, long long ldy, const void* W, long long ldw, int rows,
+                 int Nout, int Kin, void* dX, long long ldx, bool out_fp32, bool accumulate) {
+  return gemm_plain<T16>(h, st, CPT_K_GEMM_DGRAD, dY, ldy, W, ldw, rows, Kin, Nout, dX, ldx, out_fp32, accumulate, 2);
+}
+
 // dW[Nout,Kin] += dY[rows,Nout]^T . X[rows,Kin]  (both operands read in place through MN-major descriptors)
 template <typename T16>
 static int wgrad(cpt_handle* h, cudaStream_t st, const void* dY, long long ldy, const void* X, long long ldx, int rows,
                  int Nout, int Kin, float* dW, long long ldw, bool accumulate = true) {
-  return gemm_plain<T16>(h, st, CPT_K_GEMM_WGRAD, dY, ldy, X, ldx, Nout, Kin, rows, dW, ldw, true, accumulate, true);
+  return gemm_plain<T16>(h, st, CPT_K_GEMM_WGRAD, dY, ldy, X, ldx, Nout, Kin, rows, dW, ldw, true, accumulate, 3);
 }
 
 static int small_matmul(cpt_handle* h, cudaStream_t st, const float* A, long long sa0, long long sa1, const float* B,
@@ -338,7 +347,7 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
       TRY(gemm<T16>(h, st, CPT_K_GEMM_UP, tl.a16, H, d.w_i, H, p, EPI_BIAS, false));
       ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
       const long long ne = (long long)M * I;
-      gelu_fwd_kernel<T16><<<ew_grid(h, ne), 256, 0, st>>>(reinterpret_cast<const T16*>(tl.preup16), ne,
+      gelu_fwd_kernel<T16><<<ew_grid(h, ne / 8), 256, 0, st>>>(reinterpret_cast<const T16*>(tl.preup16), ne,
                                                           reinterpret_cast<T16*>(tl.inter16));
       CKL("gelu_fwd_kernel");
     }
@@ -418,7 +427,6 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   const int Vp = t.Vp;
   const float p_h = dropout ? dropout->p_hidden : 0.f, p_a = dropout ? dropout->p_attn : 0.f;
   const Drop no_drop{0u, 0u, 0u, 0u, 1.f};
-  const int DG = CPT_K_GEMM_DGRAD;
 
   CK(cudaMemsetAsync(t.dH, 0, (size_t)M * H * 4, st));
   if (head == CPT_HEAD_NSP) {
@@ -450,7 +458,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   }
   TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dlog16), n, V, Vp, g->mlm_bias));
   TRY(wgrad<T16>(h, st, t.dlog16, Vp, t.ht16, H, n, V, H, g->word_emb, H));
-  TRY(gemm_plain<T16>(h, st, DG, t.dlog16, Vp, h->word16_t, Vp, n, H, Vp, t.hd32a, H, true, false));
+  TRY(dgrad<T16>(h, st, t.dlog16, Vp, h->word16, H, n, V, H, t.hd32a, H, true, false));
   TRY(ln_bwd<T16>(h, st, t.hd32a, t.htg32, n, H, h->mlm_g, c.layer_norm_eps, true, t.hd32b, nullptr, g->mlm_ln_g,
                   g->mlm_ln_b));
   {
@@ -469,7 +477,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   }
   TRY(colsum<float>(h, st, t.hd32a, n, H, H, g->mlm_dense_b));
   TRY(wgrad<T16>(h, st, t.hd16, H, t.hx16, H, n, H, H, g->mlm_dense_w, H));
-  TRY(gemm_plain<T16>(h, st, DG, t.hd16, H, h->mlm_w16_t, H, n, H, H, t.hdx32, H, true, false));
+  TRY(dgrad<T16>(h, st, t.hd16, H, h->mlm_w16, H, n, H, H, t.hdx32, H, true, false));
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     scatter_rows_add_kernel<<<n, 256, 0, st>>>(t.hdx32, (const long long*)rows, n, H, t.dH);
@@ -489,11 +497,11 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.o_b));
     else TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
     TRY(wgrad<T16>(h, st, t.dx16, H, tl.inter16, I, M, H, I, gl.o_w, I));
-    TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_o_t, H, M, I, H, t.big16, I, false, false));
+    TRY(dgrad<T16>(h, st, t.dx16, H, d.w_o, I, M, H, I, t.big16, I, false, false));
     {  // GELU
       ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
       const long long ne = (long long)M * I;
-      gelu_bwd_kernel<T16><<<ew_grid(h, ne), 256, 0, st>>>(reinterpret_cast<const T16*>(t.big16),
+      gelu_bwd_kernel<T16><<<ew_grid(h, ne / 8), 256, 0, st>>>(reinterpret_cast<const T16*>(t.big16),
                                                           reinterpret_cast<const T16*>(tl.preup16), ne,
                                                           reinterpret_cast<T16*>(t.big16b));
       CKL("gelu_bwd_kernel");
@@ -501,7 +509,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     // intermediate.dense
     TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16b), M, I, I, gl.i_b));
     TRY(wgrad<T16>(h, st, t.big16b, I, tl.a16, H, M, I, H, gl.i_w, H));
-    TRY(gemm_plain<T16>(h, st, DG, t.big16b, I, d.w_i_t, I, M, H, I, t.dx32, H, true, true));  // += residual branch
+    TRY(dgrad<T16>(h, st, t.big16b, I, d.w_i, H, M, I, H, t.dx32, H, true, true));  // += residual branch
     // attention.output.LayerNorm  (dx1 -> t.dH)
     TRY(ln_bwd<T16>(h, st, t.dx32, tl.x1, M, H, d.ao_g, c.layer_norm_eps, true, t.dH, t.dx16, gl.ao_ln_g,
                     gl.ao_ln_b, 0, 0, 0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_AO)));
@@ -509,7 +517,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.ao_b));
     else TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
     TRY(wgrad<T16>(h, st, t.dx16, H, tl.ctx16, H, M, H, H, gl.ao_w, H));
-    TRY(gemm_plain<T16>(h, st, DG, t.dx16, H, d.w_ao_t, H, M, H, H, t.dctx16, H, false, false));
+    TRY(dgrad<T16>(h, st, t.dx16, H, d.w_ao, H, M, H, H, t.dctx16, H, false, false));
     TRY(attention_backward<T16>(h, st, tl.qkv16, t.dctx16, t.ext_mask, B, S, t.big16, dropout, p_a,
                                 (unsigned)(l * 4 + SITE_ATTN), -1));
     // query / key / value
@@ -519,7 +527,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
       TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16) + j * H, M, H, 3 * H, qkv_b[j]));
       TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
     }
-    TRY(gemm_plain<T16>(h, st, DG, t.big16, 3 * H, d.w_qkv_t, 3 * H, M, H, 3 * H, t.dH, H, true, true));  // += residual
+    TRY(dgrad<T16>(h, st, t.big16, 3 * H, d.w_qkv, H, M, 3 * H, H, t.dH, H, true, true));  // += residual
   }
 
   // ---- embeddings
@@ -527,7 +535,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     ProfScope ps(h, st, CPT_K_EMBED_BWD);
 #define CPT_EMBB_CASE(NV_)                                                                                           \
   case NV_:                                                                                                          \
-    embed_bwd_kernel<NV_><<<(B * T + 7) / 8, 256, 0, st>>>(                                                          \
+    embed_bwd_kernel<NV_><<<std::min((B * T + 7) / 8, 2 * h->num_sms), 256, 0, st>>>(                                                          \
         (const long long*)ids, (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, h->emb_g, \
         c.layer_norm_eps, t.dH, B, T, S, H, c.vocab_size, c.max_position_embeddings, c.type_vocab_size, g->word_emb, \
         g->pos_emb, g->type_emb, g->emb_ln_g, g->emb_ln_b, make_drop(dropout, p_h, SITE_EMB_TEXT));                  \

@@ -376,7 +376,11 @@ class Engine(object):
              ksplit=0):
         """out = epi(A . W^T); trans: A is [K,M], W is [K,N] and out = A^T . W; accumulate_into: fp32 [M,N] tensor
         the result is added to (returned)."""
-        if trans:
+        if trans == "b":  # out = A . W with W given as [K, N]
+            M, K = A.shape
+            N = W.shape[1]
+            epi |= 0x400
+        elif trans:
             K, M = A.shape
             N = W.shape[1]
             epi |= 0x100

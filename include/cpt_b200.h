@@ -190,7 +190,8 @@ int cpt_profile_read(cpt_handle *h, double *ms, long long *launches);
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): A, W 16-bit (dtype as in cfg) with leading dims lda/ldw (elements, multiples
  * of 8); epi: 0 bias, 1 bias+erf-GELU, 2 bias+fp32 residual; out_fp32: 0 -> 16-bit out, 1 -> fp32 out.
  * epi | 0x100: operands are given transposed, A as [K,M] and W as [K,N] (out = A^T . W, the weight-gradient form;
- * lda/ldw are then the pitches of those); epi | 0x200: out += result (fp32 out only); epi | (s << 12): split K into
+ * lda/ldw are then the pitches of those); epi | 0x400: only W is given transposed, as [K,N] (out = A . W, the
+ * data-gradient form on an nn.Linear weight); epi | 0x200: out += result (fp32 out only); epi | (s << 12): split K into
  * s pieces accumulated at the destination (with 0x200 and bias == NULL only; otherwise ignored).
  * tile_cfg: 0 = library default, else block_n (64/128/192/256) + 1000 * (CTAs per MMA: 1 or 2), e.g. 2256 =
  * 256-wide tiles computed by CTA pairs (tcgen05 cta_group::2). */

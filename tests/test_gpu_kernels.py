@@ -126,6 +126,22 @@ def test_gemm_transposed_operands_accumulate(eng, M, N, K, cfg):
         assert (acc2 - want).abs().max().item() <= 2e-3 * scale
 
 
+@pytest.mark.parametrize("M,N,K,cfg", [(1920, 768, 3072, 0), (7680, 3072, 768, 1256), (75, 768, 2304, 0),
+                                       (16, 768, 30528, 1128), (200, 72, 40, 1064)])
+def test_gemm_transposed_weight_operand(eng, M, N, K, cfg):
+    """the data-gradient form: out[M,N] = A[M,K] . W[K,N] with W read in place through an MN-major descriptor"""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = torch.randn(K, N, device="cuda", generator=g).half()
+    ref = A.float() @ W.float()
+    out = eng.gemm(A, W, out_fp32=True, tile_cfg=cfg, trans="b")
+    out16 = eng.gemm(A, W, out_fp32=False, tile_cfg=cfg, trans="b")
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-3 * scale
+    assert (out16.float() - ref).abs().max().item() <= 4e-3 * scale
+
+
 @pytest.mark.parametrize("M,N,K,ksplit", [(768, 768, 3072, 4), (100, 192, 7680, 30), (1920, 768, 768, 3)])
 def test_gemm_split_k_accumulate(eng, M, N, K, ksplit):
     g = torch.Generator(device="cuda").manual_seed(K + ksplit)

@@ -23,3 +23,14 @@ for n in gemm attn ln; do ncu -i /tmp/r01_$n.ncu-rep --page raw --csv > gpurun_o
 ncu -i /tmp/r01_gemm.ncu-rep --page source --csv > gpurun_out/r01_gemm_source.csv 2>/dev/null
 ncu -i /tmp/r01_attn.ncu-rep --page source --csv > gpurun_out/r01_attn_source.csv 2>/dev/null
 ls -la gpurun_out/r01_*; du -sh gpurun_out
+# training step: timing + per-class split, and the ncu launch list of one step
+for args in "--batch 16" "--batch 64" "--batch 16 --T 165 --R 45" "--batch 16 --dropout 0.1"; do
+  timeout 300 python tools/train_bench.py $args 2>>gpurun_out/r01_bench.err | tail -1 >> gpurun_out/r01_train_bench.jsonl
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r01_train_launches.csv \
+   python tools/train_bench.py --batch 64 --steps 1 --warmup 0 > gpurun_out/ncu_train_launch.log 2>&1
+echo "train launch list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_tc -s 12 -c 1 -f -o /tmp/r01_attn_bwd \
+   python tools/train_bench.py --batch 64 --steps 1 --warmup 0 > gpurun_out/ncu_attn_bwd.log 2>&1
+ncu -i /tmp/r01_attn_bwd.ncu-rep --page raw --csv > gpurun_out/r01_attn_bwd_raw.csv 2>/dev/null
+ls -la gpurun_out/r01_*; du -sh gpurun_out
