@@ -6,6 +6,8 @@
 //     dQ = dS K                  (A = dS, K-major;  B = K tile, MN-major)          TMEM cols 256..319, lanes = queries
 //     dV = P^T dO                (A = P  read MN-major: M = keys; B = dO MN-major)  TMEM cols 320..383, lanes = keys
 //     dK = dS^T Q                (A = dS read MN-major;           B = Q  MN-major)  TMEM cols 384..447, lanes = keys
+// With dropout on the probabilities (P~ = mask * P / (1-p) multiplied V in the forward): dP is masked and scaled the
+// same way before D and dS, and the tile that feeds dV holds P~.
 // Two threads own each query row for the softmax algebra (TMEM lane r of S, dP: warps w and w+4 share a lane quadrant
 // and take 64 key columns each; row max / sum / D meet in shared memory) and each key row for the dV / dK read-out
 // — with one warp per scheduler the kernel was issue-latency bound (ncu: 7.3 cycles per instruction, 13 % issue slots).
@@ -24,6 +26,7 @@ struct AttnBwdParams {
   const float* ext_mask;  // [B, S]
   void* dqkv;             // T16 [B*S, 3H]
   float scale;
+  Drop drop;              // dropout that sat on the probabilities in the forward (thresh = 0 -> none)
 };
 
 constexpr int kAttnBwdThreads = 256;
@@ -96,6 +99,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_tc_kernel(const __gr
   const int r = q4 * 32 + lane;
   const uint32_t t_row = tmem_base + (uint32_t(q4 * 32) << 16);
   const int c0 = half * 2;  // this thread's two 32-column chunks
+  const unsigned long long pidx0 = (((unsigned long long)b * p.nH + h) * S + r) * S;  // element index of P[b,h,r,0]
+  const bool dropping = p.drop.thresh != 0u;
   float mx = -INFINITY;
   for (int c = c0; c < c0 + 2; ++c) {
     uint32_t v[32];
@@ -122,7 +127,9 @@ __global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_tc_kernel(const __gr
       const int col = c * 32 + j;
       const float e = (col < S) ? __expf(fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) - mx) : 0.f;
       sum += e;
-      dn = fmaf(e, __uint_as_float(w[j]), dn);
+      float dp = __uint_as_float(w[j]);
+      if (dropping) dp = drop_apply(p.drop, pidx0 + col, dp);
+      dn = fmaf(e, dp, dn);
     }
   }
   statp[256 + half * 128 + r] = sum;
@@ -144,7 +151,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_tc_kernel(const __gr
       const int col = c * 32 + j;
       const float e = (col < S) ? __expf(fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) - mx) : 0.f;
       pr[j] = e * inv;
-      ds[j] = pr[j] * (__uint_as_float(w[j]) - D) * p.scale;
+      float dp = __uint_as_float(w[j]);
+      if (dropping) dp = drop_apply(p.drop, pidx0 + col, dp);
+      ds[j] = pr[j] * (dp - D) * p.scale;
+      if (dropping) pr[j] = drop_apply(p.drop, pidx0 + col, pr[j]);  // the dV operand is P~
     }
     const int kb = c >> 1;
     uint8_t* prow = p_gen + kb * 16384 + r * 128;

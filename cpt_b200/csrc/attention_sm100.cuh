@@ -23,6 +23,7 @@ struct AttnParams {
   void* ctx;              // T16 [B*S, H]
   float scale;            // 1/sqrt(dH)
   long long* trace;       // optional [gridDim.x][8] cycle counters (debug)
+  Drop drop;              // training only (attn_tc_kernel): dropout on the probabilities, thresh = 0 -> off
 };
 
 __host__ __device__ inline int attn_nkb(int S) { return (S + 63) / 64; }
@@ -127,6 +128,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_tc_kernel(const __grid_cons
       const float t = (col < S) ? fmaf(__uint_as_float(v[j]), p.scale, maskp[col]) : -INFINITY;
       e[j] = __expf(t - mx);
       sum += e[j];
+    }
+    if (p.drop.thresh) {
+      // training: P~ = mask * P / (1 - p) multiplies V; the row sum stays that of the unmasked probabilities
+      const unsigned long long pidx = (((unsigned long long)b * p.nH + h) * S + (i0 + r)) * S + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e[j] = drop_apply(p.drop, pidx + j, e[j]);
     }
     // P[r, c*32 .. +31] -> K-major 128B-swizzled A-operand tile (64-key block kb, 16-byte chunk ^ (row & 7))
     const int kb = c >> 1;

@@ -331,7 +331,7 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   const int H = h->cfg.hidden_size, nH = h->cfg.num_attention_heads;
   if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
   if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
-  AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f, h->trace};
+  AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f, h->trace, Drop{0u, 0u, 0u, 0u, 1.f}};
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {

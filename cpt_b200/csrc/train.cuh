@@ -8,32 +8,6 @@
 
 namespace cptk {
 
-// Dropout masks are a pure function of (seed, site, element index): the backward regenerates them instead of storing
-// them.  keep(idx) <=> mix32(idx, seed, site) >= p * 2^32; kept values are scaled by 1 / (1 - p).  thresh = 0 = off.
-// Element index: hidden-state sites (row * H + col) with row = b*S + s; attention site ((b*nH + h)*S + i)*S + j.
-// Sites: layer*4 + {0: attention probabilities, 1: attention.output.dense, 2: output.dense}; 0xFFFF0 text embeddings,
-// 0xFFFF1 region embeddings.  (tests/test_gpu_train.py restates this function in torch integer arithmetic.)
-struct Drop {
-  unsigned seed_lo, seed_hi, site, thresh;
-  float scale;
-};
-__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
-  unsigned x = (unsigned)idx ^ ((unsigned)(idx >> 32) * 0x9E3779B1u);
-  x ^= d.seed_lo;
-  x *= 0x85EBCA6Bu;
-  x ^= x >> 13;
-  x += d.site * 0xC2B2AE35u + d.seed_hi;
-  x ^= x >> 16;
-  x *= 0x7FEB352Du;
-  x ^= x >> 15;
-  x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  return x >= d.thresh;
-}
-__device__ __forceinline__ float drop_apply(const Drop& d, unsigned long long idx, float v) {
-  return d.thresh == 0u ? v : (drop_keep(d, idx) ? v * d.scale : 0.f);
-}
-
 // h32 / h16 rows <- dropout(rows) in place (embedding outputs).  Row m of the site lives at stream row remap(m).
 template <typename T16>
 __global__ void __launch_bounds__(256) dropout_rows_kernel(float* __restrict__ h32, T16* __restrict__ h16, int n_rows,

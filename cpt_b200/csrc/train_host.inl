@@ -157,10 +157,10 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, nH = c.num_attention_heads;
   if (S < 1 || S > 256) return fail("attention backward supports 1 <= S <= 256 (got %d)", S);
-  if (impl < 0) impl = (S <= 128 && !(p_a > 0.f) && !h->attn_bwd_simt) ? 0 : 1;
+  if (impl < 0) impl = (S <= 128 && !h->attn_bwd_simt) ? 0 : 1;
   ProfScope ps(h, st, CPT_K_ATTN_BWD);
   if (impl == 0) {
-    if (S > 128 || p_a > 0.f) return fail("tensor-core attention backward: S <= 128 and no probability dropout");
+    if (S > 128) return fail("tensor-core attention backward: S <= 128");
     CUtensorMap tq, td;
     TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
     TRY(make_tmap(&td, dctx, Cvt<T16>::kFmt, (unsigned long long)B * S, (unsigned long long)H, (unsigned long long)H, 64));
@@ -170,7 +170,7 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
       TRY(set_smem_attr(fn, kAttnBwdSmem));
       attr_set[h->device & 63] = true;
     }
-    AttnBwdParams p{B, S, H, nH, ext_mask, dqkv, 0.125f};
+    AttnBwdParams p{B, S, H, nH, ext_mask, dqkv, 0.125f, make_drop(dropout, p_a, site)};
     fn<<<dim3(nH, B), kAttnBwdThreads, kAttnBwdSmem, st>>>(tq, td, p);
     CKL("attn_bwd_tc_kernel");
     return 0;
@@ -328,14 +328,26 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
       TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, tl.h16, H, d.w_qkv, H, p, EPI_BIAS, false));
     }
     if (p_a > 0.f) {
+      // probability dropout: the single-tile tcgen05 kernel masks P on its way to shared memory (CPT_B200_ATTN_BWD=simt
+      // selects the CUDA-core pair of kernels instead)
       ProfScope ps(h, st, CPT_K_ATTN);
-      auto* fn = attn_fwd_drop_kernel<T16>;
-      const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
-      TRY(set_smem_attr(fn, smem));
-      fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16), t.ext_mask, S, H,
-                                                            0.125f, reinterpret_cast<T16*>(tl.ctx16),
-                                                            make_drop(dropout, p_a, l * 4 + SITE_ATTN));
-      CKL("attn_fwd_drop_kernel");
+      const Drop dr = make_drop(dropout, p_a, l * 4 + SITE_ATTN);
+      if (h->attn_bwd_simt) {
+        auto* fn = attn_fwd_drop_kernel<T16>;
+        const size_t smem = (size_t)S * kAttnDH * 2 * 2 + (size_t)S * 4;
+        TRY(set_smem_attr(fn, smem));
+        fn<<<dim3(c.num_attention_heads, B), 128, smem, st>>>(reinterpret_cast<const T16*>(tl.qkv16), t.ext_mask, S, H,
+                                                              0.125f, reinterpret_cast<T16*>(tl.ctx16), dr);
+        CKL("attn_fwd_drop_kernel");
+      } else {
+        CUtensorMap tq;
+        TRY(make_tmap(&tq, tl.qkv16, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
+        AttnParams ap{B, S, H, c.num_attention_heads, t.ext_mask, tl.ctx16, 0.125f, nullptr, dr};
+        auto* fn = attn_tc_kernel<T16>;
+        const size_t smem = attn_smem_bytes(S);
+        TRY(set_smem_attr(fn, smem));
+        CK(launch_k(fn, dim3(c.num_attention_heads, (S + 127) / 128, B), dim3(kAttnThreads), smem, st, 1, tq, ap));
+      }
     } else {
       TRY(attention<T16>(h, st, tl.qkv16, t.ext_mask, B, S, tl.ctx16, h->attn_impl));
     }

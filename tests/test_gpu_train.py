@@ -298,7 +298,8 @@ def make_provider(cfg, T, R, seed):
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
-@pytest.mark.parametrize("B,T,R,p_h,p_a", [(4, 50, 30, 0.1, 0.1), (2, 70, 50, 0.3, 0.0), (3, 40, 0, 0.0, 0.2)])
+@pytest.mark.parametrize("B,T,R,p_h,p_a", [(4, 50, 30, 0.1, 0.1), (2, 70, 50, 0.3, 0.0), (3, 40, 0, 0.0, 0.2),
+                                          (2, 100, 60, 0.1, 0.1), (2, 70, 50, 0.1, 0.1)])
 def test_dropout_step_against_oracle_with_the_same_masks(B, T, R, p_h, p_a, dtype):
     """training mode with active dropout (the reference's few-shot configs run hidden_dropout_prob 0.1-0.3): loss and
     every gradient against the oracle fed the same keep-masks."""
