@@ -157,10 +157,24 @@ static int attention_backward(cpt_handle* h, cudaStream_t st, const void* qkv, c
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, nH = c.num_attention_heads;
   if (S < 1 || S > 256) return fail("attention backward supports 1 <= S <= 256 (got %d)", S);
-  if (impl < 0) impl = (S <= 128 && !h->attn_bwd_simt) ? 0 : 1;
+  if (impl < 0) impl = h->attn_bwd_simt ? 1 : 0;
   ProfScope ps(h, st, CPT_K_ATTN_BWD);
+  if (impl == 0 && S > 128) {  // two query tiles x two key tiles per (head, sample)
+    CUtensorMap tq, td;
+    TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
+    TRY(make_tmap(&td, dctx, Cvt<T16>::kFmt, (unsigned long long)B * S, (unsigned long long)H, (unsigned long long)H, 64));
+    auto* fn = attn_bwd_tc2_kernel<T16>;
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      TRY(set_smem_attr(fn, kAttnBwd2Smem));
+      attr_set[h->device & 63] = true;
+    }
+    AttnBwdParams p{B, S, H, nH, ext_mask, dqkv, 0.125f, make_drop(dropout, p_a, site)};
+    fn<<<dim3(nH, B), kAttnBwdThreads, kAttnBwd2Smem, st>>>(tq, td, p);
+    CKL("attn_bwd_tc2_kernel");
+    return 0;
+  }
   if (impl == 0) {
-    if (S > 128) return fail("tensor-core attention backward: S <= 128");
     CUtensorMap tq, td;
     TRY(make_tmap(&tq, qkv, Cvt<T16>::kFmt, (unsigned long long)B * S, 3ull * H, 3ull * H, 64));
     TRY(make_tmap(&td, dctx, Cvt<T16>::kFmt, (unsigned long long)B * S, (unsigned long long)H, (unsigned long long)H, 64));

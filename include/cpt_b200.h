@@ -210,7 +210,8 @@ int cpt_gemm_trace(cpt_handle *h, long long *out, int max_ctas);
 int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext_mask, int B, int S, void *ctx,
                   int impl);
 /* d(qkv)[B*S,3H] from d(ctx)[B*S,H] (16-bit), probabilities recomputed from qkv.  impl: -1 = library choice, 0 =
- * tcgen05 kernel (S <= 128), 1 = CUDA-core kernel (any S <= 256). */
+ * tcgen05 kernels (one 128 x 128 block for S <= 128, 2 x 2 blocks with a statistics pre-pass above), 1 = CUDA-core
+ * kernel. */
 int cpt_attention_backward(cpt_handle *h, void *stream, const void *qkv, const void *dctx, const float *ext_mask,
                            int B, int S, void *dqkv, int impl);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
