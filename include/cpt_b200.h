@@ -106,9 +106,8 @@ int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, flo
  * Masks are a counter-based hash of (seed, site, element index) — regenerated by the backward, never stored — so they
  * are reproducible from the seed but are NOT the masks torch's Philox stream would draw.
  *
- * cpt_train_enable(h, 1) before cpt_set_weights: the handle also keeps transposed 16-bit weights (the W operand of
- * the dgrad GEMMs) and later cpt_set_weights calls refresh the existing buffers in stream order instead of
- * reallocating (call it after every optimizer step). */
+ * cpt_train_enable(h, 1) before cpt_set_weights: later cpt_set_weights calls refresh the handle's 16-bit copies in
+ * stream order instead of reallocating (call it after every optimizer step). */
 int cpt_train_enable(cpt_handle *h, int on);
 
 /* Gradient buffers, fp32, same shapes as the cpt_weights tensors of the same name.  The backward ADDS into them
