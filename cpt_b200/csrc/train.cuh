@@ -74,9 +74,11 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+// Columns [k*seg, (k+1)*seg) go to out_k (the packed [M, 3H] query|key|value gradient feeds three bias tensors).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int M, int N, long long ld,
-                                                     float* __restrict__ out, int vec) {
+                                                     float* __restrict__ out0, float* __restrict__ out1,
+                                                     float* __restrict__ out2, int seg, int vec) {
   __shared__ float red[4][256];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int n0 = blockIdx.x * 256 + tx * 4;
@@ -110,7 +112,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
   for (int e = 0; e < 4; ++e) red[ty][tx * 4 + e] = acc[e];
   __syncthreads();
   const int c = threadIdx.x, n = blockIdx.x * 256 + c;
-  if (n < N) atomicAdd(out + n, (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]));
+  if (n < N) {
+    const int k = n / seg;
+    float* out = k == 0 ? out0 : k == 1 ? out1 : out2;
+    atomicAdd(out + (n - k * seg), (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]));
+  }
 }
 
 __device__ __forceinline__ float gelu_exact(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -150,19 +156,41 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T16* __restrict__ i
     reinterpret_cast<uint4*>(out)[i] = pack8<T16>(f);
   }
 }
-// dpre = dpost * gelu'(pre)
+// dpre = dpost * gelu'(pre) over [M, N] (N % 8 == 0, dense rows), and dbias[n] += sum_m dpre[m, n] (the bias gradient of
+// intermediate.dense).  A thread keeps one 8-column group and walks rows blockIdx.y*kGeluRows .. +kGeluRows.
+constexpr int kGeluRows = 64;
 template <typename T16>
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T16* __restrict__ dpost, const T16* __restrict__ pre,
-                                                       long long n, T16* __restrict__ dpre) {
-  const long long nv = n >> 3;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-    float d[8], x[8];
-    unpack8<T16>(reinterpret_cast<const uint4*>(dpost)[i], d);
-    unpack8<T16>(reinterpret_cast<const uint4*>(pre)[i], x);
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T16* __restrict__ dpost, const T16* __restrict__ pre, int M,
+                                                       int N, T16* __restrict__ dpre, float* __restrict__ dbias) {
+  __shared__ float red[128][9];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;  // 128 column groups x 2 row lanes
+  const int cg = blockIdx.x * 128 + tx;                     // 8-column group
+  const bool active = cg * 8 < N;
+  const int m0 = blockIdx.y * kGeluRows, m1 = min(M, m0 + kGeluRows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+#pragma unroll 4
+    for (int m = m0 + ty; m < m1; m += 2) {
+      const long long i = ((long long)m * N >> 3) + cg;
+      float d[8], x[8];
+      unpack8<T16>(reinterpret_cast<const uint4*>(dpost)[i], d);
+      unpack8<T16>(reinterpret_cast<const uint4*>(pre)[i], x);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] *= gelu_grad(x[e]);
-    reinterpret_cast<uint4*>(dpre)[i] = pack8<T16>(d);
+      for (int e = 0; e < 8; ++e) {
+        d[e] *= gelu_grad(x[e]);
+        acc[e] += d[e];
+      }
+      reinterpret_cast<uint4*>(dpre)[i] = pack8<T16>(d);
+    }
   }
+  if (dbias == nullptr) return;
+  if (ty == 1)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[tx][e] = acc[e];
+  __syncthreads();
+  if (ty == 0 && active)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dbias + cg * 8 + e, acc[e] + red[tx][e]);
 }
 // fp32 variants for the small head tensors
 __global__ void __launch_bounds__(256) gelu_fwd32_kernel(const float* __restrict__ in, long long n,
@@ -183,17 +211,19 @@ template <typename T16, int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int M,
                                                      int H, const float* __restrict__ gamma, float eps, int do_ln,
                                                      float* __restrict__ dx32, T16* __restrict__ dx16,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rin,
-                                                     int rout, int roff, Drop drop_dy, Drop drop16) {
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ dbias, int rin, int rout, int roff,
+                                                     Drop drop_dy, Drop drop16) {
+  // dbias  : += column sums of the (dropout-masked) dx — the bias gradient of the dense layer that fed this LayerNorm.
   // drop_dy: dropout that sat between this LayerNorm's output and its consumer (embedding sites): masks dy on load.
   // drop16 : dropout that sat on the dense output feeding this LayerNorm's input: the 16-bit copy of dx (the operand
   //          of that dense layer's dgrad / wgrad GEMMs) is masked; the fp32 dx (residual branch) is not.
   __shared__ float red[8][NV * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wstride = gridDim.x * 8;
-  float4 ag[NV], ab[NV];
+  float4 ag[NV], ab[NV], ax[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int row = blockIdx.x * 8 + warp; row < M; row += wstride) {
     long long drow = row;
     if (rin > 0) drow = (long long)(row / rin) * rout + roff + (row % rin);
@@ -250,12 +280,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         o = dv[i];
       }
       if (dx32) *reinterpret_cast<float4*>(dx32 + (long long)row * H + col) = o;
+      if (drop16.thresh) {
+        const unsigned long long e = (unsigned long long)((long long)row * H + col);
+        o.x = drop_apply(drop16, e, o.x); o.y = drop_apply(drop16, e + 1, o.y);
+        o.z = drop_apply(drop16, e + 2, o.z); o.w = drop_apply(drop16, e + 3, o.w);
+      }
+      ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
       if (dx16) {
-        if (drop16.thresh) {
-          const unsigned long long e = (unsigned long long)((long long)row * H + col);
-          o.x = drop_apply(drop16, e, o.x); o.y = drop_apply(drop16, e + 1, o.y);
-          o.z = drop_apply(drop16, e + 2, o.z); o.w = drop_apply(drop16, e + 3, o.w);
-        }
         uint2 u;
         u.x = Cvt<T16>::pack2(o.x, o.y);
         u.y = Cvt<T16>::pack2(o.z, o.w);
@@ -263,21 +294,22 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       }
     }
   }
-  if (!do_ln || dgamma == nullptr) return;
-  // block reduction of the per-warp partial dgamma / dbeta, then one atomic per column per CTA
+  // block reduction of the per-warp partial dgamma / dbeta / dbias, then one atomic per column per CTA
 #pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
+    if (dst == nullptr || (which < 2 && !do_ln)) continue;  // uniform across the CTA
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = (i * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(&red[warp][col]) = which == 0 ? ag[i] : ab[i];
+      *reinterpret_cast<float4*>(&red[warp][col]) = which == 0 ? ag[i] : which == 1 ? ab[i] : ax[i];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NV * 128; c += 256) {
       float sg = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) sg += red[w][c];
-      atomicAdd((which == 0 ? dgamma : dbeta) + c, sg);
+      atomicAdd(dst + c, sg);
     }
     __syncthreads();
   }

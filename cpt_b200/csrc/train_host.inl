@@ -115,27 +115,30 @@ static int ew_grid(const cpt_handle* h, long long n) {
 }
 
 template <typename T>
-static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, long long ld, float* out) {
+static int colsum(cpt_handle* h, cudaStream_t st, const T* in, int M, int N, long long ld, float* out,
+                  float* out1 = nullptr, float* out2 = nullptr, int seg = 0) {
   if (M <= 0 || !out) return 0;
+  if (seg <= 0) seg = N;
   ProfScope ps(h, st, CPT_K_COLSUM);
   const int vec = ((ld * sizeof(T)) % (4 * sizeof(T)) == 0) && (reinterpret_cast<uintptr_t>(in) % (4 * sizeof(T)) == 0);
-  colsum_kernel<T><<<dim3((N + 255) / 256, (M + kColsumRows - 1) / kColsumRows), 256, 0, st>>>(in, M, N, ld, out, vec);
+  colsum_kernel<T><<<dim3((N + 255) / 256, (M + kColsumRows - 1) / kColsumRows), 256, 0, st>>>(in, M, N, ld, out, out1, out2, seg, vec);
   CKL("colsum_kernel");
   return 0;
 }
 
 template <typename T16>
 static int ln_bwd(cpt_handle* h, cudaStream_t st, const float* dy, const float* x, int M, int H, const float* gamma,
-                  float eps, bool do_ln, float* dx32, void* dx16, float* dgamma, float* dbeta, int rin = 0,
-                  int rout = 0, int roff = 0, Drop drop_dy = Drop{0, 0, 0, 0, 1.f}, Drop drop16 = Drop{0, 0, 0, 0, 1.f}) {
+                  float eps, bool do_ln, float* dx32, void* dx16, float* dgamma, float* dbeta, float* dbias,
+                  int rin = 0, int rout = 0, int roff = 0, Drop drop_dy = Drop{0, 0, 0, 0, 1.f},
+                  Drop drop16 = Drop{0, 0, 0, 0, 1.f}) {
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN_BWD);
   const int grid = std::min((M + 7) / 8, 2 * h->num_sms);
 #define CPT_LNB_CASE(NV_)                                                                                         \
   case NV_:                                                                                                       \
     ln_bwd_kernel<T16, NV_><<<grid, 256, 0, st>>>(dy, x, M, H, gamma, eps, do_ln ? 1 : 0, dx32,                   \
-                                                  reinterpret_cast<T16*>(dx16), dgamma, dbeta, rin, rout, roff,   \
-                                                  drop_dy, drop16);                                               \
+                                                  reinterpret_cast<T16*>(dx16), dgamma, dbeta, dbias, rin, rout,  \
+                                                  roff, drop_dy, drop16);                                         \
     break;
   switch (H / 128) {
     CPT_LNB_CASE(1) CPT_LNB_CASE(2) CPT_LNB_CASE(3) CPT_LNB_CASE(4) CPT_LNB_CASE(5) CPT_LNB_CASE(6) CPT_LNB_CASE(7)
@@ -486,7 +489,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   TRY(wgrad<T16>(h, st, t.dlog16, Vp, t.ht16, H, n, V, H, g->word_emb, H));
   TRY(dgrad<T16>(h, st, t.dlog16, Vp, h->word16, H, n, V, H, t.hd32a, H, true, false));
   TRY(ln_bwd<T16>(h, st, t.hd32a, t.htg32, n, H, h->mlm_g, c.layer_norm_eps, true, t.hd32b, nullptr, g->mlm_ln_g,
-                  g->mlm_ln_b));
+                  g->mlm_ln_b, nullptr));
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     const long long ne = (long long)n * H;
@@ -517,31 +520,26 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     const TapeLayer& tl = t.layers[l];
     const cpt_layer_grads& gl = g->layers[l];
     // output.LayerNorm
-    TRY(ln_bwd<T16>(h, st, t.dH, tl.x2, M, H, d.o_g, c.layer_norm_eps, true, t.dx32, t.dx16, gl.o_ln_g, gl.o_ln_b, 0, 0,
-                    0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_DOWN)));
-    // output.dense: x2 = a + dropout(inter W2^T + b2); t.dx16 carries the masked gradient of the dense output
-    if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.o_b));
-    else TRY(colsum<float>(h, st, t.dx32, M, H, H, gl.o_b));
+    // output.dense: x2 = a + dropout(inter W2^T + b2); t.dx16 carries the masked gradient of the dense output, whose
+    // column sums (the bias gradient) the same kernel accumulates
+    TRY(ln_bwd<T16>(h, st, t.dH, tl.x2, M, H, d.o_g, c.layer_norm_eps, true, t.dx32, t.dx16, gl.o_ln_g, gl.o_ln_b,
+                    gl.o_b, 0, 0, 0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_DOWN)));
     TRY(wgrad<T16>(h, st, t.dx16, H, tl.inter16, I, M, H, I, gl.o_w, I));
     TRY(dgrad<T16>(h, st, t.dx16, H, d.w_o, I, M, H, I, t.big16, I, false, false));
-    {  // GELU
+    {  // GELU backward + the bias gradient of intermediate.dense
       ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
-      const long long ne = (long long)M * I;
-      gelu_bwd_kernel<T16><<<ew_grid(h, ne / 8), 256, 0, st>>>(reinterpret_cast<const T16*>(t.big16),
-                                                          reinterpret_cast<const T16*>(tl.preup16), ne,
-                                                          reinterpret_cast<T16*>(t.big16b));
+      gelu_bwd_kernel<T16><<<dim3((I / 8 + 127) / 128, (M + kGeluRows - 1) / kGeluRows), 256, 0, st>>>(
+          reinterpret_cast<const T16*>(t.big16), reinterpret_cast<const T16*>(tl.preup16), M, I,
+          reinterpret_cast<T16*>(t.big16b), gl.i_b);
       CKL("gelu_bwd_kernel");
     }
     // intermediate.dense
-    TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16b), M, I, I, gl.i_b));
     TRY(wgrad<T16>(h, st, t.big16b, I, tl.a16, H, M, I, H, gl.i_w, H));
     TRY(dgrad<T16>(h, st, t.big16b, I, d.w_i, H, M, I, H, t.dx32, H, true, true));  // += residual branch
     // attention.output.LayerNorm  (dx1 -> t.dH)
     TRY(ln_bwd<T16>(h, st, t.dx32, tl.x1, M, H, d.ao_g, c.layer_norm_eps, true, t.dH, t.dx16, gl.ao_ln_g,
-                    gl.ao_ln_b, 0, 0, 0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_AO)));
+                    gl.ao_ln_b, gl.ao_b, 0, 0, 0, no_drop, make_drop(dropout, p_h, l * 4 + SITE_AO)));
     // attention.output.dense
-    if (p_h > 0.f) TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.dx16), M, H, H, gl.ao_b));
-    else TRY(colsum<float>(h, st, t.dH, M, H, H, gl.ao_b));
     TRY(wgrad<T16>(h, st, t.dx16, H, tl.ctx16, H, M, H, H, gl.ao_w, H));
     TRY(dgrad<T16>(h, st, t.dx16, H, d.w_ao, H, M, H, H, t.dctx16, H, false, false));
     TRY(attention_backward<T16>(h, st, tl.qkv16, t.dctx16, t.ext_mask, B, S, t.big16, dropout, p_a,
@@ -549,8 +547,8 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     // query / key / value
     float* qkv_b[3] = {gl.q_b, gl.k_b, gl.v_b};
     float* qkv_w[3] = {gl.q_w, gl.k_w, gl.v_w};
+    TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16), M, 3 * H, 3 * H, qkv_b[0], qkv_b[1], qkv_b[2], H));
     for (int j = 0; j < 3; ++j) {
-      TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16) + j * H, M, H, 3 * H, qkv_b[j]));
       TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
     }
     TRY(dgrad<T16>(h, st, t.big16, 3 * H, d.w_qkv, H, M, 3 * H, H, t.dH, H, true, true));  // += residual
@@ -577,8 +575,8 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   if (R > 0) {
     const int F = c.img_feature_dim, Mi = B * R;
     TRY(ln_bwd<T16>(h, st, t.dH, t.imgpre32, Mi, H, h->img_g, c.img_layer_norm_eps, c.use_img_layernorm != 0,
-                    t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, R, S, T, make_drop(dropout, p_h, SITE_EMB_IMG)));
-    TRY(colsum<float>(h, st, t.dimg32, Mi, H, H, g->img_b));
+                    t.dimg32, t.dimg16, g->img_ln_g, g->img_ln_b, g->img_b, R, S, T,
+                    make_drop(dropout, p_h, SITE_EMB_IMG)));
     TRY(wgrad<T16>(h, st, t.dimg16, H, t.img16, h->Fp, Mi, H, h->Fp, t.dwimg, h->Fp, false));
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
     add_rows_kernel<<<ew_grid(h, (long long)H * F), 256, 0, st>>>(t.dwimg, h->Fp, H, F, g->img_w, F);

@@ -208,6 +208,69 @@ def test_nsp_loss_and_all_grads_against_oracle(B, T, R, ignore, dtype):
                 LOSS_SCALE[dtype], 16 * 2 + 9)
 
 
+def test_training_defaults_and_explicit_position_ids():
+    """token_type_ids=None, attention_mask=None, explicit position_ids (the optional arguments of
+    REC_MLM_CPT.forward, modeling_rec.py:137-138) in the training step, against the oracle."""
+    from oracle import cpt_oracle as O
+    dtype = "fp16"
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=4)
+    B, T, R = 3, 30, 12
+    b = synth_batch(cfg, B, T, R, seed=9)
+    pos = (torch.arange(T)[None, :] + torch.tensor([[0], [3], [7]])).contiguous()
+    labels = torch.full((B, T + R), -1, dtype=torch.long)
+    labels[torch.arange(B), b["mask_pos"]] = torch.tensor([11, 12, 13])
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ones = torch.ones(B, T + R, dtype=torch.long)  # attention_mask=None means "attend everywhere" on our side
+    ref_loss = O.rec_mlm_cpt(leaf, cfg, b["input_ids"], None, ones, masked_lm_labels=labels, position_ids=pos,
+                             img_feats=b["img_feats"])[0]
+    ref_loss.backward()
+    rec = build_rec(cfg, sd, dtype)
+    loss, _ = rec(b["input_ids"].cuda(), masked_lm_labels=labels.cuda(), position_ids=pos.cuda(),
+                  img_feats=b["img_feats"].cuda())
+    (loss * LOSS_SCALE[dtype]).backward()
+    rec.bert.train_engine()[0].check()
+    assert abs(loss.item() - ref_loss.item()) <= LTOL[dtype] * abs(ref_loss.item())
+
+    def key_of(k):
+        key = k if k.startswith("bert.") else "cls.predictions." + k[len("cls."):]
+        return None if key == "cls.predictions.decoder.weight" else key
+
+    compare_all(rec.named_parameters(), {k: v.grad for k, v in leaf.items()}, key_of, dtype, LOSS_SCALE[dtype], 40)
+
+
+def test_training_error_paths():
+    cfg = C.oscar_tiny(num_hidden_layers=1)
+    sd = synth_state_dict(cfg, seed=2)
+    rec = build_rec(cfg, sd, "bf16")
+    b = synth_batch(cfg, 2, 20, 8, seed=2)
+    d = {k: v.cuda() for k, v in b.items()}
+    none = torch.full((2, 28), -1, dtype=torch.long).cuda()
+    with pytest.raises(RuntimeError):  # no labelled position: the reference's loss would be NaN
+        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"], masked_lm_labels=none)
+    labels = none.clone()
+    labels[:, 2] = 5
+    with pytest.raises(NotImplementedError):
+        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+            masked_lm_labels=labels, head_mask=torch.ones(1, 2).cuda())
+    # frozen parameters get no gradient, the rest still do
+    for n, p in rec.named_parameters():
+        if "embeddings" in n:
+            p.requires_grad_(False)
+    loss = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+               masked_lm_labels=labels)[0]
+    loss.backward()
+    named = dict(rec.named_parameters())
+    assert named["bert.embeddings.word_embeddings.weight"].grad is None
+    assert named["bert.encoder.layer.0.output.dense.weight"].grad is not None
+    # under no_grad the labelled call returns the reference's (loss, scores) through the inference path
+    rec.eval()
+    with torch.no_grad():
+        out = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                  masked_lm_labels=labels)
+    assert out[0].dim() == 0 and out[1].shape == (2, 28, cfg.vocab_size)
+
+
 def test_accumulation_scaling_and_optimizer_step():
     """loss / accum as grad_output, gradients accumulating over micro-batches (gqa_cpt.py:446-458), then an optimizer
     step: the handle must pick up the updated fp32 parameters and the loss on the same batch must drop."""
