@@ -82,6 +82,7 @@ SYMBOLS = {
                                    _p]),
     "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _p, _sz,
                                     C.POINTER(Grads)]),
+    "cpt_adamw_step": (_i, [_i, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),
     "cpt_launch_count": (_ll, [_p]),

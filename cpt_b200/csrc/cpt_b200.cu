@@ -20,6 +20,7 @@
 #include "attention_sm100.cuh"
 #include "attention_bwd_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "optim.cuh"
 #include "rowwise.cuh"
 #include "train.cuh"
 
@@ -132,6 +133,7 @@ struct cpt_handle {
   float *pool_w = nullptr, *pool_b = nullptr;
   float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
   void *mlm_w16 = nullptr, *word16 = nullptr;
+  int down_ksplit = 1;                             // CPT_B200_DOWN_KSPLIT: split-K pieces of the FFN-down GEMM (A/B experiment)
   int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
   int train = 0;                                   // cpt_train_enable: cpt_set_weights refreshes in place, no LN-folded copies
   unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
@@ -314,7 +316,7 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
   if (p.ksplit > 1) {
     // split-K only where partial products can be added at the destination; pieces of at least 4 k-blocks
     const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
-    if (!p.tma_reduce || p.bias) p.ksplit = 1;
+    if (!p.tma_reduce) p.ksplit = 1;
     else p.ksplit = std::max(1, std::min(p.ksplit, num_kb / 4));
   }
   if (epi == EPI_BIAS && !out_fp32) return launch_gemm_bn<EPI_BIAS, T16, T16>(h, st, c, ta, tb, to, p);
@@ -773,7 +775,7 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
         p.M = M; p.N = H; p.K = I; p.out = w.pre32; p.ldo = H; p.bias = d.b_o;
         float* o32 = (l == L - 1) ? seq_out : w.h32;
         if (h->reduce_resid && h->tma_store) {
-          p.out = w.a32; p.tma_reduce = 1;
+          p.out = w.a32; p.tma_reduce = 1; p.ksplit = h->down_ksplit;
           TRY(gemm<T16>(h, st, CPT_K_GEMM_DOWN, w.inter16, I, d.w_o, I, p, EPI_BIAS, true));
           TRY(layernorm<T16>(h, st, w.a32, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, o32,
                              (l == L - 1) ? nullptr : w.h16));
@@ -874,6 +876,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   cudaMemset(h->err_flag, 0, 16);
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
+  if (const char* e = getenv("CPT_B200_DOWN_KSPLIT")) h->down_ksplit = atoi(e);
   if (const char* e = getenv("CPT_B200_ATTN_BWD")) h->attn_bwd_simt = strcmp(e, "simt") == 0;
   if (const char* e = getenv("CPT_B200_FOLD_LN")) h->fold_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_RESID_IN_LN")) h->resid_in_ln = atoi(e) != 0;
@@ -1090,6 +1093,21 @@ size_t cpt_train_tape_bytes(const cpt_handle* h, int B, int T, int R, int n_rows
 CPT_TRAIN_ENTRY(mlm, CPT_HEAD_MLM)
 CPT_TRAIN_ENTRY(nsp, CPT_HEAD_NSP)
 #undef CPT_TRAIN_ENTRY
+
+static_assert(sizeof(cpt_adam_tensor) == sizeof(AdamTensor) && sizeof(cpt_adam_chunk) == sizeof(AdamChunk),
+              "optimizer table layouts");
+int cpt_adamw_step(int device, void* stream, const cpt_adam_tensor* tensors, const cpt_adam_chunk* chunks, int n_chunks,
+                   float beta1, float beta2, float eps, int mode, const float* grad_scale) {
+  if (!tensors || !chunks || n_chunks < 0) return fail("cpt_adamw_step: bad argument");
+  if (mode != 0 && mode != 1) return fail("cpt_adamw_step: mode must be 0 (torch) or 1 (pytorch-transformers 1.x)");
+  if (n_chunks == 0) return 0;
+  DeviceGuard g(device);
+  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamTensor*>(tensors),
+                                                           reinterpret_cast<const AdamChunk*>(chunks), beta1, beta2, eps,
+                                                           mode, grad_scale);
+  CKL("adamw_kernel");
+  return 0;
+}
 
 int cpt_check_async_error(cpt_handle* h, void* stream) {
   if (!h) return fail("NULL handle");

@@ -41,7 +41,8 @@ struct GemmParams {
   // descriptors.  Single-CTA tiles only.
   int trans;
   // ksplit > 1: the K range is cut into ksplit pieces handled as separate work items that all ADD their partial
-  // product into `out` (needs tma_reduce and no bias): fills the machine when M x N is a handful of tiles and K is long
+  // product into `out` (needs tma_reduce; the bias rides with the first piece): fills the machine when M x N is a
+  // handful of tiles and K is long
   // (weight gradients: 768 x 768 outputs over K = 7680 rows)
   int ksplit;
   // ---- LayerNorm folding (see DESIGN.md "LayerNorm folding"); all optional (nullptr = off)
@@ -360,7 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
       // per-column vectors -> smem while the tile's MMAs are still running (a global load per chunk sat on the
       // critical path of every chunk: ncu long_scoreboard on the bias FADDs)
-      stage_vec(sv0, p.bias, ncol0);
+      stage_vec(sv0, (ct / mn_ctiles) == 0 ? p.bias : nullptr, ncol0);  // split-K: the first K piece carries the bias
       if (norm) stage_vec(sv1, p.gvec, ncol0);
       if (kResid && rnorm) {
         stage_vec(sv1, p.rgamma, ncol0);

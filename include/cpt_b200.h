@@ -164,6 +164,27 @@ int cpt_train_backward_nsp(cpt_handle *h, void *stream, const int64_t *input_ids
                            const int64_t *targets, int n_rows, const cpt_dropout *dropout, const float *grad_loss,
                            void *tape, size_t tape_bytes, const cpt_grads *grads);
 
+/* ---- optimizer step (SURVEY.md 8f "optimizer") -----------------------------------------------------------------
+ * One launch updates every parameter tensor.  mode 0 = torch.optim.AdamW (fewshot/refcoco_cpt.py:342); mode 1 =
+ * pytorch-transformers 1.x AdamW (fewshot/gqa_cpt.py:342, vcr_nsp_cpt.py; weight decay applied after the Adam update,
+ * eps added to sqrt(v) before the bias correction).  `tensors` and `chunks` are DEVICE arrays the binding builds:
+ * chunk i covers elements [offset, offset+count) of tensor `tensor`, count <= 16384.  grad_scale: optional device
+ * scalar every gradient is multiplied by (loss-scale / clipping coefficient), NULL = 1. */
+typedef struct {
+  float *p;       /* parameter (fp32 master weight), updated in place */
+  const float *g; /* gradient                                          */
+  float *m, *v;   /* exp_avg, exp_avg_sq                               */
+  int64_t n;
+  float lr, wd;   /* the group's learning rate and weight decay        */
+  float bc1, bc2; /* 1 - beta1^t, 1 - beta2^t of this tensor (1, 1 when bias correction is off) */
+} cpt_adam_tensor;
+typedef struct {
+  int32_t tensor, count;
+  int64_t offset;
+} cpt_adam_chunk;
+int cpt_adamw_step(int device, void *stream, const cpt_adam_tensor *tensors, const cpt_adam_chunk *chunks,
+                   int n_chunks, float beta1, float beta2, float eps, int mode, const float *grad_scale);
+
 /* Blocks until `stream` drains; reports device-side input errors (token id / position out of range, the
  * IndexError the reference's nn.Embedding would raise) and launch failures. */
 int cpt_check_async_error(cpt_handle *h, void *stream);

@@ -1,0 +1,127 @@
+"""The native multi-tensor AdamW (cpt_adamw_step through cpt_b200.optimization.AdamW) against the CPU oracle, in both
+semantics, with parameter groups, tensors that are not a multiple of the chunk size, parameters without gradient, a
+schedule changing lr between steps, and the gradient scale.  Tolerance: fp32 arithmetic in a different association
+order (fused multiply-adds) — 2e-6 relative to the parameter scale after 6 steps."""
+import pytest
+import torch
+
+from oracle import optim_oracle as OO
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(gen):
+    shapes = [(1000, 33), (16384,), (16385,), (7,), (300, 128), (1,)]
+    return [torch.randn(*s, generator=gen) for s in shapes]
+
+
+@pytest.mark.parametrize("torch_semantics", [False, True])
+@pytest.mark.parametrize("correct_bias", [True, False])
+def test_adamw_against_oracle(torch_semantics, correct_bias):
+    from cpt_b200.optimization import AdamW, WarmupLinearSchedule
+    if torch_semantics and not correct_bias:
+        pytest.skip("torch.optim.AdamW always corrects the bias")
+    gen = torch.Generator().manual_seed(3)
+    host = make_params(gen)
+    params = [torch.nn.Parameter(t.clone().cuda()) for t in host]
+    frozen = torch.nn.Parameter(torch.ones(5).cuda())  # never receives a gradient
+    groups = [{"params": params[:3] + [frozen], "weight_decay": 0.05}, {"params": params[3:], "weight_decay": 0.0}]
+    eps = 1e-8 if torch_semantics else 1e-6
+    opt = AdamW(groups, lr=2e-3, betas=(0.9, 0.98), eps=eps, correct_bias=correct_bias,
+                torch_semantics=torch_semantics)
+    sched = WarmupLinearSchedule(opt, warmup_steps=2, t_total=10)
+    ref, states = [t.clone() for t in host], [dict() for _ in host]
+    for step in range(6):
+        lr = opt.param_groups[0]["lr"]
+        for i, p in enumerate(params):
+            g = torch.randn(*host[i].shape, generator=gen) * (0.3 + step)
+            p.grad = g.cuda()
+            wd = 0.05 if i < 3 else 0.0
+            if torch_semantics:
+                OO.adamw_torch(ref[i], g, states[i], lr, (0.9, 0.98), eps, wd)
+            else:
+                OO.adamw_hf1(ref[i], g, states[i], lr, (0.9, 0.98), eps, wd, correct_bias)
+        opt.step()
+        sched.step()
+    torch.cuda.synchronize()
+    for i, p in enumerate(params):
+        err = (p.detach().cpu() - ref[i]).abs().max().item()
+        assert err <= 2e-6 * max(1.0, ref[i].abs().max().item()), (i, err)
+        st = opt.state[p]
+        assert st["step"] == 6
+        assert (st["exp_avg"].cpu() - states[i]["exp_avg"]).abs().max().item() < 1e-5
+        assert (st["exp_avg_sq"].cpu() - states[i]["exp_avg_sq"]).abs().max().item() < 1e-4
+    assert torch.equal(frozen.detach().cpu(), torch.ones(5)) and len(opt.state[frozen]) == 0
+
+
+def test_adamw_grad_scale_and_state_dict_roundtrip():
+    from cpt_b200.optimization import AdamW
+    gen = torch.Generator().manual_seed(5)
+    p = torch.nn.Parameter(torch.randn(5000, generator=gen).cuda())
+    q = torch.nn.Parameter(p.detach().clone())
+    g = torch.randn(5000, generator=gen).cuda()
+    a, b = AdamW([p], lr=1e-2), AdamW([q], lr=1e-2)
+    p.grad = g * 128.0
+    a.step(grad_scale=torch.tensor(1.0 / 128.0, device="cuda"))
+    q.grad = g.clone()
+    b.step()
+    assert (p - q).abs().max().item() < 1e-6
+    sd = a.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    c = AdamW([p], lr=1e-2)
+    c.load_state_dict(sd)
+    p.grad = g.clone()
+    c.step()
+    q.grad = g.clone()
+    b.step()
+    assert (p - q).abs().max().item() < 1e-6
+
+
+def test_adamw_rejects_cpu_parameters():
+    from cpt_b200.optimization import AdamW
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        AdamW([p]).step()
+
+
+def test_few_shot_loop_with_native_optimizer():
+    """the GQA few-shot loop shape (gqa_cpt.py:428-462): grouped parameters, clip_grad_norm_, scheduler, zero_grad"""
+    from cpt_b200 import config as C
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    from cpt_b200.modeling_rec import REC_MLM_CPT
+    from cpt_b200.optimization import AdamW, WarmupConstantSchedule
+    from cpt_b200.synthetic import synth_batch, synth_state_dict
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    cfg.hidden_dropout_prob = 0.1
+    sd = synth_state_dict(cfg, seed=12)
+    pre = BertImgForPreTraining(cfg)
+    pre.load_state_dict(sd, strict=False)
+    pre.tie_weights()
+    model = REC_MLM_CPT(cfg)
+    model.copy_from_pretraining_model(pre.cuda())
+    no_decay = ["bias", "LayerNorm.weight"]
+    groups = [{"params": [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)],
+               "weight_decay": 0.05},
+              {"params": [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)],
+               "weight_decay": 0.0}]
+    opt = AdamW(groups, lr=5e-4, eps=1e-8)
+    sched = WarmupConstantSchedule(opt, warmup_steps=2)
+    b = synth_batch(cfg, 8, 40, 20, seed=4)
+    d = {k: v.cuda() for k, v in b.items()}
+    labels = torch.full((8, 60), -1, dtype=torch.long)
+    labels[torch.arange(8), b["mask_pos"]] = torch.arange(8) % 3 + 20
+    labels = labels.cuda()
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(12):
+        model.train()
+        loss, _ = model(input_ids=d["input_ids"], attention_mask=d["attention_mask"],
+                        token_type_ids=d["token_type_ids"], masked_lm_labels=labels, img_feats=d["img_feats"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        sched.step()
+        opt.step()
+        model.zero_grad()
+        losses.append(loss.item())
+    assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.3, losses  # finite and going down
