@@ -136,6 +136,11 @@ struct cpt_handle {
   int down_ksplit = 1;                             // CPT_B200_DOWN_KSPLIT: split-K pieces of the FFN-down GEMM (A/B experiment)
   int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
   int train = 0;                                   // cpt_train_enable: cpt_set_weights refreshes in place, no LN-folded copies
+  // the copy list of the last cpt_set_weights (host mirror + device tables) — replayed as one launch
+  std::vector<CopyEntry> copy_list;
+  std::vector<CopyEntry> copy_list_dev_mirror;
+  void *copy_entries_dev = nullptr, *copy_chunks_dev = nullptr;
+  int copy_n_chunks = 0;
   unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
   float *nsp_w = nullptr, *nsp_b = nullptr;
   std::vector<LayerDev> layers;
@@ -477,11 +482,21 @@ static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
 
 // ------------------------------------------------------------------------------------------------ weights
 template <typename T16>
-static int cast_w(cudaStream_t st, const float* src, long long rows, int cols, int ldo, void* dst) {
+static int cast_now(cudaStream_t st, const float* src, long long rows, int cols, int ldo, void* dst) {
   const long long total = rows * ldo;
   const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   cast_weight_kernel<T16><<<grid, 256, 0, st>>>(src, rows, cols, ldo, reinterpret_cast<T16*>(dst));
   CKL("cast_weight_kernel");
+  return 0;
+}
+
+// weight copies are RECORDED while cpt_set_weights walks the state dict and issued as one launch at its end
+static void rec_copy(cpt_handle* h, const float* src, void* dst, long long rows, int cols, int ldo, int is16) {
+  h->copy_list.push_back(CopyEntry{src, dst, rows, cols, ldo, is16, 0});
+}
+template <typename T16>
+static int cast_w(cpt_handle* h, const float* src, long long rows, int cols, int ldo, void* dst) {
+  rec_copy(h, src, dst, rows, cols, ldo, 1);
   return 0;
 }
 // (re)allocation policy of cpt_set_weights: a training handle whose previous call covered the same tensors keeps
@@ -496,7 +511,7 @@ static int copy_vec(cpt_handle* h, bool reuse, cudaStream_t st, const float* src
     return 0;
   }
   TRY(walloc(h, reuse, (void**)dst, n * 4));
-  CK(cudaMemcpyAsync(*dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  rec_copy(h, src, *dst, 1, (int)n, (int)n, 0);
   return 0;
 }
 template <typename T16>
@@ -505,6 +520,39 @@ static int transpose16(cudaStream_t st, const void* in, int R, int C, long long 
   transpose16_kernel<T16><<<grid, 256, 0, st>>>(reinterpret_cast<const T16*>(in), R, C, ld_in,
                                                  reinterpret_cast<T16*>(out), ld_out);
   CKL("transpose16_kernel");
+  return 0;
+}
+
+// issue the recorded copies: one launch; the device tables are reused while the (source, destination) list is unchanged
+template <typename T16>
+static int flush_copies(cpt_handle* h, cudaStream_t st) {
+  if (h->copy_list.empty()) return 0;
+  const size_t n = h->copy_list.size();
+  const bool same = h->copy_entries_dev && h->copy_list_dev_mirror.size() == n &&
+                    memcmp(h->copy_list_dev_mirror.data(), h->copy_list.data(), n * sizeof(CopyEntry)) == 0;
+  if (!same) {
+    std::vector<CopyChunk> chunks;
+    for (size_t e = 0; e < n; ++e) {
+      const long long total = h->copy_list[e].rows * h->copy_list[e].ldo;
+      for (long long f = 0; f < total; f += kCopyChunk)
+        chunks.push_back(CopyChunk{(int)e, (int)std::min<long long>(kCopyChunk, total - f), f});
+    }
+    CK(cudaStreamSynchronize(st));  // an earlier launch may still be reading the old tables
+    if (h->copy_entries_dev) cudaFree(h->copy_entries_dev);
+    if (h->copy_chunks_dev) cudaFree(h->copy_chunks_dev);
+    h->copy_entries_dev = h->copy_chunks_dev = nullptr;
+    CK(cudaMalloc(&h->copy_entries_dev, n * sizeof(CopyEntry)));
+    CK(cudaMalloc(&h->copy_chunks_dev, std::max<size_t>(1, chunks.size()) * sizeof(CopyChunk)));
+    CK(cudaMemcpy(h->copy_entries_dev, h->copy_list.data(), n * sizeof(CopyEntry), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->copy_chunks_dev, chunks.data(), chunks.size() * sizeof(CopyChunk), cudaMemcpyHostToDevice));
+    h->copy_n_chunks = (int)chunks.size();
+    h->copy_list_dev_mirror = h->copy_list;
+  }
+  if (h->copy_n_chunks > 0) {
+    refresh_weights_kernel<T16><<<h->copy_n_chunks, 256, 0, st>>>(
+        reinterpret_cast<const CopyEntry*>(h->copy_entries_dev), reinterpret_cast<const CopyChunk*>(h->copy_chunks_dev));
+    CKL("refresh_weights_kernel");
+  }
   return 0;
 }
 
@@ -534,6 +582,7 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     h->layers.assign(L, LayerDev{});
   }
   h->has_weights = false;
+  h->copy_list.clear();
   h->word = w->word_emb;
   h->pos = w->pos_emb;
   h->type = w->type_emb;
@@ -544,7 +593,7 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     if (c.use_img_layernorm && (!w->img_ln_g || !w->img_ln_b))
       return fail("cpt_set_weights: use_img_layernorm=1 needs bert.LayerNorm weights");
     TRY(walloc(h, reuse, &h->w_img, (size_t)H * h->Fp * 2));
-    TRY(cast_w<T16>(st, w->img_w, H, F, h->Fp, h->w_img));
+    TRY(cast_w<T16>(h, w->img_w, H, F, h->Fp, h->w_img));
     TRY(copy_vec(h, reuse, st, w->img_b, H, &h->b_img));
     TRY(copy_vec(h, reuse, st, w->img_ln_g, H, &h->img_g));
     TRY(copy_vec(h, reuse, st, w->img_ln_b, H, &h->img_b));
@@ -557,23 +606,23 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     for (const float* q : need)
       if (!q) return fail("cpt_set_weights: layer %d has a NULL tensor", l);
     TRY(walloc(h, reuse, &d.w_qkv, (size_t)3 * H * H * 2));
-    TRY(cast_w<T16>(st, s.q_w, H, H, H, d.w_qkv));
-    TRY(cast_w<T16>(st, s.k_w, H, H, H, (char*)d.w_qkv + (size_t)H * H * 2));
-    TRY(cast_w<T16>(st, s.v_w, H, H, H, (char*)d.w_qkv + (size_t)2 * H * H * 2));
+    TRY(cast_w<T16>(h, s.q_w, H, H, H, d.w_qkv));
+    TRY(cast_w<T16>(h, s.k_w, H, H, H, (char*)d.w_qkv + (size_t)H * H * 2));
+    TRY(cast_w<T16>(h, s.v_w, H, H, H, (char*)d.w_qkv + (size_t)2 * H * H * 2));
     TRY(walloc(h, reuse, (void**)&d.b_qkv, (size_t)3 * H * 4));
-    CK(cudaMemcpyAsync(d.b_qkv, s.q_b, H * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(d.b_qkv + H, s.k_b, H * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(d.b_qkv + 2 * H, s.v_b, H * 4, cudaMemcpyDeviceToDevice, st));
+    rec_copy(h, s.q_b, d.b_qkv, 1, H, H, 0);
+    rec_copy(h, s.k_b, d.b_qkv + H, 1, H, H, 0);
+    rec_copy(h, s.v_b, d.b_qkv + 2 * H, 1, H, H, 0);
     TRY(walloc(h, reuse, &d.w_ao, (size_t)H * H * 2));
-    TRY(cast_w<T16>(st, s.ao_w, H, H, H, d.w_ao));
+    TRY(cast_w<T16>(h, s.ao_w, H, H, H, d.w_ao));
     TRY(copy_vec(h, reuse, st, s.ao_b, H, &d.b_ao));
     TRY(copy_vec(h, reuse, st, s.ao_ln_g, H, &d.ao_g));
     TRY(copy_vec(h, reuse, st, s.ao_ln_b, H, &d.ao_b));
     TRY(walloc(h, reuse, &d.w_i, (size_t)I * H * 2));
-    TRY(cast_w<T16>(st, s.i_w, I, H, H, d.w_i));
+    TRY(cast_w<T16>(h, s.i_w, I, H, H, d.w_i));
     TRY(copy_vec(h, reuse, st, s.i_b, I, &d.b_i));
     TRY(walloc(h, reuse, &d.w_o, (size_t)H * I * 2));
-    TRY(cast_w<T16>(st, s.o_w, H, I, I, d.w_o));
+    TRY(cast_w<T16>(h, s.o_w, H, I, I, d.w_o));
     TRY(copy_vec(h, reuse, st, s.o_b, H, &d.b_o));
     TRY(copy_vec(h, reuse, st, s.o_ln_g, H, &d.o_g));
     TRY(copy_vec(h, reuse, st, s.o_ln_b, H, &d.o_b));
@@ -615,15 +664,16 @@ static int set_weights_impl(cpt_handle* h, const cpt_weights* w, cudaStream_t st
     TRY(copy_vec(h, reuse, st, w->mlm_bias, c.vocab_size, &h->mlm_bias));
     // 16-bit copies for the full-vocabulary scores path (tensor-core GEMM over all rows)
     TRY(walloc(h, reuse, &h->mlm_w16, (size_t)H * H * 2));
-    TRY(cast_w<T16>(st, w->mlm_dense_w, H, H, H, h->mlm_w16));
+    TRY(cast_w<T16>(h, w->mlm_dense_w, H, H, H, h->mlm_w16));
     TRY(walloc(h, reuse, &h->word16, (size_t)c.vocab_size * H * 2));
-    TRY(cast_w<T16>(st, w->word_emb, c.vocab_size, H, H, h->word16));
+    TRY(cast_w<T16>(h, w->word_emb, c.vocab_size, H, H, h->word16));
   }
   h->has_nsp = has_nsp;
   if (h->has_nsp) {
     TRY(copy_vec(h, reuse, st, w->nsp_w, (size_t)c.num_contrast_classes * H, &h->nsp_w));
     TRY(copy_vec(h, reuse, st, w->nsp_b, c.num_contrast_classes, &h->nsp_b));
   }
+  TRY(flush_copies<T16>(h, st));
   h->has_weights = true;
   h->weights_sig = sig;
   return 0;
@@ -917,6 +967,8 @@ int cpt_destroy(cpt_handle* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   free_owned(h);
+  if (h->copy_entries_dev) cudaFree(h->copy_entries_dev);
+  if (h->copy_chunks_dev) cudaFree(h->copy_chunks_dev);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1216,7 +1268,7 @@ int cpt_layernorm(cpt_handle* h, void* stream, const float* x, int M, const floa
 int cpt_cast16(cpt_handle* h, void* stream, const float* x, long long rows, int cols, int ld_out, void* out16) {
   if (!h) return fail("NULL handle");
   DeviceGuard g(h->device);
-#define CALL(T16) cast_w<T16>((cudaStream_t)stream, x, rows, cols, ld_out, out16)
+#define CALL(T16) cast_now<T16>((cudaStream_t)stream, x, rows, cols, ld_out, out16)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

@@ -199,6 +199,36 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
   }
 }
 
+// All weight copies of one cpt_set_weights in ONE launch: entry e converts / copies src[rows, cols] fp32 into
+// dst[rows, ldo] (16-bit zero-padded, or fp32 when is16 == 0); a chunk table maps blockIdx.x to (entry, first element).
+// A training step refreshes ~180 tensors after every optimizer step; one launch each cost more host time than the
+// copies took on the GPU.
+struct CopyEntry {
+  const float* src;
+  void* dst;
+  long long rows;
+  int cols, ldo, is16, pad;
+};
+struct CopyChunk {
+  int entry, count;
+  long long first;
+};
+constexpr int kCopyChunk = 32768;
+template <typename T16>
+__global__ void __launch_bounds__(256) refresh_weights_kernel(const CopyEntry* __restrict__ entries,
+                                                              const CopyChunk* __restrict__ chunks) {
+  const CopyChunk c = chunks[blockIdx.x];
+  const CopyEntry e = entries[c.entry];
+  for (int i = threadIdx.x; i < c.count; i += 256) {
+    const long long k = c.first + i;
+    const long long r = k / e.ldo;
+    const int col = (int)(k % e.ldo);
+    const float v = col < e.cols ? e.src[r * e.cols + col] : 0.f;
+    if (e.is16) reinterpret_cast<T16*>(e.dst)[k] = Cvt<T16>::from(v);
+    else reinterpret_cast<float*>(e.dst)[k] = v;
+  }
+}
+
 // LayerNorm folding, weight side (once per weight load): the consumer GEMM of a LayerNorm output
 //   LN(x) W^T + b = rstd * (x (gamma .* W)^T - mu * g) + c,   g_n = sum_k fp16(gamma_k W_nk),  c_n = sum_k beta_k W_nk + b_n
 // so the GEMM can read the PRE-LayerNorm rows x and finish the normalisation in its epilogue.  g is summed from the

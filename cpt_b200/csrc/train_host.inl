@@ -211,11 +211,13 @@ static int gemm_plain(cpt_handle* h, cudaStream_t st, int tag, const void* A, lo
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = nullptr;
   p.tma_reduce = accumulate ? 1 : 0;
   p.trans = trans;
-  if (trans == 3 && accumulate) {
-    // weight gradients: few output tiles, long K -> cut K until the work items cover the SMs about twice
+  if (accumulate) {
+    // accumulate-into-output products can cut K: weight gradients (few output tiles, K = all rows) until the work items
+    // cover the SMs about twice; data gradients of small batches (fewer tiles than SMs) until they cover them once
     const int bn = N >= 2048 ? 256 : 192;
     const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
-    p.ksplit = std::max(1, (2 * h->num_sms + tiles - 1) / tiles);
+    if (trans == 3) p.ksplit = std::max(1, (2 * h->num_sms + tiles - 1) / tiles);
+    else if (tiles < h->num_sms) p.ksplit = std::max(1, h->num_sms / tiles);
   }
   return gemm<T16>(h, st, tag, A, lda, W, ldw, p, EPI_BIAS, out_fp32);
 }
