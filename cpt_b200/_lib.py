@@ -55,7 +55,7 @@ class Grads(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("p_hidden", C.c_float), ("p_attn", C.c_float), ("seed", C.c_uint64)]
+    _fields_ = [("p_hidden", C.c_float), ("p_attn", C.c_float), ("seed", C.c_uint64), ("seed_dev", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/cpt_b200.h declares

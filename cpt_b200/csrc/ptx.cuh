@@ -340,13 +340,20 @@ struct Cvt<__nv_bfloat16> {
 struct Drop {
   unsigned seed_lo, seed_hi, site, thresh;
   float scale;
+  const unsigned* seed_dev;  // when non-NULL the 64-bit seed is read from device memory at run time (lo, hi): a
+                             // captured CUDA graph replays with a fresh seed
 };
 __device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  unsigned lo = d.seed_lo, hi = d.seed_hi;
+  if (d.seed_dev) {
+    lo = __ldg(d.seed_dev);
+    hi = __ldg(d.seed_dev + 1);
+  }
   unsigned x = (unsigned)idx ^ ((unsigned)(idx >> 32) * 0x9E3779B1u);
-  x ^= d.seed_lo;
+  x ^= lo;
   x *= 0x85EBCA6Bu;
   x ^= x >> 13;
-  x += d.site * 0xC2B2AE35u + d.seed_hi;
+  x += d.site * 0xC2B2AE35u + hi;
   x ^= x >> 16;
   x *= 0x7FEB352Du;
   x ^= x >> 15;

@@ -101,6 +101,7 @@ static Drop make_drop(const cpt_dropout* d, float p, unsigned site) {
   if (!d || !(p > 0.f)) return r;
   r.seed_lo = (unsigned)(d->seed & 0xffffffffull);
   r.seed_hi = (unsigned)(d->seed >> 32);
+  r.seed_dev = reinterpret_cast<const unsigned*>(d->seed_dev);
   const double t = (double)p * 4294967296.0;
   r.thresh = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
   if (r.thresh == 0u) r.thresh = 1u;

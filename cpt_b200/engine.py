@@ -31,6 +31,13 @@ def _chk_tensor(name, t, dtype, device, shape=None):
     return t.contiguous()
 
 
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
 def layer_keys(i):
     p = "bert.encoder.layer.%d." % i
     return {"q_w": p + "attention.self.query.weight", "q_b": p + "attention.self.query.bias",
@@ -95,6 +102,8 @@ class Engine(object):
         # launches of a forward cost ~1.8 ms of host time enqueued one by one, 3 us replayed
         self.use_graphs = os.environ.get("CPT_B200_GRAPHS", "1") != "0"
         self._graphs, self._seen, self._replayed_launches = {}, {}, 0
+        self.use_train_graphs = os.environ.get("CPT_B200_TRAIN_GRAPHS", "1") != "0"
+        self._tgraphs, self._tseen, self._ptr_sig = {}, {}, None
         self._profiling = False
 
     def close(self):
@@ -138,6 +147,11 @@ class Engine(object):
         w.layers = C.cast(layers, C.POINTER(_lib.LayerWeights))
         self._graphs.clear()  # captured graphs hold the old 16-bit weight buffers
         self._seen.clear()
+        ptr_sig = tuple(t.data_ptr() for t in keep)
+        if ptr_sig != self._ptr_sig:  # a tensor moved: the handle may reallocate, captured training graphs are stale
+            self._tgraphs.clear()
+            self._tseen.clear()
+            self._ptr_sig = ptr_sig
         with torch.cuda.device(dev):
             _lib.check(self.lib.cpt_set_weights(self._h, C.byref(w), _stream()))
         self.weights_version += 1
@@ -201,39 +215,7 @@ class Engine(object):
             img = _chk_tensor("img_feats", img_feats, torch.float32, dev, (B, R, self.cfg.img_feature_dim))
         return B, T, R, ids, seg, msk, pos, img
 
-    def train_forward(self, head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets,
-                      dropout=None):
-        """head "mlm": loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled
-        positions `rows` (flat b*S+s indices) with labels `targets`; head "nsp": loss of
-        NSPCPT.forward(next_sentence_label=...) (modeling_vcr.py:120-127), rows = b*S of the labelled samples.
-        dropout = (p_hidden, p_attn, seed) or None.  Returns (loss, saved) — `saved` feeds train_backward."""
-        if not self.train:
-            raise CptError("cpt_b200: this engine was not created with train=True")
-        B, T, R, ids, seg, msk, pos, img = self._train_inputs(input_ids, token_type_ids, attention_mask,
-                                                               position_ids, img_feats)
-        dev = self.device
-        rows = _chk_tensor("rows", rows, torch.int64, dev)
-        targets = _chk_tensor("targets", targets, torch.int64, dev, tuple(rows.shape))
-        n = int(rows.numel())
-        drop = _lib.Dropout(0.0, 0.0, 0)
-        if dropout is not None:
-            drop = _lib.Dropout(float(dropout[0]), float(dropout[1]), int(dropout[2]) & 0xFFFFFFFFFFFFFFFF)
-        with torch.cuda.device(dev):
-            nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
-            tape = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
-            loss = torch.empty((), dtype=torch.float32, device=dev)
-            fwd = self.lib.cpt_train_forward_mlm if head == "mlm" else self.lib.cpt_train_forward_nsp
-            _lib.check(fwd(self._h, _stream(), _ptr(ids), _ptr(seg), _ptr(msk), _ptr(pos), _ptr(img), B, T, R,
-                           _ptr(rows), _ptr(targets), n, C.byref(drop), _ptr(tape), tape.numel(), _ptr(loss)))
-        saved = dict(head=head, drop=drop, B=B, T=T, R=R, ids=ids, seg=seg, pos=pos, rows=rows, targets=targets, n=n, tape=tape,
-                     version=self.weights_version)
-        return loss, saved
-
-    def train_backward(self, saved, grad_loss, grads):
-        """Adds d(grad_loss * loss)/d(param) into `grads` (dict keyed like the state_dict, fp32 tensors shaped
-        like the parameters)."""
-        if saved["version"] != self.weights_version:
-            raise CptError("cpt_b200: weights were reloaded between the training forward and its backward")
+    def _grads_struct(self, head, grads):
         dev = self.device
         keep = []
 
@@ -249,7 +231,7 @@ class Engine(object):
             return _ptr(t)
 
         g = _lib.Grads()
-        unused = ("pooler_w", "pooler_b", "nsp_w", "nsp_b") if saved["head"] == "mlm" else \
+        unused = ("pooler_w", "pooler_b", "nsp_w", "nsp_b") if head == "mlm" else \
             ("mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")
         for f in _lib.GRAD_GLOBAL_FIELDS:
             setattr(g, f, gp(GLOBAL_KEYS[f], f.startswith("img_") or f in unused))
@@ -259,13 +241,174 @@ class Engine(object):
             for f, key in layer_keys(i).items():
                 setattr(layers[i], f, gp(key))
         g.layers = C.cast(layers, C.POINTER(_lib.LayerGrads))
-        gl = _chk_tensor("grad_loss", grad_loss.reshape(()), torch.float32, dev)
-        s = saved
+        return g, (layers, keep)
+
+    def _raw_forward(self, s):
+        fwd = self.lib.cpt_train_forward_mlm if s["head"] == "mlm" else self.lib.cpt_train_forward_nsp
+        _lib.check(fwd(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]), _ptr(s["msk"]), _ptr(s["pos"]),
+                       _ptr(s["img"]), s["B"], s["T"], s["R"], _ptr(s["rows"]), _ptr(s["targets"]), s["n"],
+                       C.byref(s["drop"]), _ptr(s["tape"]), s["tape"].numel(), _ptr(s["loss"])))
+
+    def _raw_backward(self, s, gl, g):
+        bwd = self.lib.cpt_train_backward_mlm if s["head"] == "mlm" else self.lib.cpt_train_backward_nsp
+        _lib.check(bwd(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]), _ptr(s["pos"]), s["B"], s["T"], s["R"],
+                       _ptr(s["rows"]), _ptr(s["targets"]), s["n"], C.byref(s["drop"]), _ptr(gl), _ptr(s["tape"]),
+                       s["tape"].numel(), C.byref(g)))
+
+    def train_forward(self, head, input_ids, token_type_ids, attention_mask, position_ids, img_feats, rows, targets,
+                      dropout=None):
+        """head "mlm": loss of REC_MLM_CPT.forward(masked_lm_labels=...) (modeling_rec.py:146-149) at the labelled
+        positions `rows` (flat b*S+s indices) with labels `targets`; head "nsp": loss of
+        NSPCPT.forward(next_sentence_label=...) (modeling_vcr.py:120-127), rows = b*S of the labelled samples.
+        dropout = (p_hidden, p_attn, seed) or None.  Returns (loss, saved) — `saved` feeds train_backward.
+
+        A step is ~400 small launches; for few-shot batches the launch sequence, not the arithmetic, sets the time.
+        The second time a step SHAPE (head, B, T, R, number of labelled rows, which optional inputs are present,
+        dropout probabilities) is seen, the forward — and then its backward — are captured into CUDA graphs over
+        persistent staging buffers and replayed from then on (inputs are copied into the staging buffers, the
+        dropout seed is read from device memory).  CPT_B200_TRAIN_GRAPHS=0 turns this off."""
+        if not self.train:
+            raise CptError("cpt_b200: this engine was not created with train=True")
+        B, T, R, ids, seg, msk, pos, img = self._train_inputs(input_ids, token_type_ids, attention_mask,
+                                                               position_ids, img_feats)
+        dev = self.device
+        rows = _chk_tensor("rows", rows, torch.int64, dev)
+        targets = _chk_tensor("targets", targets, torch.int64, dev, tuple(rows.shape))
+        n = int(rows.numel())
+        p_h, p_a, seed = (0.0, 0.0, 0) if dropout is None else (float(dropout[0]), float(dropout[1]), int(dropout[2]))
+        key = (head, B, T, R, n, seg is None, msk is None, pos is None, img is None, p_h, p_a)
+        st = None
+        if self.use_train_graphs and not self._profiling and not torch.cuda.is_current_stream_capturing():
+            st = self._tgraphs.get(key)
+            if st is None:
+                c = self._tseen.get(key, 0) + 1
+                self._tseen[key] = c
+                if c >= 2 and len(self._tgraphs) < 8:
+                    st = self._new_train_state(key, head, B, T, R, n, seg, msk, pos, img, p_h, p_a)
+                    self._tgraphs[key] = st
+            if st is not None and st["pending"]:
+                st["pending"] = False  # an un-backpropagated forward still owns the tape: run this one eagerly
+                st = None
+        if st is None:
+            with torch.cuda.device(dev):
+                nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
+                s = dict(head=head, B=B, T=T, R=R, n=n, ids=ids, seg=seg, msk=msk, pos=pos, img=img, rows=rows,
+                         targets=targets, drop=_lib.Dropout(p_h, p_a, seed & 0xFFFFFFFFFFFFFFFF, None),
+                         tape=torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev),
+                         loss=torch.empty((), dtype=torch.float32, device=dev), version=self.weights_version,
+                         graph=None)
+                self._raw_forward(s)
+            return s["loss"], s
+        # graph path: refresh the staging buffers, replay
         with torch.cuda.device(dev):
-            bwd = self.lib.cpt_train_backward_mlm if s["head"] == "mlm" else self.lib.cpt_train_backward_nsp
-            _lib.check(bwd(self._h, _stream(), _ptr(s["ids"]), _ptr(s["seg"]), _ptr(s["pos"]), s["B"], s["T"], s["R"],
-                           _ptr(s["rows"]), _ptr(s["targets"]), s["n"], C.byref(s["drop"]), _ptr(gl), _ptr(s["tape"]),
-                           s["tape"].numel(), C.byref(g)))
+            for name, t in (("ids", ids), ("seg", seg), ("msk", msk), ("pos", pos), ("img", img), ("rows", rows),
+                            ("targets", targets)):
+                if t is not None:
+                    st[name].copy_(t, non_blocking=True)
+            st["seed"].fill_(seed)
+            if st["fwd"] is None:
+                # warm-up run + captured run are both counted by the library, and exactly two runs execute
+                l0 = self.lib.cpt_launch_count(self._h)
+                st["fwd"] = self._capture(lambda: self._raw_forward(st))
+                st["fwd_launches"] = int(self.lib.cpt_launch_count(self._h) - l0) // 2
+            else:
+                st["fwd"].replay()
+                self._replayed_launches += st["fwd_launches"]
+            st["pending"] = True
+            st["gen"] += 1
+            saved = dict(graph=st, gen=st["gen"], head=head, version=self.weights_version)
+            return st["loss"].clone(), saved
+
+    def _capture(self, fn):
+        """Capture fn's launches on a side stream into a CUDA graph (fn runs once, un-captured, first: lazy one-time
+        initialisation inside the library must not land in the graph), replay it once, return it."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        fn()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                fn()
+        cur.wait_stream(side)
+        g.replay()
+        return g
+
+    def _new_train_state(self, key, head, B, T, R, n, seg, msk, pos, img, p_h, p_a):
+        dev, i64 = self.device, torch.int64
+        with torch.cuda.device(dev):
+            st = dict(head=head, B=B, T=T, R=R, n=n, pending=False, gen=0, fwd=None, bwd=None, slab=None, layout=None,
+                      ids=torch.zeros(B, T, dtype=i64, device=dev),
+                      seg=None if seg is None else torch.zeros(B, T, dtype=i64, device=dev),
+                      msk=None if msk is None else torch.zeros(B, T + R, dtype=i64, device=dev),
+                      pos=None if pos is None else torch.zeros(B, T, dtype=i64, device=dev),
+                      img=None if img is None else torch.zeros(B, R, self.cfg.img_feature_dim, device=dev),
+                      rows=torch.zeros(n, dtype=i64, device=dev), targets=torch.zeros(n, dtype=i64, device=dev),
+                      seed=torch.zeros(1, dtype=i64, device=dev), loss=torch.zeros((), device=dev),
+                      grad_loss=torch.ones((), device=dev))
+            st["drop"] = _lib.Dropout(p_h, p_a, 0, st["seed"].data_ptr())
+            nbytes = self.lib.cpt_train_tape_bytes(self._h, B, T, R, n)
+            st["tape"] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+            st["fwd_launches"] = st["bwd_launches"] = 0
+        return st
+
+    def grad_buffers(self, saved, keys, shapes):
+        """fp32 gradient buffers for `keys` (zero-filled): views of one slab.  On the graph path the slab is persistent
+        (its addresses are baked into the captured backward) and train_backward hands back a copy."""
+        sizes = [(_numel(s) + 63) // 64 * 64 for s in shapes]
+        st = saved.get("graph")
+        if st is not None and st["slab"] is not None and st["layout"] == (tuple(keys), tuple(shapes)):
+            slab = st["slab"]
+        else:
+            slab = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+            if st is not None:
+                st["slab"], st["layout"], st["bwd"] = slab, (tuple(keys), tuple(shapes)), None
+        return self._views(slab, keys, shapes, sizes)
+
+    @staticmethod
+    def _views(slab, keys, shapes, sizes):
+        out, off = {}, 0
+        for k, s, n in zip(keys, shapes, sizes):
+            out[k] = slab[off:off + _numel(s)].view(s)
+            off += n
+        return out
+
+    def train_backward(self, saved, grad_loss, grads):
+        """Adds d(grad_loss * loss)/d(param) into `grads` (from grad_buffers).  Returns the dict holding the results
+        (on the graph path a copy of the persistent slab, so that the caller owns what it accumulates)."""
+        if saved["version"] != self.weights_version:
+            raise CptError("cpt_b200: weights were reloaded between the training forward and its backward")
+        dev = self.device
+        gl = _chk_tensor("grad_loss", grad_loss.reshape(()), torch.float32, dev)
+        st = saved.get("graph")
+        if st is None:
+            g, keep = self._grads_struct(saved["head"], grads)
+            with torch.cuda.device(dev):
+                self._raw_backward(saved, gl, g)
+            return grads
+        if saved["gen"] != st["gen"]:
+            raise CptError("cpt_b200: the tape of this forward was overwritten by a later forward of the same shape "
+                           "before backward() ran; set CPT_B200_TRAIN_GRAPHS=0 for this usage pattern")
+        with torch.cuda.device(dev):
+            st["grad_loss"].copy_(gl, non_blocking=True)
+            if st["bwd"] is None:
+                g, keep = self._grads_struct(saved["head"], grads)
+                st["_bwd_keep"] = (g, keep)
+
+                def run():
+                    st["slab"].zero_()
+                    self._raw_backward(st, st["grad_loss"], g)
+
+                l0 = self.lib.cpt_launch_count(self._h)
+                st["bwd"] = self._capture(run)
+                st["bwd_launches"] = int(self.lib.cpt_launch_count(self._h) - l0) // 2
+            else:
+                st["bwd"].replay()
+                self._replayed_launches += st["bwd_launches"]
+            st["pending"] = False
+            keys, shapes = st["layout"]
+            sizes = [(_numel(s) + 63) // 64 * 64 for s in shapes]
+            return self._views(st["slab"].clone(), keys, shapes, sizes)
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

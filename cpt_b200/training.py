@@ -27,13 +27,6 @@ def trainable_keys(cfg, head, has_img=True):
     return keys
 
 
-def _numel(shape):
-    n = 1
-    for d in shape:
-        n *= d
-    return n
-
-
 class _Loss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, keys, inputs, *params):
@@ -48,13 +41,8 @@ class _Loss(torch.autograd.Function):
     def backward(ctx, grad_loss):
         eng = ctx.engine
         # one zero-filled slab for every gradient (one memset instead of ~200 fill launches); 256-byte aligned views
-        sizes = [(_numel(s) + 63) // 64 * 64 for s in ctx.shapes]
-        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=eng.device)
-        grads, off = {}, 0
-        for k, s, n in zip(ctx.keys, ctx.shapes, sizes):
-            grads[k] = slab[off:off + _numel(s)].view(s)
-            off += n
-        eng.train_backward(ctx.saved, grad_loss.to(torch.float32), grads)
+        grads = eng.grad_buffers(ctx.saved, ctx.keys, ctx.shapes)
+        grads = eng.train_backward(ctx.saved, grad_loss.to(torch.float32), grads)
         ctx.saved = None  # drop the tape
         out = tuple(grads[k] if ctx.needs_input_grad[3 + i] else None for i, k in enumerate(ctx.keys))
         return (None, None, None) + out

@@ -130,6 +130,8 @@ typedef struct {
   float p_hidden; /* config.hidden_dropout_prob            */
   float p_attn;   /* config.attention_probs_dropout_prob   */
   uint64_t seed;  /* fresh per forward (the binding draws it from torch's CPU generator) */
+  const uint64_t *seed_dev; /* optional DEVICE copy of the seed, read by the kernels at run time instead of `seed`:
+                               lets a captured CUDA graph of the step replay with a new seed */
 } cpt_dropout;
 
 /* Which loss head a training call runs. */

@@ -239,6 +239,43 @@ def test_training_defaults_and_explicit_position_ids():
     compare_all(rec.named_parameters(), {k: v.grad for k, v in leaf.items()}, key_of, dtype, LOSS_SCALE[dtype], 40)
 
 
+def test_graph_replayed_steps_match_eager_steps(monkeypatch):
+    """From the second step of a shape on, forward and backward replay CUDA graphs over staging buffers: the loss and
+    every gradient must equal those of the eager launch sequence on the same inputs, with inputs, labels and dropout
+    seeds changing from step to step."""
+    def run(graphs):
+        monkeypatch.setenv("CPT_B200_TRAIN_GRAPHS", "1" if graphs else "0")
+        cfg = C.oscar_tiny(num_hidden_layers=2)
+        sd = synth_state_dict(cfg, seed=31)
+        rec = build_rec(cfg, sd, "bf16")
+        rec.config.hidden_dropout_prob = rec.config.attention_probs_dropout_prob = 0.1
+        torch.manual_seed(77)
+        out = []
+        for step in range(4):
+            b = synth_batch(cfg, 3, 40, 24, seed=100 + step)
+            d = {k: v.cuda() for k, v in b.items()}
+            labels = torch.full((3, 64), -1, dtype=torch.long)
+            labels[torch.arange(3), b["mask_pos"]] = torch.arange(3) + 5 + step
+            rec.zero_grad()
+            loss = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                       masked_lm_labels=labels.cuda())[0]
+            (loss * 0.5).backward()
+            g = {k: p.grad.clone() for k, p in rec.named_parameters() if p.grad is not None}
+            out.append((loss.item(), g))
+        eng = rec.bert.train_engine()[0]
+        return out, len(eng._tgraphs)
+
+    eager, n0 = run(False)
+    graph, n1 = run(True)
+    assert n0 == 0 and n1 == 1
+    for (le, ge), (lg, gg) in zip(eager, graph):
+        assert abs(le - lg) <= 1e-6 * abs(le)
+        assert ge.keys() == gg.keys()
+        for k in ge:
+            # atomics / reduce-adds reorder fp32 sums between runs: allow rounding-level differences only
+            assert (ge[k] - gg[k]).abs().max().item() <= 2e-5 * max(ge[k].abs().max().item(), 1e-12), k
+
+
 def test_training_error_paths():
     cfg = C.oscar_tiny(num_hidden_layers=1)
     sd = synth_state_dict(cfg, seed=2)
