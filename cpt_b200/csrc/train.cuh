@@ -157,16 +157,17 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T16* __restrict__ i
   }
 }
 // dpre = dpost * gelu'(pre) over [M, N] (N % 8 == 0, dense rows), and dbias[n] += sum_m dpre[m, n] (the bias gradient of
-// intermediate.dense).  A thread keeps one 8-column group and walks rows blockIdx.y*kGeluRows .. +kGeluRows.
-constexpr int kGeluRows = 64;
+// intermediate.dense).  A thread keeps one 8-column group and walks `rows_per_cta` rows (chosen by the host so that the
+// grid covers the SMs a few times even for few-shot batches: 24 CTAs took 40 us at M = 480).
 template <typename T16>
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T16* __restrict__ dpost, const T16* __restrict__ pre, int M,
-                                                       int N, T16* __restrict__ dpre, float* __restrict__ dbias) {
+                                                       int N, T16* __restrict__ dpre, float* __restrict__ dbias,
+                                                       int rows_per_cta) {
   __shared__ float red[128][9];
   const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;  // 128 column groups x 2 row lanes
   const int cg = blockIdx.x * 128 + tx;                     // 8-column group
   const bool active = cg * 8 < N;
-  const int m0 = blockIdx.y * kGeluRows, m1 = min(M, m0 + kGeluRows);
+  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (active) {
 #pragma unroll 4
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
   const float* row = logits + (long long)i * ld;
   const float scale = g[0] / (float)n, l = lse[i];
   const long long tgt = targets[i];
-  for (int v = threadIdx.x; v < ld16; v += 256) {
+  for (int v = blockIdx.y * 256 + threadIdx.x; v < ld16; v += gridDim.y * 256) {
     float d = 0.f;
     if (v < V) d = scale * (expf(row[v] - l) - (v == tgt ? 1.f : 0.f));
     dlogits[(long long)i * ld16 + v] = Cvt<T16>::from(d);

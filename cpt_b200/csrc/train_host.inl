@@ -484,7 +484,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   // ---- MLM head
   {
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
-    ce_bwd_kernel<T16><<<n, 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, grad_loss,
+    ce_bwd_kernel<T16><<<dim3(n, std::max(1, std::min(32, 2 * h->num_sms / n))), 256, 0, st>>>(t.logits, t.ldl, n, V, (const long long*)targets, t.lse, grad_loss,
                                           reinterpret_cast<T16*>(t.dlog16), Vp);
     CKL("ce_bwd_kernel");
   }
@@ -531,9 +531,11 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     TRY(dgrad<T16>(h, st, t.dx16, H, d.w_o, I, M, H, I, t.big16, I, false, false));
     {  // GELU backward + the bias gradient of intermediate.dense
       ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
-      gelu_bwd_kernel<T16><<<dim3((I / 8 + 127) / 128, (M + kGeluRows - 1) / kGeluRows), 256, 0, st>>>(
+      const int gx = (I / 8 + 127) / 128;
+      const int rpc = std::max(4, std::min(64, (M * gx + 4 * h->num_sms - 1) / (4 * h->num_sms)));  // ~4 CTAs per SM
+      gelu_bwd_kernel<T16><<<dim3(gx, (M + rpc - 1) / rpc), 256, 0, st>>>(
           reinterpret_cast<const T16*>(t.big16), reinterpret_cast<const T16*>(tl.preup16), M, I,
-          reinterpret_cast<T16*>(t.big16b), gl.i_b);
+          reinterpret_cast<T16*>(t.big16b), gl.i_b, rpc);
       CKL("gelu_bwd_kernel");
     }
     // intermediate.dense
