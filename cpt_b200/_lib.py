@@ -73,6 +73,7 @@ SYMBOLS = {
     "cpt_mlm_scores_workspace_bytes": (_sz, [_p, _ll]),
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
     "cpt_train_enable": (_i, [_p, _i]),
+    "cpt_train_set_progress_callback": (_i, [_p, _p, _p]),
     "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),
     "cpt_train_forward_mlm": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _sz,
                                    _p]),
@@ -95,6 +96,8 @@ SYMBOLS = {
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),
     "cpt_cast16": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
 }
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)  # cpt_progress_fn
 
 _lib = None
 

@@ -101,3 +101,26 @@ def pick_per_query(logits, fanouts, mode="zsl"):
     block = score[idx.clamp(max=score.shape[0] - 1)]                       # [n_q, mx, width]
     block = torch.where(valid[:, :, None], block, torch.full_like(block, float("-inf")))
     return block.reshape(n_q, mx * width).argmax(1)
+
+
+def enable_overlapped_grad_sync(ddp_model, process_group=None):
+    """Training over several GPUs: average the gradients INSIDE the native backward, group by group as
+    they become final (loss head, layer L-1, ..., layer 0, embeddings), overlapping NCCL with the remaining backward
+    kernels — and tell DistributedDataParallel not to reduce them a second time.
+
+        model = DistributedDataParallel(model, device_ids=[rank], find_unused_parameters=True)   # reference code
+        cpt_b200.comm.enable_overlapped_grad_sync(model)                                          # one extra line
+
+    Without this call DDP's own bucketed all-reduce runs after the whole native backward (correct, not overlapped).
+    Every parameter of the wrapped module must get its gradient from the native step (true for REC_MLM_CPT / NSPCPT).
+    """
+    from torch.distributed.algorithms.ddp_comm_hooks import debugging_hooks
+    module = ddp_model.module if hasattr(ddp_model, "module") else ddp_model
+    bert = getattr(module, "bert", module)
+    group = process_group if process_group is not None else dist.group.WORLD
+    bert._slot.grad_sync_group = group
+    if bert._slot.train_engine is not None:
+        bert._slot.train_engine.grad_sync_group = group
+    if hasattr(ddp_model, "register_comm_hook"):
+        ddp_model.register_comm_hook(None, debugging_hooks.noop_hook)
+    return ddp_model

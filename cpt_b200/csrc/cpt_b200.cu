@@ -133,6 +133,8 @@ struct cpt_handle {
   float *pool_w = nullptr, *pool_b = nullptr;
   float *mlm_w = nullptr, *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *mlm_bias = nullptr;
   void *mlm_w16 = nullptr, *word16 = nullptr;
+  cpt_progress_fn progress_cb = nullptr;           // cpt_train_set_progress_callback
+  void* progress_user = nullptr;
   int small_m_tiles = 1;                           // CPT_B200_SMALL_M=0: no narrower tiles for small row counts
   int down_ksplit = 1;                             // CPT_B200_DOWN_KSPLIT: split-K pieces of the FFN-down GEMM (A/B experiment)
   int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
@@ -1119,6 +1121,13 @@ int cpt_train_enable(cpt_handle* h, int on) {
   if (!h) return fail("NULL handle");
   if ((h->train != 0) != (on != 0)) h->has_weights = false;  // the next cpt_set_weights rebuilds the copies
   h->train = on != 0;
+  return 0;
+}
+
+int cpt_train_set_progress_callback(cpt_handle* h, cpt_progress_fn fn, void* user) {
+  if (!h) return fail("NULL handle");
+  h->progress_cb = fn;
+  h->progress_user = user;
   return 0;
 }
 

@@ -517,6 +517,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
   }
   }
 
+  if (h->progress_cb) h->progress_cb(h->progress_user, 0);
   // ---- encoder layers, last to first.  t.dH = gradient of the layer's output
   for (int l = L - 1; l >= 0; --l) {
     const LayerDev& d = h->layers[l];
@@ -557,6 +558,7 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
       TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
     }
     TRY(dgrad<T16>(h, st, t.big16, 3 * H, d.w_qkv, H, M, 3 * H, H, t.dH, H, true, true));  // += residual
+    if (h->progress_cb) h->progress_cb(h->progress_user, L - l);
   }
 
   // ---- embeddings
@@ -587,5 +589,6 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     add_rows_kernel<<<ew_grid(h, (long long)H * F), 256, 0, st>>>(t.dwimg, h->Fp, H, F, g->img_w, F);
     CKL("add_rows_kernel");
   }
+  if (h->progress_cb) h->progress_cb(h->progress_user, L + 1);
   return 0;
 }

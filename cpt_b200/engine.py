@@ -104,6 +104,8 @@ class Engine(object):
         self._graphs, self._seen, self._replayed_launches = {}, {}, 0
         self.use_train_graphs = os.environ.get("CPT_B200_TRAIN_GRAPHS", "1") != "0"
         self._tgraphs, self._tseen, self._ptr_sig = {}, {}, None
+        self.grad_sync_group = None  # set by comm.enable_overlapped_grad_sync: all-reduce gradients inside the backward
+        self._progress_cb = None
         self._profiling = False
 
     def close(self):
@@ -278,7 +280,8 @@ class Engine(object):
         p_h, p_a, seed = (0.0, 0.0, 0) if dropout is None else (float(dropout[0]), float(dropout[1]), int(dropout[2]))
         key = (head, B, T, R, n, seg is None, msk is None, pos is None, img is None, p_h, p_a)
         st = None
-        if self.use_train_graphs and not self._profiling and not torch.cuda.is_current_stream_capturing():
+        if (self.use_train_graphs and not self._profiling and self.grad_sync_group is None
+                and not torch.cuda.is_current_stream_capturing()):
             st = self._tgraphs.get(key)
             if st is None:
                 c = self._tseen.get(key, 0) + 1
@@ -384,7 +387,10 @@ class Engine(object):
         if st is None:
             g, keep = self._grads_struct(saved["head"], grads)
             with torch.cuda.device(dev):
-                self._raw_backward(saved, gl, g)
+                if self.grad_sync_group is not None and saved.get("groups"):
+                    self._backward_with_grad_sync(saved, gl, g, grads)
+                else:
+                    self._raw_backward(saved, gl, g)
             return grads
         if saved["gen"] != st["gen"]:
             raise CptError("cpt_b200: the tape of this forward was overwritten by a later forward of the same shape "
@@ -409,6 +415,44 @@ class Engine(object):
             keys, shapes = st["layout"]
             sizes = [(_numel(s) + 63) // 64 * 64 for s in shapes]
             return self._views(st["slab"].clone(), keys, shapes, sizes)
+
+    def _backward_with_grad_sync(self, saved, gl, g, grads):
+        """Data-parallel backward: each gradient group (loss head, layer L-1, ..., layer 0, embeddings) is averaged over
+        the ranks by an asynchronous NCCL all-reduce issued the moment its last kernel has been enqueued
+        (cpt_train_set_progress_callback), so the exchange overlaps the rest of the backward instead of following it
+        (the reference's DDP reducer does the same per 25 MB bucket).  Gradients of a group are one
+        contiguous range of the slab (training.trainable_groups)."""
+        import torch.distributed as dist
+        group = self.grad_sync_group
+        ranges = []
+        for keys in saved["groups"]:
+            ts = [grads[k] for k in keys if k in grads]
+            if not ts:
+                ranges.append(None)
+                continue
+            base = ts[0]._base if ts[0]._base is not None else ts[0]
+            lo = min(t.storage_offset() for t in ts)
+            hi = max(t.storage_offset() + t.numel() for t in ts)
+            ranges.append(base.view(-1)[lo:hi])
+        works, err = [], []
+
+        def on_stage(_user, stage):
+            try:
+                if stage < len(ranges) and ranges[stage] is not None:
+                    works.append(dist.all_reduce(ranges[stage], op=dist.ReduceOp.AVG, group=group, async_op=True))
+            except Exception as e:  # never let an exception cross the C frame
+                err.append(e)
+
+        cb = _lib.PROGRESS_FN(on_stage)
+        _lib.check(self.lib.cpt_train_set_progress_callback(self._h, cb, None))
+        try:
+            self._raw_backward(saved, gl, g)
+        finally:
+            _lib.check(self.lib.cpt_train_set_progress_callback(self._h, None, None))
+        if err:
+            raise err[0]
+        for w in works:
+            w.wait()  # stream-level wait: the current stream sees the averaged gradients
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

@@ -135,6 +135,7 @@ class _EngineSlot(object):
     def __init__(self):
         self.engine, self.sig, self.heads, self.frozen = None, None, {}, False
         self.train_engine, self.train_sig = None, None
+        self.grad_sync_group = None  # comm.enable_overlapped_grad_sync
 
     def __deepcopy__(self, memo):
         return _EngineSlot()
@@ -295,6 +296,7 @@ class BertImgModel(BertPreTrainedModel):
             dtype = (getattr(self.config, "cpt_b200_train_dtype", None)
                      or os.environ.get("CPT_B200_TRAIN_DTYPE", "bf16"))
             slot.train_engine = Engine(self.config, dev, dtype=dtype, train=True)
+            slot.train_engine.grad_sync_group = slot.grad_sync_group
             slot.train_sig = None
         if sig != slot.train_sig:
             slot.train_engine.load_state_dict(sd)

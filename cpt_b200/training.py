@@ -20,11 +20,24 @@ _UNUSED = {"mlm": ("pooler_w", "pooler_b", "nsp_w", "nsp_b"),
            "nsp": ("mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias")}
 
 
+_HEAD_FIELDS = ("mlm_dense_w", "mlm_dense_b", "mlm_ln_g", "mlm_ln_b", "mlm_bias", "pooler_w", "pooler_b", "nsp_w",
+                "nsp_b")
+
+
+def trainable_groups(cfg, head, has_img=True):
+    """Parameter keys in the order the backward COMPLETES their gradients (include/cpt_b200.h, progress callback):
+    [loss head], [layer L-1], ..., [layer 0], [embeddings + region embedding].  The gradient slab is laid out in this
+    order so that each group is one contiguous range a data-parallel run can all-reduce as soon as it is final."""
+    ok = [f for f in GLOBAL_KEYS if f not in _UNUSED[head] and (has_img or not f.startswith("img_"))]
+    groups = [[GLOBAL_KEYS[f] for f in ok if f in _HEAD_FIELDS]]
+    for i in reversed(range(cfg.num_hidden_layers)):
+        groups.append(list(layer_keys(i).values()))
+    groups.append([GLOBAL_KEYS[f] for f in ok if f not in _HEAD_FIELDS])
+    return groups
+
+
 def trainable_keys(cfg, head, has_img=True):
-    keys = [k for f, k in GLOBAL_KEYS.items() if f not in _UNUSED[head] and (has_img or not f.startswith("img_"))]
-    for i in range(cfg.num_hidden_layers):
-        keys.extend(layer_keys(i).values())
-    return keys
+    return [k for g in trainable_groups(cfg, head, has_img) for k in g]
 
 
 class _Loss(torch.autograd.Function):
@@ -34,6 +47,7 @@ class _Loss(torch.autograd.Function):
         loss, saved = engine.train_forward(head, input_ids, token_type_ids, attention_mask, position_ids, img_feats,
                                            rows, targets, dropout)
         ctx.engine, ctx.keys, ctx.saved = engine, keys, saved
+        saved["groups"] = trainable_groups(engine.cfg, head, img_feats is not None and img_feats.shape[1] > 0)
         ctx.shapes = [tuple(p.shape) for p in params]
         return loss
 

@@ -154,6 +154,16 @@ int cpt_train_backward_mlm(cpt_handle *h, void *stream, const int64_t *input_ids
                            const int64_t *targets, int n_rows, const cpt_dropout *dropout, const float *grad_loss,
                            void *tape, size_t tape_bytes, const cpt_grads *grads);
 
+/* Progress notifications of cpt_train_backward_*: `fn(user, stage)` is called on the host, from inside the backward
+ * call, right after the launches that COMPLETE a group of gradients have been enqueued on the stream:
+ *   stage 0            the loss head's tensors (cls.* / pooler / seq_relationship; not the tied word embeddings)
+ *   stage 1 .. L       encoder layer L-1 .. 0  (stage s completes layer L - s)
+ *   stage L + 1        everything else (embedding tables, embedding LayerNorm, region embedding)
+ * A data-parallel binding launches the gradient all-reduce of that group from the callback, so that the exchange
+ * overlaps the rest of the backward.  fn == NULL removes the callback. */
+typedef void (*cpt_progress_fn)(void *user, int stage);
+int cpt_train_set_progress_callback(cpt_handle *h, cpt_progress_fn fn, void *user);
+
 /* The VCR few-shot loss: CrossEntropyLoss(ignore_index=-1)(cls.seq_relationship(pooled), next_sentence_label) —
  * NSPCPT.forward, Oscar/oscar/modeling/modeling_vcr.py:115-129, as vcr_nsp_cpt.py:434-473 trains it.
  * rows int64 [n_rows]: b*(T+R) of the samples whose label is not -1 (the [CLS] rows); targets their labels. */

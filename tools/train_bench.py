@@ -24,7 +24,16 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--ddp", default="", choices=["", "ddp", "overlap"],
+                    help="under torchrun: wrap in DistributedDataParallel; 'overlap' = comm.enable_overlapped_grad_sync")
     a = ap.parse_args()
+    rank = 0
+    if a.ddp:
+        import torch.distributed as dist
+        rank = int(os.environ["RANK"])
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl")
     from cpt_b200.modeling_bert import BertImgForPreTraining
     from cpt_b200.modeling_rec import REC_MLM_CPT
     cfg = C.oscar_base(num_hidden_layers=a.layers)
@@ -37,6 +46,13 @@ def main():
     rec = REC_MLM_CPT(cfg)
     rec.copy_from_pretraining_model(pre.cuda())
     rec.train()
+    net = rec
+    if a.ddp:
+        net = torch.nn.parallel.DistributedDataParallel(rec, device_ids=[torch.cuda.current_device()],
+                                                        find_unused_parameters=True)
+        if a.ddp == "overlap":
+            from cpt_b200 import comm
+            comm.enable_overlapped_grad_sync(net)
     B, T, R = a.batch, a.T, a.R
     b = synth_batch(cfg, B, T, R, seed=2)
     d = {k: v.cuda() for k, v in b.items()}
@@ -48,7 +64,7 @@ def main():
 
     def step():
         opt.zero_grad(set_to_none=True)
-        loss, _ = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+        loss, _ = net(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
                       masked_lm_labels=labels)
         loss.backward()
         opt.step()
@@ -64,6 +80,17 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    if a.ddp:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"workload": "REC_MLM_CPT train step under DDP (%s), Oscar-base B=%d/GPU S=%d dropout=%g, "
+                                          "%d GPUs" % (a.ddp, a.batch, a.T + a.R, a.dropout, dist.get_world_size()),
+                              "ms_per_step_max_over_ranks": round(t.item(), 3),
+                              "samples_per_s": round(a.batch * dist.get_world_size() / t.item() * 1e3, 1)}))
+        dist.destroy_process_group()
+        return
     # fwd / bwd / optimizer split with events
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     opt.zero_grad(set_to_none=True)
