@@ -137,6 +137,58 @@ def make_cpu_reference(cfg, sd, vids):
             "oracle/cpt_oracle.py (torch fp32 CPU restatement; reference modules unavailable: %s)" % why
 
 
+def cpu_train_leg(cfg, sd, batch=8, iters=2):
+    """One few-shot training step (forward with labels + backward, no optimizer) of the reference's own REC_MLM_CPT on
+    the host cores, on a bounded sample — the CPU baseline of the `train_step` leg.  Falls back to autograd through the
+    oracle port when baseline/_ref is absent."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = synth_batch(cfg, batch, T_TEXT, R_REG, seed=88)
+    labels = torch.full((batch, T_TEXT + R_REG), -1, dtype=torch.long)
+    labels[torch.arange(batch), b["mask_pos"]] = 2000 + torch.arange(batch) % 7
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        if not os.path.isfile(os.path.join(ref_root, "oscar", "modeling", "modeling_rec.py")):
+            raise ImportError("baseline/_ref/oscar is not installed")
+        from oracle import ref_shim
+        ref_shim.install(ref_root)
+        from oscar.modeling.modeling_bert import BertImgForPreTraining as RefPre
+        from oscar.modeling.modeling_rec import REC_MLM_CPT as RefRec
+        d = cfg.to_dict()
+        v = d.pop("vocab_size")
+        rcfg = ref_shim.BertConfig(v, **d)
+        pre = RefPre(rcfg)
+        pre.load_state_dict(sd, strict=False)
+        pre.tie_weights()
+        rec = RefRec(rcfg)
+        rec.copy_from_pretraining_model(pre)
+        rec.train()
+
+        def step():
+            rec.zero_grad()
+            loss = rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
+                       masked_lm_labels=labels)[0]
+            loss.backward()
+        kind = "reference"
+    except Exception:  # noqa: BLE001
+        from oracle import cpt_oracle as O
+        leaf = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+
+        def step():
+            for t in leaf.values():
+                t.grad = None
+            O.rec_mlm_cpt(leaf, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"], masked_lm_labels=labels,
+                          img_feats=b["img_feats"], training=True)[0].backward()
+        kind = "port"
+    step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    per = (time.perf_counter() - t0) / iters
+    return {"value": batch / per, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d timed forward+backward passes (1 warm-up) of a %d-row batch, %.2f s per pass, fp32 CPU, no "
+                      "optimizer step" % (iters, batch, per)}
+
+
 def cpu_leg(cfg, sd, vids, batch, iters, warmup=1):
     torch.set_num_threads(os.cpu_count() or 1)
     step, kind, what = make_cpu_reference(cfg, sd, vids)
@@ -228,7 +280,7 @@ def _train_leg_timed(model, step, steps, warmup, B, S):
     return {"workload": "REC_MLM_CPT few-shot training step: forward with tape + backward + fused AdamW, Oscar-base, "
                         "batch %d, S=%d, dropout 0.1, bf16 GEMM operands / fp32 master weights" % (B, S),
             "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "steps": steps, "warmup": warmup,
-            "gpu_launches_per_step": (eng.launch_count() - l0) / steps, "loss": float(loss)}
+            "gpu_launches_per_step": (eng.launch_count() - l0) / steps, "loss": float(loss.detach())}
 
 
 def main():
@@ -412,6 +464,8 @@ def main():
         if rank == 0 and world == 1:
             try:
                 train = train_leg(cfg, model, devb[0], dev)
+                if not args.no_cpu_baseline:
+                    train["cpu_baseline"] = cpu_train_leg(cfg, sd)
             except Exception as e:  # never let the extra leg take the headline line down
                 train = {"error": str(e)[:200]}
 
