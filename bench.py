@@ -464,10 +464,14 @@ def main():
         if rank == 0 and world == 1:
             try:
                 train = train_leg(cfg, model, devb[0], dev)
-                if not args.no_cpu_baseline:
-                    train["cpu_baseline"] = cpu_train_leg(cfg, sd)
             except Exception as e:  # never let the extra leg take the headline line down
                 train = {"error": str(e)[:200]}
+            if "error" not in train and not args.no_cpu_baseline:
+                try:
+                    with torch.enable_grad():
+                        train["cpu_baseline"] = cpu_train_leg(cfg, sd)
+                except Exception as e:
+                    train["cpu_baseline"] = {"error": str(e)[:200]}
 
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,7 +1,9 @@
 // Kernels of the training step (forward with a tape, backward for every parameter of
-// REC_MLM_CPT — /root/reference/Oscar/oscar/fewshot/{refcoco_cpt.py:231-250, gqa_cpt.py:428-462}).  The heavy lifting
-// (all dgrad / wgrad products) reuses the tcgen05 GEMM of gemm_sm100.cuh on transposed 16-bit operands; this file holds
-// the row-wise / element-wise pieces and a CUDA-core attention backward (few-shot batches are a handful of rows).
+// REC_MLM_CPT / NSPCPT — /root/reference/Oscar/oscar/fewshot/{refcoco_cpt.py:231-250, gqa_cpt.py:428-462,
+// vcr_nsp_cpt.py:434-473}).  The matrix products (every dgrad / wgrad) are the tcgen05 GEMM of gemm_sm100.cuh reading
+// its operands in place through K-major or MN-major descriptors; the attention backward is attention_bwd_sm100.cuh.
+// This file holds the row-wise / element-wise pieces (LayerNorm, GELU, embedding and cross-entropy backward, dropout,
+// bias column sums) and CUDA-core attention kernels kept as cross-checks (CPT_B200_ATTN_BWD=simt).
 #pragma once
 #include "ptx.cuh"
 #include "rowwise.cuh"
