@@ -100,6 +100,24 @@ def run_case(name):
         out["grad_none"] = sorted(k for k, p in named.items() if p.grad is None)
         wg = named["bert.embeddings.word_embeddings.weight"].grad
         out["grad_word_rowsum"] = wg.double().sum(1).float()
+        # the VCR few-shot step (vcr_nsp_cpt.py:434-461): NSPCPT with next_sentence_label, dropout forced to 0.
+        # rec and nsp share `bert`: clear the MLM gradients first
+        rec.zero_grad()
+        nsp.train()
+        for mod in nsp.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        nsp_labels = torch.arange(B) % cfg.num_contrast_classes
+        if B > 2:
+            nsp_labels[1] = -1  # ignore_index
+        nloss = nsp(ids, seg, mask, next_sentence_label=nsp_labels, img_feats=feats)[0]
+        nloss.backward()
+        out["nsp_labels"] = nsp_labels.clone()
+        out["nsp_loss"] = nloss.detach().clone()
+        nnamed = dict(nsp.named_parameters())
+        for k in ("cls.weight", "cls.bias", "bert.pooler.dense.weight", "bert.encoder.layer.1.attention.self.value.weight",
+                  "bert.encoder.layer.0.output.LayerNorm.bias", "bert.embeddings.position_embeddings.weight"):
+            out["nsp_grad:" + k] = nnamed[k].grad.clone()
     path = os.path.join(HERE, name + ".pt")
     torch.save(out, path)
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))

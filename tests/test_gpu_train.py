@@ -127,6 +127,35 @@ def test_loss_and_grads_against_reference_golden(golden_dir, name, dtype):
     assert none == g["grad_none"], (none, g["grad_none"])
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["tiny_s120", "tiny_noimgln_s40"])
+def test_nsp_loss_and_grads_against_reference_golden(golden_dir, name, dtype):
+    """the VCR few-shot step against loss / gradient fixtures of the reference's own NSPCPT (modeling_vcr.py)"""
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    from cpt_b200.modeling_vcr import NSPCPT
+    g, cfg, sd, b, vids = load_case(golden_dir, name)
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0
+    cfg.cpt_b200_train_dtype = dtype
+    pre = BertImgForPreTraining(cfg)
+    pre.load_state_dict(sd, strict=False)
+    pre.tie_weights()
+    nsp = NSPCPT(cfg)
+    nsp.copy_from_pretraining_model(pre.cuda())
+    nsp.train()
+    d = {k: v.cuda() for k, v in b.items()}
+    loss = nsp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+               next_sentence_label=g["nsp_labels"].cuda())[0]
+    (loss * LOSS_SCALE[dtype]).backward()
+    nsp.bert.train_engine()[0].check()
+    assert abs(loss.item() - g["nsp_loss"].item()) <= LTOL[dtype] * abs(g["nsp_loss"].item())
+    named = dict(nsp.named_parameters())
+    worst = {}
+    for key, ref in g.items():
+        if key.startswith("nsp_grad:"):
+            worst[key[9:]] = rel_err(named[key[9:]].grad.cpu() / LOSS_SCALE[dtype], ref)
+    assert len(worst) == 6 and max(worst.values()) <= GTOL[dtype], worst
+
+
 def oracle_grads(cfg, sd, b, labels):
     from oracle import cpt_oracle as O
     leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}

@@ -77,6 +77,28 @@ def test_oracle_training_loss_and_grads(golden_dir, name):
     assert (wsum - g["grad_word_rowsum"]).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("name", ["tiny_s120", "tiny_noimgln_s40"])
+def test_oracle_nsp_training_loss_and_grads(golden_dir, name):
+    """NSPCPT with next_sentence_label (the VCR few-shot step) — fixtures from the reference's own modeling_vcr.py."""
+    g, cfg, sd, b, vids = load_case(golden_dir, name)
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
+    loss = O.nsp_cpt(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                     next_sentence_label=g["nsp_labels"], img_feats=b["img_feats"], training=True)[0]
+    loss.backward()
+    assert abs(float(loss) - float(g["nsp_loss"])) < 1e-5
+    ren = {"cls.weight": "cls.seq_relationship.weight", "cls.bias": "cls.seq_relationship.bias"}
+    n = 0
+    for k, ref in g.items():
+        if not k.startswith("nsp_grad:"):
+            continue
+        gr = sd[ren.get(k[9:], k[9:])].grad
+        assert (gr - ref).abs().max() < 1e-6 + 1e-4 * ref.abs().max(), k
+        n += 1
+    assert n == 6
+
+
 def test_state_dict_keys_match_reference(golden_dir):
     g, cfg, sd, _, _ = load_case(golden_dir, "tiny_s120")
     assert sorted(sd.keys()) == g["state_dict_keys"]
