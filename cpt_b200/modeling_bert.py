@@ -12,6 +12,7 @@ output_attentions, encoder_history_states, 3-D attention masks, dis_code* featur
 """
 import logging
 import os
+import threading
 
 import torch
 from torch import nn
@@ -130,12 +131,34 @@ def nsp_head_tensors(linear):
 
 
 class _EngineSlot(object):
-    """Holds the (non-copyable, non-picklable) native handle; deepcopy / pickle yield an empty slot."""
+    """Holds the (non-copyable, non-picklable) native handle; deepcopy / pickle yield an empty slot.
+
+    nn.DataParallel (the non-distributed multi-GPU branch of the reference scripts, gqa_cpt.py:358-359) replicates a
+    module by copying its __dict__, so every replica shares this object while its parameters live on another device
+    and its forward runs on another thread: `for_device` hands each device its own slot (own handle, own head
+    tensors), created under a lock."""
 
     def __init__(self):
         self.engine, self.sig, self.heads, self.frozen = None, None, {}, False
         self.train_engine, self.train_sig = None, None
         self.grad_sync_group = None  # comm.enable_overlapped_grad_sync
+        self.home, self._per_device, self._lock = None, {}, threading.Lock()
+
+    def for_device(self, dev):
+        if dev.type != "cuda":
+            return self
+        with self._lock:
+            if self.home is None:
+                self.home = dev
+            if self.home == dev:
+                return self
+            s = self._per_device.get(dev)
+            if s is None:
+                s = _EngineSlot()
+                # replicas get freshly broadcast parameter tensors on every forward: never skip the weight check
+                s.home, s.frozen, s.grad_sync_group = dev, False, self.grad_sync_group
+                self._per_device[dev] = s
+            return s
 
     def __deepcopy__(self, memo):
         return _EngineSlot()
@@ -242,24 +265,36 @@ class BertImgModel(BertPreTrainedModel):
 
     # -- engine plumbing ----------------------------------------------------------------------------------------
     def _named_tensors(self):
-        sd = {"bert." + k: v for k, v in self.state_dict(keep_vars=True).items()}
-        sd.update(self._slot.heads)
+        # like state_dict(keep_vars=True), but also valid on nn.DataParallel replicas, whose (non-leaf) parameter
+        # copies are plain attributes recorded in `_former_parameters` instead of `_parameters`
+        sd = {}
+        for mname, sub in self.named_modules():
+            pre = "bert." + (mname + "." if mname else "")
+            for src in (sub._parameters, getattr(sub, "_former_parameters", {}), sub._buffers):
+                for k, v in src.items():
+                    if v is not None:
+                        sd[pre + k] = v
+        sd.update(self._dev_slot().heads)
         return sd
+
+    def _dev_slot(self):
+        return self._slot.for_device(self.embeddings.word_embeddings.weight.device)
 
     def register_head_tensors(self, tensors):
         """Called by the task wrappers (REC_MLM_CPT, NSPCPT, BertImgForPreTraining) so their head weights ride in
         the same native handle as the encoder."""
-        cur = self._slot.heads
+        slot = self._dev_slot()
+        cur = slot.heads
         if any(cur.get(k) is not v for k, v in tensors.items()):
             cur.update(tensors)
-            self._slot.sig = None
+            slot.sig = None
 
     def freeze_engine_weights(self, frozen=True):
         """Skip the per-forward 'did any parameter change?' scan (inference loops with fixed weights)."""
         self._slot.frozen = frozen
 
     def engine(self):
-        slot = self._slot
+        slot = self._dev_slot()
         if slot.frozen and slot.engine is not None and slot.sig is not None:
             return slot.engine
         sd = self._named_tensors()
@@ -283,7 +318,7 @@ class BertImgModel(BertPreTrainedModel):
         """The handle of the training step: 16-bit GEMM copies in bf16 by default (gradients span more binades than
         fp16 holds without loss scaling; config.cpt_b200_train_dtype / CPT_B200_TRAIN_DTYPE override), transposed
         copies for the dgrad GEMMs, refreshed in place from the fp32 parameters whenever one of them changed."""
-        slot = self._slot
+        slot = self._dev_slot()
         sd = self._named_tensors()
         dev = self.embeddings.word_embeddings.weight.device
         if dev.type != "cuda":

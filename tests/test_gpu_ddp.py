@@ -22,3 +22,31 @@ def test_ddp_gradients_match_whole_batch(mode):
     env = dict(os.environ, NCCL_DEBUG="WARN")
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DDP_TRAIN_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_replicas_get_their_own_handles():
+    """torch.nn.DataParallel (gqa_cpt.py:358-359, the non-distributed multi-GPU branch): module replicas share the
+    Python object graph but run on other devices from other threads — each device must get its own native handle."""
+    from cpt_b200 import config as C
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    from cpt_b200.modeling_rec import REC_MLM_CPT
+    from cpt_b200.synthetic import synth_batch, synth_state_dict
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=8)
+    pre = BertImgForPreTraining(cfg)
+    pre.load_state_dict(sd, strict=False)
+    pre.tie_weights()
+    rec = REC_MLM_CPT(cfg)
+    rec.copy_from_pretraining_model(pre.cuda(0))
+    rec.eval()
+    b = synth_batch(cfg, 6, 30, 10, seed=8)
+    d = {k: v.cuda(0) for k, v in b.items()}
+    with torch.no_grad():
+        single = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
+        dp = torch.nn.DataParallel(rec, device_ids=[0, 1])
+        for _ in range(2):
+            multi = dp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
+    assert multi.shape == single.shape
+    assert (multi - single).abs().max().item() <= 1e-5 * single.abs().max().item()
+    assert len(rec.bert._slot._per_device) == 1
