@@ -343,9 +343,9 @@ class BertImgModel(BertPreTrainedModel):
 
     def _check_mode(self):
         if self._dropout_active():
-            raise NotImplementedError("cpt_b200: forward in training mode with active dropout is not built yet — "
-                                      "set hidden_dropout_prob = attention_probs_dropout_prob = 0 or call "
-                                      "model.eval()")
+            raise NotImplementedError("cpt_b200: a label-free forward in train() mode with active dropout has no "
+                                      "native path (dropout is applied by the training step, i.e. the call with "
+                                      "masked_lm_labels / next_sentence_label) — call model.eval() for inference")
 
     # -- forward ------------------------------------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,

@@ -39,7 +39,10 @@ class REC_MLM_CPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
         self.bert.register_head_tensors(self.cls.head_tensors())
-        if masked_lm_labels is not None and torch.is_grad_enabled() and self._any_requires_grad():
+        # labelled call: the native training step when a gradient can be asked for — or when dropout is active (train()
+        # mode under no_grad, e.g. a loss probe): only that path applies dropout
+        if masked_lm_labels is not None and ((torch.is_grad_enabled() and self._any_requires_grad())
+                                             or self.bert._dropout_active()):
             return self._train_step(input_ids, token_type_ids, attention_mask, masked_lm_labels, position_ids,
                                     head_mask, img_feats, mask_pos)
         if (mask_pos is not None and masked_lm_labels is None and head_mask is None

@@ -33,8 +33,9 @@ class NSPCPT(BertPreTrainedModel):
             raise RuntimeError("cpt_b200: NSPCPT scores with the pre-training seq_relationship head; call "
                                "copy_from_pretraining_model(BertImgForPreTraining) first (modeling_vcr.py:90-92)")
         self.bert.register_head_tensors(nsp_head_tensors(self.cls))
-        if (next_sentence_label is not None and torch.is_grad_enabled()
-                and any(p.requires_grad for p in self.parameters())):
+        if next_sentence_label is not None and ((torch.is_grad_enabled()
+                                                 and any(p.requires_grad for p in self.parameters()))
+                                                or self.bert._dropout_active()):
             return self._train_step(input_ids, token_type_ids, attention_mask, next_sentence_label, position_ids,
                                     head_mask, img_feats)
         outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,

@@ -497,6 +497,13 @@ def test_dropout_is_seeded_by_torch_and_off_in_eval():
     rec.eval()  # eval mode: no dropout, even through the (grad-enabled) training entry point
     e1, e2 = run(), run()
     assert e1 == e2
+    # train() mode under no_grad with labels: still the dropout forward (a loss probe), no graph recorded
+    rec.train()
+    with torch.no_grad():
+        torch.manual_seed(5)
+        probe = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                    masked_lm_labels=labels)[0]
+    assert not probe.requires_grad and probe.item() == a
     # a forward without labels in train mode with active dropout has no native path
     rec.train()
     with pytest.raises(NotImplementedError):
