@@ -135,6 +135,7 @@ struct cpt_handle {
   void *mlm_w16 = nullptr, *word16 = nullptr;
   cpt_progress_fn progress_cb = nullptr;           // cpt_train_set_progress_callback
   void* progress_user = nullptr;
+  int ln_ctas_per_sm = 2;                          // CPT_B200_LN_CTAS: persistent LayerNorm CTAs per SM (A/B experiment)
   int small_m_tiles = 1;                           // CPT_B200_SMALL_M=0: no narrower tiles for small row counts
   int down_ksplit = 1;                             // CPT_B200_DOWN_KSPLIT: split-K pieces of the FFN-down GEMM (A/B experiment)
   int attn_bwd_simt = 0;                           // CPT_B200_ATTN_BWD=simt: CUDA-core attention backward everywhere
@@ -430,7 +431,7 @@ static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long l
   if (M <= 0) return 0;
   ProfScope ps(h, st, CPT_K_LN);
   // persistent: 2 CTAs of 8 warps per SM, each warp walks rows with the next row's loads in flight
-  const int ln_grid = (M + 7) / 8 < 2 * h->num_sms ? (M + 7) / 8 : 2 * h->num_sms;
+  const int ln_grid = (M + 7) / 8 < h->ln_ctas_per_sm * h->num_sms ? (M + 7) / 8 : h->ln_ctas_per_sm * h->num_sms;
 #define CPT_LN_CASE(NV_)                                                                                             \
   case NV_:                                                                                                          \
     CK(launch_k(ln_rows_kernel<T16, NV_>, dim3(ln_grid), dim3(256), 0, st, 1, x, reinterpret_cast<const T16*>(x16), ldx, \
@@ -941,6 +942,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   h->owned.push_back(h->err_flag);
   if (const char* e = getenv("CPT_B200_ATTN")) h->attn_impl = (strcmp(e, "simt") == 0) ? 1 : 0;
   if (const char* e = getenv("CPT_B200_DOWN_KSPLIT")) h->down_ksplit = atoi(e);
+  if (const char* e = getenv("CPT_B200_LN_CTAS")) h->ln_ctas_per_sm = std::max(1, atoi(e));
   if (const char* e = getenv("CPT_B200_SMALL_M")) h->small_m_tiles = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_ATTN_BWD")) h->attn_bwd_simt = strcmp(e, "simt") == 0;
   if (const char* e = getenv("CPT_B200_FOLD_LN")) h->fold_ln = atoi(e) != 0;
