@@ -554,8 +554,12 @@ static int train_backward_impl(cpt_handle* h, int head, cudaStream_t st, const i
     float* qkv_b[3] = {gl.q_b, gl.k_b, gl.v_b};
     float* qkv_w[3] = {gl.q_w, gl.k_w, gl.v_w};
     TRY(colsum<T16>(h, st, reinterpret_cast<const T16*>(t.big16), M, 3 * H, 3 * H, qkv_b[0], qkv_b[1], qkv_b[2], H));
-    for (int j = 0; j < 3; ++j) {
-      TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
+    if (qkv_w[1] == qkv_w[0] + (size_t)H * H && qkv_w[2] == qkv_w[1] + (size_t)H * H) {
+      // the three gradients are adjacent in the caller's slab: one [3H, H] product instead of three
+      TRY(wgrad<T16>(h, st, t.big16, 3 * H, tl.h16, H, M, 3 * H, H, qkv_w[0], H));
+    } else {
+      for (int j = 0; j < 3; ++j)
+        TRY(wgrad<T16>(h, st, t.big16 + (size_t)j * H * 2, 3 * H, tl.h16, H, M, H, H, qkv_w[j], H));
     }
     TRY(dgrad<T16>(h, st, t.big16, 3 * H, d.w_qkv, H, M, 3 * H, H, t.dH, H, true, true));  // += residual
     if (h->progress_cb) h->progress_cb(h->progress_user, L - l);

@@ -31,7 +31,10 @@ def trainable_groups(cfg, head, has_img=True):
     ok = [f for f in GLOBAL_KEYS if f not in _UNUSED[head] and (has_img or not f.startswith("img_"))]
     groups = [[GLOBAL_KEYS[f] for f in ok if f in _HEAD_FIELDS]]
     for i in reversed(range(cfg.num_hidden_layers)):
-        groups.append(list(layer_keys(i).values()))
+        lk = layer_keys(i)
+        # query / key / value weight gradients adjacent: the backward then writes them as ONE [3H, H] product
+        first = [lk["q_w"], lk["k_w"], lk["v_w"]]
+        groups.append(first + [k for k in lk.values() if k not in first])
     groups.append([GLOBAL_KEYS[f] for f in ok if f not in _HEAD_FIELDS])
     return groups
 
