@@ -279,6 +279,11 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
     CK(cudaMemsetAsync(t.ext_mask, 0, (size_t)M * 4, st));
   }
   char* h16_0 = L > 0 ? t.layers[0].h16 : t.dx16;
+  // Without hidden-state dropout the fp32 residual stream is written straight into the tape slot the next dense layer
+  // accumulates into (x1 / x2 hold "residual + dense output"), so no copy of the residual is ever made; with dropout
+  // the residual stays in a scratch buffer and one elementwise pass forms residual + dropout(dense output).
+  const bool in_place = !(p_h > 0.f) && L > 0;
+  float* const emb32 = in_place ? t.layers[0].x1 : t.h32;
   {
     ProfScope ps(h, st, CPT_K_EMBED);
 #define CPT_EMB_CASE(NV_)                                                                                            \
@@ -286,7 +291,7 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
     CK(launch_k(embed_text_ln_kernel<T16, NV_>, dim3((B * T + 7) / 8), dim3(256), 0, st, 1, (const long long*)ids,    \
                 (const long long*)seg, (const long long*)pos_ids, h->word, h->pos, h->type, (const float*)h->emb_g,  \
                 (const float*)h->emb_b, c.layer_norm_eps, B, T, S, H, c.vocab_size, c.max_position_embeddings,       \
-                c.type_vocab_size, t.h32, reinterpret_cast<T16*>(h16_0), h->err_flag));                              \
+                c.type_vocab_size, emb32, reinterpret_cast<T16*>(h16_0), h->err_flag));                              \
     break;
     switch (H / 128) {
       CPT_EMB_CASE(1) CPT_EMB_CASE(2) CPT_EMB_CASE(3) CPT_EMB_CASE(4) CPT_EMB_CASE(5) CPT_EMB_CASE(6) CPT_EMB_CASE(7)
@@ -307,7 +312,7 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
     p.M = Mi; p.N = H; p.K = F; p.out = t.imgpre32; p.ldo = H; p.bias = h->b_img;
     TRY(gemm<T16>(h, st, CPT_K_GEMM_IMG, t.img16, h->Fp, h->w_img, h->Fp, p, EPI_BIAS, true));
     TRY(layernorm<T16>(h, st, t.imgpre32, H, Mi, H, h->img_g, h->img_b, c.img_layer_norm_eps,
-                       c.use_img_layernorm != 0, t.h32, h16_0, R, S, T));
+                       c.use_img_layernorm != 0, emb32, h16_0, R, S, T));
   }
   if (p_h > 0.f) {  // dropout on the embedding outputs (BertEmbeddings.dropout; modeling_bert.py:266 for regions)
     ProfScope ps(h, st, CPT_K_TRAIN_ROWWISE);
@@ -335,7 +340,7 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
       CKL("dropout_add_kernel");
       return 0;
     }
-    CK(cudaMemcpyAsync(x, resid, act, cudaMemcpyDeviceToDevice, st));
+    if (resid != x) CK(cudaMemcpyAsync(x, resid, act, cudaMemcpyDeviceToDevice, st));
     p.out = x; p.tma_reduce = 1;
     return gemm<T16>(h, st, tag, A, K, W, K, p, EPI_BIAS, true);
   };
@@ -371,8 +376,9 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
     } else {
       TRY(attention<T16>(h, st, tl.qkv16, t.ext_mask, B, S, tl.ctx16, h->attn_impl));
     }
-    TRY(dense_residual(CPT_K_GEMM_AO, tl.ctx16, H, d.w_ao, d.b_ao, t.h32, tl.x1, l * 4 + SITE_AO));
-    TRY(layernorm<T16>(h, st, tl.x1, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, t.a32, tl.a16));
+    TRY(dense_residual(CPT_K_GEMM_AO, tl.ctx16, H, d.w_ao, d.b_ao, in_place ? tl.x1 : t.h32, tl.x1, l * 4 + SITE_AO));
+    float* const a32 = in_place ? tl.x2 : t.a32;
+    TRY(layernorm<T16>(h, st, tl.x1, H, M, H, d.ao_g, d.ao_b, c.layer_norm_eps, true, a32, tl.a16));
     {
       GemmParams p{};
       p.M = M; p.N = I; p.K = H; p.out = tl.preup16; p.ldo = I; p.bias = d.b_i;
@@ -383,8 +389,9 @@ static int train_forward_impl(cpt_handle* h, int head, cudaStream_t st, const in
                                                           reinterpret_cast<T16*>(tl.inter16));
       CKL("gelu_fwd_kernel");
     }
-    TRY(dense_residual(CPT_K_GEMM_DOWN, tl.inter16, I, d.w_o, d.b_o, t.a32, tl.x2, l * 4 + SITE_DOWN));
-    TRY(layernorm<T16>(h, st, tl.x2, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true, (l == L - 1) ? t.seq32 : t.h32,
+    TRY(dense_residual(CPT_K_GEMM_DOWN, tl.inter16, I, d.w_o, d.b_o, a32, tl.x2, l * 4 + SITE_DOWN));
+    TRY(layernorm<T16>(h, st, tl.x2, H, M, H, d.o_g, d.o_b, c.layer_norm_eps, true,
+                       (l == L - 1) ? t.seq32 : (in_place ? t.layers[l + 1].x1 : t.h32),
                        (l == L - 1) ? nullptr : t.layers[l + 1].h16));
   }
   if (L == 0) CK(cudaMemcpyAsync(t.seq32, t.h32, act, cudaMemcpyDeviceToDevice, st));
