@@ -301,6 +301,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    real_stdout = None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -308,6 +309,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+        # ... and whatever a library still writes to fd 1 (NCCL's version banner) goes to stderr: the JSON line is
+        # written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group(backend="nccl", device_id=dev)
 
     from cpt_b200.modeling_bert import BertImgForPreTraining
@@ -506,7 +512,11 @@ def main():
             out["cpu_baseline"] = cpu
         if train:
             out["train_step"] = train
-        print(json.dumps(out))
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(out) + "\n").encode())
+        else:
+            print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
