@@ -279,12 +279,12 @@ static int launch_gemm_bn(cpt_handle* h, cudaStream_t st, GemmChoice c, const CU
 }
 
 // tile choice per GEMM class; cfg = block_n + 1000 * (1 + pair), 0 = default for the class
-static GemmChoice pick_gemm(const cpt_handle* h, int tag, int M, int N, int K, int cfg) {
+static GemmChoice pick_gemm(const cpt_handle* h, int tag, int M, int N, int K, int cfg, int ksplit = 1) {
   GemmChoice c{h->gemm_choice[tag].bn, h->gemm_choice[tag].pair};
   // few-shot / single-query batches: when the default tiling yields fewer work items than a quarter of the SMs,
   // narrower single-CTA tiles spread the same work over more SMs (measured: B=1 latency 0.87 -> 0.70 ms, B=4 training
   // step 4.27 -> 4.09 ms; at M = 1920 the default tiling is still the better one).  CPT_B200_SMALL_M=0 turns it off.
-  if (c.bn == 0 && cfg == 0 && h->small_m_tiles) {
+  if (c.bn == 0 && cfg == 0 && h->small_m_tiles && ksplit <= 1) {  // split-K already multiplies the work items
     const int bn0 = N >= 2048 ? 256 : 192;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
     if (m_tiles * ((N + bn0 - 1) / bn0) * 4 <= h->num_sms) {
@@ -308,7 +308,7 @@ static int gemm(cpt_handle* h, cudaStream_t st, int tag, const void* A, long lon
                 GemmParams p, int epi, bool out_fp32, int cfg = 0) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   ProfScope ps(h, st, tag);
-  GemmChoice c = pick_gemm(h, tag, p.M, p.N, p.K, cfg);
+  GemmChoice c = pick_gemm(h, tag, p.M, p.N, p.K, cfg, p.ksplit);
   if (p.trans) c.pair = 0;
   p.trace = h->trace;
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));

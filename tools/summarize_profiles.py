@@ -101,7 +101,11 @@ def main():
     traffic = {}
     for title, name in (("GEMM kernels of one layer (QKV, attention-out, FFN-up, FFN-down)", "gemm"),
                         ("attention forward", "attn"), ("LayerNorm", "ln"),
-                        ("attention backward (training, S=120)", "attn_bwd")):
+                        ("attention backward (training, S=120)", "attn_bwd"),
+                        ("backward GEMMs of one encoder layer at B=64 (in launch order: FFN-down wgrad [trans=3, "
+                         "split-K] and dgrad [trans=2], FFN-up wgrad and dgrad, attention-out wgrad and dgrad, merged QKV "
+                         "wgrad and dgrad; captured one commit before the tile choice became split-K aware — k4 ran 64-wide tiles here, "
+                         "192-wide since)", "bwd_gemm")):
         p = os.path.join(G, "%s_%s_raw.csv" % (TAG, name))
         if not os.path.exists(p):
             continue
