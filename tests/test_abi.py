@@ -1,5 +1,6 @@
 """CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/cpt_b200.h declares;
 the host layer refuses to run without a CUDA device (no CPU fallback exists)."""
+import ctypes
 import os
 import re
 
@@ -43,6 +44,20 @@ def test_struct_layouts_match_header():
     names = [n for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body("cpt_config"))
              for n in re.findall(r"\w+", decl)]
     assert names == [f[0] for f in _lib.Config._fields_]
+    # training / optimizer structs
+    assert tuple(re.findall(r"\*(\w+)", body("cpt_layer_grads"))) == _lib.LAYER_FIELDS
+    assert tuple(re.findall(r"\*(\w+)", body("cpt_grads"))) == _lib.GRAD_GLOBAL_FIELDS + ("layers",)
+    drop = [n for decl in re.findall(r"(?:float|uint64_t|const uint64_t)\s+([^;]+);", body("cpt_dropout"))
+            for n in re.findall(r"\w+", decl)]
+    assert drop == [f[0] for f in _lib.Dropout._fields_]
+    assert ctypes.sizeof(_lib.Dropout) == 24 and ctypes.sizeof(_lib.Grads) == 8 * (len(_lib.GRAD_GLOBAL_FIELDS) + 1)
+    from cpt_b200 import optimization as OPT
+    adam = [n for decl in re.findall(r"(?:const float|float|int64_t)\s+([^;]+);", body("cpt_adam_tensor"))
+            for n in re.findall(r"\w+", decl)]
+    assert adam == list(OPT._TENSOR.names) and OPT._TENSOR.itemsize == 56
+    chunk = [n for decl in re.findall(r"(?:int32_t|int64_t)\s+([^;]+);", body("cpt_adam_chunk"))
+             for n in re.findall(r"\w+", decl)]
+    assert chunk == list(OPT._CHUNK.names) and OPT._CHUNK.itemsize == 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
