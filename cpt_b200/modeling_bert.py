@@ -7,8 +7,9 @@ oscar/modeling/modeling_utils.py:680-875 — same constructor and forward signat
 same return tuples, same state_dict keys.  The nn.Modules below only HOLD parameters (so optimizers, DDP,
 state_dict, .to() see exactly the reference's tensors); the arithmetic of forward() runs in cpt_b200/csrc
 through the C ABI.  Features the CPT path never uses raise instead of silently differing: head_mask,
-output_attentions, encoder_history_states, 3-D attention masks, dis_code* feature types, active dropout
-(training mode) — the training path is not built yet.
+output_attentions, encoder_history_states, 3-D attention masks, dis_code* feature types, and a label-free forward in
+train() mode with active dropout (dropout belongs to the native training step, cpt_b200/training.py, reached through
+the task wrappers' calls with labels).
 """
 import logging
 import os
