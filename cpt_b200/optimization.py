@@ -101,6 +101,10 @@ class AdamW(Optimizer):
                 C.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else C.c_void_p(0)))
         # tdev / keep stay referenced until the launch is enqueued; the caching allocator keeps the stream order
         del keep
+        # the kernel wrote the parameters behind torch's back: bump their version counters so that whoever caches on
+        # them (the engines' "did a weight change?" check that refreshes the 16-bit copies, autograd's saved-tensor
+        # checks) sees the update
+        torch.autograd.graph.increment_version([p for p, _, _ in items])
 
 
 class WarmupLinearSchedule(LambdaLR):

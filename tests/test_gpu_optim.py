@@ -62,7 +62,9 @@ def test_adamw_grad_scale_and_state_dict_roundtrip():
     g = torch.randn(5000, generator=gen).cuda()
     a, b = AdamW([p], lr=1e-2), AdamW([q], lr=1e-2)
     p.grad = g * 128.0
+    v0 = p._version
     a.step(grad_scale=torch.tensor(1.0 / 128.0, device="cuda"))
+    assert p._version > v0  # the in-place update must be visible to version-based caches (engine weight refresh)
     q.grad = g.clone()
     b.step()
     assert (p - q).abs().max().item() < 1e-6
@@ -114,6 +116,8 @@ def test_few_shot_loop_with_native_optimizer():
     labels = labels.cuda()
     torch.manual_seed(0)
     losses = []
+    probe = dict(model.named_parameters())["bert.encoder.layer.1.output.dense.weight"]
+    w0 = probe.detach().clone()
     for _ in range(12):
         model.train()
         loss, _ = model(input_ids=d["input_ids"], attention_mask=d["attention_mask"],
@@ -125,3 +129,16 @@ def test_few_shot_loop_with_native_optimizer():
         model.zero_grad()
         losses.append(loss.item())
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.3, losses  # finite and going down
+    # the training handle must have picked up every optimizer step: its forward on the final weights equals a fresh
+    # model's forward on a copy of them (a stale 16-bit copy would give the step-0 loss instead)
+    assert (probe.detach() - w0).abs().max().item() > 0
+    model.eval()
+    cfg.hidden_dropout_prob = 0.0
+    with torch.enable_grad():
+        l_trained = model(input_ids=d["input_ids"], attention_mask=d["attention_mask"],
+                          token_type_ids=d["token_type_ids"], masked_lm_labels=labels, img_feats=d["img_feats"])[0]
+    with torch.no_grad():
+        scores = model(input_ids=d["input_ids"], attention_mask=d["attention_mask"],
+                       token_type_ids=d["token_type_ids"], img_feats=d["img_feats"])[0]
+        l_infer = torch.nn.functional.cross_entropy(scores.view(-1, cfg.vocab_size), labels.view(-1), ignore_index=-1)
+    assert abs(l_trained.item() - l_infer.item()) <= 5e-3 * abs(l_infer.item()), (l_trained.item(), l_infer.item())
