@@ -65,6 +65,17 @@ class _Loss(torch.autograd.Function):
         return (None, None, None) + out
 
 
+def _check_targets(targets, n_classes, what):
+    """Labels other than ignore_index must be class indices: torch's CrossEntropyLoss raises for anything else (a
+    device-side assert on CUDA); the native kernels index the logits row with them, so check before launching.  The
+    stream was already synchronised by the nonzero() that produced `targets`."""
+    lo, hi = torch.aminmax(targets)
+    lo, hi = int(lo), int(hi)
+    if lo < 0 or hi >= n_classes:
+        raise RuntimeError("cpt_b200: %s holds a target outside [0, %d) other than ignore_index -1 (min %d, max %d)"
+                           % (what, n_classes, lo, hi))
+
+
 def draw_dropout(cfg, training):
     """(p_hidden, p_attn, seed) for one forward, or None.  The seed comes from torch's default CPU generator, so
     torch.manual_seed() makes a run reproducible (the masks themselves are this library's, include/cpt_b200.h)."""
@@ -84,6 +95,7 @@ def mlm_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     if rows.numel() == 0:
         raise RuntimeError("cpt_b200: masked_lm_labels has no labelled position (the reference returns NaN here)")
     targets = flat[rows].contiguous()
+    _check_targets(targets, engine.cfg.vocab_size, "masked_lm_labels")
     has_img = img_feats is not None and img_feats.shape[1] > 0
     keys = [k for k in trainable_keys(engine.cfg, "mlm", has_img) if k in named_params]
     params = [named_params[k] for k in keys]
@@ -101,6 +113,7 @@ def nsp_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     if keep.numel() == 0:
         raise RuntimeError("cpt_b200: next_sentence_label has no labelled sample (the reference returns NaN here)")
     targets = flat[keep].contiguous()
+    _check_targets(targets, int(getattr(engine.cfg, "num_contrast_classes", 2)), "next_sentence_label")
     rows = (keep * S).contiguous()  # the [CLS] row of every labelled sample
     has_img = img_feats is not None and img_feats.shape[1] > 0
     keys = [k for k in trainable_keys(engine.cfg, "nsp", has_img) if k in named_params]

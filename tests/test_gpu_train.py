@@ -314,6 +314,10 @@ def test_training_error_paths():
     none = torch.full((2, 28), -1, dtype=torch.long).cuda()
     with pytest.raises(RuntimeError):  # no labelled position: the reference's loss would be NaN
         rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"], masked_lm_labels=none)
+    bad = none.clone()
+    bad[0, 1] = cfg.vocab_size  # out-of-range class index: torch's CrossEntropyLoss asserts, we raise
+    with pytest.raises(RuntimeError):
+        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"], masked_lm_labels=bad)
     labels = none.clone()
     labels[:, 2] = 5
     with pytest.raises(NotImplementedError):
