@@ -298,11 +298,13 @@ def test_graph_replayed_steps_match_eager_steps(monkeypatch):
     graph, n1 = run(True)
     assert n0 == 0 and n1 == 1
     for (le, ge), (lg, gg) in zip(eager, graph):
-        assert abs(le - lg) <= 1e-6 * abs(le)
+        assert abs(le - lg) <= 1e-5 * abs(le)
         assert ge.keys() == gg.keys()
         for k in ge:
-            # atomics / reduce-adds reorder fp32 sums between runs: allow rounding-level differences only
-            assert (ge[k] - gg[k]).abs().max().item() <= 2e-5 * max(ge[k].abs().max().item(), 1e-12), k
+            # atomics / reduce-adds reorder fp32 sums between runs, and a last-bit difference can flip the 16-bit
+            # rounding of an element of the gradient stream: allow rounding-level differences only (a wrong seed,
+            # stale staging buffer or stale tape gives O(1) differences)
+            assert (ge[k] - gg[k]).abs().max().item() <= 2e-4 * max(ge[k].abs().max().item(), 1e-12), k
 
 
 def test_training_error_paths():
