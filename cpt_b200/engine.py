@@ -284,6 +284,8 @@ class Engine(object):
                 and not torch.cuda.is_current_stream_capturing()):
             st = self._tgraphs.get(key)
             if st is None:
+                if len(self._tseen) > 4096:  # ever-changing shapes: do not let the sightings table grow without bound
+                    self._tseen.clear()
                 c = self._tseen.get(key, 0) + 1
                 self._tseen[key] = c
                 if c >= 2 and len(self._tgraphs) < 8:
