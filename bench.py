@@ -355,7 +355,7 @@ def main():
         for i in range(args.warmup if args.profile_only else max(args.warmup, 2 * NROT)):
             out = step_resident(i)
             if world > 1:
-                comm.all_gather_logits(out)
+                comm.all_gather_logits(out, sizes=[B] * world)
         if args.profile_only:
             for i in range(args.steps):
                 step_resident(i)
@@ -374,7 +374,7 @@ def main():
         for i in range(args.steps):
             out = step_resident(i)
             if world > 1:
-                comm.all_gather_logits(out)  # the path's only collective: the final [B,K] logits
+                comm.all_gather_logits(out, sizes=[B] * world)  # the path's only collective: the final [B,K] logits
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -417,7 +417,7 @@ def main():
                           mask_pos=b["mask_pos"], vocab_ids=vids)[0]
                 slot_free[s].record(main_stream)
                 if world > 1:
-                    comm.all_gather_logits(o)
+                    comm.all_gather_logits(o, sizes=[B] * world)
                 out_host[s].copy_(o, non_blocking=True)
             torch.cuda.synchronize()
 

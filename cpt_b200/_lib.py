@@ -8,8 +8,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcpt_b200.so")
-ABI_VERSION = 2
-K_COUNT = 21  # CPT_K_COUNT
+ABI_VERSION = 3
+K_COUNT = 22  # CPT_K_COUNT
 
 
 class CptError(RuntimeError):
@@ -58,6 +58,14 @@ class Dropout(C.Structure):
     _fields_ = [("p_hidden", C.c_float), ("p_attn", C.c_float), ("seed", C.c_uint64), ("seed_dev", C.c_void_p)]
 
 
+class ChainStage(C.Structure):
+    """cpt_chain_stage: one stage of the dataflow chain kernel (kind 0 GEMM, 1 LayerNorm)."""
+    _fields_ = [(n, C.c_int32) for n in ("kind", "M", "N", "K", "gelu", "out_fp32", "ksplit", "dep_stage")] + [
+        ("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("ln_in", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("eps", C.c_float), ("out32", C.c_void_p), ("out16", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/cpt_b200.h declares
 _i, _ll, _sz, _p, _f = C.c_int, C.c_longlong, C.c_size_t, C.c_void_p, C.c_float
 SYMBOLS = {
@@ -91,6 +99,7 @@ SYMBOLS = {
     "cpt_profile_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "cpt_gemm_trace": (_i, [_p, C.POINTER(_ll), _i]),
     "cpt_gemm": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _i, _p, _ll, _i]),
+    "cpt_chain_run": (_i, [_p, _p, C.POINTER(ChainStage), _i]),
     "cpt_attention": (_i, [_p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_attention_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),

@@ -47,25 +47,48 @@ def shard_queries(fanouts, rank=None, world=None):
     return q0, q1, r0, r0 + sum(fanouts[q0:q1])
 
 
-def all_gather_logits(local):
-    """[B_local, K] -> [sum_r B_r, K] on every rank, rank order preserved.  Ranks may hold different B_r (the last
-    shard of a split is ragged): sizes are exchanged first, then one padded all_gather."""
+def shard_rows(fanouts, world=None):
+    """Rows held by every rank under `shard_queries` — computable locally on each rank, so the gather below needs no
+    size exchange."""
+    world = get_world_size() if world is None else world
+    out = []
+    for r in range(world):
+        _, _, r0, r1 = shard_queries(fanouts, r, world)
+        out.append(r1 - r0)
+    return out
+
+
+def all_gather_logits(local, sizes=None):
+    """[B_local, K] -> [sum_r B_r, K] on every rank, rank order preserved, with ONE collective and NO device->host
+    synchronisation on the fast path.
+
+    sizes: rows held by each rank (`shard_rows(fanouts)`; every rank can compute it from the fan-outs, or pass
+    [B] * world for equal shards).  Then the exchange is a single fixed-shape all_gather_into_tensor —
+    asynchronous on the stream, so a replayed CUDA graph of the encoder is never serialised against it
+    (the reference's two pickle gathers, Oscar/oscar/utils/comm.py:102-142, synchronise twice per call).
+    sizes=None keeps the general ragged form: sizes are exchanged first (one host sync for all ranks' sizes)."""
     world = get_world_size()
     if world == 1:
         return local
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        got = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(got, n)
+        sizes = got.tolist()  # the one synchronisation of the ragged form
+    sizes = [int(x) for x in sizes]
+    if len(sizes) != world or sizes[get_rank()] != local.shape[0]:
+        raise ValueError("all_gather_logits: sizes %r do not describe this rank's %d rows" % (sizes, local.shape[0]))
     mx = max(sizes)
-    if local.shape[0] != mx:
-        pad = torch.zeros((mx - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        local = torch.cat((local, pad), 0)
-    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous())
-    if all(s == mx for s in sizes):
+    tail = tuple(local.shape[1:])
+    send = local.contiguous()
+    if local.shape[0] != mx:  # ragged last shard: pad to the common shape
+        send = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+        send[:local.shape[0]].copy_(local)
+    out = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)  # caching allocator: no sync
+    dist.all_gather_into_tensor(out, send)
+    if all(x == mx for x in sizes):
         return out
-    return torch.cat([out[r * mx:r * mx + s] for r, s in enumerate(sizes)], 0)
+    return torch.cat([out[r * mx:r * mx + x] for r, x in enumerate(sizes)], 0)
 
 
 def merge_by_key(dicts):

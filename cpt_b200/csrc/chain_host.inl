@@ -1,0 +1,215 @@
+// Host side of the dataflow chain kernel (chain_sm100.cuh): the list scheduler that turns a sequence of dependent
+// stages into one ordered task list per CTA pair, the launcher, and the layer chain of the encoder forward.
+// Included by cpt_b200.cu after the GEMM helpers.
+
+// One stage as the host describes it (mirrors cpt_chain_stage of the C ABI).
+struct ChainStageHost {
+  int kind = CHAIN_GEMM;
+  int M = 0, N = 0, K = 0, gelu = 0, out_fp32 = 0, ksplit = 1;
+  const void* A = nullptr;
+  long long lda = 0;
+  const void* W = nullptr;
+  long long ldw = 0;
+  const float* bias = nullptr;
+  void* out = nullptr;
+  long long ldo = 0;
+  const float *ln_in = nullptr, *gamma = nullptr, *beta = nullptr;
+  float eps = 0.f;
+  float* out32 = nullptr;
+  void* out16 = nullptr;
+  int dep_stage = -1;  // the stage whose output this one reads (-1: an earlier launch produced it)
+};
+
+static int chain_m_tiles2(int M) { return 2 * ((((M + kGemmBM - 1) / kGemmBM) + 1) / 2); }  // counters per stage
+static size_t chain_counter_bytes(int M, int n_stages) { return (size_t)n_stages * chain_m_tiles2(M) * sizeof(unsigned); }
+
+static int chain_n_tasks(const ChainStageHost& s) {
+  if (s.kind == CHAIN_LN) return (s.M + 2 * kChainLnRows - 1) / (2 * kChainLnRows);
+  const int m_tiles = (s.M + kGemmBM - 1) / kGemmBM, n_tiles = (s.N + kChainBN - 1) / kChainBN;
+  return ((m_tiles + 1) / 2) * n_tiles * std::max(1, s.ksplit);
+}
+
+// List scheduling: tasks in stage-major order (M fastest changing last: a stage's tiles complete M pair by M pair), each
+// appended to the pair that becomes free first under a crude cost model (k-blocks of the main loop + a fixed epilogue
+// share; a LayerNorm task costs about two k-blocks of epilogue-warp time).  Every list is a subsequence of ONE global
+// order in which a task's producers precede it, so with all pairs resident no wait can be circular.
+static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaStream_t stream, int* pairs_out,
+                          const int** dev_out, int* pitch_out) {
+  std::vector<int> key;
+  for (int i = 0; i < n; ++i) {
+    key.push_back(st[i].kind);
+    key.push_back(st[i].M);
+    key.push_back(st[i].N);
+    key.push_back(st[i].K);
+    key.push_back(st[i].ksplit);
+  }
+  auto it = h->chain_scheds.find(key);
+  if (it == h->chain_scheds.end()) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail("chain schedule for this shape is not built yet: run the call once outside CUDA-graph capture");
+    long long total = 0;
+    for (int i = 0; i < n; ++i) total += chain_n_tasks(st[i]);
+    int pairs = h->num_sms / 2;
+    if (total < pairs) pairs = (int)std::max<long long>(1, total);
+    std::vector<std::vector<int>> lists(pairs);
+    std::vector<double> avail(pairs, 0.0);
+    for (int i = 0; i < n; ++i) {
+      const int nt = chain_n_tasks(st[i]);
+      double cost = 2.0;
+      if (st[i].kind == CHAIN_GEMM)
+        cost = (double)((st[i].K + kGemmBK - 1) / kGemmBK) / std::max(1, st[i].ksplit) + 4.0;
+      for (int t = 0; t < nt; ++t) {
+        int best = 0;
+        for (int p = 1; p < pairs; ++p)
+          if (avail[p] < avail[best] - 1e-9) best = p;
+        lists[best].push_back((i << 24) | t);
+        avail[best] += cost;
+      }
+    }
+    size_t longest = 0;
+    for (auto& l : lists) longest = std::max(longest, l.size());
+    const int pitch = (int)longest + 1;
+    if (pitch > kChainMaxTasks) return fail("chain: %d tasks per CTA pair exceed the %d the kernel stages", pitch, kChainMaxTasks);
+    std::vector<int> flat((size_t)pairs * pitch, -1);
+    for (int p = 0; p < pairs; ++p) std::copy(lists[p].begin(), lists[p].end(), flat.begin() + (size_t)p * pitch);
+    cpt_handle::ChainSched s;
+    s.pairs = pairs;
+    s.pitch = pitch;
+    CK(cudaMalloc((void**)&s.dev, flat.size() * sizeof(int)));
+    CK(cudaMemcpy(s.dev, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->owned_chain.push_back(s.dev);
+    it = h->chain_scheds.emplace(key, s).first;
+  }
+  *pairs_out = it->second.pairs;
+  *dev_out = it->second.dev;
+  *pitch_out = it->second.pitch;
+  return 0;
+}
+
+// Runs the stages as one launch.  `counters`: chain_counter_bytes(M, n) of ZEROED device memory (the caller's: the
+// encoder forward clears its whole flag area once per call).
+template <typename T16>
+static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, int n, unsigned* counters) {
+  if (n <= 0) return 0;
+  if (n > kChainMaxStages) return fail("chain: at most %d stages", kChainMaxStages);
+  const int dt = Cvt<T16>::kFmt;
+  const int M = hs[0].M;
+  const int per = chain_m_tiles2(M);
+  ChainMaps maps;
+  memset(&maps, 0, sizeof maps);
+  ChainParams p;
+  memset(&p, 0, sizeof p);
+  p.n_stages = n;
+  int n_maps = 0;
+  for (int i = 0; i < n; ++i) {
+    const ChainStageHost& s = hs[i];
+    ChainStage& d = p.st[i];
+    if (s.M != M) return fail("chain: every stage must have the same row count");
+    d.kind = s.kind;
+    d.M = s.M;
+    d.N = s.N;
+    d.K = s.K;
+    d.gelu = s.gelu;
+    d.out_fp32 = s.out_fp32;
+    d.ksplit = std::max(1, s.ksplit);
+    d.bias = s.bias;
+    d.done = counters + (size_t)i * per;
+    if (s.dep_stage >= 0) {
+      if (s.dep_stage >= i) return fail("chain: stage %d depends on a later stage", i);
+      const ChainStageHost& ps = hs[s.dep_stage];
+      d.dep = counters + (size_t)s.dep_stage * per;
+      d.dep_target = ps.kind == CHAIN_LN
+                         ? 0u
+                         : (unsigned)(((ps.N + kChainBN - 1) / kChainBN) * std::max(1, ps.ksplit) * kGemmEpiWarps);
+    }
+    if (s.kind == CHAIN_LN) {
+      if (s.N % 128 || s.N > 1024 || s.N <= 0) return fail("chain LayerNorm: unsupported row width %d", s.N);
+      if (!s.ln_in || !s.gamma || !s.beta) return fail("chain LayerNorm: NULL argument");
+      d.ln_in = s.ln_in;
+      d.gamma = s.gamma;
+      d.beta = s.beta;
+      d.eps = s.eps;
+      d.out32 = s.out32;
+      d.out16 = s.out16;
+      continue;
+    }
+    if (n_maps >= kChainMaxMaps) return fail("chain: at most %d GEMM stages", kChainMaxMaps);
+    if (!s.A || !s.W || !s.out || s.M <= 0 || s.N <= 0 || s.K <= 0) return fail("chain GEMM: bad argument");
+    if (d.ksplit > 1 && !s.out_fp32) return fail("chain GEMM: split-K needs the accumulate-into-fp32 output");
+    if (d.ksplit > 1) d.ksplit = std::max(1, std::min(d.ksplit, ((s.K + kGemmBK - 1) / kGemmBK) / 4));
+    d.map = n_maps;
+    TRY(make_tmap(&maps.a[n_maps], s.A, dt, s.M, s.K, s.lda, kGemmBM));
+    TRY(make_tmap(&maps.b[n_maps], s.W, dt, s.N, s.K, s.ldw, kChainBN / 2));
+    if (s.out_fp32)
+      TRY(make_tmap_ex(&maps.o[n_maps], s.out, 2, s.M, s.N, s.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+    else
+      TRY(make_tmap_ex(&maps.o[n_maps], s.out, dt, s.M, s.N, s.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    ++n_maps;
+  }
+  // the schedule depends on the clamped ksplit: key it on what the kernel will decode
+  std::vector<ChainStageHost> eff(hs, hs + n);
+  for (int i = 0; i < n; ++i) eff[i].ksplit = p.st[i].ksplit;
+  for (int i = 0; i < n; ++i)  // a GEMM producer's target counts its (clamped) K pieces
+    if (hs[i].dep_stage >= 0 && eff[hs[i].dep_stage].kind == CHAIN_GEMM)
+      p.st[i].dep_target = (unsigned)(((eff[hs[i].dep_stage].N + kChainBN - 1) / kChainBN) * eff[hs[i].dep_stage].ksplit *
+                                      kGemmEpiWarps);
+  int pairs = 0;
+  TRY(chain_schedule(h, eff.data(), n, st, &pairs, &p.tasks, &p.pitch));
+  auto* fn = chain_kernel<T16>;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    TRY(set_smem_attr(fn, ChainCfg::kSmemBytes));
+    attr_set[h->device & 63] = true;
+  }
+  ProfScope ps(h, st, CPT_K_CHAIN);
+  CK(launch_k(fn, dim3(pairs * 2), dim3(kGemmThreads), ChainCfg::kSmemBytes, st, 2, maps, p));
+  return 0;
+}
+
+// One encoder layer after its attention kernel, plus the next layer's QKV projection, as ONE launch
+// (modeling_bert.py:85 BertSelfOutput, :144 BertIntermediate, :145 BertOutput, then :38-40 of layer l+1).
+//   ctx16 -> [attention.output.dense + bias] += h32 -> LayerNorm -> a32 / a16 -> [intermediate.dense, GELU] -> inter16
+//   -> [output.dense + bias] += a32 -> LayerNorm -> out32 (h32 or seq_out) / h16 -> [QKV of layer l+1] -> qkv16
+template <typename T16>
+static int chain_layer(cpt_handle* h, cudaStream_t st, const Workspace& w, int l, int M, float* out32, bool last,
+                       unsigned* counters) {
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size;
+  const LayerDev& d = h->layers[l];
+  ChainStageHost s[6];
+  int n = 0;
+  {  // attention.output.dense (+bias), added into the residual stream h32
+    ChainStageHost& g = s[n++];
+    g.M = M; g.N = H; g.K = H; g.out_fp32 = 1; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;
+    g.out = w.h32; g.ldo = H;
+  }
+  {  // BertSelfOutput.LayerNorm
+    ChainStageHost& g = s[n++];
+    g.kind = CHAIN_LN; g.M = M; g.N = H; g.ln_in = w.h32; g.gamma = d.ao_g; g.beta = d.ao_b; g.eps = c.layer_norm_eps;
+    g.out32 = w.a32; g.out16 = w.a16; g.dep_stage = 0;
+  }
+  {  // intermediate.dense + bias + erf-GELU
+    ChainStageHost& g = s[n++];
+    g.M = M; g.N = I; g.K = H; g.gelu = 1; g.A = w.a16; g.lda = H; g.W = d.w_i; g.ldw = H; g.bias = d.b_i;
+    g.out = w.inter16; g.ldo = I; g.dep_stage = 1;
+  }
+  {  // output.dense (+bias), added into a32
+    ChainStageHost& g = s[n++];
+    g.M = M; g.N = H; g.K = I; g.out_fp32 = 1; g.ksplit = h->chain_down_ksplit; g.A = w.inter16; g.lda = I; g.W = d.w_o;
+    g.ldw = I; g.bias = d.b_o; g.out = w.a32; g.ldo = H; g.dep_stage = 2;
+  }
+  {  // BertOutput.LayerNorm
+    ChainStageHost& g = s[n++];
+    g.kind = CHAIN_LN; g.M = M; g.N = H; g.ln_in = w.a32; g.gamma = d.o_g; g.beta = d.o_b; g.eps = c.layer_norm_eps;
+    g.out32 = out32; g.out16 = last ? nullptr : w.h16; g.dep_stage = 3;
+  }
+  if (!last) {  // the next layer's query / key / value projection
+    const LayerDev& nx = h->layers[l + 1];
+    ChainStageHost& g = s[n++];
+    g.M = M; g.N = 3 * H; g.K = H; g.A = w.h16; g.lda = H; g.W = nx.w_qkv; g.ldw = H; g.bias = nx.b_qkv;
+    g.out = w.qkv16; g.ldo = 3 * H; g.dep_stage = 4;
+  }
+  return run_chain<T16>(h, st, s, n, counters);
+}

@@ -1,0 +1,469 @@
+// Dataflow "chain" kernel for sm_100a: SEVERAL dependent stages of one encoder layer in ONE persistent launch.
+//
+// The reference runs one CaptionBertLayer (Oscar/oscar/modeling/modeling_bert.py:139-147) as ~25 ATen launches; round 1
+// of this library ran it as 7 (QKV GEMM | attention | attention-out GEMM | LayerNorm | FFN-up GEMM | FFN-down GEMM |
+// LayerNorm), every kernel boundary costing a drain (the slowest CTA's last epilogue), a grid-wide dependency wait and a
+// pipeline refill: ~35 % of each short-K GEMM launch.  Here the stages that follow the attention kernel,
+//     attention.output.dense (+bias +residual)   -> BertSelfOutput.LayerNorm
+//  -> intermediate.dense (+bias, erf-GELU)       -> output.dense (+bias +residual) -> BertOutput.LayerNorm
+//  -> the NEXT layer's fused query/key/value projection,
+// are ONE launch: a stage is a list of TASKS (a 256 x 256 output tile computed by a CTA pair with
+// tcgen05.mma.cta_group::2, or 64 rows of LayerNorm), every task waits for the rows it reads through counters in global
+// memory (L2) and publishes the rows it wrote the same way, and the host gives every CTA pair an ordered task list
+// (list scheduling in stage-major order, so a task only ever waits for tasks that precede it in every list: no
+// deadlock with all pairs resident).  There is no grid-wide barrier anywhere: while the last tiles of one stage are
+// still in their epilogues, pairs that are done already run the next stage's tiles on rows that are complete.
+//
+//   roles per CTA (as gemm_sm100.cuh): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (leader CTA), warps 2..9
+//   = epilogue (TMEM -> registers -> bias / GELU -> swizzled staging -> TMA bulk store, or cp.reduce.async.bulk .add
+//   into the fp32 residual stream) AND the LayerNorm tasks (a warp owns a row; two-pass statistics in registers).
+//   The MMA issuer runs up to two accumulators ahead of the epilogue warps, so LayerNorm tasks hide behind main loops.
+//
+//   cross-CTA ordering:  writer: bulk stores complete (cp.async.bulk.wait_group 0) / generic stores fenced
+//                                -> fence.proxy.async -> red.release.gpu on the counter
+//                        reader: ld.acquire.gpu spin on the counter -> fence.proxy.async -> TMA loads / ld.global.cg
+#pragma once
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+namespace cptk {
+
+constexpr int kChainMaxStages = 8;
+constexpr int kChainMaxMaps = 4;
+constexpr int kChainBN = 256;
+constexpr int kChainLnRows = 32;     // rows per CTA per LayerNorm task (4 per epilogue warp); a pair task = 64 rows
+constexpr int kChainMaxTasks = 512;  // per CTA pair (the list is staged in shared memory)
+
+enum ChainKind { CHAIN_GEMM = 0, CHAIN_LN = 1 };
+
+struct ChainStage {
+  int kind;
+  // CHAIN_GEMM: out[M,N] (+)= epi(A[M,K] . W[N,K]^T + bias);  CHAIN_LN: out[M,N] = LayerNorm(ln_in[M,N]) gamma + beta
+  int M, N, K;
+  int gelu;      // erf-GELU after the bias (BertIntermediate)
+  int out_fp32;  // 1: the fp32 tile is ADDED into the destination by the TMA store (residual already there); 0: 16-bit
+  int ksplit;    // K cut into pieces that all add into the destination (out_fp32 only)
+  int map;       // index of this stage's tensor maps in ChainMaps
+  const float* bias;
+  const float* ln_in;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out32;  // LayerNorm outputs (either may be NULL)
+  void* out16;
+  // readiness counters, one per 128-row M tile
+  const unsigned* dep;  // rows this stage READS are complete when dep[mt] >= target (NULL: produced by an earlier launch)
+  unsigned dep_target;  // 0 = "the number of rows in the M tile" (the producer is a LayerNorm stage)
+  unsigned* done;       // this stage adds here: GEMM +1 per epilogue warp per (tile, K piece); LayerNorm + rows
+};
+
+struct ChainMaps {
+  CUtensorMap a[kChainMaxMaps], b[kChainMaxMaps], o[kChainMaxMaps];
+};
+
+struct ChainParams {
+  int n_stages;
+  ChainStage st[kChainMaxStages];
+  const int* tasks;  // [pairs][pitch]: (stage << 24) | index, -1 terminated
+  int pitch;
+};
+
+struct ChainCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;           // this CTA's 128 rows
+  static constexpr int kBBytes = (kChainBN / 2) * kGemmBK * 2;    // this CTA's half of the 256 weight rows
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 5;
+  static constexpr int kStageEpi = 4096;                          // one 32 x 32 fp32 block per epilogue warp
+  static constexpr int kBiasBytes = (kChainBN / 2) * 4;
+  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kBiasBytes);
+  static constexpr int kTaskBytes = kChainMaxTasks * 4;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256 + kTaskBytes;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory");
+};
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void flag_add_release(unsigned* addr, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+// Bounded like mbar_wait: a scheduling bug becomes a trapped launch, not a hung GPU.
+__device__ __forceinline__ void flag_wait_ge(const unsigned* addr, unsigned target) {
+  unsigned v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    if (v >= target) break;
+    if (++spins > (1u << 23)) {
+      printf("cpt_b200: chain dependency wait timed out (block %d thread %d: have %u need %u)\n", blockIdx.x, threadIdx.x,
+             v, target);
+      __trap();
+    }
+    __nanosleep(32);
+  }
+}
+
+// LayerNorm of up to 4 rows by one warp (BertLayerNorm: biased variance, eps inside the sqrt, two-pass statistics);
+// rows come straight from L2 (ld.global.cg: another SM wrote them during this launch).
+template <typename T16>
+__device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int nrows, int lane) {
+  const int H = s.N, nv = H >> 7;  // float4 per lane (H % 128 == 0, H <= 1024)
+  for (int r = 0; r < nrows; r += 2) {
+    float4 x[2][kMaxVec];
+    const int two = (r + 1 < nrows) ? 2 : 1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k < two) {
+        const float4* src = reinterpret_cast<const float4*>(s.ln_in + (long long)(row0 + r + k) * H);
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i)
+          if (i < nv) x[k][i] = __ldcg(src + i * 32 + lane);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k < two) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i)
+          if (i < nv) sum += (x[k][i].x + x[k][i].y) + (x[k][i].z + x[k][i].w);
+        const float mean = warp_sum(sum) / (float)H;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+          if (i < nv) {
+            const float a = x[k][i].x - mean, b = x[k][i].y - mean, c = x[k][i].z - mean, d = x[k][i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+          }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + s.eps);
+        const long long orow = (long long)(row0 + r + k) * H;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+          if (i < nv) {
+            const int col = (i * 32 + lane) * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(s.gamma + col));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(s.beta + col));
+            float4 y;
+            y.x = (x[k][i].x - mean) * rstd * g.x + b.x;
+            y.y = (x[k][i].y - mean) * rstd * g.y + b.y;
+            y.z = (x[k][i].z - mean) * rstd * g.z + b.z;
+            y.w = (x[k][i].w - mean) * rstd * g.w + b.w;
+            if (s.out32) *reinterpret_cast<float4*>(s.out32 + orow + col) = y;
+            if (s.out16) {
+              uint2 u;
+              u.x = Cvt<T16>::pack2(y.x, y.y);
+              u.y = Cvt<T16>::pack2(y.z, y.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(s.out16) + orow + col) = u;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  using Cfg = ChainCfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = kChainBN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t bars = epi_base + Cfg::kEpiBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
+  const int* task_s = reinterpret_cast<const int*>(epi_gen + Cfg::kEpiBytes + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair_id = blockIdx.x >> 1;
+
+  pdl_launch_dependents();
+  // the task list is static data (uploaded when the schedule was built): staged before the dependency wait
+  {
+    int* dst = reinterpret_cast<int*>(epi_gen + Cfg::kEpiBytes + 256);
+    const int* src = p.tasks + (long long)pair_id * p.pitch;
+    for (int i = threadIdx.x; i < p.pitch; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s)
+      if (p.st[s].kind == CHAIN_GEMM) {
+        tma_prefetch_desc(&maps.a[p.st[s].map]);
+        tma_prefetch_desc(&maps.b[p.st[s].map]);
+        tma_prefetch_desc(&maps.o[p.st[s].map]);
+      }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 2 * kGemmEpiWarps);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  tc_fence_after();
+  pdl_wait();  // outputs of the previous launch (attention context, residual stream) are visible from here on
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // decode of a GEMM task: cluster tile (256 rows x 256 columns) and K piece
+  struct TileAt {
+    int m0, n0, kb_begin, kb_end, ks;
+  };
+  auto decode = [&](const ChainStage& s, int idx) {
+    const int m_tiles = (s.M + kGemmBM - 1) / kGemmBM, n_tiles = (s.N + BN - 1) / BN;
+    const int mn = ((m_tiles + 1) >> 1) * n_tiles;
+    const int ksplit = s.ksplit > 1 ? s.ksplit : 1;
+    const int num_kb = (s.K + kGemmBK - 1) / kGemmBK;
+    const int tile = idx % mn, ks = idx / mn;
+    TileAt t;
+    t.m0 = ((tile / n_tiles) * 2 + (int)crank) * kGemmBM;
+    t.n0 = (tile % n_tiles) * BN;
+    t.kb_begin = (int)((long long)ks * num_kb / ksplit);
+    t.kb_end = (int)((long long)(ks + 1) * num_kb / ksplit);
+    t.ks = ks;
+    return t;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0;; ++i) {
+        const int task = task_s[i];
+        if (task < 0) break;
+        const ChainStage& s = p.st[task >> 24];
+        if (s.kind != CHAIN_GEMM) continue;
+        const TileAt t = decode(s, task & 0xFFFFFF);
+        const CUtensorMap* ma = &maps.a[s.map];
+        const CUtensorMap* mb = &maps.b[s.map];
+        if (s.dep != nullptr && t.m0 < s.M) {  // this CTA's 128 rows of the A operand
+          const unsigned target = s.dep_target ? s.dep_target : (unsigned)min(kGemmBM, s.M - t.m0);
+          flag_wait_ge(s.dep + t.m0 / kGemmBM, target);
+          fence_proxy_async_global();
+        }
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          // both CTAs' bytes are counted on the leader's barrier (the leader alone issues the MMAs)
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+          tma_load_2d_2cta(sa, ma, lbar, kb * kGemmBK, t.m0);
+          tma_load_2d_2cta(sb, mb, lbar, kb * kGemmBK, t.n0 + (int)crank * (BN / 2));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(2 * kGemmBM, BN, Cvt<T16>::kFmt, 0, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int i = 0;; ++i) {
+        const int task = task_s[i];
+        if (task < 0) break;
+        const ChainStage& s = p.st[task >> 24];
+        if (s.kind != CHAIN_GEMM) continue;
+        const TileAt t = decode(s, task & 0xFFFFFF);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        ++it;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            umma_f16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, ((kb - t.kb_begin) | k) != 0);
+          umma_commit_2cta_mc(empty_bar(stage), 3);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2cta_mc(tfull_bar(acc), 3);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue + LayerNorm (8 warps)
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;  // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    uint8_t* pad = epi_gen + ew * Cfg::kStageEpi;
+    const uint32_t pad_u32 = epi_base + ew * Cfg::kStageEpi;
+    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * Cfg::kStageEpi + ew * Cfg::kBiasBytes);
+    bool staging_busy = false;  // a bulk store may still be reading this warp's staging block
+    int it = 0;
+    for (int i = 0;; ++i) {
+      const int task = task_s[i];
+      if (task < 0) break;
+      const ChainStage& s = p.st[task >> 24];
+      if (s.kind == CHAIN_LN) {
+        // ---- 64 rows per pair task: this CTA's 32, 4 per warp
+        const int row0 = ((task & 0xFFFFFF) * 2 + (int)crank) * kChainLnRows + ew * 4;
+        if (row0 < s.M) {
+          const int nrows = min(4, s.M - row0);
+          const int mt = row0 / kGemmBM;
+          if (s.dep != nullptr) {
+            if (lane == 0) {
+              const unsigned target = s.dep_target ? s.dep_target : (unsigned)min(kGemmBM, s.M - mt * kGemmBM);
+              flag_wait_ge(s.dep + mt, target);
+            }
+            __syncwarp();
+          }
+          chain_ln_rows<T16>(s, row0, nrows, lane);
+          __threadfence();
+          __syncwarp();
+          if (lane == 0 && s.done != nullptr) {
+            fence_proxy_async_global();
+            flag_add_release(s.done + mt, (unsigned)nrows);
+          }
+        }
+        continue;
+      }
+      // ---- GEMM tile epilogue
+      const TileAt t = decode(s, task & 0xFFFFFF);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      ++it;
+      const CUtensorMap* mo = &maps.o[s.map];
+      const int mrow0 = t.m0 + q * 32;
+      const int ncol0 = t.n0 + half * kColsPerWarp;
+      const bool f32out = s.out_fp32 != 0;
+      {  // this warp's bias slice -> smem while the tile's MMAs are still running (the first K piece carries the bias)
+        const float* src = (t.ks == 0) ? s.bias : nullptr;
+        const int nb = ncol0 + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr) {
+          if (nb + 3 < s.N) {
+            b4 = __ldg(reinterpret_cast<const float4*>(src + nb));
+          } else {
+            if (nb < s.N) b4.x = __ldg(src + nb);
+            if (nb + 1 < s.N) b4.y = __ldg(src + nb + 1);
+            if (nb + 2 < s.N) b4.z = __ldg(src + nb + 2);
+          }
+        }
+        *reinterpret_cast<float4*>(sv0 + lane * 4) = b4;
+        __syncwarp();
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
+      if (mrow0 < s.M) {
+        constexpr int NC = kColsPerWarp / 32;
+        uint32_t rbuf[32];
+        tmem_ld_32x32b_x32(t_row, rbuf);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int nc = ncol0 + c * 32;
+          const bool live = nc < s.N;  // warp-uniform
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sv0 + c * 32 + j);
+            v[j] = __uint_as_float(rbuf[j]) + b4.x;
+            v[j + 1] = __uint_as_float(rbuf[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(rbuf[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(rbuf[j + 3]) + b4.w;
+          }
+          if (s.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) gelu_erf4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (staging_busy) {  // the store that last read the staging block must have drained its smem reads
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            staging_busy = false;
+          }
+          if (c + 1 < NC) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+          if (live) {
+            if (f32out) {
+              uint8_t* brow = pad + lane * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(brow + ((j ^ (lane & 7)) * 16)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint8_t* brow = pad + lane * 64;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = Cvt<T16>::pack2(v[8 * j + 0], v[8 * j + 1]);
+                u.y = Cvt<T16>::pack2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = Cvt<T16>::pack2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = Cvt<T16>::pack2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(brow + ((j ^ ((lane >> 1) & 3)) * 16)) = u;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (f32out) tma_reduce_add_2d(mo, pad_u32, nc, mrow0);
+              else tma_store_2d(mo, pad_u32, nc, mrow0);
+              tma_store_commit();
+            }
+            staging_busy = true;
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        // publish: this warp's blocks of the tile are in L2
+        tma_store_wait<0>();
+        if (s.done != nullptr) {
+          fence_proxy_async_global();
+          flag_add_release(s.done + t.m0 / kGemmBM, 1u);
+        }
+      }
+      staging_busy = false;
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer may still signal it / read its smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+}  // namespace cptk

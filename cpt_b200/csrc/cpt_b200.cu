@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "attention_sm100.cuh"
 #include "attention_bwd_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "chain_sm100.cuh"
 #include "optim.cuh"
 #include "rowwise.cuh"
 #include "train.cuh"
@@ -148,6 +150,15 @@ struct cpt_handle {
   unsigned weights_sig = 0;                        // which optional tensors the current allocations cover
   float *nsp_w = nullptr, *nsp_b = nullptr;
   std::vector<LayerDev> layers;
+  // dataflow chain kernel (chain_sm100.cuh): one launch per layer for everything between two attention kernels
+  int chain = 1;                 // CPT_B200_CHAIN=0: the round-1 launch sequence (one kernel per GEMM / LayerNorm)
+  int chain_min_rows = 1024;     // below this many rows the narrow-tile GEMMs of the unfused path spread better
+  int chain_down_ksplit = 1;     // CPT_B200_CHAIN_KSPLIT: K pieces of the FFN-down tiles
+  struct ChainSched { int pairs = 0, pitch = 0; int* dev = nullptr; };
+  std::map<std::vector<int>, ChainSched> chain_scheds;  // per chain shape: the task lists of the CTA pairs
+  std::vector<void*> owned_chain;
+  unsigned* chain_counters = nullptr;  // cpt_chain_run (tests): readiness counters
+  size_t chain_counters_bytes = 0;
   int* err_flag = nullptr;
   int attn_impl = 0;
   int fold_ln = 0;       // CPT_B200_FOLD_LN=1: LayerNorm folded into the neighbouring GEMM epilogues (slower, kept for study)
@@ -465,6 +476,8 @@ struct Workspace {
   char* pre16;
   size_t stats_bytes;
   char *h16, *a16, *ctx16, *qkv16, *inter16, *img16;
+  unsigned* flags;     // readiness counters of the chain kernel: [L][6 stages][M tiles]
+  size_t flags_bytes;
   size_t total;
 };
 static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
@@ -491,9 +504,13 @@ static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
   w.img16 = take((size_t)B * R * h->Fp * 2);
   w.stats_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * 2 * M * 2 * 4;  // [L][2][M](sum, sumsq)
   w.stats = (float*)take(w.stats_bytes);
+  w.flags_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * 6 * (2 * ((M + 255) / 256)) * sizeof(unsigned);
+  w.flags = (unsigned*)take(w.flags_bytes);
   w.total = off + 256;
   return w;
 }
+
+#include "chain_host.inl"
 
 // ------------------------------------------------------------------------------------------------ weights
 template <typename T16>
@@ -710,6 +727,10 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   if (!ws_ptr || ws_bytes < w.total) return fail("workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
   if (!ids || !seq_out) return fail("input_ids and seq_out must be non-NULL");
 
+  const bool use_chain = h->chain && !h->train && !(h->fold_ln && !hidden_states) && L > 0 && h->tma_store &&
+                         h->reduce_resid && M >= h->chain_min_rows;
+  const size_t chain_ctr_per_layer = chain_counter_bytes(M, 6);
+  if (use_chain) CK(cudaMemsetAsync(w.flags, 0, chain_ctr_per_layer * L, st));  // first: keeps the PDL chain unbroken
   // K4: additive mask
   if (mask) {
     ProfScope ps(h, st, CPT_K_EXTMASK);
@@ -751,7 +772,23 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   if (hidden_states) CK(cudaMemcpyAsync(hidden_states, w.h32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
 
   const bool fold = h->fold_ln && !h->train && !hidden_states && L > 0;
-  if (fold) {
+  if (use_chain) {
+    // two launches per layer: the attention kernel, then ONE dataflow launch for attention-out + LayerNorm + FFN-up +
+    // FFN-down + LayerNorm + the next layer's QKV projection (chain_sm100.cuh)
+    {
+      GemmParams p{};
+      p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = h->layers[0].b_qkv;
+      TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, h->layers[0].w_qkv, H, p, EPI_BIAS, false));
+    }
+    for (int l = 0; l < L; ++l) {
+      TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));
+      float* o32 = (l == L - 1) ? seq_out : w.h32;
+      TRY(chain_layer<T16>(h, st, w, l, M, o32, l == L - 1,
+                           w.flags + (size_t)l * (chain_ctr_per_layer / sizeof(unsigned))));
+      if (hidden_states)
+        CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  } else if (fold) {
     // LayerNorm folded into the GEMMs on either side of it (DESIGN.md "LayerNorm folding"): the stream buffers hold
     // PRE-LayerNorm rows (fp32 + 16-bit) plus per-row (sum, sum of squares); no LayerNorm kernel runs between GEMMs.
     CK(cudaMemsetAsync(w.stats, 0, w.stats_bytes, st));
@@ -951,6 +988,9 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_TMA_STORE")) h->tma_store = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_SPLIT")) h->split = atoi(e);
   if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_CHAIN")) h->chain = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
+  if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
       cudaMemset(h->trace, 0, (size_t)h->num_sms * 128);
@@ -986,6 +1026,8 @@ int cpt_destroy(cpt_handle* h) {
   free_owned(h);
   if (h->copy_entries_dev) cudaFree(h->copy_entries_dev);
   if (h->copy_chunks_dev) cudaFree(h->copy_chunks_dev);
+  for (void* q : h->owned_chain) cudaFree(q);
+  if (h->chain_counters) cudaFree(h->chain_counters);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1204,7 +1246,7 @@ static const char* kKernelNames[CPT_K_COUNT] = {"ext_mask", "embed_text_ln", "ca
                                                  "gemm_qkv", "attention", "gemm_attn_out", "gemm_ffn_up",
                                                  "gemm_ffn_down", "head_matvec", "gemm_head", "gemm_other",
                                                  "gemm_dgrad", "gemm_wgrad", "attention_bwd", "train_rowwise",
-                                                 "transpose16", "colsum", "layernorm_bwd", "embed_bwd"};
+                                                 "transpose16", "colsum", "layernorm_bwd", "embed_bwd", "chain"};
 const char* cpt_kernel_name(int tag) { return (tag >= 0 && tag < CPT_K_COUNT) ? kKernelNames[tag] : ""; }
 long long cpt_launch_count(const cpt_handle* h) { return h ? h->launches : 0; }
 
@@ -1257,6 +1299,34 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
   p.ksplit = (epi >> 12) & 0xff;
   epi &= 0xff;
 #define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, tile_cfg)
+  return DISPATCH_DTYPE(h, CALL);
+#undef CALL
+}
+
+int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, int n_stages) {
+  if (!h || !stages || n_stages <= 0 || n_stages > kChainMaxStages) return fail("cpt_chain_run: bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<ChainStageHost> hs(n_stages);
+  for (int i = 0; i < n_stages; ++i) {
+    const cpt_chain_stage& s = stages[i];
+    ChainStageHost& d = hs[i];
+    d.kind = s.kind == 1 ? CHAIN_LN : CHAIN_GEMM;
+    d.M = s.M; d.N = s.N; d.K = s.K; d.gelu = s.gelu; d.out_fp32 = s.out_fp32; d.ksplit = s.ksplit;
+    d.A = s.A; d.lda = s.lda; d.W = s.W; d.ldw = s.ldw; d.bias = s.bias; d.out = s.out; d.ldo = s.ldo;
+    d.ln_in = s.ln_in; d.gamma = s.gamma; d.beta = s.beta; d.eps = s.eps; d.out32 = s.out32; d.out16 = s.out16;
+    d.dep_stage = s.dep_stage;
+  }
+  const size_t need = chain_counter_bytes(hs[0].M, n_stages);
+  if (need > h->chain_counters_bytes) {
+    CK(cudaStreamSynchronize(st));
+    if (h->chain_counters) cudaFree(h->chain_counters);
+    h->chain_counters = nullptr;
+    CK(cudaMalloc((void**)&h->chain_counters, need));
+    h->chain_counters_bytes = need;
+  }
+  CK(cudaMemsetAsync(h->chain_counters, 0, need, st));
+#define CALL(T16) run_chain<T16>(h, st, hs.data(), n_stages, h->chain_counters)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

@@ -587,6 +587,30 @@ class Engine(object):
                                          1 if out_fp32 else 0, _ptr(out), out.stride(0), tile_cfg))
         return out
 
+    def chain(self, stages):
+        """Run dependent stages as ONE dataflow launch (cpt_chain_run).  `stages`: dicts with kind "gemm"
+        (A, W, bias, out, gelu, accumulate, ksplit, dep) or "ln" (x, gamma, beta, eps, out32, out16, dep); `dep` is the
+        index of the stage whose output the stage reads (or None)."""
+        arr = (_lib.ChainStage * len(stages))()
+        for i, s in enumerate(stages):
+            c = arr[i]
+            c.dep_stage = -1 if s.get("dep") is None else int(s["dep"])
+            if s["kind"] == "ln":
+                x = s["x"]
+                c.kind, c.M, c.N = 1, x.shape[0], x.shape[1]
+                c.ln_in, c.gamma, c.beta, c.eps = x.data_ptr(), s["gamma"].data_ptr(), s["beta"].data_ptr(), s["eps"]
+                c.out32 = 0 if s.get("out32") is None else s["out32"].data_ptr()
+                c.out16 = 0 if s.get("out16") is None else s["out16"].data_ptr()
+            else:
+                A, W, out = s["A"], s["W"], s["out"]
+                c.kind, c.M, c.K, c.N = 0, A.shape[0], A.shape[1], W.shape[0]
+                c.gelu, c.out_fp32, c.ksplit = int(bool(s.get("gelu"))), int(out.dtype == torch.float32), int(s.get("ksplit", 1))
+                c.A, c.lda, c.W, c.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
+                c.bias = 0 if s.get("bias") is None else s["bias"].data_ptr()
+                c.out, c.ldo = out.data_ptr(), out.stride(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cpt_chain_run(self._h, _stream(), arr, len(stages)))
+
     def gemm_trace(self, n=148):
         buf = (C.c_longlong * (16 * n))()
         _lib.check(self.lib.cpt_gemm_trace(self._h, buf, n))

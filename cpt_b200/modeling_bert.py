@@ -142,6 +142,10 @@ class _EngineSlot(object):
     def __init__(self):
         self.engine, self.sig, self.heads, self.frozen = None, None, {}, False
         self.train_engine, self.train_sig = None, None
+        # Set by every native backward (training._Loss.backward): an optimizer step may follow, and optimizers that
+        # update through `p.data` (pytorch-transformers 1.x AdamW, apex) do NOT bump the autograd version counters the
+        # signatures below key on — so after a backward both handles refresh their 16-bit copies unconditionally.
+        self.dirty_train, self.dirty_infer = False, False
         self.grad_sync_group = None  # comm.enable_overlapped_grad_sync
         self.home, self._per_device, self._lock = None, {}, threading.Lock()
 
@@ -296,7 +300,7 @@ class BertImgModel(BertPreTrainedModel):
 
     def engine(self):
         slot = self._dev_slot()
-        if slot.frozen and slot.engine is not None and slot.sig is not None:
+        if slot.frozen and slot.engine is not None and slot.sig is not None and not slot.dirty_infer:
             return slot.engine
         sd = self._named_tensors()
         dev = self.embeddings.word_embeddings.weight.device
@@ -310,9 +314,9 @@ class BertImgModel(BertPreTrainedModel):
             dtype = getattr(self.config, "cpt_b200_dtype", None) or os.environ.get("CPT_B200_DTYPE", "fp16")
             slot.engine = Engine(self.config, dev, dtype=dtype)
             slot.sig = None
-        if sig != slot.sig:
+        if sig != slot.sig or slot.dirty_infer:
             slot.engine.load_state_dict(sd)
-            slot.sig = sig
+            slot.sig, slot.dirty_infer = sig, False
         return slot.engine
 
     def train_engine(self):
@@ -334,9 +338,10 @@ class BertImgModel(BertPreTrainedModel):
             slot.train_engine = Engine(self.config, dev, dtype=dtype, train=True)
             slot.train_engine.grad_sync_group = slot.grad_sync_group
             slot.train_sig = None
-        if sig != slot.train_sig:
+        slot.train_engine.owner_slot = slot
+        if sig != slot.train_sig or slot.dirty_train:
             slot.train_engine.load_state_dict(sd)
-            slot.train_sig = sig
+            slot.train_sig, slot.dirty_train = sig, False
         return slot.train_engine, sd
 
     def _dropout_active(self):

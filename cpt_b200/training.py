@@ -57,6 +57,12 @@ class _Loss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         eng = ctx.engine
+        if ctx.saved is None:
+            raise RuntimeError("cpt_b200: backward() was called a second time on the same training step; the tape of a "
+                               "step is released by its first backward (retain_graph=True is not supported)")
+        slot = getattr(eng, "owner_slot", None)
+        if slot is not None:  # an optimizer step may follow: see _EngineSlot.dirty_*
+            slot.dirty_train = slot.dirty_infer = True
         # one zero-filled slab for every gradient (one memset instead of ~200 fill launches); 256-byte aligned views
         grads = eng.grad_buffers(ctx.saved, ctx.keys, ctx.shapes)
         grads = eng.train_backward(ctx.saved, grad_loss.to(torch.float32), grads)
@@ -90,6 +96,13 @@ def mlm_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     """CrossEntropyLoss(ignore_index=-1) of the MLM scores against masked_lm_labels [B,S], differentiable with
     respect to `named_params` (dict keyed like the state_dict).  Returns (loss, rows): rows = flat indices of the
     labelled positions."""
+    B, T = input_ids.shape
+    S = T + (0 if img_feats is None else img_feats.shape[1])
+    if tuple(masked_lm_labels.shape) != (B, S):
+        # the reference's CrossEntropyLoss raises a batch-size mismatch here (modeling_rec.py:146-149); the native
+        # kernels index rows of the [B*S, H] stream with these positions
+        raise ValueError("cpt_b200: masked_lm_labels must have shape [B, T+R] = %s, got %s"
+                         % ((B, S), tuple(masked_lm_labels.shape)))
     flat = masked_lm_labels.reshape(-1)
     rows = torch.nonzero(flat != -1, as_tuple=False).squeeze(1)  # device -> host sync on its size, once per step
     if rows.numel() == 0:
@@ -108,6 +121,9 @@ def nsp_loss(engine, named_params, input_ids, token_type_ids, attention_mask, po
     """CrossEntropyLoss(ignore_index=-1) of cls.seq_relationship(pooled) against next_sentence_label [B]
     (modeling_vcr.py:120-127), differentiable with respect to `named_params`."""
     flat = next_sentence_label.reshape(-1)
+    if flat.numel() != input_ids.shape[0]:
+        raise ValueError("cpt_b200: next_sentence_label must hold one label per sample (%d), got %d"
+                         % (input_ids.shape[0], flat.numel()))
     S = input_ids.shape[1] + (0 if img_feats is None else img_feats.shape[1])
     keep = torch.nonzero(flat != -1, as_tuple=False).squeeze(1)
     if keep.numel() == 0:

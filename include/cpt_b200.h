@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CPT_B200_ABI_VERSION 2
+#define CPT_B200_ABI_VERSION 3
 
 typedef struct cpt_handle cpt_handle;
 
@@ -206,7 +206,7 @@ enum {
   CPT_K_EXTMASK = 0, CPT_K_EMBED, CPT_K_CAST, CPT_K_GEMM_IMG, CPT_K_LN, CPT_K_GEMM_QKV, CPT_K_ATTN,
   CPT_K_GEMM_AO, CPT_K_GEMM_UP, CPT_K_GEMM_DOWN, CPT_K_HEAD, CPT_K_GEMM_HEAD, CPT_K_GEMM_OTHER,
   CPT_K_GEMM_DGRAD, CPT_K_GEMM_WGRAD, CPT_K_ATTN_BWD, CPT_K_TRAIN_ROWWISE, CPT_K_TRANSPOSE, CPT_K_COLSUM, CPT_K_LN_BWD,
-  CPT_K_EMBED_BWD, CPT_K_COUNT
+  CPT_K_EMBED_BWD, CPT_K_CHAIN, CPT_K_COUNT
 };
 const char *cpt_kernel_name(int tag);
 /* kernels launched by this handle since cpt_create */
@@ -246,6 +246,29 @@ int cpt_attention(cpt_handle *h, void *stream, const void *qkv, const float *ext
  * kernel. */
 int cpt_attention_backward(cpt_handle *h, void *stream, const void *qkv, const void *dctx, const float *ext_mask,
                            int B, int S, void *dqkv, int impl);
+/* Dataflow chain (cpt_b200/csrc/chain_sm100.cuh): up to 8 dependent stages over the same M rows as ONE persistent
+ * launch — the encoder forward runs attention.output.dense + LayerNorm + intermediate.dense + output.dense + LayerNorm +
+ * the next layer's query/key/value projection (modeling_bert.py:85,144-145, then :38-40) this way.  A stage is
+ *   kind 0: out[M,N] = A[M,K] . W[N,K]^T + bias (16-bit operands; gelu: erf-GELU; out_fp32 = 0: 16-bit out,
+ *           out_fp32 = 1: the fp32 tile is ADDED into `out` (which already holds the residual); ksplit: K pieces), or
+ *   kind 1: out32 / out16 [M,N] = LayerNorm(ln_in[M,N]) * gamma + beta.
+ * dep_stage: the earlier stage whose output this one reads (-1: data from an earlier launch); rows are handed from
+ * stage to stage through readiness counters per 128-row tile, there is no grid-wide barrier. */
+typedef struct {
+  int32_t kind, M, N, K, gelu, out_fp32, ksplit, dep_stage;
+  const void *A;
+  int64_t lda;
+  const void *W;
+  int64_t ldw;
+  const float *bias;
+  void *out;
+  int64_t ldo;
+  const float *ln_in, *gamma, *beta;
+  float eps;
+  float *out32;
+  void *out16;
+} cpt_chain_stage;
+int cpt_chain_run(cpt_handle *h, void *stream, const cpt_chain_stage *stages, int n_stages);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
 int cpt_layernorm(cpt_handle *h, void *stream, const float *x, int M, const float *gamma, const float *beta,
                   float eps, float *out32, void *out16);

@@ -30,6 +30,10 @@ def _worker(rank, world, port, fanouts, q):
         local = full[r0:r1].clone()                                # this rank's rows
         gathered = comm.all_gather_logits(local)
         ok = torch.equal(gathered, full)
+        # fast path: every rank derives all ranks' row counts from the fan-outs -> no size exchange, no host sync
+        sizes = comm.shard_rows(fanouts)
+        ok = ok and sizes[rank] == r1 - r0 and sum(sizes) == sum(fanouts)
+        ok = ok and torch.equal(comm.all_gather_logits(local, sizes=sizes), full)
         picks = comm.pick_per_query(gathered, fanouts, "zsl")
         ref = torch.tensor([O.refcoco_zsl_pick(full[sum(fanouts[:i]):sum(fanouts[:i + 1])]) for i in range(len(fanouts))])
         ok = ok and torch.equal(picks.cpu(), ref)
