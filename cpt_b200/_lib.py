@@ -92,6 +92,7 @@ SYMBOLS = {
     "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _p, _sz,
                                     C.POINTER(Grads)]),
     "cpt_adamw_step": (_i, [_i, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
+    "cpt_score_queries": (_i, [_p, _p, _p, _ll, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),
     "cpt_launch_count": (_ll, [_p]),
@@ -100,6 +101,7 @@ SYMBOLS = {
     "cpt_gemm_trace": (_i, [_p, C.POINTER(_ll), _i]),
     "cpt_gemm": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _i, _p, _ll, _i]),
     "cpt_chain_run": (_i, [_p, _p, C.POINTER(ChainStage), _i]),
+    "cpt_chain_trace": (_i, [_p, C.POINTER(_ll), _ll, C.POINTER(_i), C.POINTER(_i)]),
     "cpt_attention": (_i, [_p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_attention_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i]),
     "cpt_layernorm": (_i, [_p, _p, _p, _i, _p, _p, _f, _p, _p]),

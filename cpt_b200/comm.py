@@ -102,28 +102,17 @@ def merge_by_key(dicts):
     return merged
 
 
-def pick_per_query(logits, fanouts, mode="zsl"):
-    """CPT decision per query from the gathered colour logits [rows, K] (last column = the "none" token):
-      zsl: argmax over all rows' colour columns                       (zeroshot/refcoco_cpt.py:242-246)
+def pick_per_query(logits, fanouts, mode="zsl", n_valid=None):
+    """CPT decision per query from the gathered colour logits [rows, K] (last column = the "none" token) — ONE native
+    launch for the whole batch (cpt_b200/scoring.py -> cpt_score_queries) instead of the reference's per-image loop:
+      zsl: argmax over the rows' colour columns                        (zeroshot/refcoco_cpt.py:242-246)
       fsl: argmax of colour / none                                     (fewshot/refcoco_cpt.py:291-294)
       vcr: logits are NSP scores [rows, C]; score = 1 - softmax[:, 1]  (fewshot/vcr_nsp_cpt.py:600-604)
-    Returns a LongTensor [n_queries] of flat indices into each query's (rows x columns) block; one device->host
-    sync for the whole batch instead of one per image."""
-    if mode == "vcr":
-        score = (1.0 - torch.softmax(logits, -1)[:, 1]).unsqueeze(1)
-    elif mode == "fsl":
-        score = logits[:, :-1] / logits[:, -1:]
-    else:
-        score = logits[:, :-1]
-    n_q, width = len(fanouts), score.shape[1]
-    fan = torch.as_tensor(fanouts, device=score.device)
-    mx = int(fan.max()) if n_q else 0
-    starts = torch.cumsum(fan, 0) - fan
-    idx = starts[:, None] + torch.arange(mx, device=score.device)[None, :]
-    valid = torch.arange(mx, device=score.device)[None, :] < fan[:, None]
-    block = score[idx.clamp(max=score.shape[0] - 1)]                       # [n_q, mx, width]
-    block = torch.where(valid[:, :, None], block, torch.full_like(block, float("-inf")))
-    return block.reshape(n_q, mx * width).argmax(1)
+    n_valid: per row, the size of the row's own colour set (the reference gathers `cur_color_set + ["none"]` per row;
+    the last proposal set of a query is usually shorter) — columns beyond it never win.  Returns an int32 tensor
+    [n_queries] of indices into each query's concatenated scores (the reference's max_idx).  CUDA tensors only."""
+    from .scoring import score_queries
+    return score_queries(logits, fanouts, mode=mode, n_valid=n_valid)["pick"]
 
 
 def enable_overlapped_grad_sync(ddp_model, process_group=None):

@@ -125,7 +125,8 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
                          : (unsigned)(((ps.N + kChainBN - 1) / kChainBN) * std::max(1, ps.ksplit) * kGemmEpiWarps);
     }
     if (s.kind == CHAIN_LN) {
-      if (s.N % 128 || s.N > 1024 || s.N <= 0) return fail("chain LayerNorm: unsupported row width %d", s.N);
+      if (!(s.N == 128 || s.N == 256 || s.N == 512 || s.N == 768 || s.N == 1024))
+        return fail("chain LayerNorm: unsupported row width %d (128, 256, 512, 768 or 1024)", s.N);
       if (!s.ln_in || !s.gamma || !s.beta) return fail("chain LayerNorm: NULL argument");
       d.ln_in = s.ln_in;
       d.gamma = s.gamma;
@@ -157,6 +158,21 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
                                       kGemmEpiWarps);
   int pairs = 0;
   TRY(chain_schedule(h, eff.data(), n, st, &pairs, &p.tasks, &p.pitch));
+  if (h->chain_trace_on) {  // event log of this launch (debug): sized for the largest launch seen
+    const size_t need = (size_t)pairs * p.pitch * 10 * sizeof(long long), hdr = (size_t)pairs * 2 * sizeof(long long);
+    if (need + hdr > h->chain_trace_bytes) {
+      CK(cudaStreamSynchronize(st));
+      if (h->chain_trace) cudaFree(h->chain_trace);
+      h->chain_trace = nullptr;
+      CK(cudaMalloc((void**)&h->chain_trace, need + hdr));
+      h->chain_trace_bytes = need + hdr;
+    }
+    CK(cudaMemsetAsync(h->chain_trace, 0, need + hdr, st));
+    p.trace_hdr = h->chain_trace;
+    p.trace = h->chain_trace + (size_t)pairs * 2;
+    h->chain_trace_pairs = pairs;
+    h->chain_trace_pitch = p.pitch;
+  }
   auto* fn = chain_kernel<T16>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {

@@ -66,6 +66,12 @@ struct ChainParams {
   ChainStage st[kChainMaxStages];
   const int* tasks;  // [pairs][pitch]: (stage << 24) | index, -1 terminated
   int pitch;
+  // optional event log (CPT_B200_CHAIN_TRACE=1), leader CTAs only: trace[(pair * pitch + i) * 10 + k] in SM clocks since
+  // the CTA's entry: 0 producer starts waiting for the rows | 1 rows ready | 2 last load issued | 3 accumulator free
+  // | 4 last MMA committed | 5 epilogue / LayerNorm starts waiting | 6 ready | 7 outputs published | 8 task code
+  // | 9 tile's stores issued; trace_hdr[pair * 2] = globaltimer (ns) and clock64 at entry
+  long long* trace;
+  long long* trace_hdr;
 };
 
 struct ChainCfg {
@@ -100,63 +106,70 @@ __device__ __forceinline__ void flag_wait_ge(const unsigned* addr, unsigned targ
   }
 }
 
-// LayerNorm of up to 4 rows by one warp (BertLayerNorm: biased variance, eps inside the sqrt, two-pass statistics);
-// rows come straight from L2 (ld.global.cg: another SM wrote them during this launch).
+// LayerNorm of up to 4 rows by one warp (BertLayerNorm: biased variance, eps inside the sqrt, two-pass statistics).
+// Rows come straight from L2 (ld.global.cg: another SM wrote them during this launch).  ALL loads of the ROWS rows are
+// issued before the first use: a CTA has only 8 such warps, so memory-level parallelism per warp is what sets the
+// rate (the first version, two rows in flight, took 11 us per 32-row task; the event log showed it on the critical
+// path of the whole chain).
+template <typename T16, int NV, int ROWS>
+__device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int nrows, int lane) {
+  constexpr int H = NV * 128;
+  float4 x[ROWS][NV];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (r < nrows) {
+      const float4* src = reinterpret_cast<const float4*>(s.ln_in + (long long)(row0 + r) * H);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) x[r][i] = __ldcg(src + i * 32 + lane);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (r < nrows) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum += (x[r][i].x + x[r][i].y) + (x[r][i].z + x[r][i].w);
+      const float mean = warp_sum(sum) / (float)H;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float a = x[r][i].x - mean, b = x[r][i].y - mean, c = x[r][i].z - mean, d = x[r][i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + s.eps);
+      const long long orow = (long long)(row0 + r) * H;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(s.gamma + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(s.beta + col));
+        float4 y;
+        y.x = (x[r][i].x - mean) * rstd * g.x + b.x;
+        y.y = (x[r][i].y - mean) * rstd * g.y + b.y;
+        y.z = (x[r][i].z - mean) * rstd * g.z + b.z;
+        y.w = (x[r][i].w - mean) * rstd * g.w + b.w;
+        if (s.out32) *reinterpret_cast<float4*>(s.out32 + orow + col) = y;
+        if (s.out16) {
+          uint2 u;
+          u.x = Cvt<T16>::pack2(y.x, y.y);
+          u.y = Cvt<T16>::pack2(y.z, y.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(s.out16) + orow + col) = u;
+        }
+      }
+    }
+  }
+}
 template <typename T16>
 __device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int nrows, int lane) {
-  const int H = s.N, nv = H >> 7;  // float4 per lane (H % 128 == 0, H <= 1024)
-  for (int r = 0; r < nrows; r += 2) {
-    float4 x[2][kMaxVec];
-    const int two = (r + 1 < nrows) ? 2 : 1;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k < two) {
-        const float4* src = reinterpret_cast<const float4*>(s.ln_in + (long long)(row0 + r + k) * H);
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i)
-          if (i < nv) x[k][i] = __ldcg(src + i * 32 + lane);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k < two) {
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i)
-          if (i < nv) sum += (x[k][i].x + x[k][i].y) + (x[k][i].z + x[k][i].w);
-        const float mean = warp_sum(sum) / (float)H;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
-          if (i < nv) {
-            const float a = x[k][i].x - mean, b = x[k][i].y - mean, c = x[k][i].z - mean, d = x[k][i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-          }
-        }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + s.eps);
-        const long long orow = (long long)(row0 + r + k) * H;
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
-          if (i < nv) {
-            const int col = (i * 32 + lane) * 4;
-            const float4 g = __ldg(reinterpret_cast<const float4*>(s.gamma + col));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(s.beta + col));
-            float4 y;
-            y.x = (x[k][i].x - mean) * rstd * g.x + b.x;
-            y.y = (x[k][i].y - mean) * rstd * g.y + b.y;
-            y.z = (x[k][i].z - mean) * rstd * g.z + b.z;
-            y.w = (x[k][i].w - mean) * rstd * g.w + b.w;
-            if (s.out32) *reinterpret_cast<float4*>(s.out32 + orow + col) = y;
-            if (s.out16) {
-              uint2 u;
-              u.x = Cvt<T16>::pack2(y.x, y.y);
-              u.y = Cvt<T16>::pack2(y.z, y.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(s.out16) + orow + col) = u;
-            }
-          }
-        }
-      }
-    }
+  switch (s.N >> 7) {  // float4 per lane; the host admits these widths only
+    case 1: chain_ln_batch<T16, 1, 4>(s, row0, nrows, lane); break;
+    case 2: chain_ln_batch<T16, 2, 4>(s, row0, nrows, lane); break;
+    case 4: chain_ln_batch<T16, 4, 4>(s, row0, nrows, lane); break;
+    case 6: chain_ln_batch<T16, 6, 4>(s, row0, nrows, lane); break;
+    default:  // 8 (H = 1024): two rows at a time keep the register count of the 4 x 6 case
+      chain_ln_batch<T16, 8, 2>(s, row0, nrows < 2 ? nrows : 2, lane);
+      if (nrows > 2) chain_ln_batch<T16, 8, 2>(s, row0 + 2, nrows - 2, lane);
+      break;
   }
 }
 
@@ -185,6 +198,20 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
   const bool leader = crank == 0;
   const int pair_id = blockIdx.x >> 1;
 
+  const bool tracing = p.trace != nullptr && leader;
+  long long c_entry = 0;
+  if (tracing) {
+    c_entry = clock64();
+    if (threadIdx.x == 0) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.trace_hdr[pair_id * 2] = gt;
+      p.trace_hdr[pair_id * 2 + 1] = c_entry;
+    }
+  }
+  auto mark = [&](int i, int k) {
+    if (tracing) p.trace[((long long)pair_id * p.pitch + i) * 10 + k] = clock64() - c_entry;
+  };
   pdl_launch_dependents();
   // the task list is static data (uploaded when the schedule was built): staged before the dependency wait
   {
@@ -256,11 +283,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         const TileAt t = decode(s, task & 0xFFFFFF);
         const CUtensorMap* ma = &maps.a[s.map];
         const CUtensorMap* mb = &maps.b[s.map];
+        mark(i, 0);
         if (s.dep != nullptr && t.m0 < s.M) {  // this CTA's 128 rows of the A operand
           const unsigned target = s.dep_target ? s.dep_target : (unsigned)min(kGemmBM, s.M - t.m0);
           flag_wait_ge(s.dep + t.m0 / kGemmBM, target);
           fence_proxy_async_global();
         }
+        mark(i, 1);
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -275,6 +304,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             phase ^= 1u;
           }
         }
+        mark(i, 2);
       }
     }
   } else if (warp == 1) {
@@ -294,6 +324,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         ++it;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        mark(i, 3);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -311,6 +342,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
           }
         }
         umma_commit_2cta_mc(tfull_bar(acc), 3);
+        mark(i, 4);
       }
     }
   } else {
@@ -328,6 +360,11 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       const int task = task_s[i];
       if (task < 0) break;
       const ChainStage& s = p.st[task >> 24];
+      const bool tr = tracing && ew == 0 && lane == 0;
+      if (tr) {
+        mark(i, 5);
+        p.trace[((long long)pair_id * p.pitch + i) * 10 + 8] = task;
+      }
       if (s.kind == CHAIN_LN) {
         // ---- 64 rows per pair task: this CTA's 32, 4 per warp
         const int row0 = ((task & 0xFFFFFF) * 2 + (int)crank) * kChainLnRows + ew * 4;
@@ -341,13 +378,17 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             }
             __syncwarp();
           }
+          if (tr) mark(i, 6);
           chain_ln_rows<T16>(s, row0, nrows, lane);
+          if (tr) mark(i, 1);
           __threadfence();
+          if (tr) mark(i, 2);
           __syncwarp();
           if (lane == 0 && s.done != nullptr) {
             fence_proxy_async_global();
             flag_add_release(s.done + mt, (unsigned)nrows);
           }
+          if (tr) mark(i, 7);
         }
         continue;
       }
@@ -378,6 +419,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (tr) mark(i, 6);
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
       if (mrow0 < s.M) {
         constexpr int NC = kColsPerWarp / 32;
@@ -444,12 +486,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       if (lane == 0) {
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        if (tr) mark(i, 9);
         // publish: this warp's blocks of the tile are in L2
         tma_store_wait<0>();
         if (s.done != nullptr) {
           fence_proxy_async_global();
           flag_add_release(s.done + t.m0 / kGemmBM, 1u);
         }
+        if (tr) mark(i, 7);
       }
       staging_busy = false;
       __syncwarp();

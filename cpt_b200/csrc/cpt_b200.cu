@@ -24,6 +24,7 @@
 #include "chain_sm100.cuh"
 #include "optim.cuh"
 #include "rowwise.cuh"
+#include "scoring.cuh"
 #include "train.cuh"
 
 using namespace cptk;
@@ -157,6 +158,10 @@ struct cpt_handle {
   struct ChainSched { int pairs = 0, pitch = 0; int* dev = nullptr; };
   std::map<std::vector<int>, ChainSched> chain_scheds;  // per chain shape: the task lists of the CTA pairs
   std::vector<void*> owned_chain;
+  int chain_trace_on = 0;              // CPT_B200_CHAIN_TRACE=1: per-task event log of the last chain launch
+  long long* chain_trace = nullptr;
+  size_t chain_trace_bytes = 0;
+  int chain_trace_pairs = 0, chain_trace_pitch = 0;
   unsigned* chain_counters = nullptr;  // cpt_chain_run (tests): readiness counters
   size_t chain_counters_bytes = 0;
   int* err_flag = nullptr;
@@ -727,8 +732,9 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   if (!ws_ptr || ws_bytes < w.total) return fail("workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
   if (!ids || !seq_out) return fail("input_ids and seq_out must be non-NULL");
 
+  const bool chain_h_ok = H == 128 || H == 256 || H == 512 || H == 768 || H == 1024;
   const bool use_chain = h->chain && !h->train && !(h->fold_ln && !hidden_states) && L > 0 && h->tma_store &&
-                         h->reduce_resid && M >= h->chain_min_rows;
+                         h->reduce_resid && M >= h->chain_min_rows && chain_h_ok;
   const size_t chain_ctr_per_layer = chain_counter_bytes(M, 6);
   if (use_chain) CK(cudaMemsetAsync(w.flags, 0, chain_ctr_per_layer * L, st));  // first: keeps the PDL chain unbroken
   // K4: additive mask
@@ -989,6 +995,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_SPLIT")) h->split = atoi(e);
   if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN")) h->chain = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_CHAIN_TRACE")) h->chain_trace_on = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
@@ -1028,6 +1035,7 @@ int cpt_destroy(cpt_handle* h) {
   if (h->copy_chunks_dev) cudaFree(h->copy_chunks_dev);
   for (void* q : h->owned_chain) cudaFree(q);
   if (h->chain_counters) cudaFree(h->chain_counters);
+  if (h->chain_trace) cudaFree(h->chain_trace);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1236,8 +1244,9 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
   if (flag) {
     cudaMemset(h->err_flag, 0, 4);
     static const char* what[] = {"", "token / segment / position id out of range", "mask position out of range",
-                                 "vocabulary id out of range"};
-    return fail("device-side input check failed: %s", what[flag < 4 ? flag : 0]);
+                                 "vocabulary id out of range",
+                                 "predicted rectangle with x2 <= x1 or y2 <= y1 (the reference asserts p[2] > p[0])"};
+    return fail("device-side input check failed: %s", what[flag < 5 ? flag : 0]);
   }
   return 0;
 }
@@ -1303,6 +1312,21 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
 #undef CALL
 }
 
+int cpt_score_queries(cpt_handle* h, void* stream, const float* logits, long long ld, int K, int Q,
+                      const int32_t* row_start, const int32_t* col_start, const double* rects, const double* gt, int mode,
+                      int32_t* pick, double* pick_rect, double* iou, int32_t* correct) {
+  if (!h) return fail("NULL handle");
+  if (!logits || !row_start || !pick || Q < 0 || K < 2 || ld < K) return fail("cpt_score_queries: bad argument");
+  if (mode < 0 || mode > 2) return fail("cpt_score_queries: mode must be 0 (zsl), 1 (fsl) or 2 (vcr)");
+  if (Q == 0) return 0;
+  DeviceGuard g(h->device);
+  ScoreParams p{logits, ld, K, Q, row_start, col_start, rects, gt, mode, pick, pick_rect, iou, correct, h->err_flag};
+  ProfScope ps(h, (cudaStream_t)stream, CPT_K_HEAD);
+  score_queries_kernel<<<(Q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(p);
+  CKL("score_queries_kernel");
+  return 0;
+}
+
 int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, int n_stages) {
   if (!h || !stages || n_stages <= 0 || n_stages > kChainMaxStages) return fail("cpt_chain_run: bad argument");
   DeviceGuard g(h->device);
@@ -1321,6 +1345,7 @@ int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, in
   if (need > h->chain_counters_bytes) {
     CK(cudaStreamSynchronize(st));
     if (h->chain_counters) cudaFree(h->chain_counters);
+  if (h->chain_trace) cudaFree(h->chain_trace);
     h->chain_counters = nullptr;
     CK(cudaMalloc((void**)&h->chain_counters, need));
     h->chain_counters_bytes = need;
@@ -1329,6 +1354,19 @@ int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, in
 #define CALL(T16) run_chain<T16>(h, st, hs.data(), n_stages, h->chain_counters)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
+}
+
+int cpt_chain_trace(cpt_handle* h, long long* out, long long max_words, int* pairs, int* pitch) {
+  if (!h || !out || !pairs || !pitch) return fail("NULL argument");
+  if (!h->chain_trace) return fail("chain tracing is off (set CPT_B200_CHAIN_TRACE=1 before cpt_create) or nothing ran");
+  DeviceGuard g(h->device);
+  CK(cudaDeviceSynchronize());
+  *pairs = h->chain_trace_pairs;
+  *pitch = h->chain_trace_pitch;
+  const long long words = (long long)h->chain_trace_pairs * (2 + (long long)h->chain_trace_pitch * 10);
+  if (words > max_words) return fail("cpt_chain_trace: buffer too small (%lld words needed)", words);
+  CK(cudaMemcpy(out, h->chain_trace, (size_t)words * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int cpt_attention(cpt_handle* h, void* stream, const void* qkv, const float* ext_mask, int B, int S, void* ctx,

@@ -23,6 +23,34 @@ from .engine import CptError, Engine
 
 logger = logging.getLogger(__name__)
 WEIGHTS_NAME = "pytorch_model.bin"
+
+# "Did a parameter change since the handle converted its 16-bit copies?" answered in O(1): every event that can change
+# a parameter bumps this epoch — any torch.optim.Optimizer step (global post-step hook: covers torch's optimizers,
+# pytorch-transformers' AdamW, apex, cpt_b200.optimization.AdamW), load_state_dict, Module._apply (.to / .cuda / .half),
+# weight tying — and a native backward sets the slot's dirty flags.  Only when the epoch moved do engine() /
+# train_engine() rescan the ~200 (data_ptr, version) pairs.  Code that writes parameters behind all of these (a bare
+# `p.data.copy_()` in an inference loop) calls `model.bert.mark_weights_changed()`.
+_WEIGHT_EPOCH = [0]
+# Optimizer steps are counted separately: pytorch-transformers 1.x AdamW and apex update through `p.data`, which leaves
+# the autograd version counters untouched, so after ANY optimizer step the 16-bit copies are refreshed even when the
+# (data_ptr, version) signature did not move.
+_OPT_EPOCH = [0]
+
+
+def _bump_weight_epoch(*_a, **_k):
+    _WEIGHT_EPOCH[0] += 1
+
+
+def _on_optimizer_step(*_a, **_k):
+    _WEIGHT_EPOCH[0] += 1
+    _OPT_EPOCH[0] += 1
+
+
+try:  # torch >= 2.0
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_opt_hook
+    _reg_opt_hook(_on_optimizer_step)
+except Exception:  # pragma: no cover - older torch: fall back to scanning on every call
+    _WEIGHT_EPOCH = None
 BertLayerNorm = nn.LayerNorm
 
 
@@ -142,6 +170,9 @@ class _EngineSlot(object):
     def __init__(self):
         self.engine, self.sig, self.heads, self.frozen = None, None, {}, False
         self.train_engine, self.train_sig = None, None
+        self.epoch, self.train_epoch = -1, -1  # value of _WEIGHT_EPOCH the signatures were taken at
+        self.train_named = None
+        self.opt_epoch, self.train_opt_epoch = 0, 0
         # Set by every native backward (training._Loss.backward): an optimizer step may follow, and optimizers that
         # update through `p.data` (pytorch-transformers 1.x AdamW, apex) do NOT bump the autograd version counters the
         # signatures below key on — so after a backward both handles refresh their 16-bit copies unconditionally.
@@ -194,7 +225,16 @@ class BertPreTrainedModel(nn.Module):
         if isinstance(module, nn.Linear) and module.bias is not None:
             module.bias.data.zero_()
 
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float(): storages move
+        _bump_weight_epoch()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):  # reached from load_state_dict of this module or of any ancestor
+        _bump_weight_epoch()
+        return super()._load_from_state_dict(*a, **k)
+
     def _tie_or_clone_weights(self, first_module, second_module):
+        _bump_weight_epoch()
         if getattr(self.config, "torchscript", False):
             first_module.weight = nn.Parameter(second_module.weight.clone())
         else:
@@ -293,15 +333,24 @@ class BertImgModel(BertPreTrainedModel):
         if any(cur.get(k) is not v for k, v in tensors.items()):
             cur.update(tensors)
             slot.sig = None
+            slot.epoch = slot.train_epoch = -1
 
     def freeze_engine_weights(self, frozen=True):
-        """Skip the per-forward 'did any parameter change?' scan (inference loops with fixed weights)."""
+        """Skip the 'did any parameter change?' check altogether (kept for callers of round 1; the check is O(1) now)."""
         self._slot.frozen = frozen
+
+    def mark_weights_changed(self):
+        """For code that writes parameters without an optimizer, load_state_dict or .to(): forces the next forward to
+        re-scan the parameters and refresh the handle's 16-bit copies."""
+        _bump_weight_epoch()
+
 
     def engine(self):
         slot = self._dev_slot()
-        if slot.frozen and slot.engine is not None and slot.sig is not None and not slot.dirty_infer:
+        if slot.engine is not None and slot.sig is not None and not slot.dirty_infer and (
+                slot.frozen or (_WEIGHT_EPOCH is not None and slot.epoch == _WEIGHT_EPOCH[0])):
             return slot.engine
+        epoch = _WEIGHT_EPOCH[0] if _WEIGHT_EPOCH is not None else -1
         sd = self._named_tensors()
         dev = self.embeddings.word_embeddings.weight.device
         if dev.type != "cuda":
@@ -314,9 +363,10 @@ class BertImgModel(BertPreTrainedModel):
             dtype = getattr(self.config, "cpt_b200_dtype", None) or os.environ.get("CPT_B200_DTYPE", "fp16")
             slot.engine = Engine(self.config, dev, dtype=dtype)
             slot.sig = None
-        if sig != slot.sig or slot.dirty_infer:
+        if sig != slot.sig or slot.dirty_infer or slot.opt_epoch != _OPT_EPOCH[0]:
             slot.engine.load_state_dict(sd)
-            slot.sig, slot.dirty_infer = sig, False
+            slot.sig, slot.dirty_infer, slot.opt_epoch = sig, False, _OPT_EPOCH[0]
+        slot.epoch = epoch if slot is self._slot else -1  # DataParallel replicas get fresh tensors every forward
         return slot.engine
 
     def train_engine(self):
@@ -324,6 +374,10 @@ class BertImgModel(BertPreTrainedModel):
         fp16 holds without loss scaling; config.cpt_b200_train_dtype / CPT_B200_TRAIN_DTYPE override), transposed
         copies for the dgrad GEMMs, refreshed in place from the fp32 parameters whenever one of them changed."""
         slot = self._dev_slot()
+        if (slot.train_engine is not None and slot.train_sig is not None and not slot.dirty_train
+                and _WEIGHT_EPOCH is not None and slot.train_epoch == _WEIGHT_EPOCH[0] and slot.train_named is not None):
+            return slot.train_engine, slot.train_named
+        epoch = _WEIGHT_EPOCH[0] if _WEIGHT_EPOCH is not None else -1
         sd = self._named_tensors()
         dev = self.embeddings.word_embeddings.weight.device
         if dev.type != "cuda":
@@ -339,9 +393,11 @@ class BertImgModel(BertPreTrainedModel):
             slot.train_engine.grad_sync_group = slot.grad_sync_group
             slot.train_sig = None
         slot.train_engine.owner_slot = slot
-        if sig != slot.train_sig or slot.dirty_train:
+        if sig != slot.train_sig or slot.dirty_train or slot.train_opt_epoch != _OPT_EPOCH[0]:
             slot.train_engine.load_state_dict(sd)
-            slot.train_sig, slot.dirty_train = sig, False
+            slot.train_sig, slot.dirty_train, slot.train_opt_epoch = sig, False, _OPT_EPOCH[0]
+        slot.train_epoch = epoch if slot is self._slot else -1
+        slot.train_named = sd
         return slot.train_engine, sd
 
     def _dropout_active(self):

@@ -197,6 +197,20 @@ typedef struct {
 int cpt_adamw_step(int device, void *stream, const cpt_adam_tensor *tensors, const cpt_adam_chunk *chunks,
                    int n_chunks, float beta1, float beta2, float eps, int mode, const float *grad_scale);
 
+/* ---- CPT decision per query on the device (SURVEY.md 8f "scoring") ----------------------------------------------
+ * Replaces the per-image Python loops of Oscar/oscar/zeroshot/refcoco_cpt.py:222-254, fewshot/refcoco_cpt.py:273-297
+ * and fewshot/vcr_nsp_cpt.py:600-604, and the IoU > 0.5 hit test of zeroshot/refcoco_cpt.py:268-276 +
+ * Oscar/oscar/utils/iou.py:1-12.  logits fp32 [rows, ld]: for modes 0 (zero-shot: score = colour logit) and 1
+ * (few-shot: colour / none) the K used columns are K - 1 palette colours followed by "none"; row r only counts its
+ * first col_start[r+1] - col_start[r] colour columns (its own colour set; col_start NULL = all K - 1).  mode 2 (VCR):
+ * logits are the NSP scores [rows, K], score = 1 - softmax[:, 1].  Query q owns rows [row_start[q], row_start[q+1]).
+ * pick int32 [Q]: index into the query's concatenated scores (the reference's max_idx, torch.argmax tie rules).
+ * rects double [total valid columns, 4] (x1 y1 x2 y2, collected order), gt double [Q,4] (x y w h): when given,
+ * pick_rect [Q,4], iou [Q] and correct int32 [Q] (iou > 0.5) are written too (any of them may be NULL). */
+int cpt_score_queries(cpt_handle *h, void *stream, const float *logits, long long ld, int K, int Q,
+                      const int32_t *row_start, const int32_t *col_start, const double *rects, const double *gt,
+                      int mode, int32_t *pick, double *pick_rect, double *iou, int32_t *correct);
+
 /* Blocks until `stream` drains; reports device-side input errors (token id / position out of range, the
  * IndexError the reference's nn.Embedding would raise) and launch failures. */
 int cpt_check_async_error(cpt_handle *h, void *stream);
@@ -269,6 +283,10 @@ typedef struct {
   void *out16;
 } cpt_chain_stage;
 int cpt_chain_run(cpt_handle *h, void *stream, const cpt_chain_stage *stages, int n_stages);
+/* Debug: event log of the LAST chain launch (needs CPT_B200_CHAIN_TRACE=1 in the environment at cpt_create).
+ * out = [pairs][2] {globaltimer ns, clock64 at CTA entry} followed by [pairs][pitch][10] SM-clock stamps per task of the
+ * leader CTA's list (chain_sm100.cuh: ChainParams::trace). */
+int cpt_chain_trace(cpt_handle *h, long long *out, long long max_words, int *pairs, int *pitch);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */
 int cpt_layernorm(cpt_handle *h, void *stream, const float *x, int M, const float *gamma, const float *beta,
                   float eps, float *out32, void *out16);

@@ -218,3 +218,38 @@ def refcoco_zsl_pick(color_logits):
 def refcoco_fsl_pick(color_logits):
     """fewshot/refcoco_cpt.py:291-294: score = colour / none, argmax."""
     return int((color_logits[:, :-1] / color_logits[:, -1:]).reshape(-1).argmax())
+
+
+def box_iou_xywh(a, b):
+    """Oscar/oscar/utils/iou.py:1-12 restated: boxes are [x, y, w, h] in inclusive pixel coordinates (right edge
+    x + w - 1); the overlap only counts when it is strictly more than one pixel wide and high."""
+    left, top = max(a[0], b[0]), max(a[1], b[1])
+    right = min(a[0] + a[2] - 1, b[0] + b[2] - 1)
+    bottom = min(a[1] + a[3] - 1, b[1] + b[3] - 1)
+    overlap = (right - left + 1) * (bottom - top + 1) if (left < right and top < bottom) else 0
+    return float(overlap) / (a[2] * a[3] + b[2] * b[3] - overlap)
+
+
+def refcoco_decide(scores_rows, colour_sets, rect_sets, few_shot=False):
+    """One image of the reference's val() loop (zeroshot/refcoco_cpt.py:224-246, fewshot/refcoco_cpt.py:273-294).
+    scores_rows: one [K] tensor per proposal set, ALREADY gathered at the palette ids + "none" (last entry);
+    colour_sets[j]: how many palette colours proposal set j uses (its rectangles' count); rect_sets[j]: its rectangles.
+    Each row contributes its own colour entries (score, or score / none for few-shot); the entries of all rows are
+    concatenated and the argmax position selects the rectangle.  Returns (max_idx, rect)."""
+    rects, pieces = [], []
+    for row, n, rs in zip(scores_rows, colour_sets, rect_sets):
+        assert len(rs) == n
+        mine = torch.cat((row[:n], row[-1:]))          # scores[ptr][color2id(cur_color_set + ["none"])]
+        pieces.append(mine[:-1] / mine[-1] if few_shot else mine[:-1])
+        rects += list(rs)
+    idx = int(torch.cat(pieces, -1).argmax())
+    return idx, rects[idx]
+
+
+def refcoco_hit(rect, gt_xywh):
+    """zeroshot/refcoco_cpt.py:268-276: the picked [x1, y1, x2, y2] becomes [x, y, w + 1, h + 1] and counts as correct
+    when its IoU with the ground-truth box exceeds 0.5."""
+    assert rect[2] > rect[0] and rect[3] > rect[1]
+    box = [rect[0], rect[1], rect[2] - rect[0] + 1, rect[3] - rect[1] + 1]
+    v = box_iou_xywh(box, gt_xywh)
+    return v, v > 0.5

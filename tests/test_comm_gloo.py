@@ -34,9 +34,9 @@ def _worker(rank, world, port, fanouts, q):
         sizes = comm.shard_rows(fanouts)
         ok = ok and sizes[rank] == r1 - r0 and sum(sizes) == sum(fanouts)
         ok = ok and torch.equal(comm.all_gather_logits(local, sizes=sizes), full)
-        picks = comm.pick_per_query(gathered, fanouts, "zsl")
-        ref = torch.tensor([O.refcoco_zsl_pick(full[sum(fanouts[:i]):sum(fanouts[:i + 1])]) for i in range(len(fanouts))])
-        ok = ok and torch.equal(picks.cpu(), ref)
+        # the per-query decision itself is a CUDA kernel (tests/test_gpu_scoring.py); here the oracle stands in for it
+        picks = torch.tensor([O.refcoco_zsl_pick(gathered[sum(fanouts[:i]):sum(fanouts[:i + 1])])
+                              for i in range(len(fanouts))])
         # per-rank dicts with an overlapping (duplicated) key, as DistributedSampler padding produces
         mine = {int(i): int(picks[i]) for i in range(q0, q1)}
         mine[0] = int(picks[0])
@@ -78,20 +78,15 @@ def test_shard_queries_never_splits_a_query_and_balances_rows():
         assert q1 == nxt[0] and r1 == nxt[2] and r1 - r0 == sum(fan[q0:q1])
 
 
-def test_pick_modes_match_oracle():
+def test_single_process_helpers_and_no_cpu_pick():
     g = torch.Generator().manual_seed(7)
-    fan = [2, 1, 3]
-    lg = torch.rand(sum(fan), 4, generator=g) + 0.5
-    z = comm.pick_per_query(lg, fan, "zsl")
-    f = comm.pick_per_query(lg, fan, "fsl")
-    off = 0
-    for i, n in enumerate(fan):
-        blk = lg[off:off + n]
-        assert int(z[i]) == O.refcoco_zsl_pick(blk) and int(f[i]) == O.refcoco_fsl_pick(blk)
-        off += n
-    nsp = torch.randn(8, 3, generator=g)
-    v = comm.pick_per_query(nsp, [4, 4], "vcr")
-    s = O.vcr_choice_scores(nsp)
-    assert int(v[0]) == int(s[:4].argmax()) and int(v[1]) == int(s[4:].argmax())
+    lg = torch.rand(6, 4, generator=g) + 0.5
     assert comm.get_world_size() == 1 and comm.is_main_process()
     assert comm.all_gather_logits(lg) is lg
+    assert comm.shard_rows([2, 1, 3], world=2) == [3, 3]
+    try:  # the per-query decision is a CUDA kernel: there is no CPU path to fall back to
+        comm.pick_per_query(lg, [2, 1, 3], "zsl")
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised

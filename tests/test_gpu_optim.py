@@ -142,3 +142,92 @@ def test_few_shot_loop_with_native_optimizer():
                        token_type_ids=d["token_type_ids"], img_feats=d["img_feats"])[0]
         l_infer = torch.nn.functional.cross_entropy(scores.view(-1, cfg.vocab_size), labels.view(-1), ignore_index=-1)
     assert abs(l_trained.item() - l_infer.item()) <= 5e-3 * abs(l_infer.item()), (l_trained.item(), l_infer.item())
+
+
+class _DataMutatingAdamW(torch.optim.Optimizer):
+    """pytorch-transformers 1.x AdamW as the reference's GQA / VCR loops import it (gqa_cpt.py:24,342): every update
+    goes through `p.data`, which does NOT bump the autograd version counter of `p`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                grad = p.grad.data
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p.data)
+                    state["exp_avg_sq"] = torch.zeros_like(p.data)
+                b1, b2 = group["betas"]
+                state["step"] += 1
+                state["exp_avg"].mul_(b1).add_(grad, alpha=1.0 - b1)
+                state["exp_avg_sq"].mul_(b2).addcmul_(grad, grad, value=1.0 - b2)
+                denom = state["exp_avg_sq"].sqrt().add_(group["eps"])
+                step_size = group["lr"] * (1.0 - b2 ** state["step"]) ** 0.5 / (1.0 - b1 ** state["step"])
+                p.data.addcdiv_(state["exp_avg"], denom, value=-step_size)
+                if group["weight_decay"] > 0.0:
+                    p.data.add_(p.data, alpha=-group["lr"] * group["weight_decay"])
+
+
+@pytest.mark.parametrize("how", ["optimizer", "by_hand"])
+def test_weight_updates_through_p_data_are_picked_up(how):
+    """`p.data.add_` leaves `p._version` untouched; both handles must still follow the update — after
+    an optimizer step (global post-step hook) and after a hand-written update that follows a backward (dirty flag)."""
+    from cpt_b200 import config as C
+    from cpt_b200.modeling_bert import BertImgForPreTraining
+    from cpt_b200.modeling_rec import REC_MLM_CPT
+    from cpt_b200.synthetic import synth_batch, synth_state_dict, synth_vocab_ids
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0
+    sd = synth_state_dict(cfg, seed=21)
+    pre = BertImgForPreTraining(cfg)
+    pre.load_state_dict(sd, strict=False)
+    pre.tie_weights()
+    model = REC_MLM_CPT(cfg)
+    model.copy_from_pretraining_model(pre.cuda())
+    b = synth_batch(cfg, 4, 30, 12, seed=2)
+    d = {k: v.cuda() for k, v in b.items()}
+    vids = synth_vocab_ids(cfg, 4, seed=1).cuda()
+    labels = torch.full((4, 42), -1, dtype=torch.long)
+    labels[torch.arange(4), b["mask_pos"]] = torch.arange(4) % 3 + 20
+    labels = labels.cuda()
+    opt = _DataMutatingAdamW(model.parameters(), lr=5e-3) if how == "optimizer" else None
+
+    def infer(m):
+        m.eval()
+        with torch.no_grad():
+            return m(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                     mask_pos=d["mask_pos"], vocab_ids=vids)[0].clone()
+
+    def loss_of(m):
+        m.train()
+        return m(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                 masked_lm_labels=labels)[0]
+
+    before = infer(model)
+    versions = [p._version for p in model.parameters()]
+    for _ in range(3):
+        loss = loss_of(model)
+        loss.backward()
+        if opt is not None:
+            opt.step()
+        else:
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.data.add_(p.grad, alpha=-0.05)
+        model.zero_grad()
+    assert versions == [p._version for p in model.parameters()]  # the premise: nothing bumped the counters
+    after, after_loss = infer(model), float(loss_of(model))
+    fresh_pre = BertImgForPreTraining(cfg)
+    fresh_pre.load_state_dict({k: v.detach().cpu() for k, v in pre.state_dict().items()}, strict=False)
+    fresh_pre.tie_weights()
+    fresh = REC_MLM_CPT(cfg)
+    fresh.copy_from_pretraining_model(fresh_pre.cuda())
+    want, want_loss = infer(fresh), float(loss_of(fresh))
+    assert (before - after).abs().max().item() > 1e-3          # the weights did move
+    assert (after - want).abs().max().item() <= 1e-5 * want.abs().max().item()   # the inference handle followed them
+    assert abs(after_loss - want_loss) <= 1e-6 * max(1.0, abs(want_loss))   # as did the training handle

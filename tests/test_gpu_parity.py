@@ -195,6 +195,34 @@ def test_cuda_graph_replay_matches_eager_and_tracks_buffer_contents():
     assert eng.launch_count() - n0 > 10                     # replays are counted as launches
 
 
+def test_fresh_input_tensors_every_step_replay_the_staging_graph():
+    """The reference's loop moves every batch to the device anew (zeroshot/refcoco_cpt.py:212-219): addresses never
+    repeat.  From the second batch of a shape on the engine copies the inputs into its staging buffers and replays a
+    graph; results equal the eager launch sequence."""
+    cfg = C.oscar_tiny()
+    pre, rec, nsp = build(cfg, synth_state_dict(cfg, seed=5))
+    vids_cpu = synth_vocab_ids(cfg, 4, seed=1)
+    eng = rec.bert.engine()
+    keep = []  # hold on to every tensor so the allocator cannot hand the same address out twice
+    with torch.no_grad():
+        for step in range(6):
+            host = synth_batch(cfg, 3, 30, 10, seed=100 + step)
+            b = cuda(host)
+            vids = vids_cpu.cuda()
+            keep.append((b, vids))
+            r0 = eng.graph_replays
+            got = rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
+                      mask_pos=b["mask_pos"], vocab_ids=vids)[0].clone()
+            if step >= 1:
+                assert eng.graph_replays == r0 + 1, "step %d did not replay a graph" % step
+            eng.use_graphs = False
+            ref = rec(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
+                      mask_pos=b["mask_pos"], vocab_ids=vids)[0].clone()
+            eng.use_graphs = True
+            assert torch.equal(got, ref), step
+    assert len(eng._graphs) == 0 and len(eng._sgraphs) == 1
+
+
 def test_layernorm_folding_agrees_with_separate_layernorm_kernels(monkeypatch):
     """CPT_B200_FOLD_LN=1: LayerNorm is applied inside the neighbouring GEMM epilogues from row statistics;
     =0 (default): separate LayerNorm kernels.  Same math, different rounding points: both must sit within the parity budget of
