@@ -80,6 +80,7 @@ SYMBOLS = {
     "cpt_mlm_scores_forward": (_i, [_p, _p, _p, _ll, _p, _sz, _p]),
     "cpt_mlm_scores_workspace_bytes": (_sz, [_p, _ll]),
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
+    "cpt_head_linear": (_i, [_p, _p, _p, _i, _p, _p, _i, _p]),
     "cpt_train_enable": (_i, [_p, _i]),
     "cpt_train_set_progress_callback": (_i, [_p, _p, _p]),
     "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),
@@ -92,6 +93,7 @@ SYMBOLS = {
     "cpt_train_backward_nsp": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, C.POINTER(Dropout), _p, _p, _sz,
                                     C.POINTER(Grads)]),
     "cpt_adamw_step": (_i, [_i, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
+    "cpt_grad_clip_scale": (_i, [_i, _p, _p, _p, _i, _f, _p, _p, _p, _p]),
     "cpt_score_queries": (_i, [_p, _p, _p, _ll, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),

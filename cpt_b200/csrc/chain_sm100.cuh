@@ -112,8 +112,9 @@ __device__ __forceinline__ void flag_wait_ge(const unsigned* addr, unsigned targ
 // rate (the first version, two rows in flight, took 11 us per 32-row task; the event log showed it on the critical
 // path of the whole chain).
 template <typename T16, int NV, int ROWS>
-__device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int nrows, int lane) {
+__device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int nrows, int lane, long long* tmark) {
   constexpr int H = NV * 128;
+  const long long t_begin = tmark ? clock64() : 0;
   float4 x[ROWS][NV];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
@@ -130,6 +131,7 @@ __device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int n
 #pragma unroll
       for (int i = 0; i < NV; ++i) sum += (x[r][i].x + x[r][i].y) + (x[r][i].z + x[r][i].w);
       const float mean = warp_sum(sum) / (float)H;
+      if (tmark && r == 0) tmark[0] = clock64() - t_begin;   // row 0 arrived
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -137,6 +139,7 @@ __device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int n
         q += (a * a + b * b) + (c * c + d * d);
       }
       const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + s.eps);
+      if (tmark && r == 0) tmark[3] = clock64() - t_begin;   // row 0 statistics done
       const long long orow = (long long)(row0 + r) * H;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -156,19 +159,20 @@ __device__ __noinline__ void chain_ln_batch(const ChainStage& s, int row0, int n
           *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(s.out16) + orow + col) = u;
         }
       }
+      if (tmark && r == 0) tmark[4] = clock64() - t_begin;   // row 0 stored
     }
   }
 }
 template <typename T16>
-__device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int nrows, int lane) {
+__device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int nrows, int lane, long long* tmark) {
   switch (s.N >> 7) {  // float4 per lane; the host admits these widths only
-    case 1: chain_ln_batch<T16, 1, 4>(s, row0, nrows, lane); break;
-    case 2: chain_ln_batch<T16, 2, 4>(s, row0, nrows, lane); break;
-    case 4: chain_ln_batch<T16, 4, 4>(s, row0, nrows, lane); break;
-    case 6: chain_ln_batch<T16, 6, 4>(s, row0, nrows, lane); break;
+    case 1: chain_ln_batch<T16, 1, 4>(s, row0, nrows, lane, tmark); break;
+    case 2: chain_ln_batch<T16, 2, 4>(s, row0, nrows, lane, tmark); break;
+    case 4: chain_ln_batch<T16, 4, 4>(s, row0, nrows, lane, tmark); break;
+    case 6: chain_ln_batch<T16, 6, 4>(s, row0, nrows, lane, tmark); break;
     default:  // 8 (H = 1024): two rows at a time keep the register count of the 4 x 6 case
-      chain_ln_batch<T16, 8, 2>(s, row0, nrows < 2 ? nrows : 2, lane);
-      if (nrows > 2) chain_ln_batch<T16, 8, 2>(s, row0 + 2, nrows - 2, lane);
+      chain_ln_batch<T16, 8, 2>(s, row0, nrows < 2 ? nrows : 2, lane, tmark);
+      if (nrows > 2) chain_ln_batch<T16, 8, 2>(s, row0 + 2, nrows - 2, lane, nullptr);
       break;
   }
 }
@@ -379,7 +383,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             __syncwarp();
           }
           if (tr) mark(i, 6);
-          chain_ln_rows<T16>(s, row0, nrows, lane);
+          chain_ln_rows<T16>(s, row0, nrows, lane,
+                             tr ? p.trace + ((long long)pair_id * p.pitch + i) * 10 : nullptr);
           if (tr) mark(i, 1);
           __threadfence();
           if (tr) mark(i, 2);

@@ -1169,6 +1169,16 @@ int cpt_nsp_forward(cpt_handle* h, void* stream, const float* pooled, int B, flo
                      nullptr, C, B, H, C, ACT_NONE, out, C);
 }
 
+int cpt_head_linear(cpt_handle* h, void* stream, const float* x, int B, const float* W, const float* bias, int C,
+                    float* out) {
+  if (!h) return fail("NULL handle");
+  if (!x || !W || !out || B <= 0 || C <= 0) return fail("cpt_head_linear: bad argument");
+  DeviceGuard g(h->device);
+  const int H = h->cfg.hidden_size;
+  return head_matvec(h, (cudaStream_t)stream, x, H, 1, nullptr, nullptr, nullptr, 0.f, W, H, bias, nullptr, C, B, H, C,
+                     ACT_NONE, out, C);
+}
+
 int cpt_train_enable(cpt_handle* h, int on) {
   if (!h) return fail("NULL handle");
   if ((h->train != 0) != (on != 0)) h->has_weights = false;  // the next cpt_set_weights rebuilds the copies
@@ -1232,6 +1242,19 @@ int cpt_adamw_step(int device, void* stream, const cpt_adam_tensor* tensors, con
                                                            reinterpret_cast<const AdamChunk*>(chunks), beta1, beta2, eps,
                                                            mode, grad_scale);
   CKL("adamw_kernel");
+  return 0;
+}
+
+int cpt_grad_clip_scale(int device, void* stream, const cpt_adam_tensor* tensors, const cpt_adam_chunk* chunks,
+                        int n_chunks, float max_norm, const float* grad_scale_in, void* scratch, float* norm_out,
+                        float* scale_out) {
+  if (!tensors || !chunks || n_chunks <= 0 || !scratch || !norm_out || !scale_out || !(max_norm > 0.f))
+    return fail("cpt_grad_clip_scale: bad argument");
+  DeviceGuard g(device);
+  grad_clip_scale_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const AdamChunk*>(chunks), max_norm, grad_scale_in,
+      reinterpret_cast<double*>(scratch), norm_out, scale_out);
+  CKL("grad_clip_scale_kernel");
   return 0;
 }
 

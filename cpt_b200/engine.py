@@ -583,6 +583,18 @@ class Engine(object):
             _lib.check(self.lib.cpt_nsp_forward(self._h, _stream(), _ptr(p), B, _ptr(out)))
         return out
 
+    def head_linear(self, pooled, weight, bias):
+        """out[B,C] = pooled W^T + b with caller-held fp32 weights (VCRQAR_NSPCPT's per-call head choice)."""
+        dev = self.device
+        p = _chk_tensor("pooled_output", pooled, torch.float32, dev)
+        w = _chk_tensor("head weight", weight.detach(), torch.float32, dev, (weight.shape[0], self.cfg.hidden_size))
+        b = None if bias is None else _chk_tensor("head bias", bias.detach(), torch.float32, dev, (weight.shape[0],))
+        with torch.cuda.device(dev):
+            out = torch.empty(p.shape[0], w.shape[0], dtype=torch.float32, device=dev)
+            _lib.check(self.lib.cpt_head_linear(self._h, _stream(), _ptr(p), p.shape[0], _ptr(w), _ptr(b), w.shape[0],
+                                                _ptr(out)))
+        return out
+
     def check(self):
         """Synchronise and surface device-side input errors (out-of-range ids, the reference's IndexError)."""
         with torch.cuda.device(self.device):

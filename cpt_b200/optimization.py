@@ -38,10 +38,16 @@ class AdamW(Optimizer):
         self.torch_semantics = bool(torch_semantics)
         self._lib = _lib.load()
         self._chunks = {}  # (numel tuple) -> device chunk table
+        self._clip_state = {}  # device -> (scratch, [norm, scale]) of the fused gradient clipping
+        self.last_grad_norm = None
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=None):
-        """grad_scale: optional fp32 device scalar every gradient is multiplied by inside the update."""
+    def step(self, closure=None, grad_scale=None, max_grad_norm=None):
+        """grad_scale: optional fp32 device scalar every gradient is multiplied by inside the update.
+        max_grad_norm: fuses `torch.nn.utils.clip_grad_norm_(parameters, max_grad_norm)` (gqa_cpt.py:454) into the
+        step: one extra launch reduces the global gradient norm on the device and the update multiplies every gradient
+        by min(1, max_norm / (norm + 1e-6)) as it reads it — the gradients are left untouched and nothing
+        synchronises.  The norm of the last such step is kept in `self.last_grad_norm` (a device scalar)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -49,7 +55,7 @@ class AdamW(Optimizer):
         # betas / eps are per launch: one launch per distinct (betas, eps) among the groups (normally one)
         launches = {}
         for group in self.param_groups:
-            key = (tuple(group["betas"]), float(group["eps"]))
+            bkey = (tuple(group["betas"]), float(group["eps"]))
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -65,20 +71,48 @@ class AdamW(Optimizer):
                     state["step"] = 0
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                state["step"] += 1
-                launches.setdefault(key, []).append((p, group, state))
-        for (betas, eps), items in launches.items():
+                elif not isinstance(state["step"], int):  # a checkpoint of torch.optim.AdamW stores a tensor
+                    state["step"] = int(state["step"])
+                # one launch per (device, betas, eps): a launch runs on one device with that device's pointers
+                launches.setdefault((p.device,) + bkey, []).append((p, group, state))
+        if max_grad_norm is not None and launches:
+            grad_scale = self._clip_scale([it for items in launches.values() for it in items], float(max_grad_norm),
+                                          grad_scale)
+        for (_dev, betas, eps), items in launches.items():
             self._launch(items, betas, eps, grad_scale)
+            for _p, _g, state in items:  # counted only once the launch has been enqueued
+                state["step"] += 1
         return loss
 
-    def _launch(self, items, betas, eps, grad_scale):
+    def _clip_scale(self, items, max_norm, grad_scale):
+        devs = {p.device for p, _, _ in items}
+        if len(devs) != 1:
+            raise RuntimeError("cpt_b200.optimization.AdamW: max_grad_norm needs all parameters on one device")
+        dev = items[0][0].device
+        tdev, ck, keep = self._tables(items, (0.0, 0.0))
+        st = self._clip_state.get(dev)
+        if st is None:
+            st = (torch.zeros(2, dtype=torch.float64, device=dev), torch.zeros(2, dtype=torch.float32, device=dev))
+            self._clip_state[dev] = st
+        scratch, out = st
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.cpt_grad_clip_scale(
+                dev.index, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(tdev.data_ptr()),
+                C.c_void_p(ck[0].data_ptr()), ck[1], max_norm,
+                C.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else C.c_void_p(0),
+                C.c_void_p(scratch.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + 4)))
+        del keep
+        self.last_grad_norm = out[0]
+        return out[1:2]
+
+    def _tables(self, items, betas):
         dev = items[0][0].device
         tab = np.zeros(len(items), dtype=_TENSOR)
         keep = []
         for i, (p, group, state) in enumerate(items):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             keep.append(g)
-            t = state["step"]
+            t = state["step"] + 1  # the step this launch performs
             correct = group["correct_bias"] or self.torch_semantics
             tab[i] = (p.data_ptr(), g.data_ptr(), state["exp_avg"].data_ptr(), state["exp_avg_sq"].data_ptr(),
                       p.numel(), group["lr"], group["weight_decay"],
@@ -94,6 +128,11 @@ class AdamW(Optimizer):
             ck = (torch.from_numpy(arr.view(np.uint8).copy()).to(dev), len(rows))
             self._chunks[(dev, sizes)] = ck
         tdev = torch.from_numpy(tab.view(np.uint8)).pin_memory().to(dev, non_blocking=True)
+        return tdev, ck, keep
+
+    def _launch(self, items, betas, eps, grad_scale):
+        dev = items[0][0].device
+        tdev, ck, keep = self._tables(items, betas)
         with torch.cuda.device(dev):
             _lib.check(self._lib.cpt_adamw_step(
                 dev.index, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(tdev.data_ptr()),

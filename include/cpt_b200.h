@@ -97,6 +97,12 @@ size_t cpt_mlm_scores_workspace_bytes(const cpt_handle *h, long long rows);
 /* NSPCPT head: cls.seq_relationship(pooled) — Oscar/oscar/modeling/modeling_vcr.py:120-121.  out fp32 [B,C]. */
 int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, float *out);
 
+/* A classification head on the pooled vector with CALLER-held weights: out[B,C] = x[B,H] W[C,H]^T + bias, all fp32
+ * device pointers — the two heads of VCRQAR_NSPCPT (`cls_ans` / `cls_rat`, Oscar/oscar/modeling/modeling_vcr.py:
+ * 194-252, selected per call by `head=`) without re-registering the handle's weights at every switch. */
+int cpt_head_linear(cpt_handle *h, void *stream, const float *x, int B, const float *W, const float *bias, int C,
+                    float *out);
+
 /* ---- training step ------------------------------------------------------------------
  * loss = CrossEntropyLoss(ignore_index=-1)(cls(bert(...)).view(-1, V), masked_lm_labels.view(-1)) and its gradient
  * with respect to every parameter — REC_MLM_CPT.forward with masked_lm_labels, modeling_rec.py:137-150, as the
@@ -196,6 +202,15 @@ typedef struct {
 } cpt_adam_chunk;
 int cpt_adamw_step(int device, void *stream, const cpt_adam_tensor *tensors, const cpt_adam_chunk *chunks,
                    int n_chunks, float beta1, float beta2, float eps, int mode, const float *grad_scale);
+
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm) (Oscar/oscar/fewshot/gqa_cpt.py:454, vcr_nsp_cpt.py) fused with
+ * the update: one launch over the same tables computes norm_out = ||grad_scale_in * g||_2 over ALL tensors and
+ * scale_out = grad_scale_in * min(1, max_norm / (norm + 1e-6)); pass scale_out as cpt_adamw_step's grad_scale.  The
+ * gradients themselves are not modified.  scratch: 16 bytes of device memory, zeroed once by the caller (the kernel
+ * leaves it zeroed).  grad_scale_in may be NULL (= 1). */
+int cpt_grad_clip_scale(int device, void *stream, const cpt_adam_tensor *tensors, const cpt_adam_chunk *chunks,
+                        int n_chunks, float max_norm, const float *grad_scale_in, void *scratch, float *norm_out,
+                        float *scale_out);
 
 /* ---- CPT decision per query on the device (SURVEY.md 8f "scoring") ----------------------------------------------
  * Replaces the per-image Python loops of Oscar/oscar/zeroshot/refcoco_cpt.py:222-254, fewshot/refcoco_cpt.py:273-297

@@ -231,3 +231,39 @@ def test_weight_updates_through_p_data_are_picked_up(how):
     assert (before - after).abs().max().item() > 1e-3          # the weights did move
     assert (after - want).abs().max().item() <= 1e-5 * want.abs().max().item()   # the inference handle followed them
     assert abs(after_loss - want_loss) <= 1e-6 * max(1.0, abs(want_loss))   # as did the training handle
+
+
+@pytest.mark.parametrize("max_norm,gs", [(1.0, None), (0.05, None), (1e6, None), (1.0, 1.0 / 64.0)])
+def test_fused_global_norm_clip_matches_clip_grad_norm(max_norm, gs):
+    """optimizer.step(max_grad_norm=m) == torch.nn.utils.clip_grad_norm_(params, m); optimizer.step()
+    (gqa_cpt.py:454-456): same norm, same update, gradients left untouched."""
+    from cpt_b200.optimization import AdamW
+    gen = torch.Generator().manual_seed(9)
+    host = make_params(gen)
+    grads = [torch.randn(*t.shape, generator=gen) * (0.01 + 0.3 * i) for i, t in enumerate(host)]
+
+    def fresh():
+        ps = [torch.nn.Parameter(t.clone().cuda()) for t in host]
+        for p, g in zip(ps, grads):
+            p.grad = (g / gs if gs else g).clone().cuda()
+        groups = [{"params": ps[:3], "weight_decay": 0.05}, {"params": ps[3:], "weight_decay": 0.0, "betas": (0.8, 0.9)}]
+        return ps, AdamW(groups, lr=1e-2)
+
+    scale = torch.tensor(gs, device="cuda") if gs else None
+    a_params, a = fresh()
+    before = [p.grad.clone() for p in a_params]
+    a.step(max_grad_norm=max_norm, grad_scale=scale)
+    b_params, b = fresh()
+    if gs:
+        for p in b_params:
+            p.grad.mul_(gs)
+    want_norm = torch.nn.utils.clip_grad_norm_(b_params, max_norm)
+    b.step()
+    torch.cuda.synchronize()
+    assert abs(float(a.last_grad_norm) - float(want_norm)) <= 2e-6 * float(want_norm)
+    for pa, pb, g0 in zip(a_params, b_params, before):
+        assert torch.equal(pa.grad, g0)   # the fused form never writes the gradients
+        assert (pa.detach() - pb.detach()).abs().max().item() <= 2e-6 * max(1.0, pb.detach().abs().max().item())
+    a.step(max_grad_norm=max_norm, grad_scale=scale)   # the scratch was left zeroed: a second step sees the same norm
+    torch.cuda.synchronize()
+    assert abs(float(a.last_grad_norm) - float(want_norm)) <= 2e-6 * float(want_norm)

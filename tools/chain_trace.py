@@ -98,6 +98,9 @@ def main():
                 d["ework"] += (rec[1] - rec[6]) / GHZ / 1e3 if rec[6] else 0.0
                 d["publish"] += (rec[7] - rec[1]) / GHZ / 1e3 if rec[6] else 0.0
                 d["mma"] += (rec[2] - rec[1]) / GHZ / 1e3 if rec[6] else 0.0   # = the __threadfence alone
+                d["dep"] += rec[0] / GHZ / 1e3      # LayerNorm: row 0 loaded (since the call)
+                d["issue"] += rec[3] / GHZ / 1e3    # ... its statistics done
+                d["mma_gap"] += rec[4] / GHZ / 1e3  # ... its outputs stored
     print("kernel span by the log: %.1f us; %d pairs" % (end_all, len(ev)))
     print("%-5s %5s %8s %8s | per task (us): %7s %7s %7s %8s %7s %7s %7s" %
           ("stage", "tasks", "first", "last", "depwait", "issue", "mma", "mma_gap", "e.wait", "e.work", "publish"))
