@@ -18,10 +18,11 @@ struct ChainStageHost {
   float* out32 = nullptr;
   void* out16 = nullptr;
   int dep_stage = -1;  // the stage whose output this one reads (-1: an earlier launch produced it)
+  // GEMM with the LayerNorm in its epilogue: out32 / out16 = LayerNorm(A W^T + bias + resid) gamma + beta
+  int ln = 0;
+  const float* resid = nullptr;
+  long long ldr = 0;
 };
-
-static int chain_m_tiles2(int M) { return 2 * ((((M + kGemmBM - 1) / kGemmBM) + 1) / 2); }  // counters per stage
-static size_t chain_counter_bytes(int M, int n_stages) { return (size_t)n_stages * chain_m_tiles2(M) * sizeof(unsigned); }
 
 static int chain_n_tasks(const ChainStageHost& s) {
   if (s.kind == CHAIN_LN) return (s.M + 2 * kChainLnRows - 1) / (2 * kChainLnRows);
@@ -42,6 +43,7 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
     key.push_back(st[i].N);
     key.push_back(st[i].K);
     key.push_back(st[i].ksplit);
+    key.push_back(st[i].ln);
   }
   auto it = h->chain_scheds.find(key);
   if (it == h->chain_scheds.end()) {
@@ -60,12 +62,21 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
       double cost = 2.0;
       if (st[i].kind == CHAIN_GEMM)
         cost = (double)((st[i].K + kGemmBK - 1) / kGemmBK) / std::max(1, st[i].ksplit) + 4.0;
+      // the N tiles of one M pair of a fused-LayerNorm stage wait for each other's row statistics inside their
+      // epilogues: they must sit on DISTINCT pairs (a pair runs its list in order)
+      const int group = (st[i].kind == CHAIN_GEMM && st[i].ln) ? (st[i].N + kChainBN - 1) / kChainBN : 1;
+      if (group > pairs) return fail("chain: a fused LayerNorm stage needs at least %d CTA pairs", group);
+      std::vector<int> used;
       for (int t = 0; t < nt; ++t) {
-        int best = 0;
-        for (int p = 1; p < pairs; ++p)
-          if (avail[p] < avail[best] - 1e-9) best = p;
+        if (t % group == 0) used.clear();
+        int best = -1;
+        for (int p = 0; p < pairs; ++p) {
+          if (std::find(used.begin(), used.end(), p) != used.end()) continue;
+          if (best < 0 || avail[p] < avail[best] - 1e-9) best = p;
+        }
+        used.push_back(best);
         lists[best].push_back((i << 24) | t);
-        avail[best] += cost;
+        avail[best] += cost + (group > 1 ? 6.0 : 0.0);
       }
     }
     size_t longest = 0;
@@ -91,7 +102,8 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
 // Runs the stages as one launch.  `counters`: chain_counter_bytes(M, n) of ZEROED device memory (the caller's: the
 // encoder forward clears its whole flag area once per call).
 template <typename T16>
-static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, int n, unsigned* counters) {
+static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, int n, unsigned* counters,
+                     float2* part) {
   if (n <= 0) return 0;
   if (n > kChainMaxStages) return fail("chain: at most %d stages", kChainMaxStages);
   const int dt = Cvt<T16>::kFmt;
@@ -102,7 +114,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
   ChainParams p;
   memset(&p, 0, sizeof p);
   p.n_stages = n;
-  int n_maps = 0;
+  int n_maps = 0, n_fused = 0;
   for (int i = 0; i < n; ++i) {
     const ChainStageHost& s = hs[i];
     ChainStage& d = p.st[i];
@@ -115,11 +127,12 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
     d.out_fp32 = s.out_fp32;
     d.ksplit = std::max(1, s.ksplit);
     d.bias = s.bias;
-    d.done = counters + (size_t)i * per;
+    d.done = counters + (size_t)(2 * i) * per;
+    d.map2 = -1;
     if (s.dep_stage >= 0) {
       if (s.dep_stage >= i) return fail("chain: stage %d depends on a later stage", i);
       const ChainStageHost& ps = hs[s.dep_stage];
-      d.dep = counters + (size_t)s.dep_stage * per;
+      d.dep = counters + (size_t)(2 * s.dep_stage) * per;
       d.dep_target = ps.kind == CHAIN_LN
                          ? 0u
                          : (unsigned)(((ps.N + kChainBN - 1) / kChainBN) * std::max(1, ps.ksplit) * kGemmEpiWarps);
@@ -137,6 +150,36 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       continue;
     }
     if (n_maps >= kChainMaxMaps) return fail("chain: at most %d GEMM stages", kChainMaxMaps);
+    if (s.ln) {
+      if (!(s.N == 128 || s.N == 256 || s.N == 512 || s.N == 768 || s.N == 1024))
+        return fail("chain fused LayerNorm: unsupported row width %d", s.N);
+      if (!s.A || !s.W || !s.resid || !s.gamma || !s.beta || (!s.out32 && !s.out16) || s.M <= 0 || s.K <= 0)
+        return fail("chain fused LayerNorm: bad argument");
+      if ((s.ldr & 3) || (reinterpret_cast<uintptr_t>(s.resid) & 15)) return fail("chain fused LayerNorm: residual alignment");
+      if (n_fused >= 2 || !part) return fail("chain: at most two fused LayerNorm stages per launch");
+      d.ln = 1;
+      d.ksplit = 1;
+      d.resid = s.resid;
+      d.ldr = s.ldr;
+      d.gamma = s.gamma;
+      d.beta = s.beta;
+      d.eps = s.eps;
+      d.out32 = s.out32;
+      d.out16 = s.out16;
+      d.sflag = counters + (size_t)(2 * i + 1) * per;
+      d.part = part + (size_t)n_fused * (2 * ((s.N + kChainBN - 1) / kChainBN)) * chain_rows_padded(s.M);
+      ++n_fused;
+      d.map = n_maps;
+      TRY(make_tmap(&maps.a[n_maps], s.A, dt, s.M, s.K, s.lda, kGemmBM));
+      TRY(make_tmap(&maps.b[n_maps], s.W, dt, s.N, s.K, s.ldw, kChainBN / 2));
+      if (s.out32) TRY(make_tmap_ex(&maps.o[n_maps], s.out32, 2, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+      if (s.out16) {
+        TRY(make_tmap_ex(&maps.o2[n_maps], s.out16, dt, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+        d.map2 = n_maps;
+      }
+      ++n_maps;
+      continue;
+    }
     if (!s.A || !s.W || !s.out || s.M <= 0 || s.N <= 0 || s.K <= 0) return fail("chain GEMM: bad argument");
     if (d.ksplit > 1 && !s.out_fp32) return fail("chain GEMM: split-K needs the accumulate-into-fp32 output");
     if (d.ksplit > 1) d.ksplit = std::max(1, std::min(d.ksplit, ((s.K + kGemmBK - 1) / kGemmBK) / 4));
@@ -186,46 +229,60 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
 
 // One encoder layer after its attention kernel, plus the next layer's QKV projection, as ONE launch
 // (modeling_bert.py:85 BertSelfOutput, :144 BertIntermediate, :145 BertOutput, then :38-40 of layer l+1).
-//   ctx16 -> [attention.output.dense + bias] += h32 -> LayerNorm -> a32 / a16 -> [intermediate.dense, GELU] -> inter16
-//   -> [output.dense + bias] += a32 -> LayerNorm -> out32 (h32 or seq_out) / h16 -> [QKV of layer l+1] -> qkv16
+//   fused LayerNorm (default): 4 stages
+//     ctx16 -> [attention.output.dense + bias + h32 -> LayerNorm] -> a32 / a16 -> [intermediate.dense, GELU] -> inter16
+//     -> [output.dense + bias + a32 -> LayerNorm] -> out32 (h32 or seq_out) / h16 -> [QKV of layer l+1] -> qkv16
+//   CPT_B200_CHAIN_FUSE_LN=0: 6 stages, the dense outputs are ADDED into the fp32 stream by TMA reduce stores and the
+//     LayerNorms run as row tasks between the GEMM stages
 template <typename T16>
 static int chain_layer(cpt_handle* h, cudaStream_t st, const Workspace& w, int l, int M, float* out32, bool last,
                        unsigned* counters) {
   const cpt_config& c = h->cfg;
   const int H = c.hidden_size, I = c.intermediate_size;
   const LayerDev& d = h->layers[l];
+  const bool fuse = h->chain_fuse_ln != 0;
   ChainStageHost s[6];
   int n = 0;
-  {  // attention.output.dense (+bias), added into the residual stream h32
+  {  // attention.output.dense (+bias) + residual (+ BertSelfOutput.LayerNorm)
     ChainStageHost& g = s[n++];
-    g.M = M; g.N = H; g.K = H; g.out_fp32 = 1; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;
-    g.out = w.h32; g.ldo = H;
+    g.M = M; g.N = H; g.K = H; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;
+    if (fuse) {
+      g.ln = 1; g.resid = w.h32; g.ldr = H; g.gamma = d.ao_g; g.beta = d.ao_b; g.eps = c.layer_norm_eps;
+      g.out32 = w.a32; g.out16 = w.a16;
+    } else {
+      g.out_fp32 = 1; g.out = w.h32; g.ldo = H;
+    }
   }
-  {  // BertSelfOutput.LayerNorm
+  if (!fuse) {  // BertSelfOutput.LayerNorm
     ChainStageHost& g = s[n++];
     g.kind = CHAIN_LN; g.M = M; g.N = H; g.ln_in = w.h32; g.gamma = d.ao_g; g.beta = d.ao_b; g.eps = c.layer_norm_eps;
-    g.out32 = w.a32; g.out16 = w.a16; g.dep_stage = 0;
+    g.out32 = w.a32; g.out16 = w.a16; g.dep_stage = n - 2;
   }
   {  // intermediate.dense + bias + erf-GELU
     ChainStageHost& g = s[n++];
     g.M = M; g.N = I; g.K = H; g.gelu = 1; g.A = w.a16; g.lda = H; g.W = d.w_i; g.ldw = H; g.bias = d.b_i;
-    g.out = w.inter16; g.ldo = I; g.dep_stage = 1;
+    g.out = w.inter16; g.ldo = I; g.dep_stage = n - 2;
   }
-  {  // output.dense (+bias), added into a32
+  {  // output.dense (+bias) + residual (+ BertOutput.LayerNorm)
     ChainStageHost& g = s[n++];
-    g.M = M; g.N = H; g.K = I; g.out_fp32 = 1; g.ksplit = h->chain_down_ksplit; g.A = w.inter16; g.lda = I; g.W = d.w_o;
-    g.ldw = I; g.bias = d.b_o; g.out = w.a32; g.ldo = H; g.dep_stage = 2;
+    g.M = M; g.N = H; g.K = I; g.A = w.inter16; g.lda = I; g.W = d.w_o; g.ldw = I; g.bias = d.b_o; g.dep_stage = n - 2;
+    if (fuse) {
+      g.ln = 1; g.resid = w.a32; g.ldr = H; g.gamma = d.o_g; g.beta = d.o_b; g.eps = c.layer_norm_eps;
+      g.out32 = out32; g.out16 = last ? nullptr : w.h16;
+    } else {
+      g.out_fp32 = 1; g.ksplit = h->chain_down_ksplit; g.out = w.a32; g.ldo = H;
+    }
   }
-  {  // BertOutput.LayerNorm
+  if (!fuse) {  // BertOutput.LayerNorm
     ChainStageHost& g = s[n++];
     g.kind = CHAIN_LN; g.M = M; g.N = H; g.ln_in = w.a32; g.gamma = d.o_g; g.beta = d.o_b; g.eps = c.layer_norm_eps;
-    g.out32 = out32; g.out16 = last ? nullptr : w.h16; g.dep_stage = 3;
+    g.out32 = out32; g.out16 = last ? nullptr : w.h16; g.dep_stage = n - 2;
   }
   if (!last) {  // the next layer's query / key / value projection
     const LayerDev& nx = h->layers[l + 1];
     ChainStageHost& g = s[n++];
     g.M = M; g.N = 3 * H; g.K = H; g.A = w.h16; g.lda = H; g.W = nx.w_qkv; g.ldw = H; g.bias = nx.b_qkv;
-    g.out = w.qkv16; g.ldo = 3 * H; g.dep_stage = 4;
+    g.out = w.qkv16; g.ldo = 3 * H; g.dep_stage = n - 2;
   }
-  return run_chain<T16>(h, st, s, n, counters);
+  return run_chain<T16>(h, st, s, n, counters, w.part);
 }

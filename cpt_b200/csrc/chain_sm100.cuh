@@ -45,6 +45,16 @@ struct ChainStage {
   int ksplit;    // K cut into pieces that all add into the destination (out_fp32 only)
   int map;       // index of this stage's tensor maps in ChainMaps
   const float* bias;
+  // CHAIN_GEMM with ln != 0 — dense + bias + residual + LayerNorm in the tile's epilogue (BertSelfOutput / BertOutput):
+  //   x = A W^T + bias + resid, out32 / out16 = LayerNorm(x) gamma + beta.  A row's statistics span the stage's N tiles
+  //   (other CTA pairs): every (tile, column half) publishes (mean, M2) of its 128 columns per row in `part`, bumps
+  //   sflag[m tile], waits until all 2 * n_tiles partials of the M tile are there and merges them (Chan et al.).
+  int ln;
+  int map2;              // tensor map of out16 (16-bit), -1: none
+  const float* resid;    // fp32 [M, ldr]
+  long long ldr;
+  float2* part;          // [n_tiles * 2][rows padded to the M-tile grid] (mean, M2) of 128 columns
+  unsigned* sflag;       // [m_tiles] += 1 per epilogue warp per tile once its partials are published
   const float* ln_in;
   const float* gamma;
   const float* beta;
@@ -58,7 +68,7 @@ struct ChainStage {
 };
 
 struct ChainMaps {
-  CUtensorMap a[kChainMaxMaps], b[kChainMaxMaps], o[kChainMaxMaps];
+  CUtensorMap a[kChainMaxMaps], b[kChainMaxMaps], o[kChainMaxMaps], o2[kChainMaxMaps];
 };
 
 struct ChainParams {
@@ -80,12 +90,24 @@ struct ChainCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = 5;
   static constexpr int kStageEpi = 4096;                          // one 32 x 32 fp32 block per epilogue warp
-  static constexpr int kBiasBytes = (kChainBN / 2) * 4;
-  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kBiasBytes);
+  static constexpr int kStage16 = 2048;                           // ... and one 32 x 32 16-bit block (fused LayerNorm)
+  static constexpr int kBiasBytes = 3 * (kChainBN / 2) * 4;       // bias, gamma, beta slices of the warp's 128 columns
+  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kStage16 + kBiasBytes);
   static constexpr int kTaskBytes = kChainMaxTasks * 4;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256 + kTaskBytes;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory");
 };
+
+__host__ __device__ inline int chain_rows_padded(int M) { return 2 * ((((M + kGemmBM - 1) / kGemmBM) + 1) / 2) * kGemmBM; }
+inline int chain_m_tiles2(int M) { return 2 * ((((M + kGemmBM - 1) / kGemmBM) + 1) / 2); }  // counters per stage
+// per stage: the "rows published" counters and the "row statistics published" counters of a fused LayerNorm
+inline size_t chain_counter_bytes(int M, int n_stages) {
+  return (size_t)n_stages * 2 * chain_m_tiles2(M) * sizeof(unsigned);
+}
+// scratch of the fused LayerNorm epilogues: (mean, M2) per row per 128-column slice, for up to two such stages
+inline size_t chain_part_bytes(int M, int N) {
+  return (size_t)2 * (2 * ((N + kChainBN - 1) / kChainBN)) * chain_rows_padded(M) * sizeof(float2);
+}
 
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void flag_add_release(unsigned* addr, unsigned v) {
@@ -177,6 +199,175 @@ __device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int
   }
 }
 
+// per-warp shared-memory areas of the epilogue
+struct ChainEpiSmem {
+  uint8_t* pad;        // 4 KB: a 32 x 32 fp32 block (128B-swizzled TMA box / transpose area)
+  uint32_t pad_u32;
+  uint8_t* pad16;      // 2 KB: a 32 x 32 16-bit block (64B-swizzled TMA box)
+  uint32_t pad16_u32;
+  float *sv0, *sv1, *sv2;  // bias | gamma | beta of the warp's 128 columns
+};
+
+// Epilogue of a dense + bias + residual + LayerNorm tile (see ChainStage::ln).  The warp owns rows mrow0..+31 (thread =
+// row = TMEM lane) and 128 columns from ncol0; x lives in TMEM (written back over the accumulator) between the passes.
+template <typename T16>
+__device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUtensorMap* mo32, const CUtensorMap* mo16,
+                                                  int mrow0, int ncol0, int n0, int mt, uint32_t t_row,
+                                                  uint32_t tfull, uint32_t tfull_phase, const ChainEpiSmem& e, int lane,
+                                                  bool& staging_busy) {
+  constexpr int BN = kChainBN;
+  const int n_tiles = (s.N + BN - 1) / BN;
+  const int m_pad = chain_rows_padded(s.M);
+  const int n_live = max(0, min(BN / 2, s.N - ncol0));   // live columns of this warp's half (warp-uniform)
+  const bool rows_ok = mrow0 < s.M;
+  const int row = mrow0 + lane;
+  float4 rr[8];
+  auto load_resid = [&](int c) {  // 4 rows x 128 B per warp instruction: coalesced; transposed through the pad below
+    const int col = ncol0 + c * 32 + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = mrow0 + i * 4 + (lane >> 3);
+      rr[i] = (r < s.M && col < s.N) ? __ldcg(reinterpret_cast<const float4*>(s.resid + (long long)r * s.ldr + col))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (rows_ok) load_resid(0);  // in flight while the tile's MMAs finish
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  float mean_l = 0.f, m2_l = 0.f;
+  uint32_t rbuf[32];
+  if (rows_ok) {
+    // ---- pass 1a: x = acc + bias + residual -> TMEM, row sums
+    float sum = 0.f;
+    tmem_ld_32x32b_x32(t_row, rbuf);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3), piece = lane & 7;
+        *reinterpret_cast<float4*>(e.pad + rl * 128 + ((piece ^ (rl & 7)) << 4)) = rr[i];
+      }
+      __syncwarp();
+      if (c + 1 < 4) load_resid(c + 1);
+      tmem_ld_wait();
+      uint32_t x[32];
+      const int nl = max(0, min(32, n_live - c * 32));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 r4 = *reinterpret_cast<const float4*>(e.pad + lane * 128 + ((j ^ (lane & 7)) << 4));
+        const float4 b4 = *reinterpret_cast<const float4*>(e.sv0 + c * 32 + 4 * j);
+        const float x0 = __uint_as_float(rbuf[4 * j]) + b4.x + r4.x, x1 = __uint_as_float(rbuf[4 * j + 1]) + b4.y + r4.y;
+        const float x2 = __uint_as_float(rbuf[4 * j + 2]) + b4.z + r4.z, x3 = __uint_as_float(rbuf[4 * j + 3]) + b4.w + r4.w;
+        x[4 * j] = __float_as_uint(x0);
+        x[4 * j + 1] = __float_as_uint(x1);
+        x[4 * j + 2] = __float_as_uint(x2);
+        x[4 * j + 3] = __float_as_uint(x3);
+        if (4 * j < nl) sum += (x0 + x1) + (x2 + x3);  // N is a multiple of 128: whole groups of 4
+      }
+      if (c + 1 < 4) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+      tmem_st_32x32b_x32(t_row + c * 32, x);
+      __syncwarp();  // every lane has read its pad row before the next chunk's residual lands there
+    }
+    tmem_ld_wait();
+    tmem_st_wait();
+    // ---- pass 1b: centred second moment of the same 128 columns
+    mean_l = n_live > 0 ? sum / (float)n_live : 0.f;
+    tmem_ld_32x32b_x32(t_row, rbuf);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_wait();
+      const int nl = max(0, min(32, n_live - c * 32));
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        if (j < nl) {
+          const float d0 = __uint_as_float(rbuf[j]) - mean_l, d1 = __uint_as_float(rbuf[j + 1]) - mean_l;
+          q0 = fmaf(d0, d0, q0);
+          q1 = fmaf(d1, d1, q1);
+        }
+      }
+      if (c + 1 < 4) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+      m2_l += q0 + q1;
+    }
+    tmem_ld_wait();
+    s.part[(long long)(((n0 / BN) * 2 + (ncol0 - n0) / (BN / 2))) * m_pad + row] = make_float2(mean_l, m2_l);
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) flag_add_release(s.sflag + mt, 1u);
+  if (!rows_ok) return;
+  if (lane == 0) flag_wait_ge(s.sflag + mt, (unsigned)(n_tiles * kGemmEpiWarps));
+  __syncwarp();
+  // ---- merge the 2 * n_tiles partials of this row: n, mean, M2 (Chan et al. pairwise update)
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  for (int t = 0; t < 2 * n_tiles; ++t) {
+    const float nb = (float)max(0, min(BN / 2, s.N - t * (BN / 2)));
+    if (nb > 0.f) {
+      const float2 pm = __ldcg(s.part + (long long)t * m_pad + row);
+      const float tot = cnt + nb, delta = pm.x - mean;
+      mean += delta * (nb / tot);
+      m2 += pm.y + delta * delta * (cnt * nb / tot);
+      cnt = tot;
+    }
+  }
+  const float rstd = 1.0f / sqrtf(m2 / (float)s.N + s.eps);
+  // ---- pass 2: normalise, scale, shift -> fp32 stream and 16-bit shadow through TMA bulk stores
+  tmem_ld_32x32b_x32(t_row, rbuf);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int nc = ncol0 + c * 32;
+    const bool live = nc < s.N;
+    tmem_ld_wait();
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(e.sv1 + c * 32 + j);
+      const float4 b4 = *reinterpret_cast<const float4*>(e.sv2 + c * 32 + j);
+      y[j] = (__uint_as_float(rbuf[j]) - mean) * rstd * g4.x + b4.x;
+      y[j + 1] = (__uint_as_float(rbuf[j + 1]) - mean) * rstd * g4.y + b4.y;
+      y[j + 2] = (__uint_as_float(rbuf[j + 2]) - mean) * rstd * g4.z + b4.z;
+      y[j + 3] = (__uint_as_float(rbuf[j + 3]) - mean) * rstd * g4.w + b4.w;
+    }
+    if (staging_busy) {
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      staging_busy = false;
+    }
+    if (c + 1 < 4) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+    if (live) {
+      if (mo32 != nullptr) {
+        uint8_t* brow = e.pad + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(brow + ((j ^ (lane & 7)) * 16)) =
+              make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+      if (mo16 != nullptr) {
+        uint8_t* brow = e.pad16 + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = Cvt<T16>::pack2(y[8 * j + 0], y[8 * j + 1]);
+          u.y = Cvt<T16>::pack2(y[8 * j + 2], y[8 * j + 3]);
+          u.z = Cvt<T16>::pack2(y[8 * j + 4], y[8 * j + 5]);
+          u.w = Cvt<T16>::pack2(y[8 * j + 6], y[8 * j + 7]);
+          *reinterpret_cast<uint4*>(brow + ((j ^ ((lane >> 1) & 3)) * 16)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (mo32 != nullptr) tma_store_2d(mo32, e.pad_u32, nc, mrow0);
+        if (mo16 != nullptr) tma_store_2d(mo16, e.pad16_u32, nc, mrow0);
+        tma_store_commit();
+      }
+      staging_busy = true;
+    }
+    __syncwarp();
+  }
+  tmem_ld_wait();
+}
+
 template <typename T16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
@@ -229,6 +420,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         tma_prefetch_desc(&maps.a[p.st[s].map]);
         tma_prefetch_desc(&maps.b[p.st[s].map]);
         tma_prefetch_desc(&maps.o[p.st[s].map]);
+        if (p.st[s].ln && p.st[s].map2 >= 0) tma_prefetch_desc(&maps.o2[p.st[s].map2]);
       }
   }
   if (warp == 1) {
@@ -357,7 +549,15 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     constexpr int kColsPerWarp = BN / 2;
     uint8_t* pad = epi_gen + ew * Cfg::kStageEpi;
     const uint32_t pad_u32 = epi_base + ew * Cfg::kStageEpi;
-    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * Cfg::kStageEpi + ew * Cfg::kBiasBytes);
+    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * (Cfg::kStageEpi + Cfg::kStage16) + ew * Cfg::kBiasBytes);
+    ChainEpiSmem es;
+    es.pad = pad;
+    es.pad_u32 = pad_u32;
+    es.pad16 = epi_gen + kGemmEpiWarps * Cfg::kStageEpi + ew * Cfg::kStage16;
+    es.pad16_u32 = epi_base + kGemmEpiWarps * Cfg::kStageEpi + ew * Cfg::kStage16;
+    es.sv0 = sv0;
+    es.sv1 = sv0 + kColsPerWarp;
+    es.sv2 = sv0 + 2 * kColsPerWarp;
     bool staging_busy = false;  // a bulk store may still be reading this warp's staging block
     int it = 0;
     for (int i = 0;; ++i) {
@@ -420,12 +620,24 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
           }
         }
         *reinterpret_cast<float4*>(sv0 + lane * 4) = b4;
+        if (s.ln) {  // LayerNorm scale / shift of the same columns (N is a multiple of 128 for these stages)
+          const bool in = nb + 3 < s.N;
+          *reinterpret_cast<float4*>(es.sv1 + lane * 4) =
+              in ? __ldg(reinterpret_cast<const float4*>(s.gamma + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(es.sv2 + lane * 4) =
+              in ? __ldg(reinterpret_cast<const float4*>(s.beta + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncwarp();
       }
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
+      if (s.ln) {
+        chain_epilogue_ln<T16>(s, s.out32 ? mo : nullptr, s.map2 >= 0 ? &maps.o2[s.map2] : nullptr, mrow0, ncol0, t.n0,
+                               t.m0 / kGemmBM, t_row, tfull_bar(acc), acc_phase, es, lane, staging_busy);
+        if (tr) mark(i, 6);
+      } else {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (tr) mark(i, 6);
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
       if (mrow0 < s.M) {
         constexpr int NC = kColsPerWarp / 32;
         uint32_t rbuf[32];
@@ -485,6 +697,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
           __syncwarp();
         }
         tmem_ld_wait();
+      }
       }
       tc_fence_before();
       __syncwarp();

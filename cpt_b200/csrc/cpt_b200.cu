@@ -154,7 +154,10 @@ struct cpt_handle {
   // dataflow chain kernel (chain_sm100.cuh): one launch per layer for everything between two attention kernels
   int chain = 1;                 // CPT_B200_CHAIN=0: the round-1 launch sequence (one kernel per GEMM / LayerNorm)
   int chain_min_rows = 1024;     // below this many rows the narrow-tile GEMMs of the unfused path spread better
-  int chain_down_ksplit = 1;     // CPT_B200_CHAIN_KSPLIT: K pieces of the FFN-down tiles
+  int chain_down_ksplit = 1;     // CPT_B200_CHAIN_KSPLIT: K pieces of the FFN-down tiles (unfused LayerNorm only)
+  int chain_fuse_ln = 1;         // CPT_B200_CHAIN_FUSE_LN=0: LayerNorm as row tasks between the GEMM stages
+  float2* chain_part = nullptr;  // cpt_chain_run (tests): scratch of the fused LayerNorm epilogues
+  size_t chain_part_bytes = 0;
   struct ChainSched { int pairs = 0, pitch = 0; int* dev = nullptr; };
   std::map<std::vector<int>, ChainSched> chain_scheds;  // per chain shape: the task lists of the CTA pairs
   std::vector<void*> owned_chain;
@@ -481,8 +484,9 @@ struct Workspace {
   char* pre16;
   size_t stats_bytes;
   char *h16, *a16, *ctx16, *qkv16, *inter16, *img16;
-  unsigned* flags;     // readiness counters of the chain kernel: [L][6 stages][M tiles]
+  unsigned* flags;     // readiness counters of the chain kernel: [L][6 stages][2][M tiles]
   size_t flags_bytes;
+  float2* part;        // row-statistics scratch of the chain kernel's fused LayerNorm epilogues
   size_t total;
 };
 static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
@@ -509,8 +513,9 @@ static Workspace carve(const cpt_handle* h, int B, int T, int R, char* base) {
   w.img16 = take((size_t)B * R * h->Fp * 2);
   w.stats_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * 2 * M * 2 * 4;  // [L][2][M](sum, sumsq)
   w.stats = (float*)take(w.stats_bytes);
-  w.flags_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * 6 * (2 * ((M + 255) / 256)) * sizeof(unsigned);
+  w.flags_bytes = (size_t)(c.num_hidden_layers > 0 ? c.num_hidden_layers : 1) * chain_counter_bytes((int)M, 6);
   w.flags = (unsigned*)take(w.flags_bytes);
+  w.part = (float2*)take(chain_part_bytes((int)M, (int)H));
   w.total = off + 256;
   return w;
 }
@@ -996,6 +1001,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN")) h->chain = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_TRACE")) h->chain_trace_on = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_CHAIN_FUSE_LN")) h->chain_fuse_ln = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
@@ -1035,6 +1041,7 @@ int cpt_destroy(cpt_handle* h) {
   if (h->copy_chunks_dev) cudaFree(h->copy_chunks_dev);
   for (void* q : h->owned_chain) cudaFree(q);
   if (h->chain_counters) cudaFree(h->chain_counters);
+  if (h->chain_part) cudaFree(h->chain_part);
   if (h->chain_trace) cudaFree(h->chain_trace);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1363,18 +1370,30 @@ int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, in
     d.A = s.A; d.lda = s.lda; d.W = s.W; d.ldw = s.ldw; d.bias = s.bias; d.out = s.out; d.ldo = s.ldo;
     d.ln_in = s.ln_in; d.gamma = s.gamma; d.beta = s.beta; d.eps = s.eps; d.out32 = s.out32; d.out16 = s.out16;
     d.dep_stage = s.dep_stage;
+    d.ln = s.ln; d.resid = s.resid; d.ldr = s.ldr;
+  }
+  int widest = 128;
+  for (auto& d : hs) if (d.ln) widest = std::max(widest, d.N);
+  const size_t pneed = chain_part_bytes(hs[0].M, widest);
+  if (pneed > h->chain_part_bytes) {
+    CK(cudaStreamSynchronize(st));
+    if (h->chain_part) cudaFree(h->chain_part);
+    h->chain_part = nullptr;
+    CK(cudaMalloc((void**)&h->chain_part, pneed));
+    h->chain_part_bytes = pneed;
   }
   const size_t need = chain_counter_bytes(hs[0].M, n_stages);
   if (need > h->chain_counters_bytes) {
     CK(cudaStreamSynchronize(st));
     if (h->chain_counters) cudaFree(h->chain_counters);
+  if (h->chain_part) cudaFree(h->chain_part);
   if (h->chain_trace) cudaFree(h->chain_trace);
     h->chain_counters = nullptr;
     CK(cudaMalloc((void**)&h->chain_counters, need));
     h->chain_counters_bytes = need;
   }
   CK(cudaMemsetAsync(h->chain_counters, 0, need, st));
-#define CALL(T16) run_chain<T16>(h, st, hs.data(), n_stages, h->chain_counters)
+#define CALL(T16) run_chain<T16>(h, st, hs.data(), n_stages, h->chain_counters, h->chain_part)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
 }

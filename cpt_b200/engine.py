@@ -660,6 +660,15 @@ class Engine(object):
                 c.ln_in, c.gamma, c.beta, c.eps = x.data_ptr(), s["gamma"].data_ptr(), s["beta"].data_ptr(), s["eps"]
                 c.out32 = 0 if s.get("out32") is None else s["out32"].data_ptr()
                 c.out16 = 0 if s.get("out16") is None else s["out16"].data_ptr()
+            elif s.get("resid") is not None:  # dense + bias + residual + LayerNorm in the tile epilogue
+                A, W, r = s["A"], s["W"], s["resid"]
+                c.kind, c.M, c.K, c.N, c.ln, c.ksplit = 0, A.shape[0], A.shape[1], W.shape[0], 1, 1
+                c.A, c.lda, c.W, c.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
+                c.bias = 0 if s.get("bias") is None else s["bias"].data_ptr()
+                c.resid, c.ldr = r.data_ptr(), r.stride(0)
+                c.gamma, c.beta, c.eps = s["gamma"].data_ptr(), s["beta"].data_ptr(), s["eps"]
+                c.out32 = 0 if s.get("out32") is None else s["out32"].data_ptr()
+                c.out16 = 0 if s.get("out16") is None else s["out16"].data_ptr()
             else:
                 A, W, out = s["A"], s["W"], s["out"]
                 c.kind, c.M, c.K, c.N = 0, A.shape[0], A.shape[1], W.shape[0]

@@ -280,6 +280,8 @@ int cpt_attention_backward(cpt_handle *h, void *stream, const void *qkv, const v
  * the next layer's query/key/value projection (modeling_bert.py:85,144-145, then :38-40) this way.  A stage is
  *   kind 0: out[M,N] = A[M,K] . W[N,K]^T + bias (16-bit operands; gelu: erf-GELU; out_fp32 = 0: 16-bit out,
  *           out_fp32 = 1: the fp32 tile is ADDED into `out` (which already holds the residual); ksplit: K pieces), or
+ *   kind 0 with ln = 1: out32 / out16 [M,N] = LayerNorm(A . W^T + bias + resid[M,ldr]) * gamma + beta — the LayerNorm
+ *           runs in the tile epilogues, row statistics are exchanged between the N tiles of a row through L2, or
  *   kind 1: out32 / out16 [M,N] = LayerNorm(ln_in[M,N]) * gamma + beta.
  * dep_stage: the earlier stage whose output this one reads (-1: data from an earlier launch); rows are handed from
  * stage to stage through readiness counters per 128-row tile, there is no grid-wide barrier. */
@@ -296,6 +298,9 @@ typedef struct {
   float eps;
   float *out32;
   void *out16;
+  int32_t ln;
+  const float *resid;
+  int64_t ldr;
 } cpt_chain_stage;
 int cpt_chain_run(cpt_handle *h, void *stream, const cpt_chain_stage *stages, int n_stages);
 /* Debug: event log of the LAST chain launch (needs CPT_B200_CHAIN_TRACE=1 in the environment at cpt_create).

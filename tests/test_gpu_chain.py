@@ -74,6 +74,55 @@ def test_gemm_accumulate_then_layernorm(eng, M, N, K, ksplit):
     assert (o16.double() - ref).abs().max().item() <= 1.5e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (777, 768, 3072), (7680, 768, 768), (7680, 768, 3072), (130, 128, 512),
+                                   (3000, 1024, 1024), (100, 256, 64), (513, 512, 200)])
+def test_dense_residual_layernorm_in_the_epilogue(eng, M, N, K):
+    """LayerNorm(A W^T + b + resid) computed inside the GEMM tile epilogues: row statistics are exchanged between the N
+    tiles of a row (different CTA pairs) through L2."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device="cuda", dtype=torch.float16)
+    W = torch.zeros(N, Kp, device="cuda", dtype=torch.float16)
+    A[:, :K] = _rand16(g, M, K)
+    W[:, :K] = _rand16(g, N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.5   # a non-zero row mean
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    beta = torch.randn(N, device="cuda", generator=g) * 0.1
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    keep = resid.clone()
+    eng.chain([dict(kind="gemm", A=A[:, :K], W=W[:, :K], bias=bias, resid=resid, gamma=gamma, beta=beta, eps=1e-12,
+                    out32=o32, out16=o16)])
+    torch.cuda.synchronize()
+    assert torch.equal(resid, keep)   # the residual is read, never written
+    pre = A[:, :K].double() @ W[:, :K].double().t() + bias.double() + resid.double()
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma.double(), beta.double(), 1e-12)
+    assert (o32.double() - ref).abs().max().item() <= 2e-4
+    assert (o16.double() - ref).abs().max().item() <= 1.5e-3 * ref.abs().max().item()
+    # only one of the two outputs
+    o32b = torch.empty_like(o32)
+    eng.chain([dict(kind="gemm", A=A[:, :K], W=W[:, :K], bias=bias, resid=resid, gamma=gamma, beta=beta, eps=1e-12,
+                    out32=o32b)])
+    torch.cuda.synchronize()
+    assert torch.equal(o32b, o32)
+
+
+def test_fused_layernorm_statistics_are_robust_to_a_large_row_mean(eng):
+    """mean >> spread: the (mean, M2) partials are merged pairwise, not formed as E[x^2] - E[x]^2."""
+    M, N, K = 300, 768, 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A, W = _rand16(g, M, K, scale=0.01), _rand16(g, N, K, scale=0.01)
+    resid = torch.randn(M, N, device="cuda", generator=g) * 0.05 + 300.0
+    gamma, beta = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+    o32 = torch.empty(M, N, device="cuda")
+    eng.chain([dict(kind="gemm", A=A, W=W, resid=resid, gamma=gamma, beta=beta, eps=1e-12, out32=o32)])
+    torch.cuda.synchronize()
+    pre = A.double() @ W.double().t() + resid.double()
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma.double(), beta.double(), 1e-12)
+    assert (o32.double() - ref).abs().max().item() <= 5e-3   # fp32 rounding of x itself at |x| = 300 is 3e-5 / 0.05
+
+
 @pytest.mark.parametrize("M", [256, 1000, 7680])
 def test_full_layer_chain_matches_unfused_kernels(eng, M):
     """AO -> LN -> UP(GELU) -> DOWN -> LN -> QKV' as one launch == the same ops as six launches."""
@@ -122,12 +171,26 @@ def test_full_layer_chain_matches_unfused_kernels(eng, M):
                    dict(kind="gemm", A=c_o16, W=Wq, bias=bq, out=c_qkv, dep=4)])
     torch.cuda.synchronize()
     assert torch.equal(first, c_qkv)
+    # the same layer with the LayerNorms inside the dense epilogues: 4 stages, the residual buffers are only read
+    f_a32, f_o32 = torch.empty_like(h32), torch.empty_like(h32)
+    f_a16, f_o16 = torch.empty_like(c_a16), torch.empty_like(c_a16)
+    f_qkv = torch.empty_like(c_qkv)
+    eng.chain([dict(kind="gemm", A=ctx, W=Wao, bias=bao, resid=h32, gamma=g1, beta=b1, eps=1e-12, out32=f_a32, out16=f_a16),
+               dict(kind="gemm", A=f_a16, W=Wi, bias=bi, out=c_inter, gelu=1, dep=0),
+               dict(kind="gemm", A=c_inter, W=Wo, bias=bo, resid=f_a32, gamma=g2, beta=b2, eps=1e-12, out32=f_o32,
+                    out16=f_o16, dep=1),
+               dict(kind="gemm", A=f_o16, W=Wq, bias=bq, out=f_qkv, dep=2)])
+    torch.cuda.synchronize()
+    assert (f_a32 - a32).abs().max().item() <= 2e-4
+    assert (f_o32 - o32).abs().max().item() <= 5e-3
+    assert (f_qkv.float() - qkv.float()).abs().max().item() <= 1e-2 * qkv.float().abs().max().item()
 
 
 def _models(cfg, sd, chain):
     from cpt_b200.modeling_bert import BertImgForPreTraining
     from cpt_b200.modeling_rec import REC_MLM_CPT
     os.environ["CPT_B200_CHAIN"] = "1" if chain else "0"
+    os.environ["CPT_B200_CHAIN_FUSE_LN"] = "0" if chain == "tasks" else "1"
     os.environ["CPT_B200_CHAIN_MIN_ROWS"] = "1"
     try:
         pre = BertImgForPreTraining(cfg)
@@ -140,6 +203,7 @@ def _models(cfg, sd, chain):
         rec.bert.engine()  # the handle reads the environment when it is created
     finally:
         os.environ.pop("CPT_B200_CHAIN", None)
+        os.environ.pop("CPT_B200_CHAIN_FUSE_LN", None)
         os.environ.pop("CPT_B200_CHAIN_MIN_ROWS", None)
     return rec
 
@@ -154,7 +218,7 @@ def test_chained_encoder_matches_unfused_and_oracle(geom, B, T, R):
     vids = synth_vocab_ids(cfg, 7, seed=88)
     d = {k: v.to("cuda:0") for k, v in b.items()}
     outs = []
-    for chain in (True, False):
+    for chain in (True, False, "tasks"):
         rec = _models(cfg, sd, chain)
         with torch.no_grad():
             seq = rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
@@ -163,8 +227,9 @@ def test_chained_encoder_matches_unfused_and_oracle(geom, B, T, R):
             rec.bert.engine().check()
         outs.append((seq.cpu(), logits.cpu()))
         del rec
-    (seq_c, log_c), (seq_u, log_u) = outs
+    (seq_c, log_c), (seq_u, log_u), (seq_t, log_t) = outs
     assert (seq_c - seq_u).abs().max().item() <= 2e-3 * seq_u.abs().max().item()
+    assert (seq_t - seq_u).abs().max().item() <= 2e-3 * seq_u.abs().max().item()
     with torch.no_grad():
         oseq, _, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
                                       img_feats=b["img_feats"])

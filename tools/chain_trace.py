@@ -40,16 +40,23 @@ def main():
     inter = torch.empty(M, I, device="cuda", dtype=torch.float16)
     qkv = torch.empty(M, 3 * H, device="cuda", dtype=torch.float16)
     want = a.stages.split(",")
+    f32 = h32.clone()
     allst = [("ao", dict(kind="gemm", A=ctx, W=Wao, bias=bao, out=h32)),
              ("ln1", dict(kind="ln", x=h32, gamma=g1, beta=b1, eps=1e-12, out32=a32, out16=a16)),
              ("up", dict(kind="gemm", A=a16, W=Wi, bias=bi, out=inter, gelu=1)),
              ("down", dict(kind="gemm", A=inter, W=Wo, bias=bo, out=a32, ksplit=a.ksplit)),
              ("ln2", dict(kind="ln", x=a32, gamma=g2, beta=b2, eps=1e-12, out32=o32, out16=o16)),
-             ("qkv", dict(kind="gemm", A=o16, W=Wq, bias=bq, out=qkv))]
+             ("qkv", dict(kind="gemm", A=o16, W=Wq, bias=bq, out=qkv)),
+             # dense + residual + LayerNorm in the epilogue
+             ("aoln", dict(kind="gemm", A=ctx, W=Wao, bias=bao, resid=f32, gamma=g1, beta=b1, eps=1e-12, out32=a32,
+                           out16=a16)),
+             ("downln", dict(kind="gemm", A=inter, W=Wo, bias=bo, resid=a32, gamma=g2, beta=b2, eps=1e-12, out32=o32,
+                             out16=o16))]
     stages, names = [], []
-    for n, s in allst:
-        if n in want:
-            s = dict(s)
+    table = dict(allst)
+    for n in want:   # stages run in the order given on the command line
+        if n in table:
+            s = dict(table[n])
             s["dep"] = len(stages) - 1 if stages else None
             stages.append(s)
             names.append(n)
@@ -83,7 +90,7 @@ def main():
             d["first"] = min(d["first"], us(p, rec[0]) if rec[0] else start)
             d["last"] = max(d["last"], end)
             end_all = max(end_all, end)
-            if rec[3]:
+            if not names[st].startswith("ln"):
                 d["dep"] += (rec[1] - rec[0]) / GHZ / 1e3
                 d["issue"] += (rec[2] - rec[1]) / GHZ / 1e3
                 d["mma"] += (rec[4] - rec[3]) / GHZ / 1e3
@@ -118,6 +125,15 @@ def main():
                 continue
             row.append("%s%d[%.0f-%.0f]" % (names[rec[8] >> 24], rec[8] & 0xFFFFFF, us(p, rec[5]), us(p, rec[7] or rec[5])))
         print("pair %d epilogue timeline: %s" % (p, " ".join(row)))
+    shown = 0
+    for p, lst in enumerate(ev):
+        for rec in lst:
+            if (rec[8] or rec[5]) and names[rec[8] >> 24].startswith("ln") and shown < 6:
+                shown += 1
+                print("LN task raw (us): row0 loaded %.2f | stats %.2f | stored %.2f | whole call %.2f | fence %.2f | "
+                      "publish %.2f" % (rec[0] / GHZ / 1e3, rec[3] / GHZ / 1e3, rec[4] / GHZ / 1e3,
+                                        (rec[1] - rec[6]) / GHZ / 1e3, (rec[2] - rec[1]) / GHZ / 1e3,
+                                        (rec[7] - rec[2]) / GHZ / 1e3))
     if a.json:
         json.dump(dict(names=names, hdr=hdr, ev=ev), open(a.json, "w"))
 
