@@ -231,9 +231,13 @@ __device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUt
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  if (rows_ok) load_resid(0);  // in flight while the tile's MMAs finish
+  // the first residual chunk is in flight while the tile's MMAs finish — unless the residual itself is produced by an
+  // earlier stage of THIS launch: then only the tile's completion (its producer waited for those rows) orders the read
+  const bool early = s.dep == nullptr;
+  if (rows_ok && early) load_resid(0);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
+  if (rows_ok && !early) load_resid(0);
   float mean_l = 0.f, m2_l = 0.f;
   uint32_t rbuf[32];
   if (rows_ok) {

@@ -1386,8 +1386,6 @@ int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, in
   if (need > h->chain_counters_bytes) {
     CK(cudaStreamSynchronize(st));
     if (h->chain_counters) cudaFree(h->chain_counters);
-  if (h->chain_part) cudaFree(h->chain_part);
-  if (h->chain_trace) cudaFree(h->chain_trace);
     h->chain_counters = nullptr;
     CK(cudaMalloc((void**)&h->chain_counters, need));
     h->chain_counters_bytes = need;
