@@ -64,7 +64,7 @@ class ChainStage(C.Structure):
         ("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
         ("out", C.c_void_p), ("ldo", C.c_int64), ("ln_in", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("eps", C.c_float), ("out32", C.c_void_p), ("out16", C.c_void_p), ("ln", C.c_int32), ("resid", C.c_void_p),
-        ("ldr", C.c_int64)]
+        ("ldr", C.c_int64), ("part", C.c_void_p), ("rpart", C.c_void_p), ("apart", C.c_void_p), ("gvec", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/cpt_b200.h declares

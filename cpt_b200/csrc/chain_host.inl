@@ -19,9 +19,13 @@ struct ChainStageHost {
   void* out16 = nullptr;
   int dep_stage = -1;  // the stage whose output this one reads (-1: an earlier launch produced it)
   // GEMM with the LayerNorm in its epilogue: out32 / out16 = LayerNorm(A W^T + bias + resid) gamma + beta
-  int ln = 0;
+  int ln = 0;  // 1: LayerNorm finished in the epilogue; 2: deferred to the consumers (see ChainStage)
   const float* resid = nullptr;
   long long ldr = 0;
+  float2* part = nullptr;         // ln == 2: where this stage's row-statistics partials go
+  const float2* rpart = nullptr;  // ln == 2: partials of the residual's rows (NULL: residual is final)
+  const float2* apart = nullptr;  // consumer: partials of the A operand's rows; bias = c vector, gvec = g vector
+  const float* gvec = nullptr;
 };
 
 static int chain_n_tasks(const ChainStageHost& s) {
@@ -45,6 +49,7 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
     key.push_back(st[i].ksplit);
     key.push_back(st[i].ln);
   }
+  key.push_back(h->chain_groups);
   auto it = h->chain_scheds.find(key);
   if (it == h->chain_scheds.end()) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -57,8 +62,40 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
     if (total < pairs) pairs = (int)std::max<long long>(1, total);
     std::vector<std::vector<int>> lists(pairs);
     std::vector<double> avail(pairs, 0.0);
-    for (int i = 0; i < n; ++i) {
-      const int nt = chain_n_tasks(st[i]);
+    // Global task order.  groups == 1: stage-major.  groups > 1: the M pairs are cut into `groups` contiguous groups and
+    // the (stage, group) blocks are issued along anti-diagonals (stage + group = const), the blocks of one diagonal
+    // interleaved proportionally — a software pipeline over row groups: while group 0 is in a LayerNorm stage (epilogue
+    // warps only) group 1 is in the GEMM stage before it (tensor cores), and a narrow stage of one group (90 tiles on 74
+    // pairs) shares the machine with a wide stage of the other.  A task's producers ((stage - 1, same group)) sit on an
+    // earlier diagonal, so every list is still a subsequence of one order in which producers come first.
+    const int groups = std::max(1, std::min(h->chain_groups, 8));
+    struct Item { double key; int stage, idx; };
+    std::vector<Item> order;
+    {
+      const int m_pairs = (((st[0].M + kGemmBM - 1) / kGemmBM) + 1) / 2;
+      for (int i = 0; i < n; ++i) {
+        const int nt = chain_n_tasks(st[i]);
+        const int n_tiles = st[i].kind == CHAIN_GEMM ? (st[i].N + kChainBN - 1) / kChainBN : 1;
+        const int mn = m_pairs * n_tiles;
+        std::vector<int> cnt(groups, 0), seen(groups, 0);
+        auto group_of = [&](int t) {
+          const int mp = st[i].kind == CHAIN_GEMM ? (t % mn) / n_tiles : std::min(m_pairs - 1, t / 4);
+          return std::min(groups - 1, mp * groups / std::max(1, m_pairs));
+        };
+        for (int t = 0; t < nt; ++t) cnt[group_of(t)]++;
+        for (int t = 0; t < nt; ++t) {
+          const int g = group_of(t);
+          const double frac = (seen[g]++ + 0.5) / cnt[g];
+          order.push_back(Item{(double)(i + g) + frac * 0.999, i, t});
+        }
+      }
+      if (groups > 1)
+        std::stable_sort(order.begin(), order.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+    }
+    std::vector<std::vector<int>> group_used(n);  // pairs holding a tile of the current fused-LayerNorm group, per stage
+    std::vector<int> group_id(n, -1);
+    for (const Item& it : order) {
+      const int i = it.stage, t = it.idx;
       double cost = 2.0;
       if (st[i].kind == CHAIN_GEMM)
         cost = (double)((st[i].K + kGemmBK - 1) / kGemmBK) / std::max(1, st[i].ksplit) + 4.0;
@@ -66,18 +103,18 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
       // epilogues: they must sit on DISTINCT pairs (a pair runs its list in order)
       const int group = (st[i].kind == CHAIN_GEMM && st[i].ln) ? (st[i].N + kChainBN - 1) / kChainBN : 1;
       if (group > pairs) return fail("chain: a fused LayerNorm stage needs at least %d CTA pairs", group);
-      std::vector<int> used;
-      for (int t = 0; t < nt; ++t) {
-        if (t % group == 0) used.clear();
-        int best = -1;
-        for (int p = 0; p < pairs; ++p) {
-          if (std::find(used.begin(), used.end(), p) != used.end()) continue;
-          if (best < 0 || avail[p] < avail[best] - 1e-9) best = p;
-        }
-        used.push_back(best);
-        lists[best].push_back((i << 24) | t);
-        avail[best] += cost + (group > 1 ? 6.0 : 0.0);
+      if (group > 1 && t / group != group_id[i]) {
+        group_id[i] = t / group;
+        group_used[i].clear();
       }
+      int best = -1;
+      for (int p = 0; p < pairs; ++p) {
+        if (group > 1 && std::find(group_used[i].begin(), group_used[i].end(), p) != group_used[i].end()) continue;
+        if (best < 0 || avail[p] < avail[best] - 1e-9) best = p;
+      }
+      if (group > 1) group_used[i].push_back(best);
+      lists[best].push_back((i << 24) | t);
+      avail[best] += cost + (group > 1 ? 6.0 : 0.0);
     }
     size_t longest = 0;
     for (auto& l : lists) longest = std::max(longest, l.size());
@@ -127,7 +164,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
     d.out_fp32 = s.out_fp32;
     d.ksplit = std::max(1, s.ksplit);
     d.bias = s.bias;
-    d.done = counters + (size_t)(2 * i) * per;
+    d.done = nullptr;  // set below when a later stage of this launch reads this one
     d.map2 = -1;
     if (s.dep_stage >= 0) {
       if (s.dep_stage >= i) return fail("chain: stage %d depends on a later stage", i);
@@ -150,6 +187,34 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       continue;
     }
     if (n_maps >= kChainMaxMaps) return fail("chain: at most %d GEMM stages", kChainMaxMaps);
+    if (s.ln == 2) {
+      if (s.N % 128 || s.N <= 0) return fail("chain deferred LayerNorm: row width %d is not a multiple of 128", s.N);
+      if (!s.A || !s.W || !s.resid || !s.part || (!s.out32 && !s.out16) || s.M <= 0 || s.K <= 0)
+        return fail("chain deferred LayerNorm: bad argument");
+      if (s.rpart && (!s.gamma || !s.beta)) return fail("chain deferred LayerNorm: residual LayerNorm needs gamma / beta");
+      d.ln = 2;
+      d.ksplit = 1;
+      d.resid = s.resid;
+      d.ldr = s.ldr;
+      d.rpart = s.rpart;
+      d.gamma = s.gamma;
+      d.beta = s.beta;
+      d.eps = s.eps;
+      d.out32 = s.out32;
+      d.out16 = s.out16;
+      d.part = s.part;
+      d.map = d.map_r = n_maps;
+      TRY(make_tmap(&maps.a[n_maps], s.A, dt, s.M, s.K, s.lda, kGemmBM));
+      TRY(make_tmap(&maps.b[n_maps], s.W, dt, s.N, s.K, s.ldw, kChainBN / 2));
+      TRY(make_tmap_ex(&maps.r[n_maps], s.resid, 2, s.M, s.N, s.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+      if (s.out32) TRY(make_tmap_ex(&maps.o[n_maps], s.out32, 2, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+      if (s.out16) {
+        TRY(make_tmap_ex(&maps.o2[n_maps], s.out16, dt, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+        d.map2 = n_maps;
+      }
+      ++n_maps;
+      continue;
+    }
     if (s.ln) {
       if (!(s.N == 128 || s.N == 256 || s.N == 512 || s.N == 768 || s.N == 1024))
         return fail("chain fused LayerNorm: unsupported row width %d", s.N);
@@ -181,6 +246,12 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       continue;
     }
     if (!s.A || !s.W || !s.out || s.M <= 0 || s.N <= 0 || s.K <= 0) return fail("chain GEMM: bad argument");
+    if (s.apart) {
+      if (!s.gvec || !s.bias || s.K % 128) return fail("chain GEMM: folded LayerNorm needs g / c vectors and K %% 128 == 0");
+      d.apart = s.apart;
+      d.gvec = s.gvec;
+      d.eps = s.eps;
+    }
     if (d.ksplit > 1 && !s.out_fp32) return fail("chain GEMM: split-K needs the accumulate-into-fp32 output");
     if (d.ksplit > 1) d.ksplit = std::max(1, std::min(d.ksplit, ((s.K + kGemmBK - 1) / kGemmBK) / 4));
     d.map = n_maps;
@@ -192,6 +263,8 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       TRY(make_tmap_ex(&maps.o[n_maps], s.out, dt, s.M, s.N, s.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     ++n_maps;
   }
+  for (int i = 0; i < n; ++i)
+    if (hs[i].dep_stage >= 0) p.st[hs[i].dep_stage].done = counters + (size_t)(2 * hs[i].dep_stage) * per;
   // the schedule depends on the clamped ksplit: key it on what the kernel will decode
   std::vector<ChainStageHost> eff(hs, hs + n);
   for (int i = 0; i < n; ++i) eff[i].ksplit = p.st[i].ksplit;
@@ -202,7 +275,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
   int pairs = 0;
   TRY(chain_schedule(h, eff.data(), n, st, &pairs, &p.tasks, &p.pitch));
   if (h->chain_trace_on) {  // event log of this launch (debug): sized for the largest launch seen
-    const size_t need = (size_t)pairs * p.pitch * 10 * sizeof(long long), hdr = (size_t)pairs * 2 * sizeof(long long);
+    const size_t need = (size_t)pairs * p.pitch * 16 * sizeof(long long), hdr = (size_t)pairs * 2 * sizeof(long long);
     if (need + hdr > h->chain_trace_bytes) {
       CK(cudaStreamSynchronize(st));
       if (h->chain_trace) cudaFree(h->chain_trace);
@@ -243,6 +316,40 @@ static int chain_layer(cpt_handle* h, cudaStream_t st, const Workspace& w, int l
   const bool fuse = h->chain_fuse_ln != 0;
   ChainStageHost s[6];
   int n = 0;
+  if (h->chain_fuse_ln == 2) {
+    // LayerNorms deferred to their consumers: 4 GEMM stages, no LayerNorm pass and no wait inside any epilogue.
+    //   x1 = ctx Wo^T + b + LN2'(x2 of layer l-1)      -> a32 (fp32, pre-LN1), a16 (raw), statistics P1
+    //   inter = gelu(LN1(x1) W1^T + b1)                   LN1 folded: A = a16, W = gamma1 .* W1, epilogue correction from P1
+    //   x2 = inter W2^T + b2 + LN1(x1)                  -> h32 (pre-LN2), h16 (raw), statistics P2
+    //   qkv' = LN2(x2) Wqkv'^T + b                        LN2 folded into the next layer's QKV weights, correction from P2
+    // (layer 0 adds the embedding output as it is; the last layer's LN2 runs as one row kernel after the loop)
+    float2* P1 = w.part;
+    float2* P2 = w.part + (size_t)(2 * ((H + kChainBN - 1) / kChainBN)) * chain_rows_padded(M);
+    {
+      ChainStageHost& g = s[n++];
+      g.M = M; g.N = H; g.K = H; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;
+      g.ln = 2; g.resid = w.h32; g.ldr = H; g.eps = c.layer_norm_eps; g.out32 = w.a32; g.out16 = w.a16; g.part = P1;
+      if (l > 0) { g.rpart = P2; g.gamma = h->layers[l - 1].o_g; g.beta = h->layers[l - 1].o_b; }
+    }
+    {
+      ChainStageHost& g = s[n++];
+      g.M = M; g.N = I; g.K = H; g.gelu = 1; g.A = w.a16; g.lda = H; g.W = d.w_i_f; g.ldw = H; g.bias = d.c_i;
+      g.gvec = d.g_i; g.apart = P1; g.eps = c.layer_norm_eps; g.out = w.inter16; g.ldo = I; g.dep_stage = 0;
+    }
+    {
+      ChainStageHost& g = s[n++];
+      g.M = M; g.N = H; g.K = I; g.A = w.inter16; g.lda = I; g.W = d.w_o; g.ldw = I; g.bias = d.b_o; g.dep_stage = 1;
+      g.ln = 2; g.resid = w.a32; g.ldr = H; g.rpart = P1; g.gamma = d.ao_g; g.beta = d.ao_b; g.eps = c.layer_norm_eps;
+      g.out32 = w.h32; g.out16 = last ? nullptr : w.h16; g.part = P2;
+    }
+    if (!last) {
+      const LayerDev& nx = h->layers[l + 1];
+      ChainStageHost& g = s[n++];
+      g.M = M; g.N = 3 * H; g.K = H; g.A = w.h16; g.lda = H; g.W = nx.w_qkv_f; g.ldw = H; g.bias = nx.c_qkv;
+      g.gvec = nx.g_qkv; g.apart = P2; g.eps = c.layer_norm_eps; g.out = w.qkv16; g.ldo = 3 * H; g.dep_stage = 2;
+    }
+    return run_chain<T16>(h, st, s, n, counters, w.part);
+  }
   {  // attention.output.dense (+bias) + residual (+ BertSelfOutput.LayerNorm)
     ChainStageHost& g = s[n++];
     g.M = M; g.N = H; g.K = H; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;

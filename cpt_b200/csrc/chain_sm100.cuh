@@ -49,8 +49,19 @@ struct ChainStage {
   //   x = A W^T + bias + resid, out32 / out16 = LayerNorm(x) gamma + beta.  A row's statistics span the stage's N tiles
   //   (other CTA pairs): every (tile, column half) publishes (mean, M2) of its 128 columns per row in `part`, bumps
   //   sflag[m tile], waits until all 2 * n_tiles partials of the M tile are there and merges them (Chan et al.).
+  // ln == 2 — the LayerNorm is DEFERRED to the consumers (round 1's "LayerNorm folding", here with TMA stores and no
+  //   atomics): x = A W^T + bias + LN_prev(resid) is written PRE-LayerNorm (out32 fp32 / out16 raw 16-bit) together with
+  //   the (mean, M2) partials of its rows in `part`; nobody waits for anyone inside an epilogue.  LN_prev is the
+  //   LayerNorm of the residual's own rows applied on the fly from `rpart` (NULL: the residual is used as it is) with
+  //   gamma / beta / eps.  A consumer GEMM reads the raw 16-bit rows as its A operand with gamma folded into its weight
+  //   (host: fold_weight_kernel) and finishes the normalisation in its epilogue: `apart` != NULL ->
+  //   out = rstd_m (acc - mean_m gvec_n) + bias_n, (mean, rstd) merged from the producer's partials.
   int ln;
   int map2;              // tensor map of out16 (16-bit), -1: none
+  int map_r;             // tensor map of resid (fp32, 32 x 32 boxes) for ln == 2
+  const float2* rpart;   // ln == 2: partials of the residual's rows (NULL: residual already normalised)
+  const float2* apart;   // consumer side: partials of the A operand's rows (NULL: A is final)
+  const float* gvec;     // consumer side: g_n = sum_k fp16(gamma_k W_nk)
   const float* resid;    // fp32 [M, ldr]
   long long ldr;
   float2* part;          // [n_tiles * 2][rows padded to the M-tile grid] (mean, M2) of 128 columns
@@ -68,7 +79,7 @@ struct ChainStage {
 };
 
 struct ChainMaps {
-  CUtensorMap a[kChainMaxMaps], b[kChainMaxMaps], o[kChainMaxMaps], o2[kChainMaxMaps];
+  CUtensorMap a[kChainMaxMaps], b[kChainMaxMaps], o[kChainMaxMaps], o2[kChainMaxMaps], r[kChainMaxMaps];
 };
 
 struct ChainParams {
@@ -76,10 +87,11 @@ struct ChainParams {
   ChainStage st[kChainMaxStages];
   const int* tasks;  // [pairs][pitch]: (stage << 24) | index, -1 terminated
   int pitch;
-  // optional event log (CPT_B200_CHAIN_TRACE=1), leader CTAs only: trace[(pair * pitch + i) * 10 + k] in SM clocks since
+  // optional event log (CPT_B200_CHAIN_TRACE=1), leader CTAs only: trace[(pair * pitch + i) * 16 + k] in SM clocks since
   // the CTA's entry: 0 producer starts waiting for the rows | 1 rows ready | 2 last load issued | 3 accumulator free
   // | 4 last MMA committed | 5 epilogue / LayerNorm starts waiting | 6 ready | 7 outputs published | 8 task code
-  // | 9 tile's stores issued; trace_hdr[pair * 2] = globaltimer (ns) and clock64 at entry
+  // | 9 tile's stores issued | 10..13 fused LayerNorm epilogue: accumulator ready, pass 1 done, statistics of the row
+  // complete, pass 2 done; trace_hdr[pair * 2] = globaltimer (ns) and clock64 at entry
   long long* trace;
   long long* trace_hdr;
 };
@@ -88,13 +100,14 @@ struct ChainCfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;           // this CTA's 128 rows
   static constexpr int kBBytes = (kChainBN / 2) * kGemmBK * 2;    // this CTA's half of the 256 weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 4;
   static constexpr int kStageEpi = 4096;                          // one 32 x 32 fp32 block per epilogue warp
   static constexpr int kStage16 = 2048;                           // ... and one 32 x 32 16-bit block (fused LayerNorm)
+  static constexpr int kStageRes = 4096;                          // ... and the landing block of the residual (TMA)
   static constexpr int kBiasBytes = 3 * (kChainBN / 2) * 4;       // bias, gamma, beta slices of the warp's 128 columns
-  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kStage16 + kBiasBytes);
+  static constexpr int kEpiBytes = kGemmEpiWarps * (kStageEpi + kStage16 + kStageRes + kBiasBytes);
   static constexpr int kTaskBytes = kChainMaxTasks * 4;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256 + kTaskBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 512 + kTaskBytes;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory");
 };
 
@@ -199,6 +212,20 @@ __device__ __forceinline__ void chain_ln_rows(const ChainStage& s, int row0, int
   }
 }
 
+// (mean, rstd) of one row from the (mean, M2) partials of its 128-column slices (Chan et al. pairwise merge)
+__device__ __forceinline__ float2 chain_row_stats(const float2* part, int width, int m_pad, int row, float eps) {
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  for (int t = 0; t * (kChainBN / 2) < width; ++t) {
+    const float nb = (float)min(kChainBN / 2, width - t * (kChainBN / 2));
+    const float2 pm = __ldcg(part + (long long)t * m_pad + row);
+    const float tot = cnt + nb, delta = pm.x - mean;
+    mean += delta * (nb / tot);
+    m2 += pm.y + delta * delta * (cnt * nb / tot);
+    cnt = tot;
+  }
+  return make_float2(mean, 1.0f / sqrtf(m2 / (float)width + eps));
+}
+
 // per-warp shared-memory areas of the epilogue
 struct ChainEpiSmem {
   uint8_t* pad;        // 4 KB: a 32 x 32 fp32 block (128B-swizzled TMA box / transpose area)
@@ -206,7 +233,141 @@ struct ChainEpiSmem {
   uint8_t* pad16;      // 2 KB: a 32 x 32 16-bit block (64B-swizzled TMA box)
   uint32_t pad16_u32;
   float *sv0, *sv1, *sv2;  // bias | gamma | beta of the warp's 128 columns
+  uint8_t* padr;       // 4 KB: the residual's 32 x 32 fp32 block, landed by TMA (ln == 2)
+  uint32_t padr_u32;
+  uint32_t rbar;       // this warp's mbarrier for the residual loads
 };
+
+// Epilogue of a dense + bias + LN_prev(residual) tile with the LayerNorm of the RESULT deferred (ChainStage::ln == 2).
+// One pass: the residual block of chunk c + 1 is in flight (TMA) while chunk c is combined, its statistics folded into
+// the running (count, mean, M2) of this warp's 128 columns, and written out pre-LayerNorm as fp32 and raw 16-bit.
+template <typename T16>
+__device__ __forceinline__ void chain_epilogue_defer(const ChainStage& s, const CUtensorMap* mo32, const CUtensorMap* mo16,
+                                                     const CUtensorMap* mr, int mrow0, int ncol0, int n0, uint32_t t_row,
+                                                     uint32_t tfull, uint32_t tfull_phase, const ChainEpiSmem& e, int lane,
+                                                     bool& staging_busy, uint32_t& rphase) {
+  constexpr int BN = kChainBN;
+  const int m_pad = chain_rows_padded(s.M);
+  const int n_live = max(0, min(BN / 2, s.N - ncol0));
+  const bool rows_ok = mrow0 < s.M;
+  const int row = mrow0 + lane;
+  const bool early = s.dep == nullptr;  // residual (and its statistics) come from an earlier launch
+  auto load_resid = [&](int c) {
+    if (lane == 0) {
+      mbar_expect_tx(e.rbar, 4096);
+      tma_load_2d(e.padr_u32, mr, e.rbar, ncol0 + c * 32, mrow0);
+    }
+  };
+  const bool work = rows_ok && n_live > 0;
+  float2 rs = make_float2(0.f, 1.f);
+  if (work && early) {
+    load_resid(0);
+    if (s.rpart) rs = chain_row_stats(s.rpart, s.N, m_pad, row, s.eps);
+  }
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (work && !early) {
+    if (lane == 0) fence_proxy_async_global();
+    load_resid(0);
+    if (s.rpart) rs = chain_row_stats(s.rpart, s.N, m_pad, row, s.eps);
+  }
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  if (work) {
+    const float ra = s.rpart ? rs.y : 1.f, rb = s.rpart ? -rs.x * rs.y : 0.f;  // LN_prev(r) = (r * ra + rb) * gamma + beta
+    uint32_t rbuf[32];
+    tmem_ld_32x32b_x32(t_row, rbuf);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int nc = ncol0 + c * 32;
+      const bool live = nc < s.N;  // warp-uniform; N is a multiple of 128: a live chunk is whole
+      if (live) {
+        mbar_wait(e.rbar, rphase);
+        rphase ^= 1u;
+      }
+      tmem_ld_wait();
+      float x[32];
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r4 = *reinterpret_cast<const float4*>(e.padr + lane * 128 + ((j ^ (lane & 7)) << 4));
+          const float4 b4 = *reinterpret_cast<const float4*>(e.sv0 + c * 32 + 4 * j);
+          if (s.rpart) {
+            const float4 g4 = *reinterpret_cast<const float4*>(e.sv1 + c * 32 + 4 * j);
+            const float4 e4 = *reinterpret_cast<const float4*>(e.sv2 + c * 32 + 4 * j);
+            r4.x = fmaf(fmaf(r4.x, ra, rb), g4.x, e4.x);
+            r4.y = fmaf(fmaf(r4.y, ra, rb), g4.y, e4.y);
+            r4.z = fmaf(fmaf(r4.z, ra, rb), g4.z, e4.z);
+            r4.w = fmaf(fmaf(r4.w, ra, rb), g4.w, e4.w);
+          }
+          x[4 * j] = __uint_as_float(rbuf[4 * j]) + b4.x + r4.x;
+          x[4 * j + 1] = __uint_as_float(rbuf[4 * j + 1]) + b4.y + r4.y;
+          x[4 * j + 2] = __uint_as_float(rbuf[4 * j + 2]) + b4.z + r4.z;
+          x[4 * j + 3] = __uint_as_float(rbuf[4 * j + 3]) + b4.w + r4.w;
+        }
+      }
+      __syncwarp();  // every lane has read the residual block: the next one may land
+      if (c + 1 < 4 && nc + 32 < s.N) load_resid(c + 1);
+      if (c + 1 < 4) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, rbuf);
+      if (live) {
+        // statistics of these 32 values (two passes in registers), merged into the running ones
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sm += x[j];
+        const float mc = sm * (1.0f / 32.0f);
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float d0 = x[j] - mc, d1 = x[j + 1] - mc;
+          q0 = fmaf(d0, d0, q0);
+          q1 = fmaf(d1, d1, q1);
+        }
+        const float tot = cnt + 32.f, delta = mc - mean;
+        mean += delta * (32.f / tot);
+        m2 += (q0 + q1) + delta * delta * (cnt * 32.f / tot);
+        cnt = tot;
+        if (staging_busy) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          staging_busy = false;
+        }
+        if (mo32 != nullptr) {
+          uint8_t* brow = e.pad + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(brow + ((j ^ (lane & 7)) * 16)) =
+                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        if (mo16 != nullptr) {
+          uint8_t* brow = e.pad16 + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = Cvt<T16>::pack2(x[8 * j + 0], x[8 * j + 1]);
+            u.y = Cvt<T16>::pack2(x[8 * j + 2], x[8 * j + 3]);
+            u.z = Cvt<T16>::pack2(x[8 * j + 4], x[8 * j + 5]);
+            u.w = Cvt<T16>::pack2(x[8 * j + 6], x[8 * j + 7]);
+            *reinterpret_cast<uint4*>(brow + ((j ^ ((lane >> 1) & 3)) * 16)) = u;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (mo32 != nullptr) tma_store_2d(mo32, e.pad_u32, nc, mrow0);
+          if (mo16 != nullptr) tma_store_2d(mo16, e.pad16_u32, nc, mrow0);
+          tma_store_commit();
+        }
+        staging_busy = true;
+      }
+      __syncwarp();
+    }
+    tmem_ld_wait();
+  }
+  if (rows_ok)  // this slice's partial: (mean, M2) of its live columns (an empty slice is never read)
+    s.part[(long long)(((n0 / BN) * 2 + (ncol0 - n0) / (BN / 2))) * m_pad + row] = make_float2(mean, m2);
+  __threadfence();  // ordered before this warp's "rows published" increment (the caller issues it)
+  __syncwarp();
+}
+
 
 // Epilogue of a dense + bias + residual + LayerNorm tile (see ChainStage::ln).  The warp owns rows mrow0..+31 (thread =
 // row = TMEM lane) and 128 columns from ncol0; x lives in TMEM (written back over the accumulator) between the passes.
@@ -214,7 +375,7 @@ template <typename T16>
 __device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUtensorMap* mo32, const CUtensorMap* mo16,
                                                   int mrow0, int ncol0, int n0, int mt, uint32_t t_row,
                                                   uint32_t tfull, uint32_t tfull_phase, const ChainEpiSmem& e, int lane,
-                                                  bool& staging_busy) {
+                                                  bool& staging_busy, long long* tmark, long long c_entry) {
   constexpr int BN = kChainBN;
   const int n_tiles = (s.N + BN - 1) / BN;
   const int m_pad = chain_rows_padded(s.M);
@@ -237,6 +398,7 @@ __device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUt
   if (rows_ok && early) load_resid(0);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
+  if (tmark) tmark[10] = clock64() - c_entry;
   if (rows_ok && !early) load_resid(0);
   float mean_l = 0.f, m2_l = 0.f;
   uint32_t rbuf[32];
@@ -296,12 +458,14 @@ __device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUt
     tmem_ld_wait();
     s.part[(long long)(((n0 / BN) * 2 + (ncol0 - n0) / (BN / 2))) * m_pad + row] = make_float2(mean_l, m2_l);
   }
+  if (tmark) tmark[11] = clock64() - c_entry;
   __threadfence();
   __syncwarp();
   if (lane == 0) flag_add_release(s.sflag + mt, 1u);
   if (!rows_ok) return;
   if (lane == 0) flag_wait_ge(s.sflag + mt, (unsigned)(n_tiles * kGemmEpiWarps));
   __syncwarp();
+  if (tmark) tmark[12] = clock64() - c_entry;
   // ---- merge the 2 * n_tiles partials of this row: n, mean, M2 (Chan et al. pairwise update)
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
   for (int t = 0; t < 2 * n_tiles; ++t) {
@@ -370,6 +534,7 @@ __device__ __forceinline__ void chain_epilogue_ln(const ChainStage& s, const CUt
     __syncwarp();
   }
   tmem_ld_wait();
+  if (tmark) tmark[13] = clock64() - c_entry;
 }
 
 template <typename T16>
@@ -389,7 +554,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
   uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
-  const int* task_s = reinterpret_cast<const int*>(epi_gen + Cfg::kEpiBytes + 256);
+  const int* task_s = reinterpret_cast<const int*>(epi_gen + Cfg::kEpiBytes + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -409,12 +574,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     }
   }
   auto mark = [&](int i, int k) {
-    if (tracing) p.trace[((long long)pair_id * p.pitch + i) * 10 + k] = clock64() - c_entry;
+    if (tracing) p.trace[((long long)pair_id * p.pitch + i) * 16 + k] = clock64() - c_entry;
   };
   pdl_launch_dependents();
   // the task list is static data (uploaded when the schedule was built): staged before the dependency wait
   {
-    int* dst = reinterpret_cast<int*>(epi_gen + Cfg::kEpiBytes + 256);
+    int* dst = reinterpret_cast<int*>(epi_gen + Cfg::kEpiBytes + 512);
     const int* src = p.tasks + (long long)pair_id * p.pitch;
     for (int i = threadIdx.x; i < p.pitch; i += blockDim.x) dst[i] = __ldg(src + i);
   }
@@ -425,6 +590,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         tma_prefetch_desc(&maps.b[p.st[s].map]);
         tma_prefetch_desc(&maps.o[p.st[s].map]);
         if (p.st[s].ln && p.st[s].map2 >= 0) tma_prefetch_desc(&maps.o2[p.st[s].map2]);
+        if (p.st[s].ln == 2) tma_prefetch_desc(&maps.r[p.st[s].map_r]);
       }
   }
   if (warp == 1) {
@@ -437,6 +603,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 2 * kGemmEpiWarps);
       }
+      for (int w = 0; w < kGemmEpiWarps; ++w) mbar_init(bars + 8u * (2 * kStages + 6 + w), 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -553,7 +720,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     constexpr int kColsPerWarp = BN / 2;
     uint8_t* pad = epi_gen + ew * Cfg::kStageEpi;
     const uint32_t pad_u32 = epi_base + ew * Cfg::kStageEpi;
-    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * (Cfg::kStageEpi + Cfg::kStage16) + ew * Cfg::kBiasBytes);
+    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * (Cfg::kStageEpi + Cfg::kStage16 + Cfg::kStageRes) +
+                                          ew * Cfg::kBiasBytes);
     ChainEpiSmem es;
     es.pad = pad;
     es.pad_u32 = pad_u32;
@@ -562,6 +730,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     es.sv0 = sv0;
     es.sv1 = sv0 + kColsPerWarp;
     es.sv2 = sv0 + 2 * kColsPerWarp;
+    es.padr = epi_gen + kGemmEpiWarps * (Cfg::kStageEpi + Cfg::kStage16) + ew * Cfg::kStageRes;
+    es.padr_u32 = epi_base + kGemmEpiWarps * (Cfg::kStageEpi + Cfg::kStage16) + ew * Cfg::kStageRes;
+    es.rbar = bars + 8u * (2 * kStages + 6 + ew);
+    uint32_t rphase = 0;
     bool staging_busy = false;  // a bulk store may still be reading this warp's staging block
     int it = 0;
     for (int i = 0;; ++i) {
@@ -571,7 +743,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       const bool tr = tracing && ew == 0 && lane == 0;
       if (tr) {
         mark(i, 5);
-        p.trace[((long long)pair_id * p.pitch + i) * 10 + 8] = task;
+        p.trace[((long long)pair_id * p.pitch + i) * 16 + 8] = task;
       }
       if (s.kind == CHAIN_LN) {
         // ---- 64 rows per pair task: this CTA's 32, 4 per warp
@@ -588,7 +760,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
           }
           if (tr) mark(i, 6);
           chain_ln_rows<T16>(s, row0, nrows, lane,
-                             tr ? p.trace + ((long long)pair_id * p.pitch + i) * 10 : nullptr);
+                             tr ? p.trace + ((long long)pair_id * p.pitch + i) * 16 : nullptr);
           if (tr) mark(i, 1);
           __threadfence();
           if (tr) mark(i, 2);
@@ -624,7 +796,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
           }
         }
         *reinterpret_cast<float4*>(sv0 + lane * 4) = b4;
-        if (s.ln) {  // LayerNorm scale / shift of the same columns (N is a multiple of 128 for these stages)
+        if (s.apart) {  // consumer of a deferred LayerNorm: g_n of the same columns
+          const bool in = nb + 3 < s.N;
+          *reinterpret_cast<float4*>(es.sv1 + lane * 4) =
+              in ? __ldg(reinterpret_cast<const float4*>(s.gvec + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (s.ln && s.gamma != nullptr) {  // LayerNorm scale / shift of the same columns (N is a multiple of 128 here)
           const bool in = nb + 3 < s.N;
           *reinterpret_cast<float4*>(es.sv1 + lane * 4) =
               in ? __ldg(reinterpret_cast<const float4*>(s.gamma + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -634,9 +811,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         __syncwarp();
       }
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
-      if (s.ln) {
+      if (s.ln == 2) {
+        chain_epilogue_defer<T16>(s, s.out32 ? mo : nullptr, s.map2 >= 0 ? &maps.o2[s.map2] : nullptr, &maps.r[s.map_r],
+                                  mrow0, ncol0, t.n0, t_row, tfull_bar(acc), acc_phase, es, lane, staging_busy, rphase);
+        if (tr) mark(i, 6);
+      } else if (s.ln) {
         chain_epilogue_ln<T16>(s, s.out32 ? mo : nullptr, s.map2 >= 0 ? &maps.o2[s.map2] : nullptr, mrow0, ncol0, t.n0,
-                               t.m0 / kGemmBM, t_row, tfull_bar(acc), acc_phase, es, lane, staging_busy);
+                               t.m0 / kGemmBM, t_row, tfull_bar(acc), acc_phase, es, lane, staging_busy,
+                               tr ? p.trace + ((long long)pair_id * p.pitch + i) * 16 : nullptr, c_entry);
         if (tr) mark(i, 6);
       } else {
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -646,6 +828,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         constexpr int NC = kColsPerWarp / 32;
         uint32_t rbuf[32];
         tmem_ld_32x32b_x32(t_row, rbuf);
+        // A operand = raw pre-LayerNorm rows, gamma folded into W: finish the normalisation with this row's statistics
+        float fa = 1.f, fb = 0.f;  // out = fa * acc + fb * g_n + c_n
+        if (s.apart) {
+          const float2 st = chain_row_stats(s.apart, s.K, chain_rows_padded(s.M), min(mrow0 + lane, s.M - 1), s.eps);
+          fa = st.y;
+          fb = -st.x * st.y;
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int nc = ncol0 + c * 32;
@@ -655,10 +844,18 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sv0 + c * 32 + j);
-            v[j] = __uint_as_float(rbuf[j]) + b4.x;
-            v[j + 1] = __uint_as_float(rbuf[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(rbuf[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(rbuf[j + 3]) + b4.w;
+            if (s.apart) {
+              const float4 g4 = *reinterpret_cast<const float4*>(es.sv1 + c * 32 + j);
+              v[j] = fmaf(fa, __uint_as_float(rbuf[j]), fmaf(fb, g4.x, b4.x));
+              v[j + 1] = fmaf(fa, __uint_as_float(rbuf[j + 1]), fmaf(fb, g4.y, b4.y));
+              v[j + 2] = fmaf(fa, __uint_as_float(rbuf[j + 2]), fmaf(fb, g4.z, b4.z));
+              v[j + 3] = fmaf(fa, __uint_as_float(rbuf[j + 3]), fmaf(fb, g4.w, b4.w));
+            } else {
+              v[j] = __uint_as_float(rbuf[j]) + b4.x;
+              v[j + 1] = __uint_as_float(rbuf[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(rbuf[j + 2]) + b4.z;
+              v[j + 3] = __uint_as_float(rbuf[j + 3]) + b4.w;
+            }
           }
           if (s.gelu) {
 #pragma unroll
@@ -709,11 +906,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
         if (tr) mark(i, 9);
-        // publish: this warp's blocks of the tile are in L2
-        tma_store_wait<0>();
+        // publish: this warp's blocks of the tile are in L2 (a stage nobody reads within this launch only needs its
+        // staging block back: the kernel's end waits for the stores themselves)
         if (s.done != nullptr) {
+          tma_store_wait<0>();
           fence_proxy_async_global();
           flag_add_release(s.done + t.m0 / kGemmBM, 1u);
+        } else {
+          tma_store_wait_read<0>();
         }
         if (tr) mark(i, 7);
       }

@@ -155,7 +155,9 @@ struct cpt_handle {
   int chain = 1;                 // CPT_B200_CHAIN=0: the round-1 launch sequence (one kernel per GEMM / LayerNorm)
   int chain_min_rows = 1024;     // below this many rows the narrow-tile GEMMs of the unfused path spread better
   int chain_down_ksplit = 1;     // CPT_B200_CHAIN_KSPLIT: K pieces of the FFN-down tiles (unfused LayerNorm only)
-  int chain_fuse_ln = 1;         // CPT_B200_CHAIN_FUSE_LN=0: LayerNorm as row tasks between the GEMM stages
+  int chain_fuse_ln = 2;         // CPT_B200_CHAIN_FUSE_LN: 0 LayerNorm as row tasks between the GEMM stages, 1 finished
+                                 // in the dense epilogues (row statistics exchanged through L2), 2 deferred to the consumers
+  int chain_groups = 1;          // CPT_B200_CHAIN_GROUPS: row groups software-pipelined across the stages
   float2* chain_part = nullptr;  // cpt_chain_run (tests): scratch of the fused LayerNorm epilogues
   size_t chain_part_bytes = 0;
   struct ChainSched { int pairs = 0, pitch = 0; int* dev = nullptr; };
@@ -791,14 +793,26 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
       p.M = M; p.N = 3 * H; p.K = H; p.out = w.qkv16; p.ldo = 3 * H; p.bias = h->layers[0].b_qkv;
       TRY(gemm<T16>(h, st, CPT_K_GEMM_QKV, w.h16, H, h->layers[0].w_qkv, H, p, EPI_BIAS, false));
     }
-    for (int l = 0; l < L; ++l) {
-      TRY(attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl));
-      float* o32 = (l == L - 1) ? seq_out : w.h32;
-      TRY(chain_layer<T16>(h, st, w, l, M, o32, l == L - 1,
-                           w.flags + (size_t)l * (chain_ctr_per_layer / sizeof(unsigned))));
-      if (hidden_states)
-        CK(cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, st));
+    const int saved_mode = h->chain_fuse_ln;
+    if (hidden_states && h->chain_fuse_ln == 2) h->chain_fuse_ln = 1;  // per-layer outputs need finished LayerNorms
+    int rc = 0;
+    for (int l = 0; l < L && !rc; ++l) {
+      rc = attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl);
+      float* o32 = (l == L - 1 && h->chain_fuse_ln != 2) ? seq_out : w.h32;
+      if (!rc)
+        rc = chain_layer<T16>(h, st, w, l, M, o32, l == L - 1,
+                              w.flags + (size_t)l * (chain_ctr_per_layer / sizeof(unsigned)));
+      if (!rc && hidden_states &&
+          cudaMemcpyAsync(hidden_states + (size_t)(l + 1) * M * H, o32, (size_t)M * H * 4, cudaMemcpyDeviceToDevice,
+                          st) != cudaSuccess)
+        rc = fail("cudaMemcpyAsync(hidden_states) failed");
     }
+    if (!rc && h->chain_fuse_ln == 2) {  // the last layer's BertOutput.LayerNorm: h32 holds its pre-LayerNorm rows
+      const LayerDev& last = h->layers[L - 1];
+      rc = layernorm<T16>(h, st, w.h32, H, M, H, last.o_g, last.o_b, c.layer_norm_eps, true, seq_out, nullptr);
+    }
+    h->chain_fuse_ln = saved_mode;
+    TRY(rc);
   } else if (fold) {
     // LayerNorm folded into the GEMMs on either side of it (DESIGN.md "LayerNorm folding"): the stream buffers hold
     // PRE-LayerNorm rows (fp32 + 16-bit) plus per-row (sum, sum of squares); no LayerNorm kernel runs between GEMMs.
@@ -1001,7 +1015,8 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_REDUCE_RESID")) h->reduce_resid = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN")) h->chain = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_TRACE")) h->chain_trace_on = atoi(e) != 0;
-  if (const char* e = getenv("CPT_B200_CHAIN_FUSE_LN")) h->chain_fuse_ln = atoi(e) != 0;
+  if (const char* e = getenv("CPT_B200_CHAIN_FUSE_LN")) h->chain_fuse_ln = std::max(0, std::min(2, atoi(e)));
+  if (const char* e = getenv("CPT_B200_CHAIN_GROUPS")) h->chain_groups = std::max(1, atoi(e));
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
@@ -1371,6 +1386,10 @@ int cpt_chain_run(cpt_handle* h, void* stream, const cpt_chain_stage* stages, in
     d.ln_in = s.ln_in; d.gamma = s.gamma; d.beta = s.beta; d.eps = s.eps; d.out32 = s.out32; d.out16 = s.out16;
     d.dep_stage = s.dep_stage;
     d.ln = s.ln; d.resid = s.resid; d.ldr = s.ldr;
+    d.gvec = s.gvec;
+    d.part = reinterpret_cast<float2*>(s.part);
+    d.rpart = reinterpret_cast<const float2*>(s.rpart);
+    d.apart = reinterpret_cast<const float2*>(s.apart);
   }
   int widest = 128;
   for (auto& d : hs) if (d.ln) widest = std::max(widest, d.N);
@@ -1403,7 +1422,7 @@ int cpt_chain_trace(cpt_handle* h, long long* out, long long max_words, int* pai
   CK(cudaDeviceSynchronize());
   *pairs = h->chain_trace_pairs;
   *pitch = h->chain_trace_pitch;
-  const long long words = (long long)h->chain_trace_pairs * (2 + (long long)h->chain_trace_pitch * 10);
+  const long long words = (long long)h->chain_trace_pairs * (2 + (long long)h->chain_trace_pitch * 16);
   if (words > max_words) return fail("cpt_chain_trace: buffer too small (%lld words needed)", words);
   CK(cudaMemcpy(out, h->chain_trace, (size_t)words * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;

@@ -660,13 +660,18 @@ class Engine(object):
                 c.ln_in, c.gamma, c.beta, c.eps = x.data_ptr(), s["gamma"].data_ptr(), s["beta"].data_ptr(), s["eps"]
                 c.out32 = 0 if s.get("out32") is None else s["out32"].data_ptr()
                 c.out16 = 0 if s.get("out16") is None else s["out16"].data_ptr()
-            elif s.get("resid") is not None:  # dense + bias + residual + LayerNorm in the tile epilogue
+            elif s.get("resid") is not None:  # dense + bias + residual (+ LayerNorm in the tile epilogue, or deferred)
                 A, W, r = s["A"], s["W"], s["resid"]
-                c.kind, c.M, c.K, c.N, c.ln, c.ksplit = 0, A.shape[0], A.shape[1], W.shape[0], 1, 1
+                c.kind, c.M, c.K, c.N, c.ksplit = 0, A.shape[0], A.shape[1], W.shape[0], 1
+                c.ln = 2 if s.get("part") is not None else 1
                 c.A, c.lda, c.W, c.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
                 c.bias = 0 if s.get("bias") is None else s["bias"].data_ptr()
                 c.resid, c.ldr = r.data_ptr(), r.stride(0)
-                c.gamma, c.beta, c.eps = s["gamma"].data_ptr(), s["beta"].data_ptr(), s["eps"]
+                c.gamma = 0 if s.get("gamma") is None else s["gamma"].data_ptr()
+                c.beta = 0 if s.get("beta") is None else s["beta"].data_ptr()
+                c.eps = s.get("eps", 0.0)
+                c.part = 0 if s.get("part") is None else s["part"].data_ptr()
+                c.rpart = 0 if s.get("rpart") is None else s["rpart"].data_ptr()
                 c.out32 = 0 if s.get("out32") is None else s["out32"].data_ptr()
                 c.out16 = 0 if s.get("out16") is None else s["out16"].data_ptr()
             else:
@@ -676,11 +681,13 @@ class Engine(object):
                 c.A, c.lda, c.W, c.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
                 c.bias = 0 if s.get("bias") is None else s["bias"].data_ptr()
                 c.out, c.ldo = out.data_ptr(), out.stride(0)
+                if s.get("apart") is not None:  # A = raw rows of a deferred LayerNorm, W = gamma-folded weight
+                    c.apart, c.gvec, c.eps = s["apart"].data_ptr(), s["gvec"].data_ptr(), s["eps"]
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cpt_chain_run(self._h, _stream(), arr, len(stages)))
 
     def chain_trace(self):
-        """Event log of the last chain launch: (header [pairs,2], events [pairs,pitch,10]) as nested lists."""
+        """Event log of the last chain launch: (header [pairs,2], events [pairs,pitch,16]) as nested lists."""
         n = 1 << 22
         buf = (C.c_longlong * n)()
         pairs, pitch = C.c_int(), C.c_int()
@@ -688,7 +695,7 @@ class Engine(object):
         P, W = pairs.value, pitch.value
         hdr = [list(buf[2 * i:2 * i + 2]) for i in range(P)]
         off = 2 * P
-        ev = [[list(buf[off + (i * W + j) * 10:off + (i * W + j) * 10 + 10]) for j in range(W)] for i in range(P)]
+        ev = [[list(buf[off + (i * W + j) * 16:off + (i * W + j) * 16 + 16]) for j in range(W)] for i in range(P)]
         return hdr, ev
 
     def gemm_trace(self, n=148):

@@ -298,13 +298,20 @@ typedef struct {
   float eps;
   float *out32;
   void *out16;
-  int32_t ln;
+  int32_t ln; /* 1: LayerNorm finished in the epilogue; 2: deferred — out32 / out16 are PRE-LayerNorm, `part` gets the
+                 (mean, M2) partials of the rows ([2 * ceil(N / 256)][rows padded to 256] float2), the residual is
+                 normalised on the fly from `rpart` (its own partials; NULL = used as it is) with gamma / beta / eps */
   const float *resid;
   int64_t ldr;
+  void *part;
+  const void *rpart;
+  const void *apart; /* kind 0 consumer of a deferred LayerNorm: A holds raw rows, W carries gamma, bias = c vector,
+                        gvec = g vector (cpt_b200/csrc/rowwise.cuh fold_weight_kernel); statistics from `apart` */
+  const float *gvec;
 } cpt_chain_stage;
 int cpt_chain_run(cpt_handle *h, void *stream, const cpt_chain_stage *stages, int n_stages);
 /* Debug: event log of the LAST chain launch (needs CPT_B200_CHAIN_TRACE=1 in the environment at cpt_create).
- * out = [pairs][2] {globaltimer ns, clock64 at CTA entry} followed by [pairs][pitch][10] SM-clock stamps per task of the
+ * out = [pairs][2] {globaltimer ns, clock64 at CTA entry} followed by [pairs][pitch][16] SM-clock stamps per task of the
  * leader CTA's list (chain_sm100.cuh: ChainParams::trace). */
 int cpt_chain_trace(cpt_handle *h, long long *out, long long max_words, int *pairs, int *pitch);
 /* y = LayerNorm(x) rows: fp32 in, fp32 and/or 16-bit out (either may be NULL). */

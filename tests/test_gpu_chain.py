@@ -186,11 +186,72 @@ def test_full_layer_chain_matches_unfused_kernels(eng, M):
     assert (f_qkv.float() - qkv.float()).abs().max().item() <= 1e-2 * qkv.float().abs().max().item()
 
 
+def _fold(W, gamma, beta, bias):
+    """Host statement of fold_weight_kernel (cpt_b200/csrc/rowwise.cuh): LN(x) W^T + b = rstd (x (gamma .* W)^T - mu g) + c."""
+    Wf = (W.float() * gamma[None, :]).half()
+    return Wf, Wf.float().sum(1).contiguous(), (W.float() @ beta + bias).contiguous()
+
+
+def _part(M, N):
+    m_pad = ((M + 127) // 128 + 1) // 2 * 2 * 128
+    return torch.zeros(2 * ((N + 255) // 256), m_pad, 2, device="cuda")
+
+
+@pytest.mark.parametrize("M", [256, 1000, 7680])
+def test_layer_chain_with_deferred_layernorm(eng, M):
+    """The production form: no LayerNorm pass at all.  Dense outputs are written pre-LayerNorm with per-row statistics;
+    the consumer GEMMs read the raw rows with gamma folded into their weights and finish the normalisation in their
+    epilogues; the residual of the second dense is normalised on the fly."""
+    H, I = 768, 3072
+    g = torch.Generator(device="cuda").manual_seed(M + 1)
+    ctx = _rand16(g, M, H)
+    h32 = torch.randn(M, H, device="cuda", generator=g)
+    Wao, Wi, Wo, Wq = (_rand16(g, H, H, scale=0.03), _rand16(g, I, H, scale=0.03), _rand16(g, H, I, scale=0.02),
+                       _rand16(g, 3 * H, H, scale=0.03))
+    bao, bi, bo, bq = (torch.randn(n, device="cuda", generator=g) * 0.1 for n in (H, I, H, 3 * H))
+    g1, g2 = (torch.rand(H, device="cuda", generator=g) + 0.5 for _ in range(2))
+    b1, b2 = (torch.randn(H, device="cuda", generator=g) * 0.2 for _ in range(2))
+    # reference in double precision on the same 16-bit operands
+    x1 = ctx.double() @ Wao.double().t() + bao.double() + h32.double()
+    a = torch.nn.functional.layer_norm(x1, (H,), g1.double(), b1.double(), 1e-12)
+    inter = _gelu(a @ Wi.double().t() + bi.double())
+    x2 = inter @ Wo.double().t() + bo.double() + a
+    o = torch.nn.functional.layer_norm(x2, (H,), g2.double(), b2.double(), 1e-12)
+    qkv = o @ Wq.double().t() + bq.double()
+    Wi_f, gi, ci = _fold(Wi, g1, b1, bi)
+    Wq_f, gq, cq = _fold(Wq, g2, b2, bq)
+    P1, P2 = _part(M, H), _part(M, H)
+    a32, x2_32 = torch.empty_like(h32), torch.empty_like(h32)
+    a16 = torch.empty(M, H, device="cuda", dtype=torch.float16)
+    x2_16 = torch.empty_like(a16)
+    c_inter = torch.empty(M, I, device="cuda", dtype=torch.float16)
+    c_qkv = torch.empty(M, 3 * H, device="cuda", dtype=torch.float16)
+    for _ in range(2):
+        eng.chain([dict(kind="gemm", A=ctx, W=Wao, bias=bao, resid=h32, out32=a32, out16=a16, part=P1),
+                   dict(kind="gemm", A=a16, W=Wi_f, bias=ci, gvec=gi, apart=P1, eps=1e-12, out=c_inter, gelu=1, dep=0),
+                   dict(kind="gemm", A=c_inter, W=Wo, bias=bo, resid=a32, rpart=P1, gamma=g1, beta=b1, eps=1e-12,
+                        out32=x2_32, out16=x2_16, part=P2, dep=1),
+                   dict(kind="gemm", A=x2_16, W=Wq_f, bias=cq, gvec=gq, apart=P2, eps=1e-12, out=c_qkv, dep=2)])
+    torch.cuda.synchronize()
+    assert (a32.double() - x1).abs().max().item() <= 3e-5 * x1.abs().max().item()
+    assert (c_inter.double() - inter).abs().max().item() <= 4e-3 * inter.abs().max().item()
+    got_o = torch.nn.functional.layer_norm(x2_32.double(), (H,), g2.double(), b2.double(), 1e-12)
+    assert (got_o - o).abs().max().item() <= 1e-2           # fp16 rounding of inter / a16 feeds through K = 3072
+    assert (c_qkv.double() - qkv).abs().max().item() <= 1.2e-2 * qkv.abs().max().item()
+    # the partials describe the rows: merged mean / variance against torch
+    n_sl = H // 128
+    means, m2s = P2[:n_sl, :M, 0].double(), P2[:n_sl, :M, 1].double()
+    mean = means.mean(0)
+    var = (m2s.sum(0) + 128 * ((means - mean[None]) ** 2).sum(0)) / H
+    assert (mean - x2_32.double().mean(1)).abs().max().item() <= 1e-4
+    assert (var - x2_32.double().var(1, unbiased=False)).abs().max().item() <= 1e-3 * var.max().item()
+
+
 def _models(cfg, sd, chain):
     from cpt_b200.modeling_bert import BertImgForPreTraining
     from cpt_b200.modeling_rec import REC_MLM_CPT
     os.environ["CPT_B200_CHAIN"] = "1" if chain else "0"
-    os.environ["CPT_B200_CHAIN_FUSE_LN"] = "0" if chain == "tasks" else "1"
+    os.environ["CPT_B200_CHAIN_FUSE_LN"] = {"tasks": "0", "epilogue": "1"}.get(chain, "2")
     os.environ["CPT_B200_CHAIN_MIN_ROWS"] = "1"
     try:
         pre = BertImgForPreTraining(cfg)
@@ -218,7 +279,7 @@ def test_chained_encoder_matches_unfused_and_oracle(geom, B, T, R):
     vids = synth_vocab_ids(cfg, 7, seed=88)
     d = {k: v.to("cuda:0") for k, v in b.items()}
     outs = []
-    for chain in (True, False, "tasks"):
+    for chain in (True, False, "tasks", "epilogue"):
         rec = _models(cfg, sd, chain)
         with torch.no_grad():
             seq = rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
@@ -227,9 +288,10 @@ def test_chained_encoder_matches_unfused_and_oracle(geom, B, T, R):
             rec.bert.engine().check()
         outs.append((seq.cpu(), logits.cpu()))
         del rec
-    (seq_c, log_c), (seq_u, log_u), (seq_t, log_t) = outs
-    assert (seq_c - seq_u).abs().max().item() <= 2e-3 * seq_u.abs().max().item()
-    assert (seq_t - seq_u).abs().max().item() <= 2e-3 * seq_u.abs().max().item()
+    (seq_c, log_c), (seq_u, log_u), (seq_t, log_t), (seq_e, log_e) = outs
+    for other in (seq_c, seq_t, seq_e):
+        assert (other - seq_u).abs().max().item() <= 2e-3 * seq_u.abs().max().item()
+    assert not torch.equal(seq_c, seq_e)   # the switches really selected different paths
     with torch.no_grad():
         oseq, _, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
                                       img_feats=b["img_feats"])

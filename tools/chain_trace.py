@@ -52,6 +52,19 @@ def main():
                            out16=a16)),
              ("downln", dict(kind="gemm", A=inter, W=Wo, bias=bo, resid=a32, gamma=g2, beta=b2, eps=1e-12, out32=o32,
                              out16=o16))]
+    # LayerNorm deferred to the consumers (production)
+    def fold(W, gamma, beta, bias):
+        Wf = (W.float() * gamma[None, :]).half()
+        return Wf, Wf.float().sum(1).contiguous(), (W.float() @ beta + bias).contiguous()
+    m_pad = ((M + 127) // 128 + 1) // 2 * 2 * 128
+    P1, P2 = torch.zeros(6, m_pad, 2, device="cuda"), torch.zeros(6, m_pad, 2, device="cuda")
+    Wi_f, gi, ci = fold(Wi, g1, b1, bi)
+    Wq_f, gq, cq = fold(Wq, g2, b2, bq)
+    allst += [("aod", dict(kind="gemm", A=ctx, W=Wao, bias=bao, resid=f32, out32=a32, out16=a16, part=P1)),
+              ("upd", dict(kind="gemm", A=a16, W=Wi_f, bias=ci, gvec=gi, apart=P1, eps=1e-12, out=inter, gelu=1)),
+              ("downd", dict(kind="gemm", A=inter, W=Wo, bias=bo, resid=a32, rpart=P1, gamma=g1, beta=b1, eps=1e-12,
+                             out32=o32, out16=o16, part=P2)),
+              ("qkvd", dict(kind="gemm", A=o16, W=Wq_f, bias=cq, gvec=gq, apart=P2, eps=1e-12, out=qkv))]
     stages, names = [], []
     table = dict(allst)
     for n in want:   # stages run in the order given on the command line
@@ -134,6 +147,15 @@ def main():
                       "publish %.2f" % (rec[0] / GHZ / 1e3, rec[3] / GHZ / 1e3, rec[4] / GHZ / 1e3,
                                         (rec[1] - rec[6]) / GHZ / 1e3, (rec[2] - rec[1]) / GHZ / 1e3,
                                         (rec[7] - rec[2]) / GHZ / 1e3))
+    shown = 0
+    for p, lst in enumerate(ev):
+        for rec in lst:
+            if (rec[8] or rec[5]) and rec[13] and shown < 8:
+                shown += 1
+                print("fused tile %s raw (us): waited for the accumulator %.2f | pass 1 %.2f | row statistics %.2f | "
+                      "pass 2 %.2f | released+published %.2f" %
+                      (names[rec[8] >> 24], (rec[10] - rec[5]) / GHZ / 1e3, (rec[11] - rec[10]) / GHZ / 1e3,
+                       (rec[12] - rec[11]) / GHZ / 1e3, (rec[13] - rec[12]) / GHZ / 1e3, (rec[7] - rec[13]) / GHZ / 1e3))
     if a.json:
         json.dump(dict(names=names, hdr=hdr, ev=ev), open(a.json, "w"))
 
