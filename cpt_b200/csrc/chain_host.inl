@@ -152,6 +152,11 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
   memset(&p, 0, sizeof p);
   p.n_stages = n;
   int n_maps = 0, n_fused = 0;
+  // the production kernel (chain2_sm100.cuh) handles launches made of deferred-LayerNorm stages and 16-bit-output GEMM
+  // stages only; its residual tiles travel through the operand ring as 128-row boxes
+  bool lean = h->chain_lean != 0;
+  for (int i = 0; i < n; ++i)
+    lean = lean && hs[i].kind == CHAIN_GEMM && (hs[i].ln == 2 || (hs[i].ln == 0 && !hs[i].out_fp32)) && hs[i].ksplit <= 1;
   for (int i = 0; i < n; ++i) {
     const ChainStageHost& s = hs[i];
     ChainStage& d = p.st[i];
@@ -206,7 +211,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       d.map = d.map_r = n_maps;
       TRY(make_tmap(&maps.a[n_maps], s.A, dt, s.M, s.K, s.lda, kGemmBM));
       TRY(make_tmap(&maps.b[n_maps], s.W, dt, s.N, s.K, s.ldw, kChainBN / 2));
-      TRY(make_tmap_ex(&maps.r[n_maps], s.resid, 2, s.M, s.N, s.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+      TRY(make_tmap_ex(&maps.r[n_maps], s.resid, 2, s.M, s.N, s.ldr, 32, lean ? kGemmBM : 32, CU_TENSOR_MAP_SWIZZLE_128B));
       if (s.out32) TRY(make_tmap_ex(&maps.o[n_maps], s.out32, 2, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
       if (s.out16) {
         TRY(make_tmap_ex(&maps.o2[n_maps], s.out16, dt, s.M, s.N, s.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -289,13 +294,23 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
     h->chain_trace_pairs = pairs;
     h->chain_trace_pitch = p.pitch;
   }
+  ProfScope ps(h, st, CPT_K_CHAIN);
+  if (lean) {
+    auto* fn = chain2_kernel<T16>;
+    static bool attr_set2[64] = {};
+    if (!attr_set2[h->device & 63]) {
+      TRY(set_smem_attr(fn, Chain2Cfg::kSmemBytes));
+      attr_set2[h->device & 63] = true;
+    }
+    CK(launch_k(fn, dim3(pairs * 2), dim3(kGemmThreads), Chain2Cfg::kSmemBytes, st, 2, maps, p));
+    return 0;
+  }
   auto* fn = chain_kernel<T16>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
     TRY(set_smem_attr(fn, ChainCfg::kSmemBytes));
     attr_set[h->device & 63] = true;
   }
-  ProfScope ps(h, st, CPT_K_CHAIN);
   CK(launch_k(fn, dim3(pairs * 2), dim3(kGemmThreads), ChainCfg::kSmemBytes, st, 2, maps, p));
   return 0;
 }

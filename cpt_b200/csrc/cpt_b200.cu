@@ -22,6 +22,7 @@
 #include "attention_bwd_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "chain_sm100.cuh"
+#include "chain2_sm100.cuh"
 #include "optim.cuh"
 #include "rowwise.cuh"
 #include "scoring.cuh"
@@ -158,6 +159,7 @@ struct cpt_handle {
   int chain_fuse_ln = 2;         // CPT_B200_CHAIN_FUSE_LN: 0 LayerNorm as row tasks between the GEMM stages, 1 finished
                                  // in the dense epilogues (row statistics exchanged through L2), 2 deferred to the consumers
   int chain_groups = 1;          // CPT_B200_CHAIN_GROUPS: row groups software-pipelined across the stages
+  int chain_lean = 1;            // CPT_B200_CHAIN_LEAN=0: run deferred-LayerNorm launches on the general kernel
   float2* chain_part = nullptr;  // cpt_chain_run (tests): scratch of the fused LayerNorm epilogues
   size_t chain_part_bytes = 0;
   struct ChainSched { int pairs = 0, pitch = 0; int* dev = nullptr; };
@@ -1017,6 +1019,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_CHAIN_TRACE")) h->chain_trace_on = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_FUSE_LN")) h->chain_fuse_ln = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("CPT_B200_CHAIN_GROUPS")) h->chain_groups = std::max(1, atoi(e));
+  if (const char* e = getenv("CPT_B200_CHAIN_LEAN")) h->chain_lean = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
