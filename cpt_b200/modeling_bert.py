@@ -24,12 +24,13 @@ from .engine import CptError, Engine
 logger = logging.getLogger(__name__)
 WEIGHTS_NAME = "pytorch_model.bin"
 
-# "Did a parameter change since the handle converted its 16-bit copies?" answered in O(1): every event that can change
-# a parameter bumps this epoch — any torch.optim.Optimizer step (global post-step hook: covers torch's optimizers,
+# "Did a parameter change since the handle converted its 16-bit copies?" answered without walking the module tree: every
+# event that can MOVE or replace a parameter bumps this epoch — any torch.optim.Optimizer step (global post-step hook: covers torch's optimizers,
 # pytorch-transformers' AdamW, apex, cpt_b200.optimization.AdamW), load_state_dict, Module._apply (.to / .cuda / .half),
-# weight tying — and a native backward sets the slot's dirty flags.  Only when the epoch moved do engine() /
-# train_engine() rescan the ~200 (data_ptr, version) pairs.  Code that writes parameters behind all of these (a bare
-# `p.data.copy_()` in an inference loop) calls `model.bert.mark_weights_changed()`.
+# weight tying — and a native backward sets the slot's dirty flags; in-place edits (`p.mul_()`, `p.copy_()`) show up in
+# the sum of the version counters of the cached tensor list.  Only when one of these moved do engine() / train_engine()
+# walk the modules and rebuild the ~200-entry (data_ptr, version) signature.  Code that writes parameters behind all of
+# them (`p.data.copy_()` in an inference loop, no optimizer) calls `model.bert.mark_weights_changed()`.
 _WEIGHT_EPOCH = [0]
 # Optimizer steps are counted separately: pytorch-transformers 1.x AdamW and apex update through `p.data`, which leaves
 # the autograd version counters untouched, so after ANY optimizer step the 16-bit copies are refreshed even when the
@@ -173,6 +174,7 @@ class _EngineSlot(object):
         self.epoch, self.train_epoch = -1, -1  # value of _WEIGHT_EPOCH the signatures were taken at
         self.train_named = None
         self.opt_epoch, self.train_opt_epoch = 0, 0
+        self.tensors, self.version_sum, self.train_version_sum = [], -1, -1
         # Set by every native backward (training._Loss.backward): an optimizer step may follow, and optimizers that
         # update through `p.data` (pytorch-transformers 1.x AdamW, apex) do NOT bump the autograd version counters the
         # signatures below key on — so after a backward both handles refresh their 16-bit copies unconditionally.
@@ -348,7 +350,10 @@ class BertImgModel(BertPreTrainedModel):
     def engine(self):
         slot = self._dev_slot()
         if slot.engine is not None and slot.sig is not None and not slot.dirty_infer and (
-                slot.frozen or (_WEIGHT_EPOCH is not None and slot.epoch == _WEIGHT_EPOCH[0])):
+                slot.frozen or (_WEIGHT_EPOCH is not None and slot.epoch == _WEIGHT_EPOCH[0]
+                                and slot.version_sum == sum(t._version for t in slot.tensors))):
+            # nothing that can move or rewrite a parameter happened (epoch), and no in-place edit either (the sum of
+            # the autograd version counters over the cached tensor list: ~10 us, no module walk, no tuple building)
             return slot.engine
         epoch = _WEIGHT_EPOCH[0] if _WEIGHT_EPOCH is not None else -1
         sd = self._named_tensors()
@@ -367,6 +372,8 @@ class BertImgModel(BertPreTrainedModel):
             slot.engine.load_state_dict(sd)
             slot.sig, slot.dirty_infer, slot.opt_epoch = sig, False, _OPT_EPOCH[0]
         slot.epoch = epoch if slot is self._slot else -1  # DataParallel replicas get fresh tensors every forward
+        slot.tensors = list(sd.values())
+        slot.version_sum = sum(t._version for t in slot.tensors)
         return slot.engine
 
     def train_engine(self):
@@ -375,7 +382,8 @@ class BertImgModel(BertPreTrainedModel):
         copies for the dgrad GEMMs, refreshed in place from the fp32 parameters whenever one of them changed."""
         slot = self._dev_slot()
         if (slot.train_engine is not None and slot.train_sig is not None and not slot.dirty_train
-                and _WEIGHT_EPOCH is not None and slot.train_epoch == _WEIGHT_EPOCH[0] and slot.train_named is not None):
+                and _WEIGHT_EPOCH is not None and slot.train_epoch == _WEIGHT_EPOCH[0] and slot.train_named is not None
+                and slot.train_version_sum == sum(t._version for t in slot.train_named.values())):
             return slot.train_engine, slot.train_named
         epoch = _WEIGHT_EPOCH[0] if _WEIGHT_EPOCH is not None else -1
         sd = self._named_tensors()
@@ -398,6 +406,7 @@ class BertImgModel(BertPreTrainedModel):
             slot.train_sig, slot.dirty_train, slot.train_opt_epoch = sig, False, _OPT_EPOCH[0]
         slot.train_epoch = epoch if slot is self._slot else -1
         slot.train_named = sd
+        slot.train_version_sum = sum(t._version for t in sd.values())
         return slot.train_engine, sd
 
     def _dropout_active(self):
