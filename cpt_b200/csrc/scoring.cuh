@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(128) score_queries_kernel(const ScoreParams p)
   const double* g = p.gt + 4ll * q;
   const double ix1 = fmax(x1, g[0]), iy1 = fmax(y1, g[1]);
   const double ix2 = fmin(x1 + aw - 1.0, g[0] + g[2] - 1.0), iy2 = fmin(y1 + ah - 1.0, g[1] + g[3] - 1.0);
+  // explicit round-to-nearest products / sums: no fused multiply-add, so every intermediate is the double the reference's
+  // Python arithmetic produces and the IoU is bit-identical, not just the decision
   double inter = 0.0;
-  if (ix1 < ix2 && iy1 < iy2) inter = (ix2 - ix1 + 1.0) * (iy2 - iy1 + 1.0);
-  const double uni = aw * ah + g[2] * g[3] - inter;
+  if (ix1 < ix2 && iy1 < iy2) inter = __dmul_rn(ix2 - ix1 + 1.0, iy2 - iy1 + 1.0);
+  const double uni = __dadd_rn(__dadd_rn(__dmul_rn(aw, ah), __dmul_rn(g[2], g[3])), -inter);
   const double v = inter / uni;
   if (p.iou) p.iou[q] = v;
   if (p.correct) p.correct[q] = v > 0.5 ? 1 : 0;

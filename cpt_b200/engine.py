@@ -487,17 +487,30 @@ class Engine(object):
             loop hits: it moves every batch to the device anew (Oscar/oscar/zeroshot/refcoco_cpt.py:212-219), so
             addresses never repeat — without the staging graph each forward paid ~1.8 ms of host enqueue time for
             ~40 launches' worth of GPU work."""
-        def eager():
-            seq, _, _ = self.encoder_forward(input_ids, token_type_ids, attention_mask, position_ids, img_feats,
-                                             want_pooled=False)
-            return self.mlm_gather(seq, mask_pos, vocab_ids)
+        def run(t):
+            seq, _, _ = self.encoder_forward(t[0], t[1], t[2], t[3], t[4], want_pooled=False)
+            return self.mlm_gather(seq, t[5], t[6])
 
+        return self._graphed("mlm", (input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
+                                     vocab_ids), run)
+
+    def nsp_scores(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats):
+        """encoder + pooler + seq_relationship head in one (graph-replayed) call: NSPCPT.forward without labels
+        (Oscar/oscar/modeling/modeling_vcr.py:115-123), the VCR inference step (fewshot/vcr_nsp_cpt.py:597-600)."""
+        def run(t):
+            _, pooled, _ = self.encoder_forward(t[0], t[1], t[2], t[3], t[4], want_pooled=True)
+            return self.nsp(pooled)
+
+        return self._graphed("nsp", (input_ids, token_type_ids, attention_mask, position_ids, img_feats), run)
+
+    def _graphed(self, kind, ts, run):
+        """Run `run(ts)` (a fixed launch sequence over the tensors `ts`), replaying CUDA graphs as described in
+        cpt_logits."""
         if not self.use_graphs or self._profiling or torch.cuda.is_current_stream_capturing():
-            return eager()
-        ts = (input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos, vocab_ids)
+            return run(ts)
         if any(t is not None and not t.is_contiguous() for t in ts):
-            return eager()
-        key = tuple((t.data_ptr(), tuple(t.shape), t.dtype) if t is not None else None for t in ts)
+            return run(ts)
+        key = (kind,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) if t is not None else None for t in ts)
         hit = self._graphs.get(key)
         if hit is not None:
             hit[0].replay()
@@ -509,11 +522,11 @@ class Engine(object):
         if len(self._seen) > 4096:
             self._seen.clear()
         if n >= 2 and len(self._graphs) < 64:
-            g, out, n_launch = self._capture_counted(eager)
+            g, out, n_launch = self._capture_counted(lambda: run(ts))
             self._graphs[key] = (g, out, n_launch, ts)  # ts keeps the input buffers (and their addresses) alive
             return out.clone()
         # fresh buffers: the shape-keyed graph over the engine's staging buffers
-        skey = tuple((tuple(t.shape), t.dtype) if t is not None else None for t in ts)
+        skey = (kind,) + tuple((tuple(t.shape), t.dtype) if t is not None else None for t in ts)
         st = self._sgraphs.get(skey)
         if st is None:
             c = self._sseen.get(skey, 0) + 1
@@ -521,7 +534,7 @@ class Engine(object):
             if len(self._sseen) > 4096:
                 self._sseen.clear()
             if c < 2 or len(self._sgraphs) >= 16:
-                return eager()
+                return run(ts)
             with torch.cuda.device(self.device):
                 bufs = tuple(None if t is None else torch.empty_like(t) for t in ts)
             st = dict(bufs=bufs, graph=None, out=None, launches=0)
@@ -530,13 +543,8 @@ class Engine(object):
             if buf is not None:
                 buf.copy_(t, non_blocking=True)
         if st["graph"] is None:
-            b = st["bufs"]
-
-            def staged():
-                seq, _, _ = self.encoder_forward(b[0], b[1], b[2], b[3], b[4], want_pooled=False)
-                return self.mlm_gather(seq, b[5], b[6])
-
-            st["graph"], st["out"], st["launches"] = self._capture_counted(staged)
+            bufs = st["bufs"]
+            st["graph"], st["out"], st["launches"] = self._capture_counted(lambda: run(bufs))
         else:
             st["graph"].replay()
             self._replayed_launches += st["launches"]

@@ -40,10 +40,20 @@ class NSPCPT(BertPreTrainedModel):
                                                 or self.bert._dropout_active()):
             return self._train_step(input_ids, token_type_ids, attention_mask, next_sentence_label, position_ids,
                                     head_mask, img_feats)
-        outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
-                            attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
-        score = self.bert.engine().nsp(outputs[1])
-        out = (score,) + outputs[2:]
+        if (head_mask is None and not getattr(self.config, "output_hidden_states", False)
+                and not getattr(self.config, "output_attentions", False)
+                and (attention_mask is None or attention_mask.dim() == 2)):
+            # the VCR inference call: one fused (and CUDA-graph-cached) encoder + pooler + head launch sequence
+            self.bert._check_mode()
+            if attention_mask is not None and attention_mask.dtype != torch.int64:
+                attention_mask = attention_mask.to(torch.int64)
+            score = self.bert.engine().nsp_scores(input_ids, token_type_ids, attention_mask, position_ids, img_feats)
+            out = (score,)
+        else:
+            outputs = self.bert(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
+                                attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats)
+            score = self.bert.engine().nsp(outputs[1])
+            out = (score,) + outputs[2:]
         if next_sentence_label is not None:
             loss = nn.functional.cross_entropy(score.view(-1, self.num_seq_relations), next_sentence_label.view(-1),
                                                ignore_index=-1)

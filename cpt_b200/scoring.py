@@ -16,6 +16,7 @@ from .config import BertConfig
 
 MODES = {"zsl": 0, "fsl": 1, "vcr": 2}
 _handles = {}
+_index_cache = {}  # (device, fan-outs, colour-set sizes, K) -> (row_start, col_start) device tensors
 
 
 def _handle(device):
@@ -46,27 +47,35 @@ def score_queries(logits, fanouts, mode="zsl", n_valid=None, rects=None, gt=None
     lg = logits.to(torch.float32).contiguous()
     rows, K = lg.shape
     Q = len(fanouts)
-    starts = [0]
-    for f in fanouts:
-        starts.append(starts[-1] + int(f))
-    if starts[-1] != rows:
-        raise ValueError("score_queries: fan-outs sum to %d but there are %d rows" % (starts[-1], rows))
-    row_start = _i32(starts, dev)
-    col_start = None
-    if MODES[mode] != 2:
-        nv = [K - 1] * rows if n_valid is None else [int(x) for x in n_valid]
-        if len(nv) != rows or any(x < 0 or x > K - 1 for x in nv):
-            raise ValueError("score_queries: n_valid must give 0..K-1 colour columns for each of the %d rows" % rows)
-        cs = [0]
-        for x in nv:
-            cs.append(cs[-1] + x)
-        col_start = _i32(cs, dev)
+    ckey = (dev, tuple(int(f) for f in fanouts), None if n_valid is None else tuple(int(x) for x in n_valid), K,
+            MODES[mode] != 2)
+    cached = _index_cache.get(ckey)
+    if cached is None:  # the same split is scored batch after batch: its index tables are uploaded once
+        starts = [0]
+        for f in fanouts:
+            starts.append(starts[-1] + int(f))
+        if starts[-1] != rows:
+            raise ValueError("score_queries: fan-outs sum to %d but there are %d rows" % (starts[-1], rows))
+        row_start = _i32(starts, dev)
+        col_start, n_cols = None, 0
+        if MODES[mode] != 2:
+            nv = [K - 1] * rows if n_valid is None else [int(x) for x in n_valid]
+            if len(nv) != rows or any(x < 0 or x > K - 1 for x in nv):
+                raise ValueError("score_queries: n_valid must give 0..K-1 colour columns for each of the %d rows" % rows)
+            cs = [0]
+            for x in nv:
+                cs.append(cs[-1] + x)
+            col_start, n_cols = _i32(cs, dev), cs[-1]
+        if len(_index_cache) > 64:
+            _index_cache.clear()
+        cached = _index_cache[ckey] = (row_start, col_start, n_cols)
+    row_start, col_start, n_cols = cached
     out = {"pick": torch.empty(Q, dtype=torch.int32, device=dev)}
     r = g = None
     if rects is not None:
         r = torch.as_tensor(rects, dtype=torch.float64).to(dev).contiguous()
-        if col_start is not None and r.shape[0] != int(col_start[-1]):
-            raise ValueError("score_queries: %d rectangles for %d valid colour columns" % (r.shape[0], int(col_start[-1])))
+        if col_start is not None and r.shape[0] != n_cols:
+            raise ValueError("score_queries: %d rectangles for %d valid colour columns" % (r.shape[0], n_cols))
         out["rect"] = torch.empty(Q, 4, dtype=torch.float64, device=dev)
         if gt is not None:
             g = torch.as_tensor(gt, dtype=torch.float64).to(dev).contiguous()
