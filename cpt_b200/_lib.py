@@ -95,6 +95,7 @@ SYMBOLS = {
                                     C.POINTER(Grads)]),
     "cpt_adamw_step": (_i, [_i, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
     "cpt_grad_clip_scale": (_i, [_i, _p, _p, _p, _i, _f, _p, _p, _p, _p]),
+    "cpt_assemble_inputs": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "cpt_score_queries": (_i, [_p, _p, _p, _ll, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "cpt_check_async_error": (_i, [_p, _p]),
     "cpt_kernel_name": (C.c_char_p, [_i]),

@@ -26,6 +26,7 @@
 #include "optim.cuh"
 #include "rowwise.cuh"
 #include "scoring.cuh"
+#include "assemble.cuh"
 #include "train.cuh"
 
 using namespace cptk;
@@ -1293,8 +1294,10 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
     cudaMemset(h->err_flag, 0, 4);
     static const char* what[] = {"", "token / segment / position id out of range", "mask position out of range",
                                  "vocabulary id out of range",
-                                 "predicted rectangle with x2 <= x1 or y2 <= y1 (the reference asserts p[2] > p[0])"};
-    return fail("device-side input check failed: %s", what[flag < 5 ? flag : 0]);
+                                 "predicted rectangle with x2 <= x1 or y2 <= y1 (the reference asserts p[2] > p[0])",
+                                 "a sample has more region boxes than max_img_seq_len",
+                                 "a prompt without [MASK] token (the reference's input_ids.index(103) raises)"};
+    return fail("device-side input check failed: %s", what[flag < 7 ? flag : 0]);
   }
   return 0;
 }
@@ -1358,6 +1361,25 @@ int cpt_gemm(cpt_handle* h, void* stream, const void* A, long long lda, const vo
 #define CALL(T16) gemm<T16>(h, (cudaStream_t)stream, CPT_K_GEMM_OTHER, A, lda, W, ldw, p, epi, out_fp32 != 0, tile_cfg)
   return DISPATCH_DTYPE(h, CALL);
 #undef CALL
+}
+
+int cpt_assemble_inputs(cpt_handle* h, void* stream, int B, int T, int R, const float* store, const int64_t* feat_row0,
+                        const int32_t* n_boxes, const int32_t* tok_a, const int32_t* a_off, const int32_t* tok_b,
+                        const int32_t* b_off, const int32_t* has_b, int cls_id, int sep_id, int pad_id, int mask_id,
+                        int64_t* input_ids, int64_t* segment_ids, int64_t* input_mask, int64_t* mask_pos,
+                        float* img_feats) {
+  if (!h) return fail("NULL handle");
+  if (B <= 0 || T < 3 || R < 0 || !feat_row0 || !n_boxes || !tok_a || !a_off || !tok_b || !b_off || !has_b || !input_ids ||
+      !segment_ids || !input_mask || !mask_pos || (R > 0 && (!store || !img_feats)))
+    return fail("cpt_assemble_inputs: bad argument");
+  DeviceGuard g(h->device);
+  AssembleParams p{B, T, R, h->cfg.img_feature_dim, store, (const long long*)feat_row0, n_boxes, tok_a, a_off, tok_b, b_off,
+                   has_b, cls_id, sep_id, pad_id, mask_id, (long long*)input_ids, (long long*)segment_ids,
+                   (long long*)input_mask, (long long*)mask_pos, img_feats, h->err_flag};
+  ProfScope ps(h, (cudaStream_t)stream, CPT_K_CAST);
+  assemble_inputs_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p);
+  CKL("assemble_inputs_kernel");
+  return 0;
 }
 
 int cpt_score_queries(cpt_handle* h, void* stream, const float* logits, long long ld, int K, int Q,

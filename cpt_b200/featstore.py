@@ -1,0 +1,124 @@
+"""Extractor -> Oscar wire format, a binary feature store, and batch assembly on the device.
+
+The reference keeps region features as base64 inside JSON inside a TSV (`predictions.tsv`, written by
+prompt_feat/maskrcnn_benchmark/engine/inference_ref.py:129-192: one line `image_key \\t {"objects": [boxlists, caption,
+colours, rect_lists]}`, a box = {"rect", "bbox_id", "class", "conf", "feature": base64(2054 x fp32)}; the last six feature
+columns are x1/w, y1/h, x2/w, y2/h, (x2-x1)/w, (y2-y1)/h, inference_ref.py:263-274) and decodes it per sample, per box,
+in Python on every access (Oscar/oscar/datasets/refcoco_zsl_cpt_dataset.py:161-180).  At the forward's rate one B200
+consumes ~14 GB/s of features, which that path cannot deliver.  Here:
+
+  * `decode_prediction_row` reads one TSV line exactly as `decode_features` does (same tuple);
+  * `build_feature_store` converts a predictions.tsv ONCE into `features.f32` (all boxes, [rows, 2054] fp32, row-major,
+    memory-mappable) + `index.json` (per image: key, caption, the proposal sets as (first row, boxes), tags, colours,
+    rectangles);
+  * `FeatureStore` maps it, `.to(device)` puts the features in HBM (RefCOCO testA/testB/val together are a few GB of
+    the 180 GB), and `assemble()` builds a whole padded batch — input_ids, segment ids, mask, [MASK] positions and the
+    [B, R, 2054] feature tensor — with ONE launch of cpt_assemble_inputs from token-id lists (tokenisation itself stays
+    the caller's BertTokenizer).
+"""
+import base64
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FEAT_DIM = 2054
+CLS_ID, SEP_ID, MASK_ID, PAD_ID = 101, 102, 103, 0
+
+
+def decode_prediction_row(line):
+    """One `predictions.tsv` line -> (img_name, od_labels, im_feats, caption, colors, rect_lists), the tuple
+    ZSLColorFinetuneDataset.decode_features returns (refcoco_zsl_cpt_dataset.py:161-180): im_feats[i] is the fp32
+    [boxes_i, 2054] array of proposal set i, od_labels[i] its class names joined by blanks."""
+    cols = [s.strip() for s in line.split("\t")]
+    img_name, info = cols[0], json.loads(cols[1])
+    objs, caption, colors, rect_lists = info["objects"]
+    feats, labels = [], []
+    for boxlist in objs:
+        feats.append(np.stack([np.frombuffer(base64.b64decode(o["feature"]), np.float32) for o in boxlist]))
+        labels.append(" ".join(o["class"] for o in boxlist))
+    return img_name, labels, feats, caption, colors, rect_lists
+
+
+def build_feature_store(tsv_path, out_dir):
+    """predictions.tsv -> out_dir/features.f32 + out_dir/index.json.  Streams the file once; returns the number of images."""
+    os.makedirs(out_dir, exist_ok=True)
+    index, row = [], 0
+    with open(tsv_path, "r") as fin, open(os.path.join(out_dir, "features.f32"), "wb") as fout:
+        for line in fin:
+            if not line.strip():
+                continue
+            name, labels, feats, caption, colors, rects = decode_prediction_row(line)
+            sets = []
+            for f in feats:
+                if f.ndim != 2 or f.shape[1] != FEAT_DIM:
+                    raise ValueError("%s: a box feature has %s values, expected %d" % (name, f.shape[1:], FEAT_DIM))
+                fout.write(np.ascontiguousarray(f, np.float32).tobytes())
+                sets.append([row, int(f.shape[0])])
+                row += int(f.shape[0])
+            index.append({"key": name, "caption": caption, "sets": sets, "od_labels": labels, "colors": colors,
+                          "rects": rects})
+    with open(os.path.join(out_dir, "index.json"), "w") as f:
+        json.dump({"feat_dim": FEAT_DIM, "rows": row, "images": index}, f)
+    return len(index)
+
+
+class FeatureStore(object):
+    def __init__(self, store_dir):
+        meta = json.load(open(os.path.join(store_dir, "index.json")))
+        self.images = meta["images"]
+        self.rows = int(meta["rows"])
+        self.by_key = {im["key"]: i for i, im in enumerate(self.images)}
+        self.features = np.memmap(os.path.join(store_dir, "features.f32"), np.float32, "r",
+                                  shape=(self.rows, int(meta["feat_dim"])))
+        self.device_features = None
+
+    def to(self, device):
+        """All features into HBM (one pinned staging copy, one H2D)."""
+        self.device_features = torch.from_numpy(np.ascontiguousarray(self.features)).to(device)
+        return self
+
+    def set_features(self, img_idx, set_idx):
+        r0, n = self.images[img_idx]["sets"][set_idx]
+        return self.features[r0:r0 + n]
+
+    def assemble(self, samples, tokens_a, tokens_b, T=70, R=50, engine=None):
+        """One padded batch on the device.  samples: (image index, proposal-set index) per row; tokens_a / tokens_b: the
+        token-id lists of the prompt caption and of the object tags per row (tokens_b[i] None = no text_b).
+        Returns dict(input_ids, token_type_ids, attention_mask, img_feats, mask_pos) of CUDA tensors."""
+        if self.device_features is None:
+            raise _lib.CptError("cpt_b200: FeatureStore.assemble needs the store on a CUDA device: call .to('cuda') first")
+        dev = self.device_features.device
+        if engine is None:
+            from .scoring import _handle
+            engine = _handle(dev)
+        B = len(samples)
+        row0 = [self.images[i]["sets"][j][0] for i, j in samples]
+        nbox = [self.images[i]["sets"][j][1] for i, j in samples]
+        a_off, b_off, flat_a, flat_b, has_b = [0], [0], [], [], []
+        for ta, tb in zip(tokens_a, tokens_b):
+            flat_a += list(ta)
+            a_off.append(len(flat_a))
+            has_b.append(0 if tb is None else 1)
+            flat_b += list(tb or [])
+            b_off.append(len(flat_b))
+        i32 = lambda x: torch.tensor(x if len(x) else [0], dtype=torch.int32).to(dev)  # noqa: E731
+        t_row0 = torch.tensor(row0, dtype=torch.int64).to(dev)
+        t_nbox, t_a, t_ao, t_b, t_bo, t_hb = i32(nbox), i32(flat_a), i32(a_off), i32(flat_b), i32(b_off), i32(has_b)
+        out = dict(input_ids=torch.empty(B, T, dtype=torch.int64, device=dev),
+                   token_type_ids=torch.empty(B, T, dtype=torch.int64, device=dev),
+                   attention_mask=torch.empty(B, T + R, dtype=torch.int64, device=dev),
+                   mask_pos=torch.empty(B, dtype=torch.int64, device=dev),
+                   img_feats=torch.empty(B, R, self.device_features.shape[1], dtype=torch.float32, device=dev))
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(dev):
+            _lib.check(engine.lib.cpt_assemble_inputs(
+                engine._h, C.c_void_p(torch.cuda.current_stream().cuda_stream), B, T, R, p(self.device_features),
+                p(t_row0), p(t_nbox), p(t_a), p(t_ao), p(t_b), p(t_bo), p(t_hb), CLS_ID, SEP_ID, PAD_ID, MASK_ID,
+                p(out["input_ids"]), p(out["token_type_ids"]), p(out["attention_mask"]), p(out["mask_pos"]),
+                p(out["img_feats"])))
+        return out

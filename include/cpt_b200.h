@@ -212,6 +212,19 @@ int cpt_grad_clip_scale(int device, void *stream, const cpt_adam_tensor *tensors
                         int n_chunks, float max_norm, const float *grad_scale_in, void *scratch, float *norm_out,
                         float *scale_out);
 
+/* ---- host input assembly on the device (SURVEY.md 8f "input assembly") ---------------------------------------------
+ * One padded CPT batch from token-id lists and a packed region-feature store: the reference's per-sample tokenize()
+ * ([CLS] a [SEP] b [SEP], pair truncation to T - 3, segment ids, zero padding, mask over tokens and boxes —
+ * Oscar/oscar/datasets/refcoco_zsl_cpt_dataset.py:191-302), feature padding to R rows (:119-120), [MASK] position
+ * (:118) and the collate's stacking (Oscar/oscar/zeroshot/refcoco_cpt.py:159-172).  store: fp32 [rows, img_feature_dim]
+ * on the device; row b takes n_boxes[b] <= R rows from feat_row0[b].  tok_a / tok_b: flat int32 token ids with CSR
+ * offsets [B + 1]; has_b[b]: text_b was non-empty.  Outputs int64 [B,T], [B,T], [B,T+R], [B] and fp32 [B,R,F]. */
+int cpt_assemble_inputs(cpt_handle *h, void *stream, int B, int T, int R, const float *store, const int64_t *feat_row0,
+                        const int32_t *n_boxes, const int32_t *tok_a, const int32_t *a_off, const int32_t *tok_b,
+                        const int32_t *b_off, const int32_t *has_b, int cls_id, int sep_id, int pad_id, int mask_id,
+                        int64_t *input_ids, int64_t *segment_ids, int64_t *input_mask, int64_t *mask_pos,
+                        float *img_feats);
+
 /* ---- CPT decision per query on the device (SURVEY.md 8f "scoring") ----------------------------------------------
  * Replaces the per-image Python loops of Oscar/oscar/zeroshot/refcoco_cpt.py:222-254, fewshot/refcoco_cpt.py:273-297
  * and fewshot/vcr_nsp_cpt.py:600-604, and the IoU > 0.5 hit test of zeroshot/refcoco_cpt.py:268-276 +
