@@ -240,6 +240,12 @@ class BertOnlyMLMHead(nn.Module):
         return self.predictions(sequence_output)
 
 
+def _import_only(name):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("%s is un-vendored pytorch-transformers 1.x code the shim does not restate" % name)
+    return type(name, (object,), {"__init__": __init__})
+
+
 def install(reference_root=REFERENCE_ROOT):
     """Register the stand-in modules and put the reference's Oscar/ on sys.path."""
     import transformers  # the real (5.x) package stays importable
@@ -261,6 +267,11 @@ def install(reference_root=REFERENCE_ROOT):
     fu = types.ModuleType("transformers.pytorch_transformers.file_utils")
     fu.cached_path = lambda p, **kw: p
     pkg.modeling_bert, pkg.modeling_utils, pkg.file_utils = mb, mu, fu
+    # names the task scripts import at module scope (zeroshot/refcoco_cpt.py:11,24, fewshot/gqa_cpt.py:23-24); the loops
+    # the drop-in test runs (val(), evaluate()) take model and tokenizer as arguments and construct none of these
+    pkg.BertConfig, pkg.WEIGHTS_NAME = BertConfig, mu.WEIGHTS_NAME
+    for name in ("BertTokenizer", "AdamW", "WarmupLinearSchedule", "WarmupConstantSchedule"):
+        setattr(pkg, name, _import_only(name))
     for m in (pkg, mb, mu, fu):
         sys.modules[m.__name__] = m
     transformers.pytorch_transformers = pkg

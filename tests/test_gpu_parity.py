@@ -295,3 +295,88 @@ def test_other_geometries_against_oracle(H, nH, I, B, T, R):
     assert (seq - oseq).abs().max().item() <= RTOL * oseq.abs().max().item()
     row_max = rows.abs().max(dim=1, keepdim=True).values
     assert ((logits - rows[:, vids]).abs() <= RTOL * row_max).all()
+
+
+def test_pretraining_model_forward_against_oracle():
+    """BertImgForPreTraining.forward (modeling_bert.py:690-705): (prediction_scores [B,S,V], seq_relationship_score)."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=3)
+    sd = synth_state_dict(cfg, seed=9)
+    b = synth_batch(cfg, 4, 50, 30, seed=8)
+    pre, rec, nsp = build(cfg, sd)
+    d = cuda(b)
+    with torch.no_grad():
+        out = pre(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])
+        oseq, opooled, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                            img_feats=b["img_feats"])
+        oscores = O.lm_head(sd, cfg, oseq)
+        onsp = O.nsp_cpt(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"])[0]
+    pre.bert.engine().check()
+    assert len(out) == 2 and out[0].shape == (4, 80, cfg.vocab_size) and out[1].shape == (4, cfg.num_contrast_classes)
+    assert (out[0].cpu() - oscores).abs().max().item() <= 2 * RTOL * oscores.abs().max().item()
+    assert (out[1].cpu() - onsp).abs().max().item() <= RTOL * max(1.0, onsp.abs().max().item())
+    with pytest.raises(NotImplementedError):      # the pre-training loss is not on the CPT path
+        pre(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+            masked_lm_labels=torch.zeros(4, 80, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("B,T,R", [(3, 40, 24), (16, 70, 50)])
+def test_output_hidden_states_against_oracle(B, T, R):
+    """config.output_hidden_states=True (modeling_bert.py:85-103 via BertEncoder): outputs[2] holds the embedding output
+    and every layer's output.  The second shape is large enough (1920 rows) for the dataflow chain kernel."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=3)
+    cfg.output_hidden_states = True
+    sd = synth_state_dict(cfg, seed=10)
+    b = synth_batch(cfg, B, T, R, seed=12)
+    pre, rec, nsp = build(cfg, sd)
+    d = cuda(b)
+    with torch.no_grad():
+        out = rec.bert(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])
+        oseq, opooled, ohid = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                               img_feats=b["img_feats"], collect_hidden=True)
+        scores = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])
+    rec.bert.engine().check()
+    assert len(out) == 3 and len(out[2]) == cfg.num_hidden_layers + 1
+    for got, want in zip(out[2], ohid):
+        assert got.shape == want.shape
+        assert (got.cpu() - want).abs().max().item() <= RTOL * want.abs().max().item()
+    assert torch.equal(out[2][-1], out[0])
+    # REC_MLM_CPT passes them through after the scores (modeling_rec.py:144-145)
+    assert len(scores) == 2 and len(scores[1]) == cfg.num_hidden_layers + 1
+
+
+def test_vcr_two_head_model_and_nsp_graph_path():
+    """VCRQAR_NSPCPT (modeling_vcr.py:194-252): cls_ans is the pre-training head, cls_rat a copy that may diverge;
+    NSPCPT's fused (graph-replayed) call equals its module-by-module path."""
+    from oracle import cpt_oracle as O
+    from cpt_b200.modeling_vcr import VCRQAR_NSPCPT
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=14)
+    b = synth_batch(cfg, 8, 60, 30, seed=15)
+    pre, rec, nsp = build(cfg, sd)
+    two = VCRQAR_NSPCPT(cfg)
+    with pytest.raises(RuntimeError):
+        two(b["input_ids"].cuda(), head="ans")
+    two.copy_from_pretraining_model(pre)
+    two.eval()
+    assert two.cls_ans is pre.cls.seq_relationship and two.cls_rat is not two.cls_ans
+    with torch.no_grad():
+        two.cls_rat.weight.mul_(-0.5)
+        two.cls_rat.bias.add_(0.25)
+    d = cuda(b)
+    with torch.no_grad():
+        ans = two(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"], head="ans")[0]
+        rat = two(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"], head="rat")[0]
+        one = nsp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
+        one2 = nsp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
+        _, opooled, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                         img_feats=b["img_feats"])
+    nsp.bert.engine().check()
+    want_ans = opooled @ sd["cls.seq_relationship.weight"].t() + sd["cls.seq_relationship.bias"]
+    want_rat = opooled @ (-0.5 * sd["cls.seq_relationship.weight"]).t() + (sd["cls.seq_relationship.bias"] + 0.25)
+    assert (ans.cpu() - want_ans).abs().max().item() <= RTOL * max(1.0, want_ans.abs().max().item())
+    assert (rat.cpu() - want_rat).abs().max().item() <= RTOL * max(1.0, want_rat.abs().max().item())
+    assert torch.equal(one, one2) and (one.cpu() - want_ans).abs().max().item() <= RTOL * max(1.0, want_ans.abs().max().item())
+    with pytest.raises(RuntimeError):
+        two(d["input_ids"], head="")

@@ -514,3 +514,64 @@ def test_dropout_is_seeded_by_torch_and_off_in_eval():
     rec.train()
     with pytest.raises(NotImplementedError):
         rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_training_trajectory_tracks_the_fp32_reference(dtype):
+    """Why 16-bit operand rounding in the gradients is acceptable (the reference's few-shot scripts train in fp32,
+    cmds/gqa/_cpt_fsl_base.sh passes no --fp16): the per-tensor gradient error is unbiased rounding noise, so 40 AdamW
+    steps of the few-shot loop stay on the fp32 trajectory — same loss curve, same weights — instead of drifting.
+    Both arms: fixed batch, no dropout, torch.optim.AdamW(lr 1e-3, wd 0.05), fp32 master weights; the reference arm
+    is autograd through the fp32 CPU oracle."""
+    from oracle import cpt_oracle as O
+    steps, lr = 40, 1e-3
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=31)
+    B, T, R = 8, 40, 20
+    b = synth_batch(cfg, B, T, R, seed=17)
+    labels = torch.full((B, T + R), -1, dtype=torch.long)
+    labels[torch.arange(B), b["mask_pos"]] = torch.arange(B) % 3 + 20
+    # reference arm
+    leaf = {}
+    for k, v in sd.items():
+        if k != "cls.predictions.decoder.weight":
+            leaf[k] = v.clone().requires_grad_(True)
+    leaf["cls.predictions.decoder.weight"] = leaf["bert.embeddings.word_embeddings.weight"]   # tied
+    uniq = [v for k, v in leaf.items() if k != "cls.predictions.decoder.weight"]
+    opt_ref = torch.optim.AdamW(uniq, lr=lr, weight_decay=0.05)
+    ref_losses = []
+    for _ in range(steps):
+        loss = O.rec_mlm_cpt(leaf, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                             masked_lm_labels=labels, img_feats=b["img_feats"], training=False)[0]
+        opt_ref.zero_grad()
+        loss.backward()
+        opt_ref.step()
+        ref_losses.append(loss.item())
+    # this library
+    rec = build_rec(cfg, sd, dtype)
+    opt = torch.optim.AdamW(rec.parameters(), lr=lr, weight_decay=0.05)
+    d = {k: v.cuda() for k, v in b.items()}
+    lab = labels.cuda()
+    losses = []
+    for _ in range(steps):
+        loss, _ = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                      masked_lm_labels=lab)
+        opt.zero_grad()
+        (loss * LOSS_SCALE[dtype]).backward()
+        for p in rec.parameters():
+            if p.grad is not None:
+                p.grad /= LOSS_SCALE[dtype]
+        opt.step()
+        losses.append(loss.item())
+    rec.bert.train_engine()[0].check()
+    assert ref_losses[-1] < 0.5 * ref_losses[0], ref_losses        # the loop really learns
+    dev = max(abs(a - r) for a, r in zip(losses, ref_losses)) / ref_losses[0]
+    assert dev <= 2e-2, "largest loss deviation %.3e of the initial loss; ours %s ref %s" % (dev, losses[-3:], ref_losses[-3:])
+    named = dict(rec.named_parameters())
+    moved, off = 0.0, 0.0
+    for k in ("bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.0.attention.self.query.weight",
+              "bert.img_embedding.weight"):
+        moved += (leaf[k].detach() - sd[k]).norm().item() ** 2
+        off += (named[k].detach().cpu() - leaf[k].detach()).norm().item() ** 2
+    # distance between the two arms' weights, relative to how far training moved them
+    assert off ** 0.5 <= 0.1 * moved ** 0.5, (off ** 0.5, moved ** 0.5)
