@@ -593,13 +593,12 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     labels = [train_labels(b, vids, S).to(dev) for b in host]
 
-    def step(i, sync=True):
+    def step(i):
         b = devb[i % NROT]
         net.train()
-        with (net.no_sync() if (ddp is not None and not sync) else _null()):
-            loss = net(input_ids=b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=b["attention_mask"],
-                       img_feats=b["img_feats"], masked_lm_labels=labels[i % NROT])[0]
-            loss.backward()
+        loss = net(input_ids=b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=b["attention_mask"],
+                   img_feats=b["img_feats"], masked_lm_labels=labels[i % NROT])[0]
+        loss.backward()
         opt.step(max_grad_norm=1.0)  # clip_grad_norm_(1.0) fused into the native AdamW launch (gqa_cpt.py:454-456)
         sched.step()
         model.zero_grad()
@@ -610,12 +609,12 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, sync=True):
+    def timed(n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
-            loss = step(i, sync)
+            loss = step(i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -643,7 +642,13 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
         launches = eng.launch_count() - l0
         clocks = sampler.stop() if sampler else None
         n2 = max(3, args.steps // 2)
-        ms_nosync = timed(n2, sync=False)[0] / n2 if world > 1 else None
+        ms_nosync = None
+        if world > 1:   # the same step with the exchange switched off (every rank keeps its local gradients)
+            grp, eng.grad_sync_group = eng.grad_sync_group, None
+            for i in range(3):
+                step(i)
+            ms_nosync = timed(n2)[0] / n2
+            eng.grad_sync_group = grp
         # end to end: host (pinned) batch in, loss value out, every step
         hp = [{k: v.pin_memory() for k, v in b.items()} for b in host]
         lp = [x.cpu().pin_memory() for x in labels]
@@ -684,7 +689,8 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
     if ms_nosync is not None:
         out["nccl"] = {"ms_per_step_without_gradient_exchange": ms_nosync,
                        "share_of_step": max(0.0, 1.0 - ms_nosync / (ms / args.steps)),
-                       "how": "the same step under DistributedDataParallel.no_sync()"}
+                       "exchange_dtype": str(eng.grad_sync_dtype or "torch.float32"),
+                       "how": "the same step with the in-backward all-reduce switched off (local gradients)"}
     out["roofline"] = {"kernel": "whole training step (forward + backward + optimizer)", "bound": "tensor",
                        "achieved": value * fl / 1e12 / world, "peak": sustained, "unit": "TFLOP/s",
                        "frac": value * fl / 1e12 / (sustained * world),

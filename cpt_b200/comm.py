@@ -115,24 +115,86 @@ def pick_per_query(logits, fanouts, mode="zsl", n_valid=None):
     return score_queries(logits, fanouts, mode=mode, n_valid=n_valid)["pick"]
 
 
-def enable_overlapped_grad_sync(ddp_model, process_group=None):
+_SYNC_SLOTS = []        # weak references to the engine slots whose backward graphs hold NCCL operations
+_SHUTDOWN_HOOKED = [False]
+
+
+def release_sync_graphs():
+    """Destroy every captured backward that holds NCCL operations (Engine.release_sync_graphs).  Runs automatically
+    before torch.distributed.destroy_process_group() and at interpreter exit once enable_overlapped_grad_sync was used:
+    NCCL does not let go of a communicator while a CUDA graph that captured it exists."""
+    for ref in list(_SYNC_SLOTS):
+        slot = ref()
+        eng = getattr(slot, "train_engine", None) if slot is not None else None
+        if eng is not None:
+            try:
+                eng.release_sync_graphs()
+            except Exception:
+                pass
+
+
+def _register_for_shutdown(slot):
+    import atexit
+    import functools
+    import weakref
+    if not any(r() is slot for r in _SYNC_SLOTS):
+        _SYNC_SLOTS.append(weakref.ref(slot))
+    if _SHUTDOWN_HOOKED[0]:
+        return
+    _SHUTDOWN_HOOKED[0] = True
+    atexit.register(release_sync_graphs)
+    orig = dist.destroy_process_group
+
+    @functools.wraps(orig)
+    def destroy_process_group(*a, **k):
+        release_sync_graphs()
+        return orig(*a, **k)
+    dist.destroy_process_group = destroy_process_group
+
+
+def enable_overlapped_grad_sync(ddp_model, process_group=None, exchange_dtype="auto"):
     """Training over several GPUs: average the gradients INSIDE the native backward, group by group as
     they become final (loss head, layer L-1, ..., layer 0, embeddings), overlapping NCCL with the remaining backward
-    kernels — and tell DistributedDataParallel not to reduce them a second time.
+    kernels — inside the CUDA graph the backward is replayed from — and switch DistributedDataParallel's own reducer off
+    (it would copy every gradient into its buckets and walk the autograd graph every step for nothing).
 
         model = DistributedDataParallel(model, device_ids=[rank], find_unused_parameters=True)   # reference code
         cpt_b200.comm.enable_overlapped_grad_sync(model)                                          # one extra line
 
+    exchange_dtype: "fp32" (what DDP's all-reduce carries), "bf16" (half the bytes; the averaged gradient is rounded
+    once to 8 significant bits, far below the 16-bit operand rounding already inside it), or "auto" = bf16 when the
+    training handle computes in bf16, fp32 otherwise (fp16 would need the caller's loss scale to be safe).
+    `with model.no_sync():` keeps working: passes inside it stay local, and the next pass outside exchanges the
+    accumulated sum (engine._settle_unsynced), as DDP does for gradient accumulation (gqa_cpt.py:441-462).
     Without this call DDP's own bucketed all-reduce runs after the whole native backward (correct, not overlapped).
     Every parameter of the wrapped module must get its gradient from the native step (true for REC_MLM_CPT / NSPCPT).
     """
-    from torch.distributed.algorithms.ddp_comm_hooks import debugging_hooks
+    import contextlib
+    import torch
     module = ddp_model.module if hasattr(ddp_model, "module") else ddp_model
     bert = getattr(module, "bert", module)
     group = process_group if process_group is not None else dist.group.WORLD
-    bert._slot.grad_sync_group = group
-    if bert._slot.train_engine is not None:
-        bert._slot.train_engine.grad_sync_group = group
-    if hasattr(ddp_model, "register_comm_hook"):
-        ddp_model.register_comm_hook(None, debugging_hooks.noop_hook)
+    if exchange_dtype not in ("auto", "fp32", "bf16"):
+        raise ValueError("exchange_dtype must be 'auto', 'fp32' or 'bf16'")
+    slot = bert._slot
+    slot.grad_sync_group = group
+    slot.grad_sync_dtype = exchange_dtype
+    if slot.train_engine is not None:
+        slot.apply_grad_sync(slot.train_engine)
+    _register_for_shutdown(slot)
+    if hasattr(ddp_model, "require_backward_grad_sync"):
+        ddp_model.require_backward_grad_sync = False      # DDP's reducer never arms itself again
+
+        @contextlib.contextmanager
+        def no_sync():
+            eng = slot.train_engine
+            if eng is None:
+                raise RuntimeError("cpt_b200: no_sync() before the first training forward")
+            old = eng.grad_sync_skip
+            eng.grad_sync_skip = True
+            try:
+                yield
+            finally:
+                eng.grad_sync_skip = old
+        ddp_model.no_sync = no_sync
     return ddp_model

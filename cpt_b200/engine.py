@@ -106,6 +106,11 @@ class Engine(object):
         self.use_train_graphs = os.environ.get("CPT_B200_TRAIN_GRAPHS", "1") != "0"
         self._tgraphs, self._tseen, self._ptr_sig = {}, {}, None
         self.grad_sync_group = None  # set by comm.enable_overlapped_grad_sync: all-reduce gradients inside the backward
+        self.grad_sync_dtype = None  # None: exchange fp32; torch.bfloat16 / torch.float16: exchange 16-bit copies
+        self.grad_sync_skip = False  # True inside no_sync(): gradients stay local, their sum is owed to the next exchange
+        self.grad_sync_graphs = os.environ.get("CPT_B200_SYNC_GRAPHS", "1") != "0"  # NCCL inside the captured backward
+        self._unsynced = None        # (layout, fp32 slab): local gradient sums of the passes run under no_sync()
+        self._sync16 = None
         self._progress_cb = None
         self._profiling = False
 
@@ -283,7 +288,7 @@ class Engine(object):
         p_h, p_a, seed = (0.0, 0.0, 0) if dropout is None else (float(dropout[0]), float(dropout[1]), int(dropout[2]))
         key = (head, B, T, R, n, seg is None, msk is None, pos is None, img is None, p_h, p_a)
         st = None
-        if (self.use_train_graphs and not self._profiling and self.grad_sync_group is None
+        if (self.use_train_graphs and not self._profiling and (self.grad_sync_group is None or self.grad_sync_graphs)
                 and not torch.cuda.is_current_stream_capturing()):
             st = self._tgraphs.get(key)
             if st is None:
@@ -370,7 +375,7 @@ class Engine(object):
         else:
             slab = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
             if st is not None:
-                st["slab"], st["layout"], st["bwd"] = slab, (tuple(keys), tuple(shapes)), None
+                st["slab"], st["layout"], st["bwd"], st["bwd_sync"] = slab, (tuple(keys), tuple(shapes)), None, None
         return self._views(slab, keys, shapes, sizes)
 
     @staticmethod
@@ -389,48 +394,111 @@ class Engine(object):
         dev = self.device
         gl = _chk_tensor("grad_loss", grad_loss.reshape(()), torch.float32, dev)
         st = saved.get("graph")
+        sync = self.grad_sync_group is not None and bool(saved.get("groups"))
         if st is None:
             g, keep = self._grads_struct(saved["head"], grads)
             with torch.cuda.device(dev):
-                if self.grad_sync_group is not None and saved.get("groups"):
-                    self._backward_with_grad_sync(saved, gl, g, grads)
+                if sync and not self.grad_sync_skip and self._unsynced is None:
+                    self._backward_with_grad_sync(saved, gl, g, grads, saved["groups"])
                 else:
                     self._raw_backward(saved, gl, g)
+                    if sync:
+                        self._settle_unsynced(self._slab_of(grads), tuple(grads))
             return grads
         if saved["gen"] != st["gen"]:
             raise CptError("cpt_b200: the tape of this forward was overwritten by a later forward of the same shape "
                            "before backward() ran; set CPT_B200_TRAIN_GRAPHS=0 for this usage pattern")
         with torch.cuda.device(dev):
             st["grad_loss"].copy_(gl, non_blocking=True)
-            if st["bwd"] is None:
+            # two captured variants of the backward: local ("bwd"), and with the gradient exchange inside ("bwd_sync":
+            # one NCCL all-reduce per gradient group on NCCL's stream, forked / joined inside the graph)
+            in_graph = sync and not self.grad_sync_skip and self._unsynced is None
+            which = "bwd_sync" if in_graph else "bwd"
+            if st.get(which) is None:
                 g, keep = self._grads_struct(saved["head"], grads)
-                st["_bwd_keep"] = (g, keep)
+                st["_keep_" + which] = (g, keep)
+                groups = saved.get("groups")
 
                 def run():
                     st["slab"].zero_()
-                    self._raw_backward(st, st["grad_loss"], g)
+                    if in_graph:
+                        self._backward_with_grad_sync(st, st["grad_loss"], g, grads, groups)
+                    else:
+                        self._raw_backward(st, st["grad_loss"], g)
 
                 l0 = self.lib.cpt_launch_count(self._h)
-                st["bwd"] = self._capture(run)
-                st["bwd_launches"] = int(self.lib.cpt_launch_count(self._h) - l0) // 2
+                st[which] = self._capture(run)
+                st[which + "_launches"] = int(self.lib.cpt_launch_count(self._h) - l0) // 2
             else:
-                st["bwd"].replay()
-                self._replayed_launches += st["bwd_launches"]
+                st[which].replay()
+                self._replayed_launches += st[which + "_launches"]
+            if sync and not in_graph:
+                self._settle_unsynced(st["slab"], tuple(grads))
             st["pending"] = False
             keys, shapes = st["layout"]
             sizes = [(_numel(s) + 63) // 64 * 64 for s in shapes]
             return self._views(st["slab"].clone(), keys, shapes, sizes)
 
-    def _backward_with_grad_sync(self, saved, gl, g, grads):
+    @staticmethod
+    def _slab_of(grads):
+        t = next(iter(grads.values()))
+        return (t._base if t._base is not None else t).view(-1)
+
+    def _settle_unsynced(self, slab, layout):
+        """Gradient accumulation over several backward passes with the exchange only on the last one (DDP's no_sync(),
+        gqa_cpt.py:441-462 with gradient_accumulation_steps > 1).  Under no_sync() the pass stays local and its
+        gradients are added to `_unsynced`.  The first exchanging pass afterwards averages (this pass + everything
+        owed) over the ranks and hands autograd  average - owed,  so that  .grad = owed + (average - owed)  is what
+        DDP would have left there: the average of the accumulated gradients."""
+        import torch.distributed as dist
+        slab = slab.view(-1)
+        if self.grad_sync_skip:
+            if self._unsynced is None:
+                self._unsynced = (layout, torch.zeros_like(slab))
+            if self._unsynced[0] != layout or self._unsynced[1].numel() != slab.numel():
+                raise CptError("cpt_b200: the set of trained parameters changed between backward passes under no_sync()")
+            self._unsynced[1].add_(slab)
+            return
+        owed = self._unsynced
+        self._unsynced = None
+        if owed is None:
+            return
+        if owed[0] != layout or owed[1].numel() != slab.numel():
+            raise CptError("cpt_b200: the set of trained parameters changed between backward passes under no_sync()")
+        slab.add_(owed[1])
+        dist.all_reduce(slab, op=dist.ReduceOp.AVG, group=self.grad_sync_group)
+        slab.sub_(owed[1])
+
+    def release_sync_graphs(self):
+        """Destroy the captured backward graphs that hold NCCL operations.  NCCL keeps a communicator alive — and
+        ncclCommDestroy / process exit waiting — until every CUDA graph that captured one of its collectives is gone,
+        so this must run before torch.distributed.destroy_process_group() (comm.enable_overlapped_grad_sync arranges it)."""
+        n = 0
+        for st in self._tgraphs.values():
+            if st.get("bwd_sync") is not None:
+                n += 1
+            st["bwd_sync"] = None
+            st.pop("_keep_bwd_sync", None)
+        if n:
+            torch.cuda.synchronize(self.device)
+        return n
+
+    def drop_unsynced_gradients(self):
+        """zero_grad() between no_sync() passes and the exchanging pass: forget what was owed."""
+        self._unsynced = None
+
+    def _backward_with_grad_sync(self, saved, gl, g, grads, groups):
         """Data-parallel backward: each gradient group (loss head, layer L-1, ..., layer 0, embeddings) is averaged over
         the ranks by an asynchronous NCCL all-reduce issued the moment its last kernel has been enqueued
         (cpt_train_set_progress_callback), so the exchange overlaps the rest of the backward instead of following it
         (the reference's DDP reducer does the same per 25 MB bucket).  Gradients of a group are one
-        contiguous range of the slab (training.trainable_groups)."""
+        contiguous range of the slab (training.trainable_groups).  With `grad_sync_dtype` set, a 16-bit copy of the
+        range travels instead (half the bytes; the average is rounded once to that type).  Runs eagerly or inside a
+        CUDA-graph capture (NCCL's stream is forked from and joined to the capturing stream by the Work objects)."""
         import torch.distributed as dist
         group = self.grad_sync_group
         ranges = []
-        for keys in saved["groups"]:
+        for keys in groups:
             ts = [grads[k] for k in keys if k in grads]
             if not ts:
                 ranges.append(None)
@@ -438,13 +506,26 @@ class Engine(object):
             base = ts[0]._base if ts[0]._base is not None else ts[0]
             lo = min(t.storage_offset() for t in ts)
             hi = max(t.storage_offset() + t.numel() for t in ts)
-            ranges.append(base.view(-1)[lo:hi])
+            ranges.append((base.view(-1)[lo:hi], lo, hi))
+        d16 = self.grad_sync_dtype
+        if d16 is not None:
+            total = max((r[2] for r in ranges if r is not None), default=0)
+            if self._sync16 is None or self._sync16.numel() < total or self._sync16.dtype != d16:
+                if torch.cuda.is_current_stream_capturing():
+                    raise CptError("cpt_b200: internal: the 16-bit exchange buffer must exist before capture")
+                self._sync16 = torch.empty(total, dtype=d16, device=self.device)
         works, err = [], []
 
         def on_stage(_user, stage):
             try:
                 if stage < len(ranges) and ranges[stage] is not None:
-                    works.append(dist.all_reduce(ranges[stage], op=dist.ReduceOp.AVG, group=group, async_op=True))
+                    r, lo, hi = ranges[stage]
+                    if d16 is None:
+                        works.append((dist.all_reduce(r, op=dist.ReduceOp.AVG, group=group, async_op=True), None, None))
+                    else:
+                        b = self._sync16[lo:hi]
+                        b.copy_(r)
+                        works.append((dist.all_reduce(b, op=dist.ReduceOp.AVG, group=group, async_op=True), r, b))
             except Exception as e:  # never let an exception cross the C frame
                 err.append(e)
 
@@ -456,8 +537,10 @@ class Engine(object):
             _lib.check(self.lib.cpt_train_set_progress_callback(self._h, None, None))
         if err:
             raise err[0]
-        for w in works:
+        for w, r, b in works:
             w.wait()  # stream-level wait: the current stream sees the averaged gradients
+            if r is not None:
+                r.copy_(b)
 
     def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
         dev = self.device

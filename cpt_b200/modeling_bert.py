@@ -179,7 +179,7 @@ class _EngineSlot(object):
         # update through `p.data` (pytorch-transformers 1.x AdamW, apex) do NOT bump the autograd version counters the
         # signatures below key on — so after a backward both handles refresh their 16-bit copies unconditionally.
         self.dirty_train, self.dirty_infer = False, False
-        self.grad_sync_group = None  # comm.enable_overlapped_grad_sync
+        self.grad_sync_group, self.grad_sync_dtype = None, "auto"  # comm.enable_overlapped_grad_sync
         self.home, self._per_device, self._lock = None, {}, threading.Lock()
 
     def for_device(self, dev):
@@ -195,8 +195,16 @@ class _EngineSlot(object):
                 s = _EngineSlot()
                 # replicas get freshly broadcast parameter tensors on every forward: never skip the weight check
                 s.home, s.frozen, s.grad_sync_group = dev, False, self.grad_sync_group
+                s.grad_sync_dtype = self.grad_sync_dtype
                 self._per_device[dev] = s
             return s
+
+    def apply_grad_sync(self, eng):
+        eng.grad_sync_group = self.grad_sync_group
+        want = self.grad_sync_dtype
+        if want == "auto":
+            want = "bf16" if eng.dtype == "bf16" else "fp32"
+        eng.grad_sync_dtype = torch.bfloat16 if (want == "bf16" and self.grad_sync_group is not None) else None
 
     def __deepcopy__(self, memo):
         return _EngineSlot()
@@ -398,7 +406,7 @@ class BertImgModel(BertPreTrainedModel):
             dtype = (getattr(self.config, "cpt_b200_train_dtype", None)
                      or os.environ.get("CPT_B200_TRAIN_DTYPE", "bf16"))
             slot.train_engine = Engine(self.config, dev, dtype=dtype, train=True)
-            slot.train_engine.grad_sync_group = slot.grad_sync_group
+            slot.apply_grad_sync(slot.train_engine)
             slot.train_sig = None
         slot.train_engine.owner_slot = slot
         if sig != slot.train_sig or slot.dirty_train or slot.train_opt_epoch != _OPT_EPOCH[0]:

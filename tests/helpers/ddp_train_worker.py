@@ -12,6 +12,9 @@ import sys
 import torch
 import torch.distributed as dist
 
+import functools
+print = functools.partial(print, flush=True)  # noqa: A001  (a hung worker must still show how far it got)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 from cpt_b200 import config as C  # noqa: E402
@@ -19,6 +22,8 @@ from cpt_b200.synthetic import synth_batch, synth_state_dict  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)   # a hang shows where, and ends the process
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl")
@@ -41,35 +46,68 @@ def main():
     whole = copy.deepcopy(rec)  # gqa_cpt.py:384 deep-copies the model; the native handle must not be shared
     ddp = torch.nn.parallel.DistributedDataParallel(rec, device_ids=[torch.cuda.current_device()],
                                                     find_unused_parameters=True)
-    overlap = len(sys.argv) > 1 and sys.argv[1] == "overlap"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "ddp"
+    overlap = mode.startswith("overlap")
     if overlap:  # gradients averaged inside the native backward, group by group; DDP's own reducer switched off
         from cpt_b200 import comm
-        comm.enable_overlapped_grad_sync(ddp)
+        comm.enable_overlapped_grad_sync(ddp, exchange_dtype="fp32" if mode == "overlap32" else "auto")
     sl = slice(rank * per, (rank + 1) * per)
     d = {k: v[sl].cuda() for k, v in b.items()}
-    loss, _ = ddp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
-                  masked_lm_labels=labels[sl].cuda())
-    loss.backward()
-    ok = True
-    if rank == 0:
-        f = {k: v.cuda() for k, v in b.items()}
-        wl, _ = whole(f["input_ids"], f["token_type_ids"], f["attention_mask"], img_feats=f["img_feats"],
-                      masked_lm_labels=labels.cuda())
-        wl.backward()
-        ref = dict(whole.named_parameters())
-        worst = 0.0
+    f = {k: v.cuda() for k, v in b.items()}
+    wl, _ = whole(f["input_ids"], f["token_type_ids"], f["attention_mask"], img_feats=f["img_feats"],
+                  masked_lm_labels=labels.cuda())
+    wl.backward()
+    ref = dict(whole.named_parameters())
+
+    def worst_difference(scale=1.0):
+        worst, same_none = 0.0, True
         for k, p in rec.named_parameters():
             r = ref[k].grad
             if p.grad is None:
-                ok = ok and r is None
+                same_none = same_none and r is None
                 continue
             if k.endswith("attention.self.key.bias"):
                 continue
-            e = (p.grad - r).abs().max().item() / max(r.abs().max().item(), 1e-30)
+            e = (p.grad - scale * r).abs().max().item() / max(scale * r.abs().max().item(), 1e-30)
             worst = max(worst, e)
-        print("worst relative gradient difference %s vs whole batch: %.3e"
-              % ("overlapped in-backward all-reduce" if overlap else "DDP-averaged", worst))
-        ok = ok and worst < 3e-2
+        return worst, same_none
+
+    ok = True
+    # pass 0 runs eagerly, pass 1 captures the forward, pass 2 the backward (with NCCL inside when overlapped), pass 3
+    # replays both graphs: every one of them must leave the whole-batch gradient behind
+    for it in range(4 if overlap else 1):
+        rec.zero_grad()
+        loss, _ = ddp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                      masked_lm_labels=labels[sl].cuda())
+        loss.backward()
+        worst, same_none = worst_difference()
+        if rank == 0:
+            print("pass %d: worst relative gradient difference %s vs whole batch: %.3e"
+                  % (it, "overlapped in-backward all-reduce (%s)" % mode if overlap else "DDP-averaged", worst))
+        ok = ok and same_none and worst < 3e-2
+    if overlap:
+        eng = rec.bert.train_engine()[0]
+        if rank == 0:
+            print("graph replays of the training step: forward %s backward-with-exchange %s; exchange dtype %s"
+                  % (any(st["fwd"] is not None for st in eng._tgraphs.values()),
+                     any(st.get("bwd_sync") is not None for st in eng._tgraphs.values()), eng.grad_sync_dtype))
+        ok = ok and any(st.get("bwd_sync") is not None for st in eng._tgraphs.values())
+        # gradient accumulation: two local passes under no_sync(), then one exchanging pass = 3 x the whole-batch gradient
+        rec.zero_grad()
+        for k in range(3):
+            import contextlib
+            with (ddp.no_sync() if k < 2 else contextlib.nullcontext()):
+                l3, _ = ddp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                            masked_lm_labels=labels[sl].cuda())
+                l3.backward()
+        worst, _ = worst_difference(3.0)
+        if rank == 0:
+            print("accumulated over 2 no_sync() passes + 1 exchanging pass: worst difference vs 3 x whole batch %.3e" % worst)
+        ok = ok and worst < 3e-2 and eng._unsynced is None
+        rec.zero_grad()
+        loss, _ = ddp(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                      masked_lm_labels=labels[sl].cuda())
+        loss.backward()
     opt = torch.optim.AdamW([p for p in ddp.parameters() if p.requires_grad], lr=1e-3)
     opt.step()
     # all ranks must hold identical parameters after the step
@@ -87,7 +125,8 @@ def main():
         print("mean loss before %.5f after %.5f; parameters identical across ranks: %s" % (t[0] / world, t[1] / world, same))
         ok = ok and same and (t[1] < t[0]).item()
         print("DDP_TRAIN_OK" if ok else "DDP_TRAIN_FAIL")
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    dist.destroy_process_group()   # comm.enable_overlapped_grad_sync made this release the NCCL-holding graphs first
     sys.exit(0 if ok or rank != 0 else 1)
 
 

@@ -12,15 +12,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["ddp", "overlap"])
+@pytest.mark.parametrize("mode", ["ddp", "overlap", "overlap32"])
 def test_ddp_gradients_match_whole_batch(mode):
     """mode "ddp": the reference's setup, DDP's bucketed all-reduce after the native backward; mode "overlap":
-    comm.enable_overlapped_grad_sync — NCCL all-reduce per gradient group from inside the backward."""
+    comm.enable_overlapped_grad_sync — NCCL all-reduce per gradient group from inside the (graph-captured) backward,
+    exchanging bf16 copies ("overlap") or the fp32 gradients themselves ("overlap32"); also no_sync() accumulation."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517" if mode == "ddp" else "29518",
+           "127.0.0.1", "--master-port", {"ddp": "29517", "overlap": "29518", "overlap32": "29519"}[mode],
            os.path.join(ROOT, "tests", "helpers", "ddp_train_worker.py"), mode]
     env = dict(os.environ, NCCL_DEBUG="WARN")
-    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    except subprocess.TimeoutExpired as e:
+        def txt(x):
+            return x.decode(errors="replace") if isinstance(x, bytes) else (x or "")
+        pytest.fail("worker hung; stdout so far:\n" + txt(e.stdout)[-3000:] + "\nstderr:\n" + txt(e.stderr)[-2000:])
     assert out.returncode == 0 and "DDP_TRAIN_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
