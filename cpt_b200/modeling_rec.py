@@ -9,6 +9,13 @@ arguments expose what every CPT caller does right after the call
     logits = model(ids, seg, mask, img_feats=f, mask_pos=mask_pos, vocab_ids=vocab_ids)[0]  # same values
 
 so the [B,S,V] score tensor (937 MB at B=64) is never formed.  Without them the full tensor is returned.
+
+The Visual-Genome CPT caller reads SEVERAL [MASK] positions per row and needs the whole vocabulary at each of them
+(fewshot/vg_cpt.py:270-271: `[out[mask_pos].softmax(-1) for out, mask_pos in zip(output, mask_token_pos)]`).  For it:
+
+    rows = model(ids, seg, mask, img_feats=f, mask_rows=flat)[0]     # [n, V]; flat[i] = b * S + s of the i-th position
+
+(== `output.view(-1, V)[flat]`; add `vocab_ids=` to restrict the columns).
 """
 import torch
 from torch import nn
@@ -34,7 +41,7 @@ class REC_MLM_CPT(BertPreTrainedModel):
         self._tie_or_clone_weights(self.cls.decoder, self.bert.embeddings.word_embeddings)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None,
-                position_ids=None, head_mask=None, img_feats=None, *, mask_pos=None, vocab_ids=None):
+                position_ids=None, head_mask=None, img_feats=None, *, mask_pos=None, vocab_ids=None, mask_rows=None):
         if self.cls.decoder.weight is not self.bert.embeddings.word_embeddings.weight:
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
@@ -54,6 +61,23 @@ class REC_MLM_CPT(BertPreTrainedModel):
                                     attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats,
                                     want_pooled=False)
         eng = self.bert.engine()
+        if mask_rows is not None:
+            if masked_lm_labels is not None or mask_pos is not None:
+                raise ValueError("mask_rows excludes mask_pos and masked_lm_labels")
+            seq = outputs[0]
+            n_rows = seq.shape[0] * seq.shape[1]
+            flat = mask_rows.reshape(-1)
+            if flat.dtype != torch.int64 or flat.device != seq.device:
+                raise ValueError("cpt_b200: mask_rows must be an int64 tensor on the model's device")
+            if flat.numel():
+                lo, hi = torch.aminmax(flat)     # one host read: an out-of-range row would be a device-side assert
+                if int(lo) < 0 or int(hi) >= n_rows:
+                    raise ValueError("cpt_b200: mask_rows holds a row outside [0, B*S = %d)" % n_rows)
+            picked = seq.reshape(n_rows, -1).index_select(0, flat)
+            scores = eng.mlm_scores(picked)                          # [n, V]: transform + tied decoder + bias
+            if vocab_ids is not None:
+                scores = scores.index_select(1, vocab_ids)
+            return (scores,) + outputs[2:]
         if mask_pos is not None:
             if masked_lm_labels is not None:
                 raise ValueError("mask_pos/vocab_ids (gathered logits) and masked_lm_labels are exclusive")

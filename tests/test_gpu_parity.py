@@ -380,3 +380,36 @@ def test_vcr_two_head_model_and_nsp_graph_path():
     assert torch.equal(one, one2) and (one.cpu() - want_ans).abs().max().item() <= RTOL * max(1.0, want_ans.abs().max().item())
     with pytest.raises(RuntimeError):
         two(d["input_ids"], head="")
+
+
+def test_multi_mask_rows_for_the_visual_genome_caller():
+    """fewshot/vg_cpt.py:270-283: 1-3 [MASK] positions per row, softmax over the whole vocabulary at each, mean log
+    probability of a predicate's word pieces.  mask_rows=flat returns those rows without forming [B,S,V]."""
+    from oracle import cpt_oracle as O
+    cfg = C.oscar_tiny(num_hidden_layers=2)
+    sd = synth_state_dict(cfg, seed=19)
+    B, T, R = 6, 40, 20
+    b = synth_batch(cfg, B, T, R, seed=23)
+    pre, rec, nsp = build(cfg, sd)
+    d = cuda(b)
+    positions = [[3], [4, 5], [2, 3, 4], [7], [8, 9], [1, 2, 3]]
+    flat = torch.tensor([i * (T + R) + p for i, ps in enumerate(positions) for p in ps])
+    with torch.no_grad():
+        rows = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+                   mask_rows=flat.cuda())[0]
+        full = rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"])[0]
+        oseq, _, _ = O.bert_img_model(sd, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"],
+                                      img_feats=b["img_feats"])
+        want = O.lm_head(sd, cfg, oseq.reshape(B * (T + R), -1)[flat])
+    rec.bert.engine().check()
+    assert rows.shape == (len(flat), cfg.vocab_size)
+    assert (rows.cpu() - want).abs().max().item() <= 2 * RTOL * want.abs().max().item()
+    assert (rows - full.reshape(-1, cfg.vocab_size)[flat.cuda()]).abs().max().item() <= 1e-5 * want.abs().max().item()
+    # the caller's statistic: mean log-probability of a predicate's pieces at its masks (row 2 has three)
+    pred = torch.tensor([17, 230, 41])
+    got = rows[3:6].softmax(-1).cpu()[torch.arange(3), pred].log().mean()
+    ref = want[3:6].softmax(-1)[torch.arange(3), pred].log().mean()
+    assert abs(got.item() - ref.item()) <= 2e-3 * abs(ref.item())
+    with pytest.raises(ValueError):
+        rec(d["input_ids"], d["token_type_ids"], d["attention_mask"], img_feats=d["img_feats"],
+            mask_rows=torch.tensor([B * (T + R)], device="cuda"))
