@@ -14,7 +14,12 @@
 //     MMA issuer skips those slots, the epilogue warps read them in place and release them;
 //   * row statistics of a consumer are fetched BEFORE the accumulator wait whenever the epilogue warp can see that the
 //     producing stage has already published the rows (it polls the same counter the TMA producer waited on);
-//   * stores are TMA bulk stores out of double-buffered staging blocks (cp.async.bulk.wait_group.read 1).
+//   * stores are TMA bulk stores out of double-buffered staging blocks (cp.async.bulk.wait_group.read 1);
+//   * the per-column vectors (bias, gamma-sum or gamma, beta) and the per-row statistics (rstd, -mean * rstd) of a tile
+//     are fetched by a dedicated FETCH warp one task ahead, into double-buffered shared memory, and handed over through
+//     mbarriers.  (Second event log: with four operand stages in flight the SM's path to L2 holds ~1000 TMA line
+//     requests, so ANY load an epilogue warp issues waits ~1.2 us behind them — two dependent ones per tile, vectors
+//     then statistics, cost 2.5 us of the 6.3 us tile period of the FFN-up stage.  prefetch.global.L1 did not help.)
 #pragma once
 #include "chain_sm100.cuh"
 
@@ -25,14 +30,19 @@ struct Chain2Cfg {
   static constexpr int kStageBytes = ChainCfg::kStageBytes;     // 32 KB: A 128 x 64 + B 128 x 64 (16-bit) = a residual slot
   static constexpr int kPad = 4096;                             // two of these per warp: staging blocks
   static constexpr int kPad16 = 2048;
-  static constexpr int kVecBytes = 3 * (kChainBN / 2) * 4;
-  static constexpr int kEpiBytes = kGemmEpiWarps * (2 * kPad + kPad16 + kVecBytes);
+  static constexpr int kThreads = kGemmThreads + 32;            // + the fetch warp
+  static constexpr int kVecBytes = 3 * kChainBN * 4;            // bias | gamma(-sum) | beta of the tile's 256 columns
+  static constexpr int kStatBytes = kGemmBM * 8;                // (rstd, -mean * rstd) of this CTA's 128 rows
+  static constexpr int kRawPlanes = 6;                          // landing zone of the (mean, M2) planes, 1 KB each
+  static constexpr int kXchBytes = kGemmBM * 8;                 // F stage: column half 1 hands (mean, M2) to half 0
+  static constexpr int kFetchBytes = 2 * (kVecBytes + kStatBytes) + kRawPlanes * kStatBytes + kXchBytes;
+  static constexpr int kEpiBytes = kGemmEpiWarps * (2 * kPad + kPad16) + kFetchBytes;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 512 + kChainMaxTasks * 4;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory");
 };
 
 template <typename T16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(Chain2Cfg::kThreads, 1)
 chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   using Cfg = Chain2Cfg;
   constexpr int kStages = Cfg::kStages;
@@ -48,6 +58,15 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
   auto tfull_bar = [&](int a) { return bars + 8u * (3 * kStages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (3 * kStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (3 * kStages + 4);
+  auto vfull_bar = [&](int b) { return bars + 8u * (3 * kStages + 6) + 4u * (kStages + 2) + 8u * b; };
+  auto vfree_bar = [&](int b) { return bars + 8u * (3 * kStages + 6) + 4u * (kStages + 2) + 16u + 8u * b; };
+  const uint32_t fbar = bars + 8u * (3 * kStages + 6) + 4u * (kStages + 2) + 32u;  // the fetch warp's own copies
+  // the statistics half of a buffer is free again as soon as the epilogue warps have read their two numbers (at the top
+  // of a tile), a whole tile earlier than the vectors: the slow part of a fetch (dependency + planes) starts that early
+  auto sfree_bar = [&](int b) { return bars + 8u * (3 * kStages + 6) + 4u * (kStages + 2) + 56u + 8u * b; };
+  // index of the first task whose dependency wait this CTA's producer has NOT passed yet (release.cta by the producer
+  // thread, acquire.cta by the fetch warp: the rows a task's statistics describe are published once it is passed)
+  const uint32_t ready_u32 = bars + 8u * (3 * kStages + 6) + 4u * kStages;
   uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
   int* rel_cnt = reinterpret_cast<int*>(epi_gen + Cfg::kEpiBytes + 8 * (3 * kStages + 6));  // [kStages]
   const int* task_s = reinterpret_cast<const int*>(epi_gen + Cfg::kEpiBytes + 512);
@@ -77,7 +96,7 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
     int* dst = reinterpret_cast<int*>(epi_gen + Cfg::kEpiBytes + 512);
     const int* src = p.tasks + (long long)pair_id * p.pitch;
     for (int i = threadIdx.x; i < p.pitch; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (threadIdx.x < kStages) rel_cnt[threadIdx.x] = 0;
+    if (threadIdx.x <= kStages) rel_cnt[threadIdx.x] = 0;  // [kStages] = the word at ready_u32
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
@@ -98,7 +117,11 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 2 * kGemmEpiWarps);
+        mbar_init(vfull_bar(a), 1);
+        mbar_init(vfree_bar(a), kGemmEpiWarps);
+        mbar_init(sfree_bar(a), kGemmEpiWarps);
       }
+      for (int a = 0; a < 3; ++a) mbar_init(fbar + 8u * a, 1);   // landing zones 0 / 1, vectors
       fence_barrier_init();
     }
     __syncwarp();
@@ -149,6 +172,7 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
           flag_wait_ge(s.dep + t.m0 / kGemmBM, s.dep_target);
           fence_proxy_async_global();
         }
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_u32), "r"(i + 1) : "memory");
         mark(i, 1);
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -208,6 +232,162 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
         mark(i, 4);
       }
     }
+  } else if (warp == 2 + kGemmEpiWarps) {
+    // ------------------------------------------------------------------ fetch warp: vectors + row statistics, ahead of the epilogue
+    // Everything arrives by BULK COPY (the TMA path).  Measured here: with the operand ring full on every SM about
+    // 19 MB of requests are in flight chip-wide, so any request — TMA or LSU — waits ~3 us (Little's law), and LSU loads
+    // additionally trickle at ~0.1 us per line.  So the fetch must be a whole task AHEAD: the (mean, M2) planes of this
+    // CTA's 128 rows (one 1 KB plane per 256 columns of the normalised width — the F stage merges its two column
+    // halves before writing) land in one of two zones; task i + 1's copy is in flight while task i's is merged.
+    constexpr int kZonePlanes = Cfg::kRawPlanes / 2;
+    const uint32_t fetch_u32 = epi_base + kGemmEpiWarps * (2 * Cfg::kPad + Cfg::kPad16);
+    uint8_t* fetch_gen = epi_gen + kGemmEpiWarps * (2 * Cfg::kPad + Cfg::kPad16);
+    const uint32_t zone_u32 = fetch_u32 + 2 * (Cfg::kVecBytes + Cfg::kStatBytes);
+    const float2* zone = reinterpret_cast<const float2*>(fetch_gen + 2 * (Cfg::kVecBytes + Cfg::kStatBytes));
+    auto stats_of = [&](const ChainStage& st) { return st.ln == 2 ? st.rpart : st.apart; };
+    auto parts_of = [&](const ChainStage& st, const TileAt& tt) {
+      if (stats_of(st) == nullptr || tt.m0 >= st.M) return 0;
+      const int w = st.ln == 2 ? st.N : st.K;
+      return (w + BN - 1) / BN;
+    };
+    uint32_t zphase[2] = {0u, 0u};
+    uint32_t vphase = 0;
+    int held[2] = {-1, -1};   // (stage, N tile) whose vectors each buffer holds
+    // copy planes [p0, p0 + nb) of task j's rows into zone z (lane 0 issues; the zone's barrier completes when landed)
+    auto issue_planes = [&](const ChainStage& st, const TileAt& tt, int p0, int nb, int z) {
+      if (lane == 0) {
+        const uint32_t zb = fbar + 8u * z;
+        const long long m_pad = chain_rows_padded(st.M);
+        fence_proxy_async_global();
+        mbar_expect_tx(zb, (uint32_t)nb * Cfg::kStatBytes);
+        for (int j = 0; j < nb; ++j)
+          bulk_load_1d(zone_u32 + (z * kZonePlanes + j) * Cfg::kStatBytes,
+                       stats_of(st) + (long long)(p0 + j) * m_pad + tt.m0, Cfg::kStatBytes, zb);
+      }
+      __syncwarp();
+    };
+    auto rows_published = [&](int j, bool block) {   // has this CTA's producer passed task j's dependency wait?
+      unsigned rdy = 0, spins = 0;
+      for (;;) {
+        if (lane == 0) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(rdy) : "r"(ready_u32) : "memory");
+        rdy = __shfl_sync(0xffffffffu, rdy, 0);
+        if ((int)rdy > j) return true;
+        if (!block) return false;
+        if (++spins > (1u << 24)) __trap();
+        __nanosleep(32);
+      }
+    };
+    // first batch of task j -> zone j & 1, if it has planes and (block or already) its rows are published
+    auto prefetch = [&](int j, bool block) {
+      const int task = task_s[j];
+      if (task < 0) return true;
+      const ChainStage& st = p.st[task >> 24];
+      const TileAt tt = decode(st, task & 0xFFFFFF);
+      const int np = parts_of(st, tt);
+      if (np == 0) return true;
+      if (st.dep != nullptr && !rows_published(j, block)) return false;
+      issue_planes(st, tt, 0, min(np, kZonePlanes), j & 1);
+      return true;
+    };
+    bool next_issued = prefetch(0, true);
+    for (int i = 0;; ++i) {
+      const int task = task_s[i];
+      if (task < 0) break;
+      const ChainStage& s = p.st[task >> 24];
+      const TileAt t = decode(s, task & 0xFFFFFF);
+      const int buf = i & 1;
+      if (lane == 0) mark(i, 11);
+      float* vec = reinterpret_cast<float*>(fetch_gen + buf * (Cfg::kVecBytes + Cfg::kStatBytes));
+      float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(vec) + Cfg::kVecBytes);
+      const uint32_t vec_u32 = fetch_u32 + buf * (Cfg::kVecBytes + Cfg::kStatBytes);
+      const bool fold = s.apart != nullptr, resid_ln = s.ln == 2 && s.rpart != nullptr;
+      const int n_parts = parts_of(s, t);
+      const int stats_width = s.ln == 2 ? s.N : s.K;
+      const bool whole = t.n0 + BN <= s.N;   // the tile's 256 columns exist: 1 KB per vector, 16-byte aligned
+      // task i's first batch is in flight (or landed) in zone i & 1; start task i + 1's into the other zone if its rows
+      // are already known to be published — otherwise after this task has been handed over
+      next_issued = prefetch(i + 1, false);
+      float cnt[kGemmBM / 32], mean[kGemmBM / 32], m2[kGemmBM / 32];
+#pragma unroll
+      for (int k = 0; k < kGemmBM / 32; ++k) cnt[k] = mean[k] = m2[k] = 0.f;
+      for (int p0 = 0; p0 < n_parts; p0 += kZonePlanes) {
+        const int nb = min(kZonePlanes, n_parts - p0);
+        if (p0 > 0) issue_planes(s, t, p0, nb, buf);   // hidden sizes above 768: further batches, serially
+        mbar_wait(fbar + 8u * buf, zphase[buf]);
+        zphase[buf] ^= 1u;
+        const float2* z = zone + buf * kZonePlanes * kGemmBM;
+        for (int j = 0; j < nb; ++j) {
+          const float nbv = (float)min(BN, stats_width - (p0 + j) * BN);
+#pragma unroll
+          for (int k = 0; k < kGemmBM / 32; ++k) {
+            const float2 pmv = z[j * kGemmBM + k * 32 + lane];
+            const float tot = cnt[k] + nbv, delta = pmv.x - mean[k];
+            mean[k] += delta * (nbv / tot);
+            m2[k] += pmv.y + delta * delta * (cnt[k] * nbv / tot);
+            cnt[k] = tot;
+          }
+        }
+        __syncwarp();   // the zone may be overwritten
+      }
+      if (lane == 0) mark(i, 12);
+      // the epilogue warps have read what task i - 2 left here.  Waited for on EVERY task: it is what keeps this warp
+      // less than two tasks ahead (the "full" barriers below must never run two phases ahead of their waiters)
+      mbar_wait(sfree_bar(buf), ((i >> 1) & 1u) ^ 1u);
+      if (n_parts > 0) {
+#pragma unroll
+        for (int k = 0; k < kGemmBM / 32; ++k) {
+          const float rstd = 1.0f / sqrtf(m2[k] / (float)stats_width + s.eps);
+          stat[k * 32 + lane] = make_float2(rstd, -mean[k] * rstd);
+        }
+      }
+      // ---- the vectors: reloaded only when the (stage, N tile) changed; their buffer is free once the epilogue warps
+      // have finished task i - 2 (a parity wait stays correct when earlier phases were not waited for: the barrier can
+      // be at most one phase ahead, because the epilogue of task i needs this task's "full" signal)
+      if (lane == 0) mark(i, 14);
+      const int vkey = ((task >> 24) << 20) | (t.n0 / BN);
+      const bool reload = held[buf] != vkey;
+      held[buf] = vkey;
+      if (reload) mbar_wait(vfree_bar(buf), ((i >> 1) & 1u) ^ 1u);
+      if (lane == 0) mark(i, 15);
+      if (reload && (!whole || s.bias == nullptr)) {   // edge tiles (N < 256), bias-less stages: through the LSU, zero-filled
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int nb = t.n0 + h2 * (BN / 2) + lane * 4;
+          float vv[3][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool in = nb + e < s.N;
+            vv[0][e] = (in && s.bias != nullptr) ? __ldg(s.bias + nb + e) : 0.f;
+            vv[1][e] = !in ? 0.f : fold ? __ldg(s.gvec + nb + e) : resid_ln ? __ldg(s.gamma + nb + e) : 0.f;
+            vv[2][e] = (in && resid_ln) ? __ldg(s.beta + nb + e) : 0.f;
+          }
+          *reinterpret_cast<float4*>(vec + h2 * (BN / 2) + lane * 4) = make_float4(vv[0][0], vv[0][1], vv[0][2], vv[0][3]);
+          if (!whole) {
+            *reinterpret_cast<float4*>(vec + BN + h2 * (BN / 2) + lane * 4) = make_float4(vv[1][0], vv[1][1], vv[1][2], vv[1][3]);
+            *reinterpret_cast<float4*>(vec + 2 * BN + h2 * (BN / 2) + lane * 4) = make_float4(vv[2][0], vv[2][1], vv[2][2], vv[2][3]);
+          }
+        }
+      }
+      if (reload && whole && (s.bias != nullptr || fold || resid_ln)) {
+        const uint32_t vb = fbar + 16u;
+        if (lane == 0) {
+          const uint32_t bytes = (s.bias != nullptr ? 1024u : 0u) + (fold ? 1024u : 0u) + (resid_ln ? 2048u : 0u);
+          mbar_expect_tx(vb, bytes);
+          if (s.bias != nullptr) bulk_load_1d(vec_u32, s.bias + t.n0, 1024u, vb);
+          if (fold) bulk_load_1d(vec_u32 + BN * 4, s.gvec + t.n0, 1024u, vb);
+          if (resid_ln) {
+            bulk_load_1d(vec_u32 + BN * 4, s.gamma + t.n0, 1024u, vb);
+            bulk_load_1d(vec_u32 + 2 * BN * 4, s.beta + t.n0, 1024u, vb);
+          }
+        }
+        mbar_wait(vb, vphase);
+        vphase ^= 1u;
+      }
+      __syncwarp();
+      if (lane == 0) mark(i, 13);
+      if (lane == 0) mbar_arrive(vfull_bar(buf));   // release.cta: the shared-memory writes above are visible to waiters
+      if (!next_issued) next_issued = prefetch(i + 1, true);
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 2;
@@ -218,9 +398,7 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
     const uint32_t padA_u32 = epi_base + ew * (2 * Cfg::kPad);
     uint8_t* pad16 = epi_gen + kGemmEpiWarps * 2 * Cfg::kPad + ew * Cfg::kPad16;
     const uint32_t pad16_u32 = epi_base + kGemmEpiWarps * 2 * Cfg::kPad + ew * Cfg::kPad16;
-    float* sv0 = reinterpret_cast<float*>(epi_gen + kGemmEpiWarps * (2 * Cfg::kPad + Cfg::kPad16) + ew * Cfg::kVecBytes);
-    float* sv1 = sv0 + kColsPerWarp;
-    float* sv2 = sv1 + kColsPerWarp;
+    uint8_t* fetch_gen = epi_gen + kGemmEpiWarps * (2 * Cfg::kPad + Cfg::kPad16);
     int it = 0, cursor = 0;   // cursor: ring slot the next task's first k-block goes to
     uint32_t rbits = 0;       // per ring slot: parity of its next RESIDUAL fill
     int issued = 0;           // bulk-store groups of the current tile committed so far
@@ -245,62 +423,26 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
       const bool rows_ok = mrow0 < s.M;
       const int n_live = max(0, min(kColsPerWarp, s.N - ncol0));
       const int m_pad = chain_rows_padded(s.M);
-      {  // per-column vectors of this warp's 128 columns -> smem
-        const int nb = ncol0 + lane * 4;
-        const bool in = nb + 3 < s.N;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s.bias != nullptr) {
-          if (in) {
-            b4 = __ldg(reinterpret_cast<const float4*>(s.bias + nb));
-          } else {
-            if (nb < s.N) b4.x = __ldg(s.bias + nb);
-            if (nb + 1 < s.N) b4.y = __ldg(s.bias + nb + 1);
-            if (nb + 2 < s.N) b4.z = __ldg(s.bias + nb + 2);
-          }
-        }
-        *reinterpret_cast<float4*>(sv0 + lane * 4) = b4;
-        if (s.apart != nullptr)
-          *reinterpret_cast<float4*>(sv1 + lane * 4) =
-              in ? __ldg(reinterpret_cast<const float4*>(s.gvec + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s.ln == 2 && s.rpart != nullptr) {
-          *reinterpret_cast<float4*>(sv1 + lane * 4) =
-              in ? __ldg(reinterpret_cast<const float4*>(s.gamma + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(sv2 + lane * 4) =
-              in ? __ldg(reinterpret_cast<const float4*>(s.beta + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-      }
-      // row statistics this epilogue needs (of the A operand's rows for a consumer, of the residual's rows for an F
-      // stage): fetched now if the producing stage has already published the rows, else after the accumulator wait
-      const float2* stats_src = s.ln == 2 ? s.rpart : s.apart;
-      const int stats_width = s.ln == 2 ? s.N : s.K;
+      // vectors and row statistics of this tile: left in shared memory by the fetch warp (normally long before)
+      const int vbuf = i & 1;
+      mbar_wait(vfull_bar(vbuf), (i >> 1) & 1u);
+      const float* sv0 = reinterpret_cast<const float*>(fetch_gen + vbuf * (Cfg::kVecBytes + Cfg::kStatBytes)) +
+                         half * kColsPerWarp;
+      const float* sv1 = sv0 + BN;
+      const float* sv2 = sv1 + BN;
       float fa = 1.f, fb = 0.f;
-      bool have_stats = stats_src == nullptr;
-      if (!have_stats && rows_ok) {
-        unsigned ok = 1u;
-        if (s.dep != nullptr) {
-          if (lane == 0) {
-            unsigned v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(s.dep + mt) : "memory");
-            ok = v >= s.dep_target ? 1u : 0u;
-          }
-          ok = __shfl_sync(0xffffffffu, ok, 0);
-        }
-        if (ok) {
-          const float2 st = chain_row_stats(stats_src, stats_width, m_pad, min(mrow0 + lane, s.M - 1), s.eps);
-          fa = st.y;
-          fb = -st.x * st.y;
-          have_stats = true;
-        }
+      if ((s.ln == 2 ? s.rpart : s.apart) != nullptr && rows_ok) {
+        const float2 st = reinterpret_cast<const float2*>(fetch_gen + vbuf * (Cfg::kVecBytes + Cfg::kStatBytes) +
+                                                          Cfg::kVecBytes)[q * 32 + lane];
+        fa = st.x;
+        fb = st.y;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfree_bar(vbuf));
+      if (tr) mark(i, 10);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (tr) mark(i, 6);
-      if (!have_stats && rows_ok) {
-        const float2 st = chain_row_stats(stats_src, stats_width, m_pad, min(mrow0 + lane, s.M - 1), s.eps);
-        fa = st.y;
-        fb = -st.x * st.y;
-      }
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * kColsPerWarp;
       const CUtensorMap* mo = &maps.o[s.map];
       issued = 0;
@@ -411,8 +553,24 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
         rbits ^= (1u << res0) | (1u << ((res0 + 1) % kStages)) | (1u << ((res0 + 2) % kStages)) |
                  (1u << ((res0 + 3) % kStages));
         if (work) tmem_ld_wait();
-        if (rows_ok)
-          s.part[(long long)((t.n0 / BN) * 2 + half) * m_pad + mrow0 + lane] = make_float2(mean, m2);
+        {  // one (mean, M2) plane per 256-column tile: the two column halves (warps q and q + 4) merge before writing
+          float2* xch = reinterpret_cast<float2*>(fetch_gen + 2 * (Cfg::kVecBytes + Cfg::kStatBytes) +
+                                                  Cfg::kRawPlanes * Cfg::kStatBytes) + q * 32 + lane;
+          if (half == 1) *xch = make_float2(mean, m2);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (half == 0) {
+            const float2 o = *xch;
+            const float na = work ? (float)n_live : 0.f;
+            const float nb = rows_ok ? (float)max(0, min(kColsPerWarp, s.N - (t.n0 + kColsPerWarp))) : 0.f;
+            if (nb > 0.f) {
+              const float tot = na + nb, delta = o.x - mean;
+              mean += delta * (nb / tot);
+              m2 += o.y + delta * delta * (na * nb / tot);
+            }
+            if (rows_ok) s.part[(long long)(t.n0 / BN) * m_pad + mrow0 + lane] = make_float2(mean, m2);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the slot may be rewritten
+        }
         __threadfence();  // the partials are ordered before this warp's "rows published" increment below
       } else {
         // ================= C stage: out = act(fa * acc + fb * g_n + c_n) as 16 bits (fa = 1, fb = 0 without the fold)
@@ -492,6 +650,7 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
           tma_store_wait_read<0>();
         }
         if (tr) mark(i, 7);
+        mbar_arrive(vfree_bar(vbuf));
       }
       __syncwarp();
     }

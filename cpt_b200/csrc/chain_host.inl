@@ -62,6 +62,7 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
     if (total < pairs) pairs = (int)std::max<long long>(1, total);
     std::vector<std::vector<int>> lists(pairs);
     std::vector<double> avail(pairs, 0.0);
+    std::vector<int> last_key(pairs, -2);
     // Global task order.  groups == 1: stage-major.  groups > 1: the M pairs are cut into `groups` contiguous groups and
     // the (stage, group) blocks are issued along anti-diagonals (stage + group = const), the blocks of one diagonal
     // interleaved proportionally — a software pipeline over row groups: while group 0 is in a LayerNorm stage (epilogue
@@ -107,11 +108,21 @@ static int chain_schedule(cpt_handle* h, const ChainStageHost* st, int n, cudaSt
         group_id[i] = t / group;
         group_used[i].clear();
       }
+      // Affinity: a pair that just ran a tile of the same stage and the same N tile keeps its per-column vectors (the
+      // kernel's fetch warp skips reloading them) and finds the weight tile warm: it wins ties and near-ties.
+      const int n_tiles_i = st[i].kind == CHAIN_GEMM ? (st[i].N + kChainBN - 1) / kChainBN : 1;
+      const int my_key = st[i].kind == CHAIN_GEMM ? (i << 16) | (t % n_tiles_i) : -1;
       int best = -1;
+      double best_score = 0.0;
       for (int p = 0; p < pairs; ++p) {
         if (group > 1 && std::find(group_used[i].begin(), group_used[i].end(), p) != group_used[i].end()) continue;
-        if (best < 0 || avail[p] < avail[best] - 1e-9) best = p;
+        const double score = avail[p] - ((my_key >= 0 && last_key[p] == my_key) ? 2.0 : 0.0);
+        if (best < 0 || score < best_score - 1e-9) {
+          best = p;
+          best_score = score;
+        }
       }
+      last_key[best] = my_key;
       if (group > 1) group_used[i].push_back(best);
       lists[best].push_back((i << 24) | t);
       avail[best] += cost + (group > 1 ? 6.0 : 0.0);
@@ -302,7 +313,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
       TRY(set_smem_attr(fn, Chain2Cfg::kSmemBytes));
       attr_set2[h->device & 63] = true;
     }
-    CK(launch_k(fn, dim3(pairs * 2), dim3(kGemmThreads), Chain2Cfg::kSmemBytes, st, 2, maps, p));
+    CK(launch_k(fn, dim3(pairs * 2), dim3(Chain2Cfg::kThreads), Chain2Cfg::kSmemBytes, st, 2, maps, p));
     return 0;
   }
   auto* fn = chain_kernel<T16>;

@@ -112,6 +112,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(x), "r"(y), "r"(z)
                : "memory");
 }
+// plain (non-tensor) bulk copy global -> this CTA's shared memory, completing on an mbarrier; 16-byte granules
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -111,6 +111,15 @@ def main():
                     d["mma_gap"] += (rec[3] - prev_mma_end) / GHZ / 1e3
                 prev_mma_end = rec[4]
                 d["ewait"] += (rec[6] - rec[5]) / GHZ / 1e3
+                if rec[10]:
+                    d["efetch"] = d.get("efetch", 0.0) + (rec[10] - rec[5]) / GHZ / 1e3
+                if rec[13]:
+                    d["f_total"] = d.get("f_total", 0.0) + (rec[13] - rec[11]) / GHZ / 1e3
+                    d["f_ready"] = d.get("f_ready", 0.0) + ((rec[12] - rec[11]) / GHZ / 1e3 if rec[12] else 0.0)
+                    d["f_lead"] = d.get("f_lead", 0.0) + (rec[5] - rec[13]) / GHZ / 1e3
+                    d["f_planes"] = d.get("f_planes", 0.0) + (rec[14] - (rec[12] or rec[11])) / GHZ / 1e3
+                    d["f_vfree"] = d.get("f_vfree", 0.0) + (rec[15] - rec[14]) / GHZ / 1e3
+                    d["f_vec"] = d.get("f_vec", 0.0) + (rec[13] - rec[15]) / GHZ / 1e3
                 d["ework"] += (rec[9] - rec[6]) / GHZ / 1e3
                 d["publish"] += (rec[7] - rec[9]) / GHZ / 1e3
             else:  # LayerNorm task: 6 rows ready | 1 rows normalised and stored | 2 fenced | 7 published
@@ -127,9 +136,10 @@ def main():
     for st in sorted(per):
         d = per[st]
         n = d["n"]
-        print("%-5s %5d %8.1f %8.1f |                %7.2f %7.2f %7.2f %8.2f %7.2f %7.2f %7.2f" %
+        print("%-5s %5d %8.1f %8.1f |                %7.2f %7.2f %7.2f %8.2f %7.2f %7.2f %7.2f | of e.wait: vectors+statistics %.2f | fetch warp: whole %.2f (rows known published %.2f, planes %.2f, vectors' buffer free %.2f, vectors %.2f), done %.2f before the epilogue asks" %
               (names[st], n, d["first"], d["last"], d["dep"] / n, d["issue"] / n, d["mma"] / n, d["mma_gap"] / n,
-               d["ewait"] / n, d["ework"] / n, d["publish"] / n))
+               d["ewait"] / n, d["ework"] / n, d["publish"] / n, d.get("efetch", 0.0) / n, d.get("f_total", 0.0) / n, d.get("f_ready", 0.0) / n,
+               d.get("f_planes", 0.0) / n, d.get("f_vfree", 0.0) / n, d.get("f_vec", 0.0) / n, d.get("f_lead", 0.0) / n))
     # timeline of a few pairs
     for p in (0, len(ev) // 2, len(ev) - 1):
         row = []

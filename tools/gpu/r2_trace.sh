@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for st in "ln1" "ln1,up"; do
+for st in "aod,upd,downd,qkvd" "upd" "qkvd"; do
   echo "##### stages $st"
-  timeout 120 python tools/chain_trace.py --stages $st 2>&1 | cut -c1-400
+  timeout 120 python tools/chain_trace.py --stages $st 2>&1 | grep -v "^LN task\|^fused tile\|^pair" | cut -c1-330
 done

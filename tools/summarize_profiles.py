@@ -19,7 +19,11 @@ RAW_METRICS = [("duration", "gpu__time_duration.sum"), ("SM cycles", "sm__cycles
                ("tensor pipe active % (of elapsed)", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                ("regs/thread", "launch__registers_per_thread"), ("grid", "launch__grid_size"),
                ("dyn smem/CTA", "launch__shared_mem_per_block_dynamic"), ("warp instructions", "sm__inst_executed.sum"),
-               ("L2->SM bytes", "lts__t_bytes_equiv_l1sectormiss_pipe_lsu_mem_global_op_ld.sum")]
+               ("L2->SM bytes", "lts__t_bytes_equiv_l1sectormiss_pipe_lsu_mem_global_op_ld.sum"),
+               ("L2 throughput %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+               ("L2 bytes (all traffic through the LTS)", "lts__t_bytes.sum"),
+               ("L2 sectors read", "lts__t_sectors_op_read.sum"), ("L2 sectors written", "lts__t_sectors_op_write.sum"),
+               ("L1/TEX+TMA -> SM throughput %", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")]
 
 
 def short(name):
@@ -78,7 +82,7 @@ def to_bytes(val, unit):
 
 def main():
     out = ["# profiles/%s — evidence of this round (B200, one GPU; raw files: gpurun_out/%s_*, produced by "
-           "`tools/gpu/profiles.sh`, summarised by `tools/summarize_profiles.py`)\n" % (TAG, TAG)]
+           "`tools/gpu/profiles.sh` / `tools/gpu/r2_profiles.sh`, summarised by `tools/summarize_profiles.py`)\n" % (TAG, TAG)]
     bench = json.load(open(os.path.join(G, TAG + "_bench.json")))
     kernels = bench.pop("kernels", {})
     bench.pop("config", None)
@@ -99,7 +103,9 @@ def main():
     out.append("\n## ncu --set full (one capture per kernel; `--clock-control none`; ncu flushes caches between replays, "
                "so DRAM traffic is the cold-cache figure)\n")
     traffic = {}
-    for title, name in (("GEMM kernels of one layer (QKV, attention-out, FFN-up, FFN-down)", "gemm"),
+    for title, name in (("dataflow chain kernel: attention-out + residual, FFN-up (LayerNorm folded) + GELU, FFN-down + "
+                         "residual, next layer's QKV (LayerNorm folded) in ONE launch; two consecutive layers", "chain"),
+                        ("GEMM kernels of one layer (QKV, attention-out, FFN-up, FFN-down)", "gemm"),
                         ("attention forward", "attn"), ("LayerNorm", "ln"),
                         ("attention backward (training, S=120)", "attn_bwd"),
                         ("backward GEMMs of one encoder layer at B=64 (in launch order: FFN-down wgrad [trans=3, "
@@ -113,6 +119,12 @@ def main():
         if tbl is None:
             continue
         out.append("### %s\n\n%s\n" % (title, tbl))
+        if name == "chain" and data:
+            r, idx, units = data[0]
+            rd, wr = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"]
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            traffic = json.load(open(tp)) if os.path.exists(tp) else {}
+            traffic["chain"] = to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr])
         if name == "gemm":
             for cls, (r, idx, units) in zip(("gemm_qkv", "gemm_attn_out", "gemm_ffn_up", "gemm_ffn_down"), data):
                 rd, wr = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"]
