@@ -658,7 +658,7 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
         for i in range(args.steps):
             devb[i % NROT] = {k: v.to(dev, non_blocking=True) for k, v in hp[i % NROT].items()}
             labels[i % NROT] = lp[i % NROT].to(dev, non_blocking=True)
-            float(step(i))  # the loss value is read on the host, as the reference's logging does
+            float(step(i).detach())  # the loss value is read on the host, as the reference's logging does
         barrier()
         e2e_s = time.perf_counter() - t0
         if world > 1:
