@@ -313,16 +313,29 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     fan = [4] * (B // 4) if w["head"] == "nsp" else None
 
-    def call(b):
+    # the path's only collective, the final logits: by default fused into the head kernel (peer-memory stores over
+    # NVLink + one flag per peer, comm.LogitsExchange); --collective nccl = one fixed-shape NCCL all-gather instead
+    ex = None
+    if world > 1 and args.collective == "peer":
+        ex = comm.LogitsExchange(B, int(cfg.num_contrast_classes) if w["head"] == "nsp" else max(K, 1))
+
+    def call(b, gather=None):
         if w["head"] == "nsp":
             return model(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"])[0]
         return model(b["input_ids"], b["token_type_ids"], b["attention_mask"], img_feats=b["img_feats"],
-                     mask_pos=b["mask_pos"], vocab_ids=vids)[0]
+                     mask_pos=b["mask_pos"], vocab_ids=vids, gather=gather)[0]
+
+    def gathered(b):
+        if world == 1:
+            return call(b)
+        if ex is None:
+            return comm.all_gather_logits(call(b), sizes=[B] * world)
+        if w["head"] == "nsp":
+            return ex.rows(model.bert.engine(), call(b))
+        return call(b, gather=ex)
 
     def step_resident(i):
-        out = call(devb[i % NROT])
-        if world > 1:
-            out = comm.all_gather_logits(out, sizes=[B] * world)  # the path's only collective: the final logits
+        out = gathered(devb[i % NROT])
         if fan is not None:
             comm.pick_per_query(out, fan * world, "vcr")           # per-question argmax on the device
         return out
@@ -342,6 +355,8 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
             for i in range(args.steps):
                 step_resident(i)
             torch.cuda.synchronize()
+            if ex is not None:
+                ex.close()
             return None
 
         sampler = ClockSampler(dev.index) if rank == 0 else None
@@ -397,10 +412,10 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
                 if i + 1 < n:
                     upload(i + 1)  # overlaps with this step's compute
                 main_stream.wait_event(slot_ready[s])
-                o = call(slots[s])
+                o = gathered(slots[s])
                 slot_free[s].record(main_stream)
                 if world > 1:
-                    o = comm.all_gather_logits(o, sizes=[B] * world)[rank * B:(rank + 1) * B]
+                    o = o[rank * B:(rank + 1) * B]
                 out_host[s].copy_(o, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -415,6 +430,8 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         res["e2e_s"] = e2e_s
+        if ex is not None:
+            ex.close()
 
         if want_extras and rank == 0:
             # the reference's loop as it is written: fresh device tensors every step (zeroshot/refcoco_cpt.py:212-219)
@@ -517,7 +534,10 @@ def run_infer(args, w, rank, local_rank, world, dist, dev):
                       "l2": "inputs rotate over distinct batches (%d MB together) and one step streams the 16-bit weights "
                             "plus ~3 MB of activations per row: larger than the 126 MB L2"
                             % ((8 if cfg.hidden_size <= 768 else 4) * res["h2d"] // 2 ** 20),
-                      "parallelism": "dp%d (rows sharded, one fixed-shape NCCL all-gather of the logits, no host sync)" % world},
+                      "parallelism": ("dp%d (rows sharded; the logits all-gather is fused into the head kernel: P2P stores into every "
+                                      "rank's buffer over NVLink + one flag per peer, inside the replayed graph)" % world
+                                      if args.collective == "peer" else
+                                      "dp%d (rows sharded, one fixed-shape NCCL all-gather of the logits, no host sync)" % world)},
            "e2e": {"value": total / res["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
                    "d2h_bytes_per_step": res["d2h"]},
            "gpu_launches": res["launches"],
@@ -763,6 +783,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="rows per step of the CPU reference arm (0 = per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the second dtype / fresh-tensor / unmodified-call legs")
+    ap.add_argument("--collective", choices=["peer", "nccl"], default="peer",
+                    help="N > 1 inference: how the per-rank logits are gathered (fused peer-memory exchange | NCCL)")
     ap.add_argument("--profile-only", action="store_true", help="run warmup+steps once without the extra legs (ncu)")
     args = ap.parse_args()
     w = WORKLOADS[args.config]

@@ -82,6 +82,11 @@ SYMBOLS = {
     "cpt_mlm_scores_workspace_bytes": (_sz, [_p, _ll]),
     "cpt_nsp_forward": (_i, [_p, _p, _p, _i, _p]),
     "cpt_head_linear": (_i, [_p, _p, _p, _i, _p, _p, _i, _p]),
+    "cpt_exchange_create": (_i, [_i, _i, _i, _i, _i, C.POINTER(_p), _p]),
+    "cpt_exchange_connect": (_i, [_p, _p]),
+    "cpt_exchange_destroy": (_i, [_p]),
+    "cpt_exchange_rows": (_i, [_p, _p, _p, _p, _i, _p]),
+    "cpt_mlm_gather_exchange": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i, _p, _sz, _p]),
     "cpt_train_enable": (_i, [_p, _i]),
     "cpt_train_set_progress_callback": (_i, [_p, _p, _p]),
     "cpt_train_tape_bytes": (_sz, [_p, _i, _i, _i, _i]),

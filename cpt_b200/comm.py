@@ -91,6 +91,63 @@ def all_gather_logits(local, sizes=None):
     return torch.cat([out[r * mx:r * mx + x] for r, x in enumerate(sizes)], 0)
 
 
+class LogitsExchange(object):
+    """Peer-memory all-gather of the per-rank [rows_per_rank, K] logits, fused into the kernel that computes them
+    (include/cpt_b200.h, cpt_mlm_gather_exchange): every rank's decoder kernel stores its logits straight into every
+    rank's gather buffer over NVLink and raises one flag per peer; a small second kernel waits for the peers and hands
+    out the gathered [world * rows_per_rank, K] block.  No NCCL call, no host synchronisation, and both launches are
+    part of the CUDA graph the forward is replayed from.  One node, one process per GPU, equal shards; every rank must
+    make the same sequence of calls.
+
+        ex = cpt_b200.comm.LogitsExchange(rows_per_rank=B, K=len(color_ids))          # once per shape
+        logits = model(ids, seg, mask, img_feats=f, mask_pos=mp, vocab_ids=color_ids, gather=ex)[0]   # [world*B, K]
+
+    (replaces `all_gather(predictions)` of Oscar/oscar/utils/comm.py:102-142 as used in zeroshot/refcoco_cpt.py:256
+    for the scores; `rows()` does the same for rows some other kernel produced, e.g. NSP scores)."""
+
+    def __init__(self, rows_per_rank, K, device=None, group=None):
+        import ctypes as C
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("LogitsExchange needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.rows_per_rank, self.K = int(rows_per_rank), int(K)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = _lib.load()
+        handle = (C.c_ubyte * 64)()
+        ex = C.c_void_p()
+        _lib.check(self.lib.cpt_exchange_create(self.device.index, self.rank, self.world, self.rows_per_rank, self.K,
+                                                C.byref(ex), handle))
+        self._ex = ex
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)   # every rank's 64-byte CUDA IPC handle
+        blob = b"".join(handles)
+        _lib.check(self.lib.cpt_exchange_connect(self._ex, blob))
+        dist.barrier(group=self.group)   # nobody stores into a peer before that peer has finished zeroing its flags
+
+    def rows(self, engine, local):
+        """[rows_per_rank, K] fp32 rows of this rank -> [world * rows_per_rank, K] on every rank (rank order)."""
+        from . import _lib
+        from .engine import _ptr, _stream
+        if tuple(local.shape) != (self.rows_per_rank, self.K) or local.dtype != torch.float32 or not local.is_contiguous():
+            raise ValueError("LogitsExchange.rows: expected a contiguous float32 [%d, %d] tensor"
+                             % (self.rows_per_rank, self.K))
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.world * self.rows_per_rank, self.K, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.cpt_exchange_rows(engine._h, self._ex, _stream(), _ptr(local), self.rows_per_rank,
+                                                  _ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_ex", None):
+            # not a collective: once this rank's last exchange has completed it has seen every peer's flag for it, so no
+            # peer store into this buffer is outstanding
+            torch.cuda.synchronize(self.device)
+            self.lib.cpt_exchange_destroy(self._ex)
+            self._ex = None
+
+
 def merge_by_key(dicts):
     """De-duplicate per-rank result dicts the way the reference does after its gather (DistributedSampler pads by
     repeating samples): the same key must carry the same value on every rank (zeroshot/refcoco_cpt.py:256-260)."""

@@ -472,13 +472,13 @@ static int layernorm(cpt_handle* h, cudaStream_t st, const float* x, long long l
 static int head_matvec(cpt_handle* h, cudaStream_t st, const float* X, long long ldx, int x_rows_per_b,
                        const long long* x_pos, const float* ln_g, const float* ln_b, float eps, const float* W,
                        long long ldw, const float* bias, const long long* w_ids, int w_rows, int B, int H, int O,
-                       int act, float* Y, long long ldy) {
+                       int act, float* Y, long long ldy, const HeadPeers& peers = HeadPeers()) {
   if (B <= 0 || O <= 0) return 0;
   const size_t smem = (size_t)kHeadRows * H * sizeof(float);
   dim3 grid((B + kHeadRows - 1) / kHeadRows, (O + kHeadOuts - 1) / kHeadOuts);
   ProfScope ps(h, st, CPT_K_HEAD);
   CK(launch_k(head_matvec_kernel, grid, dim3(256), smem, st, 1, X, ldx, x_rows_per_b, x_pos, ln_g, ln_b, eps, W, ldw,
-              bias, w_ids, w_rows, B, H, O, act, Y, ldy, h->err_flag));
+              bias, w_ids, w_rows, B, H, O, act, Y, ldy, h->err_flag, peers));
   return 0;
 }
 
@@ -1168,6 +1168,142 @@ int cpt_mlm_gather_forward(cpt_handle* h, void* stream, const float* seq_out, in
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory exchange
+struct cpt_exchange {
+  int device = 0, rank = 0, world = 1, rows = 0, K = 0;
+  char* base = nullptr;                 // cudaMalloc: [2][world * rows * K] floats | flags[world] | ctr, ctr2, epoch
+  void* peer_base[kMaxPeers] = {};      // cudaIpcOpenMemHandle mappings (peer_base[rank] = base)
+  size_t data_bytes = 0;
+  bool connected = false;
+  HeadPeers peers;
+  unsigned* my_flags = nullptr;
+  unsigned *ctr = nullptr, *ctr2 = nullptr, *epoch = nullptr;
+};
+
+int cpt_exchange_create(int device, int rank, int world, int rows_per_rank, int K, cpt_exchange** out,
+                        unsigned char* handle) {
+  if (!out || !handle || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || rows_per_rank <= 0 || K <= 0)
+    return fail("cpt_exchange_create: bad argument (world <= %d)", kMaxPeers);
+  DeviceGuard g(device);
+  cpt_exchange* ex = new cpt_exchange();
+  ex->device = device;
+  ex->rank = rank;
+  ex->world = world;
+  ex->rows = rows_per_rank;
+  ex->K = K;
+  ex->data_bytes = (2 * (size_t)world * rows_per_rank * K * sizeof(float) + 255) & ~size_t(255);
+  const size_t total = ex->data_bytes + 256;
+  cudaError_t e = cudaMalloc((void**)&ex->base, total);
+  if (e != cudaSuccess) {
+    delete ex;
+    return fail("cpt_exchange_create: cudaMalloc(%zu): %s", total, cudaGetErrorString(e));
+  }
+  cudaMemset(ex->base, 0, total);
+  cudaDeviceSynchronize();
+  cudaIpcMemHandle_t hnd;
+  e = cudaIpcGetMemHandle(&hnd, ex->base);
+  if (e != cudaSuccess) {
+    cudaFree(ex->base);
+    delete ex;
+    return fail("cpt_exchange_create: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  static_assert(sizeof(hnd) == CPT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(handle, &hnd, sizeof(hnd));
+  *out = ex;
+  return 0;
+}
+
+int cpt_exchange_connect(cpt_exchange* ex, const unsigned char* handles) {
+  if (!ex || !handles) return fail("cpt_exchange_connect: NULL argument");
+  if (ex->connected) return fail("cpt_exchange_connect: already connected");
+  DeviceGuard g(ex->device);
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank) {
+      ex->peer_base[r] = ex->base;
+      continue;
+    }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handles + (size_t)r * CPT_IPC_HANDLE_BYTES, sizeof(hnd));
+    cudaError_t e = cudaIpcOpenMemHandle(&ex->peer_base[r], hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail("cpt_exchange_connect: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+  }
+  HeadPeers& p = ex->peers;
+  p.world = ex->world;
+  p.rank = ex->rank;
+  p.half_elems = (long long)ex->world * ex->rows * ex->K;
+  p.rank_off = (long long)ex->rank * ex->rows * ex->K;
+  for (int r = 0; r < ex->world; ++r) {
+    p.dst[r] = (float*)ex->peer_base[r];
+    p.flags[r] = (unsigned*)((char*)ex->peer_base[r] + ex->data_bytes);
+  }
+  ex->my_flags = (unsigned*)(ex->base + ex->data_bytes);
+  ex->ctr = ex->my_flags + 32;
+  ex->ctr2 = ex->my_flags + 33;
+  ex->epoch = ex->my_flags + 34;
+  p.ctr = ex->ctr;
+  p.epoch = ex->epoch;
+  ex->connected = true;
+  return 0;
+}
+
+int cpt_exchange_destroy(cpt_exchange* ex) {
+  if (!ex) return 0;
+  DeviceGuard g(ex->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < ex->world; ++r)
+    if (r != ex->rank && ex->peer_base[r]) cudaIpcCloseMemHandle(ex->peer_base[r]);
+  if (ex->base) cudaFree(ex->base);
+  delete ex;
+  return 0;
+}
+
+static int exchange_wait(cpt_handle* h, cpt_exchange* ex, cudaStream_t st, float* gathered) {
+  const long long n = ex->peers.half_elems;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(64, (n + 4095) / 4096));
+  ProfScope ps(h, st, CPT_K_HEAD);
+  CK(launch_k(exchange_wait_kernel, dim3(blocks), dim3(256), 0, st, 1, ex->peers, (const unsigned*)ex->my_flags, ex->epoch,
+              ex->ctr2, gathered, h->err_flag));
+  return 0;
+}
+
+int cpt_exchange_rows(cpt_handle* h, cpt_exchange* ex, void* stream, const float* local, int rows, float* gathered) {
+  if (!h || !ex || !local || !gathered) return fail("cpt_exchange_rows: NULL argument");
+  if (!ex->connected) return fail("cpt_exchange_rows: cpt_exchange_connect has not run");
+  if (rows != ex->rows) return fail("cpt_exchange_rows: %d rows, the exchange was created for %d per rank", rows, ex->rows);
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)rows * ex->K;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(64, (n + 4095) / 4096));
+  {
+    ProfScope ps(h, st, CPT_K_HEAD);
+    CK(launch_k(exchange_push_kernel, dim3(blocks), dim3(256), 0, st, 1, local, n, ex->peers));
+  }
+  return exchange_wait(h, ex, st, gathered);
+}
+
+int cpt_mlm_gather_exchange(cpt_handle* h, cpt_exchange* ex, void* stream, const float* seq_out, int B, int S,
+                            const int64_t* mask_pos, const int64_t* vocab_ids, int K, void* workspace,
+                            size_t workspace_bytes, float* gathered) {
+  if (!h || !ex) return fail("NULL handle");
+  if (!h->has_mlm) return fail("MLM head weights (cls.predictions.*) were not provided");
+  if (!ex->connected) return fail("cpt_mlm_gather_exchange: cpt_exchange_connect has not run");
+  const cpt_config& c = h->cfg;
+  const int H = c.hidden_size;
+  if (!seq_out || !mask_pos || !gathered) return fail("NULL argument");
+  if (B != ex->rows || K != ex->K) return fail("cpt_mlm_gather_exchange: [%d, %d] logits, the exchange was created for [%d, %d] per rank", B, K, ex->rows, ex->K);
+  if (!vocab_ids && K != c.vocab_size) return fail("vocab_ids NULL requires K == vocab_size");
+  if ((size_t)B * H * 4 + 256 > workspace_bytes || !workspace) return fail("workspace too small for the MLM head");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* t = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  TRY(head_matvec(h, st, seq_out, H, S, (const long long*)mask_pos, nullptr, nullptr, 0.f, h->mlm_w, H, h->mlm_b,
+                  nullptr, H, B, H, H, ACT_GELU, t, H));
+  // the decoder writes its logits into every rank's gather buffer and raises the flags: compute + exchange in one kernel
+  TRY(head_matvec(h, st, t, H, 1, nullptr, h->mlm_g, h->mlm_beta, c.layer_norm_eps, h->word, H, h->mlm_bias,
+                  (const long long*)vocab_ids, c.vocab_size, B, H, K, ACT_NONE, nullptr, K, ex->peers));
+  return exchange_wait(h, ex, st, gathered);
+}
+
 size_t cpt_mlm_scores_workspace_bytes(const cpt_handle* h, long long rows) {
   if (!h || rows <= 0) return 0;
   const size_t H = h->cfg.hidden_size;
@@ -1296,8 +1432,9 @@ int cpt_check_async_error(cpt_handle* h, void* stream) {
                                  "vocabulary id out of range",
                                  "predicted rectangle with x2 <= x1 or y2 <= y1 (the reference asserts p[2] > p[0])",
                                  "a sample has more region boxes than max_img_seq_len",
-                                 "a prompt without [MASK] token (the reference's input_ids.index(103) raises)"};
-    return fail("device-side input check failed: %s", what[flag < 7 ? flag : 0]);
+                                 "a prompt without [MASK] token (the reference's input_ids.index(103) raises)",
+                                 "peer-memory exchange: a rank did not arrive within 10 s (ranks must make the same calls)"};
+    return fail("device-side check failed: %s", what[flag < 8 ? flag : 0]);
   }
   return 0;
 }

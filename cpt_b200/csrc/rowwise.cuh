@@ -269,11 +269,92 @@ constexpr int kHeadRows = 8;
 constexpr int kHeadOuts = 16;
 enum HeadAct { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
 
+// Peer-memory exchange of the per-rank logits: every rank's head kernel stores its [rows, K] block
+// straight into EVERY rank's gather buffer over NVLink (P2P stores into cudaIpc-mapped memory), then raises one flag
+// per peer; a small second kernel waits for all peers' flags and hands the gathered block over.  Epochs count
+// exchanges on the device, so the pair of launches can sit in a replayed CUDA graph; two buffer halves alternate by
+// epoch parity (a rank cannot get two exchanges ahead of a peer: it needs that peer's flag for the one in between).
+constexpr int kMaxPeers = 8;
+struct HeadPeers {
+  int world = 1, rank = 0;
+  long long half_elems = 0;      // floats in one parity half: world * rows_per_rank * K
+  long long rank_off = 0;        // rank * rows_per_rank * K
+  float* dst[kMaxPeers];         // every rank's buffer (dst[rank] = the local one)
+  unsigned* flags[kMaxPeers];    // every rank's flag array [world]
+  unsigned* ctr = nullptr;       // local: blocks finished / blocks that read the epoch
+  const unsigned* epoch = nullptr;  // local: exchanges completed so far
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// after a block's last peer store: the last block of the grid raises this rank's flag on every peer
+__device__ __forceinline__ void peers_signal(const HeadPeers& pr, unsigned n_blocks) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(pr.ctr, 1u) == n_blocks - 1) {
+      *pr.ctr = 0;
+      const unsigned e = *pr.epoch + 1;
+      __threadfence_system();
+      for (int r = 0; r < pr.world; ++r) st_release_sys(pr.flags[r] + pr.rank, e);
+    }
+  }
+}
+
+// rows of any producer -> every rank's buffer (NSP scores, or logits computed by another kernel)
+__global__ void __launch_bounds__(256) exchange_push_kernel(const float* __restrict__ local, long long n, HeadPeers pr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long off = (long long)((*pr.epoch + 1) & 1u) * pr.half_elems + pr.rank_off;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    const float v = local[i];
+    for (int r = 0; r < pr.world; ++r) pr.dst[r][off + i] = v;
+  }
+  peers_signal(pr, gridDim.x);
+}
+
+// wait for every peer's flag of this exchange, copy the gathered block out, count the exchange as done
+__global__ void __launch_bounds__(256) exchange_wait_kernel(HeadPeers pr, const unsigned* __restrict__ my_flags,
+                                                            unsigned* __restrict__ epoch_rw, unsigned* __restrict__ ctr2,
+                                                            float* __restrict__ out, int* __restrict__ err) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned e = *pr.epoch + 1;
+  if (threadIdx.x < pr.world) {
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(my_flags + threadIdx.x) < e) {
+      long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ll) {   // 10 s: a peer never arrived — fail the launch instead of hanging the GPU
+        atomicExch(err, 7);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const float* src = pr.dst[pr.rank] + (long long)(e & 1u) * pr.half_elems;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < pr.half_elems; i += 256ll * gridDim.x) out[i] = __ldcg(src + i);
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(ctr2, 1u) == gridDim.x - 1) {
+    *ctr2 = 0;
+    *epoch_rw = e;   // every block has read the old value (it arrived at the counter after doing so)
+  }
+}
+
 __global__ void __launch_bounds__(256) head_matvec_kernel(
     const float* __restrict__ X, long long ldx, int x_rows_per_b, const long long* __restrict__ x_pos,
     const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, const float* __restrict__ W,
     long long ldw, const float* __restrict__ bias, const long long* __restrict__ w_ids, int w_rows, int B, int H,
-    int O, int act, float* __restrict__ Y, long long ldy, int* __restrict__ err) {
+    int O, int act, float* __restrict__ Y, long long ldy, int* __restrict__ err, HeadPeers pr) {
   extern __shared__ float xs[];  // [kHeadRows][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -339,9 +420,15 @@ __global__ void __launch_bounds__(256) head_matvec_kernel(
       if (bias) v += bias[wr];
       if (act == ACT_GELU) v = v * 0.5f * (1.0f + erff(v * 0.70710678118654752f));
       else if (act == ACT_TANH) v = tanhf(v);
-      Y[(long long)(b0 + lane) * ldy + o] = v;
+      if (pr.world > 1) {   // fused exchange: the value goes straight into every rank's gather buffer
+        const long long at = (long long)((*pr.epoch + 1) & 1u) * pr.half_elems + pr.rank_off + (long long)(b0 + lane) * ldy + o;
+        for (int r = 0; r < pr.world; ++r) pr.dst[r][at] = v;
+      } else {
+        Y[(long long)(b0 + lane) * ldy + o] = v;
+      }
     }
   }
+  if (pr.world > 1) peers_signal(pr, gridDim.x * gridDim.y);
 }
 
 }  // namespace cptk

@@ -542,7 +542,10 @@ class Engine(object):
             if r is not None:
                 r.copy_(b)
 
-    def mlm_gather(self, seq_out, mask_pos, vocab_ids=None):
+    def mlm_gather(self, seq_out, mask_pos, vocab_ids=None, exchange=None):
+        """logits[b, k] = scores[b, mask_pos[b], vocab_ids[k]] (gather-first MLM head).  exchange (a
+        comm.LogitsExchange): the decoder kernel stores into every rank's gather buffer instead and the result is the
+        gathered [world * B, K] block."""
         dev = self.device
         B, S, H = seq_out.shape
         seq = _chk_tensor("sequence_output", seq_out, torch.float32, dev)
@@ -553,13 +556,19 @@ class Engine(object):
             vid = _chk_tensor("vocab_ids", vocab_ids, torch.int64, dev)
             K = vid.numel()
         with torch.cuda.device(dev):
-            out = torch.empty(B, K, dtype=torch.float32, device=dev)
             ws = self._workspace(B * H * 4 + 512)
+            if exchange is not None:
+                out = torch.empty(exchange.world * B, K, dtype=torch.float32, device=dev)
+                _lib.check(self.lib.cpt_mlm_gather_exchange(self._h, exchange._ex, _stream(), _ptr(seq), B, S, _ptr(mp),
+                                                            _ptr(vid), K, _ptr(ws), ws.numel(), _ptr(out)))
+                return out
+            out = torch.empty(B, K, dtype=torch.float32, device=dev)
             _lib.check(self.lib.cpt_mlm_gather_forward(self._h, _stream(), _ptr(seq), B, S, _ptr(mp), _ptr(vid), K,
                                                        _ptr(ws), ws.numel(), _ptr(out)))
         return out
 
-    def cpt_logits(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos, vocab_ids):
+    def cpt_logits(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos, vocab_ids,
+                   exchange=None):
         """encoder + gathered MLM head in one call: logits[b,k] = scores[b, mask_pos[b], vocab_ids[k]].
 
         The launch sequence is replayed from CUDA graphs in two ways:
@@ -572,9 +581,9 @@ class Engine(object):
             ~40 launches' worth of GPU work."""
         def run(t):
             seq, _, _ = self.encoder_forward(t[0], t[1], t[2], t[3], t[4], want_pooled=False)
-            return self.mlm_gather(seq, t[5], t[6])
+            return self.mlm_gather(seq, t[5], t[6], exchange)
 
-        return self._graphed("mlm", (input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
+        return self._graphed("mlm" if exchange is None else ("mlm", id(exchange)), (input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
                                      vocab_ids), run)
 
     def nsp_scores(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats):

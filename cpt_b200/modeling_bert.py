@@ -432,7 +432,8 @@ class BertImgModel(BertPreTrainedModel):
         return self._encode(input_ids, token_type_ids, attention_mask, position_ids, head_mask, img_feats,
                             encoder_history_states, want_pooled=True)
 
-    def _cpt_logits(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos, vocab_ids):
+    def _cpt_logits(self, input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos, vocab_ids,
+                    gather=None):
         if getattr(self.config, "output_attentions", False):
             raise NotImplementedError("cpt_b200: attention probabilities never leave the SM (output_attentions)")
         if attention_mask is not None and attention_mask.dim() != 2:
@@ -441,7 +442,7 @@ class BertImgModel(BertPreTrainedModel):
         if attention_mask is not None and attention_mask.dtype != torch.int64:
             attention_mask = attention_mask.to(torch.int64)
         return self.engine().cpt_logits(input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
-                                        vocab_ids)
+                                        vocab_ids, exchange=gather)
 
     def _encode(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,
                 img_feats=None, encoder_history_states=None, want_pooled=True):

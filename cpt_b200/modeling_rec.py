@@ -41,7 +41,7 @@ class REC_MLM_CPT(BertPreTrainedModel):
         self._tie_or_clone_weights(self.cls.decoder, self.bert.embeddings.word_embeddings)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None,
-                position_ids=None, head_mask=None, img_feats=None, *, mask_pos=None, vocab_ids=None, mask_rows=None):
+                position_ids=None, head_mask=None, img_feats=None, *, mask_pos=None, vocab_ids=None, mask_rows=None, gather=None):
         if self.cls.decoder.weight is not self.bert.embeddings.word_embeddings.weight:
             raise RuntimeError("cpt_b200: cls.decoder.weight must stay tied to the word embeddings "
                                "(modeling_rec.py:130-135); call tie_weights()")
@@ -56,7 +56,9 @@ class REC_MLM_CPT(BertPreTrainedModel):
                 and not getattr(self.config, "output_hidden_states", False)):
             # the CPT inference call: one fused (and CUDA-graph-cached) encoder + gathered-head launch sequence
             return (self.bert._cpt_logits(input_ids, token_type_ids, attention_mask, position_ids, img_feats, mask_pos,
-                                          vocab_ids),)
+                                          vocab_ids, gather=gather),)
+        if gather is not None:
+            raise ValueError("cpt_b200: gather= (comm.LogitsExchange) goes with the gather-first call (mask_pos=...)")
         outputs = self.bert._encode(input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
                                     attention_mask=attention_mask, head_mask=head_mask, img_feats=img_feats,
                                     want_pooled=False)

@@ -97,6 +97,27 @@ size_t cpt_mlm_scores_workspace_bytes(const cpt_handle *h, long long rows);
 /* NSPCPT head: cls.seq_relationship(pooled) — Oscar/oscar/modeling/modeling_vcr.py:120-121.  out fp32 [B,C]. */
 int cpt_nsp_forward(cpt_handle *h, void *stream, const float *pooled, int B, float *out);
 
+/* ---- Peer-memory exchange of the per-rank logits (replaces the two pickle all_gathers of
+ * Oscar/oscar/utils/comm.py:102-142 as called from zeroshot/refcoco_cpt.py:256,262 for the part that matters: the
+ * [rows, K] scores).  One process per GPU on one node.  cpt_exchange_create allocates this rank's gather buffer and
+ * returns its 64-byte CUDA IPC handle; the host exchanges the handles (torch.distributed.all_gather_object) and calls
+ * cpt_exchange_connect with all of them, rank-ordered.  cpt_mlm_gather_exchange is cpt_mlm_gather_forward whose decoder
+ * kernel stores its logits directly into EVERY rank's buffer over NVLink and raises one flag per peer; a second small
+ * kernel waits for the peers' flags and writes gathered[world * rows_per_rank, K] (rank order).  Both launches can be
+ * captured in a CUDA graph (the exchange count lives on the device).  cpt_exchange_rows does the same for rows some other
+ * kernel produced (e.g. NSP scores).  Every rank must make the same sequence of exchange calls.  A peer that never
+ * arrives sets error flag 7 after 10 s instead of hanging the GPU. */
+typedef struct cpt_exchange cpt_exchange;
+#define CPT_IPC_HANDLE_BYTES 64
+int cpt_exchange_create(int device, int rank, int world, int rows_per_rank, int K, cpt_exchange **out,
+                        unsigned char *handle /* [CPT_IPC_HANDLE_BYTES] */);
+int cpt_exchange_connect(cpt_exchange *ex, const unsigned char *handles /* [world][CPT_IPC_HANDLE_BYTES] */);
+int cpt_exchange_destroy(cpt_exchange *ex);
+int cpt_exchange_rows(cpt_handle *h, cpt_exchange *ex, void *stream, const float *local, int rows, float *gathered);
+int cpt_mlm_gather_exchange(cpt_handle *h, cpt_exchange *ex, void *stream, const float *seq_out, int B, int S,
+                            const int64_t *mask_pos, const int64_t *vocab_ids, int K, void *workspace,
+                            size_t workspace_bytes, float *gathered);
+
 /* A classification head on the pooled vector with CALLER-held weights: out[B,C] = x[B,H] W[C,H]^T + bias, all fp32
  * device pointers — the two heads of VCRQAR_NSPCPT (`cls_ans` / `cls_rat`, Oscar/oscar/modeling/modeling_vcr.py:
  * 194-252, selected per call by `head=`) without re-registering the handle's weights at every switch. */

@@ -56,3 +56,21 @@ def test_data_parallel_replicas_get_their_own_handles():
     assert multi.shape == single.shape
     assert (multi - single).abs().max().item() <= 1e-5 * single.abs().max().item()
     assert len(rec.bert._slot._per_device) == 1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_memory_logits_exchange():
+    """comm.LogitsExchange: the decoder kernel stores its logits into every rank's gather buffer over NVLink (CUDA IPC
+    peer memory) and a flag kernel completes the all-gather — bit-identical to NCCL's all_gather of the same logits,
+    through eager, captured and replayed steps."""
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n, "--master-addr",
+           "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "tests", "helpers", "exchange_worker.py")]
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, NCCL_DEBUG="WARN"), capture_output=True, text=True,
+                             timeout=240)
+    except subprocess.TimeoutExpired as e:
+        def txt(x):
+            return x.decode(errors="replace") if isinstance(x, bytes) else (x or "")
+        pytest.fail("worker hung; stdout so far:\n" + txt(e.stdout)[-3000:] + "\nstderr:\n" + txt(e.stderr)[-2000:])
+    assert out.returncode == 0 and "EXCHANGE_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
