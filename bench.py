@@ -436,9 +436,8 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
         if want_extras and rank == 0:
             # the reference's loop as it is written: fresh device tensors every step (zeroshot/refcoco_cpt.py:212-219)
             n_fresh = min(args.steps, 20)
-            fresh = [{k: v.to(dev) for k, v in host[i % NROT].items()} for i in range(4)]  # shape-keyed graph warm-up
-            for b in fresh:
-                call(b)
+            for i in range(8):   # warm-up in the loop's own steady state: shape-keyed graph captured, allocator blocks recycled
+                call({k: v.to(dev, non_blocking=True) for k, v in host[i % NROT].items()})
             torch.cuda.synchronize()
             r0 = eng.graph_replays
             t0 = time.perf_counter()
@@ -703,7 +702,7 @@ def run_train(args, w, rank, local_rank, world, dist, dev):
                       "parallelism": "dp%d (DistributedDataParallel semantics; one NCCL all-reduce per gradient group, "
                                      "issued from inside the backward)" % world},
            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-           "gpu_launches": launches, "loss": float(loss),
+           "gpu_launches": launches, "loss": float(loss.detach()),
            "algorithmic_gflop_per_sample": fl / 1e9, "model_tflops": value * fl / 1e12,
            "model_frac_of_sustained_peak": value * fl / 1e12 / (sustained * world), "clocks": clocks}
     if ms_nosync is not None:

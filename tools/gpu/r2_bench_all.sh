@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_scoring.py tests/test_gpu_optim.py tests/test_gpu_parity.py -q -m gpu --tb=short 2>&1 | tail -15 | cut -c1-250
 for c in 2 4 5 3; do
   timeout 900 python bench.py --config $c --steps 30 --warmup 5 > gpurun_out/bench_c$c.json 2> gpurun_out/bench_c$c.err
   echo "config $c rc=$?"; tail -3 gpurun_out/bench_c$c.err | cut -c1-300
