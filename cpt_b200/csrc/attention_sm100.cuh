@@ -24,7 +24,25 @@ struct AttnParams {
   float scale;            // 1/sqrt(dH)
   long long* trace;       // optional [gridDim.x][8] cycle counters (debug)
   Drop drop;              // training only (attn_tc_kernel): dropout on the probabilities, thresh = 0 -> off
+  // attn_pp_kernel after a chain launch: per 128-row tile, the chain's "QKV rows published" counter and the value that
+  // means complete.  The kernel then does NOT wait for the whole previous grid (griddepcontrol.wait): its CTAs take the
+  // SMs the chain's pairs free one by one and start on the samples whose rows are there.  NULL: plain PDL ordering.
+  const unsigned* qkv_ready = nullptr;
+  unsigned qkv_target = 0;
 };
+
+__device__ __forceinline__ void attn_rows_wait(const unsigned* addr, unsigned target) {
+  unsigned v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    if (v >= target) break;
+    if (++spins > (1u << 23)) {
+      printf("cpt_b200: attention waited for QKV rows that never came (block %d: have %u need %u)\n", blockIdx.x, v, target);
+      __trap();
+    }
+    __nanosleep(64);
+  }
+}
 
 __host__ __device__ inline int attn_nkb(int S) { return (S + 63) / 64; }
 inline size_t attn_smem_bytes(int S) {
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();
+  if (p.qkv_ready == nullptr) pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -556,6 +574,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
         const int mt = item % n_mt, h = (item / n_mt) % p.nH, b = item / (n_mt * p.nH);
         const int row0 = b * S;
         const uint32_t sQ = base + s * Cfg::kSlotBytes, sK = sQ + 16384, sV = sQ + Cfg::kVOff;
+        if (p.qkv_ready != nullptr) {   // the sample's rows, published tile by tile by the chain kernel still running
+          for (int t = row0 / 128; t <= (row0 + S - 1) / 128; ++t) attn_rows_wait(p.qkv_ready + t, p.qkv_target);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         mbar_wait(bar(SLOT_FREE, s), par ^ 1u);
         mbar_expect_tx(bar(QK_FULL, s), 16384 + NCH * 8192);
         tma_load_2d(sQ, &tmap_qkv, bar(QK_FULL, s), h * kAttnDH, row0 + mt * 128);

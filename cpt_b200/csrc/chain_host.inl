@@ -18,6 +18,7 @@ struct ChainStageHost {
   float* out32 = nullptr;
   void* out16 = nullptr;
   int dep_stage = -1;  // the stage whose output this one reads (-1: an earlier launch produced it)
+  bool publish = false;  // count this stage's finished rows even without an in-launch reader (a later launch polls them)
   // GEMM with the LayerNorm in its epilogue: out32 / out16 = LayerNorm(A W^T + bias + resid) gamma + beta
   int ln = 0;  // 1: LayerNorm finished in the epilogue; 2: deferred to the consumers (see ChainStage)
   const float* resid = nullptr;
@@ -281,6 +282,12 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
   }
   for (int i = 0; i < n; ++i)
     if (hs[i].dep_stage >= 0) p.st[hs[i].dep_stage].done = counters + (size_t)(2 * hs[i].dep_stage) * per;
+  for (int i = 0; i < n; ++i)   // a stage whose rows a LATER LAUNCH reads through the counters (attention after QKV)
+    if (hs[i].publish) {
+      p.st[i].done = counters + (size_t)(2 * i) * per;
+      h->pub_ready = p.st[i].done;
+      h->pub_target = (unsigned)(((p.st[i].N + kChainBN - 1) / kChainBN) * std::max(1, p.st[i].ksplit) * kGemmEpiWarps);
+    }
   // the schedule depends on the clamped ksplit: key it on what the kernel will decode
   std::vector<ChainStageHost> eff(hs, hs + n);
   for (int i = 0; i < n; ++i) eff[i].ksplit = p.st[i].ksplit;
@@ -373,6 +380,7 @@ static int chain_layer(cpt_handle* h, cudaStream_t st, const Workspace& w, int l
       ChainStageHost& g = s[n++];
       g.M = M; g.N = 3 * H; g.K = H; g.A = w.h16; g.lda = H; g.W = nx.w_qkv_f; g.ldw = H; g.bias = nx.c_qkv;
       g.gvec = nx.g_qkv; g.apart = P2; g.eps = c.layer_norm_eps; g.out = w.qkv16; g.ldo = 3 * H; g.dep_stage = 2;
+      g.publish = h->attn_early != 0;   // the next attention launch starts on rows as they are published
     }
     return run_chain<T16>(h, st, s, n, counters, w.part);
   }

@@ -160,6 +160,9 @@ struct cpt_handle {
   int chain_fuse_ln = 2;         // CPT_B200_CHAIN_FUSE_LN: 0 LayerNorm as row tasks between the GEMM stages, 1 finished
                                  // in the dense epilogues (row statistics exchanged through L2), 2 deferred to the consumers
   int chain_groups = 1;          // CPT_B200_CHAIN_GROUPS: row groups software-pipelined across the stages
+  int attn_early = 1;            // CPT_B200_ATTN_EARLY=0: attention waits for the whole chain launch before it (plain PDL)
+  const unsigned* pub_ready = nullptr;   // set by a chain launch whose last stage publishes its rows for the next launch
+  unsigned pub_target = 0;
   int chain_lean = 1;            // CPT_B200_CHAIN_LEAN=0: run deferred-LayerNorm launches on the general kernel
   float2* chain_part = nullptr;  // cpt_chain_run (tests): scratch of the fused LayerNorm epilogues
   size_t chain_part_bytes = 0;
@@ -378,6 +381,11 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
   if (H != nH * kAttnDH) return fail("attention kernel requires head size 64 (hidden %d, heads %d)", H, nH);
   if (S < 1 || S > 256) return fail("attention kernel supports 1 <= S <= 256 (got %d)", S);
   AttnParams p{B, S, H, nH, ext_mask, ctx, 0.125f, h->trace, Drop{0u, 0u, 0u, 0u, 1.f}};
+  if (impl == 0 && h->pub_ready != nullptr && !h->trace) {   // the chain launch just before published per-tile counters
+    p.qkv_ready = h->pub_ready;
+    p.qkv_target = h->pub_target;
+  }
+  h->pub_ready = nullptr;
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {
@@ -742,6 +750,7 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   if (!ws_ptr || ws_bytes < w.total) return fail("workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
   if (!ids || !seq_out) return fail("input_ids and seq_out must be non-NULL");
 
+  h->pub_ready = nullptr;
   const bool chain_h_ok = H == 128 || H == 256 || H == 512 || H == 768 || H == 1024;
   const bool use_chain = h->chain && !h->train && !(h->fold_ln && !hidden_states) && L > 0 && h->tma_store &&
                          h->reduce_resid && M >= h->chain_min_rows && chain_h_ok;
@@ -1022,6 +1031,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_CHAIN_GROUPS")) h->chain_groups = std::max(1, atoi(e));
   if (const char* e = getenv("CPT_B200_CHAIN_LEAN")) h->chain_lean = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
+  if (const char* e = getenv("CPT_B200_ATTN_EARLY")) h->attn_early = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
