@@ -78,8 +78,14 @@ class FeatureStore(object):
         self.device_features = None
 
     def to(self, device):
-        """All features into HBM (one pinned staging copy, one H2D)."""
-        self.device_features = torch.from_numpy(np.ascontiguousarray(self.features)).to(device)
+        """All features into HBM, streamed from the memory-mapped file in 64 Ki-row pieces (no whole-store host copy)."""
+        dev = torch.device(device)
+        out = torch.empty(self.features.shape, dtype=torch.float32, device=dev)
+        step = 1 << 16
+        for r0 in range(0, self.rows, step):
+            piece = np.array(self.features[r0:r0 + step])   # a writable copy of this piece of the read-only mapping
+            out[r0:r0 + piece.shape[0]].copy_(torch.from_numpy(piece))
+        self.device_features = out
         return self
 
     def set_features(self, img_idx, set_idx):
