@@ -317,7 +317,12 @@ def infer_leg(args, w, cfg, sd, dev, rank, world, dist, dtype, want_extras):
     # NVLink + one flag per peer, comm.LogitsExchange); --collective nccl = one fixed-shape NCCL all-gather instead
     ex = None
     if world > 1 and args.collective == "peer":
-        ex = comm.LogitsExchange(B, int(cfg.num_contrast_classes) if w["head"] == "nsp" else max(K, 1))
+        try:   # raises on every rank together when CUDA IPC peer mapping is not possible on this node
+            ex = comm.LogitsExchange(B, int(cfg.num_contrast_classes) if w["head"] == "nsp" else max(K, 1))
+        except RuntimeError as e:
+            if rank == 0:
+                print("bench: %s — falling back to the NCCL all-gather" % e, file=sys.stderr)
+            args.collective = "nccl"
 
     def call(b, gather=None):
         if w["head"] == "nsp":

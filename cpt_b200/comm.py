@@ -117,14 +117,32 @@ class LogitsExchange(object):
         self.lib = _lib.load()
         handle = (C.c_ubyte * 64)()
         ex = C.c_void_p()
-        _lib.check(self.lib.cpt_exchange_create(self.device.index, self.rank, self.world, self.rows_per_rank, self.K,
-                                                C.byref(ex), handle))
-        self._ex = ex
+        err = None
+        try:
+            _lib.check(self.lib.cpt_exchange_create(self.device.index, self.rank, self.world, self.rows_per_rank,
+                                                    self.K, C.byref(ex), handle))
+        except _lib.CptError as e:
+            err, ex = e, C.c_void_p()
+        self._ex = ex if ex.value else None
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=self.group)   # every rank's 64-byte CUDA IPC handle
-        blob = b"".join(handles)
-        _lib.check(self.lib.cpt_exchange_connect(self._ex, blob))
-        dist.barrier(group=self.group)   # nobody stores into a peer before that peer has finished zeroing its flags
+        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=self.group)   # 64-byte IPC handles
+        if err is None and all(h is not None for h in handles):
+            try:
+                _lib.check(self.lib.cpt_exchange_connect(self._ex, b"".join(handles)))
+            except _lib.CptError as e:
+                err = e
+        elif err is None:
+            err = _lib.CptError("cpt_b200: a peer could not create its exchange buffer")
+        # every rank learns whether EVERY rank is connected (this all-reduce is also the barrier after which peers may
+        # store: all flags are zeroed); on failure all ranks raise together, so callers can fall back to NCCL in step
+        ok = torch.tensor([0 if err is not None else 1], device=self.device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if self._ex is not None:
+                self.lib.cpt_exchange_destroy(self._ex)
+                self._ex = None
+            raise _lib.CptError("cpt_b200: peer-memory exchange unavailable on this node (%s)"
+                                % (err if err is not None else "a peer failed to map the buffers"))
 
     def rows(self, engine, local):
         """[rows_per_rank, K] fp32 rows of this rank -> [world * rows_per_rank, K] on every rank (rank order)."""
