@@ -29,6 +29,9 @@ struct AttnParams {
   // SMs the chain's pairs free one by one and start on the samples whose rows are there.  NULL: plain PDL ordering.
   const unsigned* qkv_ready = nullptr;
   unsigned qkv_target = 0;
+  // ... and before a chain launch that starts early itself: per 128-row tile of the context rows, this kernel counts
+  // rows x heads written (complete at 128 * nH; the partial last tile is padded up once by block 0)
+  unsigned* ctx_done = nullptr;
 };
 
 __device__ __forceinline__ void attn_rows_wait(const unsigned* addr, unsigned target) {
@@ -561,6 +564,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   if (p.qkv_ready == nullptr) pdl_wait();
+  if (p.ctx_done != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && ((p.B * S) & 127) != 0)
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.ctx_done + ((p.B * S) >> 7)),
+                 "r"((128 - ((p.B * S) & 127)) * p.nH) : "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -646,6 +652,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     const int grp = (warp - 2) >> 2, q = warp & 3;
     const int r = q * 32 + lane;             // query row == TMEM lane
     float* gmask = mask_s + (warp - 2) * (NCH * 64);  // this warp's private copy of the item's key mask (no group barrier)
+    int pub_g0 = 0, pub_valid = 0;   // context rows of this warp's last store that are not yet counted in ctx_done
+    auto publish_ctx = [&](int g0, int valid) {   // after cp.async.bulk.wait_group 0: rows [g0, g0 + valid) are written
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      const int in0 = min(valid, 128 - (g0 & 127));
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.ctx_done + (g0 >> 7)), "r"(in0) : "memory");
+      if (valid > in0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.ctx_done + (g0 >> 7) + 1), "r"(valid - in0) : "memory");
+    };
     const bool tr = p.trace != nullptr && warp == 2 && lane == 0;
     long long tq = tr ? clock64() : 0;
     auto lap = [&](int slot) {
@@ -804,8 +818,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+          if (p.ctx_done != nullptr && pub_valid > 0) {   // the PREVIOUS item's store has had a whole item to land
+            tma_store_wait<0>();
+            publish_ctx(pub_g0, pub_valid);
+          }
           tma_store_3d(&tmap_ctx, stage_u32, h * kAttnDH, mt * 128 + q * 32, b);
           tma_store_commit();
+          pub_g0 = b * S + mt * 128 + q * 32;
+          pub_valid = max(0, min(32, S - (mt * 128 + q * 32)));
           if (!kDefer) {  // two slots only: the slot must be refilled as soon as possible
             tma_store_wait_read<0>();
             mbar_arrive(bar(SLOT_FREE, s));
@@ -818,6 +838,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_pp_kernel(const __grid_
     }
     if (lane == 0) {
       tma_store_wait<0>();
+      if (p.ctx_done != nullptr && pub_valid > 0) publish_ctx(pub_g0, pub_valid);
       if (pending_free >= 0) mbar_arrive(bar(SLOT_FREE, pending_free));
     }
   }

@@ -132,7 +132,7 @@ chain2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Ch
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  pdl_wait();
+  if (!p.no_wait) pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 

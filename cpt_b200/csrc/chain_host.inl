@@ -19,6 +19,8 @@ struct ChainStageHost {
   void* out16 = nullptr;
   int dep_stage = -1;  // the stage whose output this one reads (-1: an earlier launch produced it)
   bool publish = false;  // count this stage's finished rows even without an in-launch reader (a later launch polls them)
+  const unsigned* ext_dep = nullptr;  // stage 0 only: per-128-row-tile counters a still-running EARLIER launch raises
+  unsigned ext_target = 0;
   // GEMM with the LayerNorm in its epilogue: out32 / out16 = LayerNorm(A W^T + bias + resid) gamma + beta
   int ln = 0;  // 1: LayerNorm finished in the epilogue; 2: deferred to the consumers (see ChainStage)
   const float* resid = nullptr;
@@ -183,6 +185,10 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
     d.bias = s.bias;
     d.done = nullptr;  // set below when a later stage of this launch reads this one
     d.map2 = -1;
+    if (s.ext_dep != nullptr) {
+      d.dep = s.ext_dep;
+      d.dep_target = s.ext_target;
+    }
     if (s.dep_stage >= 0) {
       if (s.dep_stage >= i) return fail("chain: stage %d depends on a later stage", i);
       const ChainStageHost& ps = hs[s.dep_stage];
@@ -313,6 +319,7 @@ static int run_chain(cpt_handle* h, cudaStream_t st, const ChainStageHost* hs, i
     h->chain_trace_pitch = p.pitch;
   }
   ProfScope ps(h, st, CPT_K_CHAIN);
+  p.no_wait = (lean && hs[0].ext_dep != nullptr) ? 1 : 0;
   if (lean) {
     auto* fn = chain2_kernel<T16>;
     static bool attr_set2[64] = {};
@@ -363,6 +370,11 @@ static int chain_layer(cpt_handle* h, cudaStream_t st, const Workspace& w, int l
       g.M = M; g.N = H; g.K = H; g.A = w.ctx16; g.lda = H; g.W = d.w_ao; g.ldw = H; g.bias = d.b_ao;
       g.ln = 2; g.resid = w.h32; g.ldr = H; g.eps = c.layer_norm_eps; g.out32 = w.a32; g.out16 = w.a16; g.part = P1;
       if (l > 0) { g.rpart = P2; g.gamma = h->layers[l - 1].o_g; g.beta = h->layers[l - 1].o_b; }
+      if (h->ctx_published != nullptr) {   // the attention launch just before counts its context rows per 128-row tile:
+        g.ext_dep = h->ctx_published;      // this launch starts inside ITS tail and waits tile by tile
+        g.ext_target = 128u * (unsigned)c.num_attention_heads;
+        h->ctx_published = nullptr;
+      }
     }
     {
       ChainStageHost& g = s[n++];

@@ -87,6 +87,7 @@ struct ChainParams {
   ChainStage st[kChainMaxStages];
   const int* tasks;  // [pairs][pitch]: (stage << 24) | index, -1 terminated
   int pitch;
+  int no_wait;       // chain2: stage 0 reads rows a STILL RUNNING attention launch publishes: no griddepcontrol.wait
   // optional event log (CPT_B200_CHAIN_TRACE=1), leader CTAs only: trace[(pair * pitch + i) * 16 + k] in SM clocks since
   // the CTA's entry: 0 producer starts waiting for the rows | 1 rows ready | 2 last load issued | 3 accumulator free
   // | 4 last MMA committed | 5 epilogue / LayerNorm starts waiting | 6 ready | 7 outputs published | 8 task code

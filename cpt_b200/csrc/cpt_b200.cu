@@ -163,6 +163,11 @@ struct cpt_handle {
   int attn_early = 1;            // CPT_B200_ATTN_EARLY=0: attention waits for the whole chain launch before it (plain PDL)
   const unsigned* pub_ready = nullptr;   // set by a chain launch whose last stage publishes its rows for the next launch
   unsigned pub_target = 0;
+  int chain_early = 0;           // CPT_B200_CHAIN_EARLY=1: the chain launch too starts inside the previous launch's tail
+                                 // (attention counts its context rows per tile).  Measured: no gain (1.818 vs 1.810 ms at
+                                 // B=64; the counting costs attention what the overlap saves), so off by default.
+  unsigned* ctx_counters = nullptr;      // set by the encoder loop: where the next attention launch may count its rows
+  const unsigned* ctx_published = nullptr;  // set by that attention launch if it does; read by the chain launch after it
   int chain_lean = 1;            // CPT_B200_CHAIN_LEAN=0: run deferred-LayerNorm launches on the general kernel
   float2* chain_part = nullptr;  // cpt_chain_run (tests): scratch of the fused LayerNorm epilogues
   size_t chain_part_bytes = 0;
@@ -386,6 +391,12 @@ static int attention(cpt_handle* h, cudaStream_t st, const void* qkv, const floa
     p.qkv_target = h->pub_target;
   }
   h->pub_ready = nullptr;
+  h->ctx_published = nullptr;
+  if (impl == 0 && h->ctx_counters != nullptr && !h->trace) {
+    p.ctx_done = h->ctx_counters;
+    h->ctx_published = h->ctx_counters;
+  }
+  h->ctx_counters = nullptr;
   if (h->trace) CK(cudaMemsetAsync(h->trace, 0, (size_t)h->num_sms * 128, st));
   ProfScope ps(h, st, CPT_K_ATTN);
   if (impl == 1) {
@@ -751,6 +762,8 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
   if (!ids || !seq_out) return fail("input_ids and seq_out must be non-NULL");
 
   h->pub_ready = nullptr;
+  h->ctx_counters = nullptr;
+  h->ctx_published = nullptr;
   const bool chain_h_ok = H == 128 || H == 256 || H == 512 || H == 768 || H == 1024;
   const bool use_chain = h->chain && !h->train && !(h->fold_ln && !hidden_states) && L > 0 && h->tma_store &&
                          h->reduce_resid && M >= h->chain_min_rows && chain_h_ok;
@@ -809,6 +822,11 @@ static int encoder_forward_impl(cpt_handle* h, cudaStream_t st, const int64_t* i
     if (hidden_states && h->chain_fuse_ln == 2) h->chain_fuse_ln = 1;  // per-layer outputs need finished LayerNorms
     int rc = 0;
     for (int l = 0; l < L && !rc; ++l) {
+      unsigned* ctr_l = w.flags + (size_t)l * (chain_ctr_per_layer / sizeof(unsigned));
+      // deferred-LayerNorm chains use four of the six counter pairs: the attention launch counts its context rows in a
+      // free one, and the chain launch starts inside its tail
+      h->ctx_counters = (h->chain_early && h->chain_fuse_ln == 2 && h->chain_lean) ? ctr_l + (size_t)10 * chain_m_tiles2(M)
+                                                                                    : nullptr;
       rc = attention<T16>(h, st, w.qkv16, w.ext_mask, B, S, w.ctx16, h->attn_impl);
       float* o32 = (l == L - 1 && h->chain_fuse_ln != 2) ? seq_out : w.h32;
       if (!rc)
@@ -1032,6 +1050,7 @@ int cpt_create(const cpt_config* cfg, int device, cpt_handle** out) {
   if (const char* e = getenv("CPT_B200_CHAIN_LEAN")) h->chain_lean = atoi(e) != 0;
   if (const char* e = getenv("CPT_B200_CHAIN_MIN_ROWS")) h->chain_min_rows = atoi(e);
   if (const char* e = getenv("CPT_B200_ATTN_EARLY")) h->attn_early = atoi(e);
+  if (const char* e = getenv("CPT_B200_CHAIN_EARLY")) h->chain_early = atoi(e);
   if (const char* e = getenv("CPT_B200_CHAIN_KSPLIT")) h->chain_down_ksplit = std::max(1, atoi(e));
   if (getenv("CPT_B200_TRACE")) {
     if (cudaMalloc((void**)&h->trace, (size_t)h->num_sms * 128) == cudaSuccess) {
