@@ -175,7 +175,7 @@ class _DataMutatingAdamW(torch.optim.Optimizer):
 
 @pytest.mark.parametrize("how", ["optimizer", "by_hand"])
 def test_weight_updates_through_p_data_are_picked_up(how):
-    """ADVICE r1 (high): `p.data.add_` leaves `p._version` untouched; both handles must still follow the update — after
+    """`p.data.add_` leaves `p._version` untouched; both handles must still follow the update — after
     an optimizer step (global post-step hook) and after a hand-written update that follows a backward (dirty flag)."""
     from cpt_b200 import config as C
     from cpt_b200.modeling_bert import BertImgForPreTraining
