@@ -4,6 +4,7 @@ cpt_b200/csrc.  No CPU path exists: tensors must live on a CUDA device of comput
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -609,8 +610,17 @@ class Engine(object):
             self._replayed_launches += hit[2]
             self.graph_replays += 1
             return hit[1].clone()
-        n = self._seen.get(key, 0) + 1
-        self._seen[key] = n
+        # a pointer-keyed graph is for PERSISTENT input buffers (the caller's own staging tensors).  Fresh tensors get
+        # recycled addresses from the caching allocator, so the same key can recur without any buffer being reused:
+        # count a sighting only if the first tensor is the very object seen before.
+        first = next((t for t in ts if t is not None), None)
+        seen = self._seen.get(key)
+        if seen is not None and seen[1]() is first:
+            seen[0] += 1
+        else:
+            seen = [1, weakref.ref(first)]
+            self._seen[key] = seen
+        n = seen[0]
         if len(self._seen) > 4096:
             self._seen.clear()
         if n >= 2 and len(self._graphs) < 64:
