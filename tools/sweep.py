@@ -1,7 +1,7 @@
 """Throughput of the CUDA path over the BASELINE.json configs' shapes (inference, one GPU, CUDA-graph replay).
-    python tools/sweep.py"""
+    python tools/sweep.py [--json profiles/rNN_sweep.json]"""
+import json
 import sys
-import time
 
 import torch
 
@@ -37,6 +37,7 @@ cases = [("config 1 shape: base, B=1,   S=120 (latency)", C.oscar_base, 1, 70, 5
          ("config 4: base, 16 rows/GPU, S=210, NSP (VCR)", C.oscar_base, 16, 165, 45, 0, "nsp"),
          ("config 4 shape at B=128 rows, S=210, NSP", C.oscar_base, 128, 165, 45, 0, "nsp"),
          ("config 5: large, B=256, S=200, K=2", C.oscar_large, 256, 150, 50, 2, "mlm")]
+results = []
 for name, fac, B, T, R, K, head in cases:
     cfg = fac()
     rec, nsp = build(cfg)
@@ -52,16 +53,7 @@ for name, fac, B, T, R, K, head in cases:
     with torch.no_grad():
         for _ in range(4):
             out = step()
-        if head == "nsp":  # no graph path for the NSP wrapper: capture it here
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s), torch.cuda.graph(g, stream=s):
-                out = step()
-            torch.cuda.current_stream().wait_stream(s)
-            run = g.replay
-        else:
-            run = step
+        run = step   # both wrappers replay their launch sequence from the engine's CUDA graphs
         torch.cuda.synchronize()
         n = 30 if B * (T + R) < 30000 else 10
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -74,5 +66,9 @@ for name, fac, B, T, R, K, head in cases:
     fl = flops(cfg, T, R, K)
     print("%-58s %8.3f ms/step %9.0f samples/s  %6.0f TFLOP/s (algorithmic)" % (name, ms, B / ms * 1e3, B / ms * 1e3 * fl / 1e12),
           flush=True)
+    results.append({"case": name, "batch": B, "T": T, "R": R, "K": K, "head": head, "ms_per_step": ms,
+                    "samples_per_s": B / ms * 1e3, "algorithmic_tflops": B / ms * 1e3 * fl / 1e12})
     del rec, nsp
     torch.cuda.empty_cache()
+if "--json" in sys.argv:
+    json.dump(results, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
