@@ -580,6 +580,9 @@ class Engine(object):
             loop hits: it moves every batch to the device anew (Oscar/oscar/zeroshot/refcoco_cpt.py:212-219), so
             addresses never repeat — without the staging graph each forward paid ~1.8 ms of host enqueue time for
             ~40 launches' worth of GPU work."""
+        if exchange is not None and getattr(exchange, "_ex", None) is None:
+            raise CptError("cpt_b200: this LogitsExchange has been closed")
+
         def run(t):
             seq, _, _ = self.encoder_forward(t[0], t[1], t[2], t[3], t[4], want_pooled=False)
             return self.mlm_gather(seq, t[5], t[6], exchange)
