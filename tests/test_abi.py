@@ -106,3 +106,16 @@ def test_from_pretrained_roundtrip(tmp_path):
     assert rec2.cls.decoder.weight is rec2.bert.embeddings.word_embeddings.weight
     names = [n for n, _ in rec.named_parameters()]
     assert any("LayerNorm.weight" in n for n in names) and any(n.endswith("bias") for n in names)
+
+
+def test_exchange_argument_checks_need_no_gpu():
+    """cpt_exchange_create validates before touching CUDA: more than 8 ranks, bad rank, empty shapes -> error string."""
+    import ctypes as C
+    from cpt_b200 import _lib
+    lib = _lib.load()
+    ex, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    for rank, world, rows, K in ((0, 9, 4, 2), (2, 2, 4, 2), (0, 2, 0, 2), (0, 2, 4, 0)):
+        assert lib.cpt_exchange_create(0, rank, world, rows, K, C.byref(ex), handle) != 0
+        assert b"cpt_exchange_create" in lib.cpt_last_error()
+    assert lib.cpt_exchange_connect(None, None) != 0
+    assert lib.cpt_exchange_destroy(None) == 0
